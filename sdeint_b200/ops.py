@@ -1,0 +1,329 @@
+"""Drift / diffusion operators understood by the CUDA integrators.
+
+The reference takes arbitrary Python callables `f(y, t)` and `G(y, t)`
+(sdeint/integrate.py:124-146).  A Python callable cannot run inside a CUDA
+kernel, so on this path `f` and `G` are OPERATOR OBJECTS: either one of the
+built-in families below (linear `A.y`, constant `B`, linear columns `B_k.y`,
+and the exactly solvable test equations of sdeint/tests/test_integrate.py) or
+CUDA device-function source compiled at run time with NVRTC for sm_100a
+(`CudaDrift`, `CudaDiffusion`).
+
+Every operator is ALSO a plain Python callable with the reference's calling
+convention, `f(y, t) -> (d,)`, `G(y, t) -> (d, m)`, and a diffusion can be
+split into its m column callables with `.columns()` (the "list of g_k" form of
+integrate.py:330-334).  That host-side evaluation exists for argument
+validation (`_check_args` probes `f(y0, t0)` exactly like integrate.py:71-107)
+and so that the very same object can be handed to the reference / the oracle in
+tests.  It is never used to integrate: there is no CPU fallback.
+
+Kind ids and parameter layouts are shared with `include/sdb.h`.
+"""
+from __future__ import annotations
+
+import numbers
+
+import numpy as np
+
+# ---- kind ids (must match include/sdb.h) ---------------------------------------------
+DRIFT_LINEAR = 0      # params: A[d][d] row-major                      f = A y
+DRIFT_KP4446 = 1      # params: a, c          f = -(a + c*y)(1 - y^2)  (c=b^2 Ito, 0 Strat)
+DRIFT_KPS445 = 2      # params: s             f = -sin2y - sin4y/4 + s*2 sin y cos^3 y
+DRIFT_USER = 9        # NVRTC source
+
+DIFF_CONST = 0        # params: B[d][m] row-major                      G = B
+DIFF_LINEAR_COLS = 1  # params: B[m][d][d]                             g_k = B_k y
+DIFF_KP4446 = 2       # params: b                                      G = b (1 - y^2)
+DIFF_KPS445 = 3       # params: (none; one dummy)                      G = sqrt2 cos^2 y
+DIFF_USER = 9
+
+
+def _is_scalar(y):
+    return isinstance(y, numbers.Number) or np.ndim(y) == 0
+
+
+class DriftOp:
+    """Base class: a drift operator with a device descriptor."""
+    kind = -1
+    d = 0
+    params = np.zeros(0)
+    source = None          # CUDA source for DRIFT_USER
+
+    @property
+    def __name__(self):    # the reference's scalar wrappers copy fn.__name__ (integrate.py:64)
+        return type(self).__name__
+
+    def key(self):
+        return ("f", self.kind, self.d, self.source)
+
+
+class DiffusionOp:
+    """Base class: a diffusion operator (d x m) with a device descriptor."""
+    kind = -1
+    d = 0
+    m = 0
+    params = np.zeros(0)
+    source = None
+
+    @property
+    def __name__(self):
+        return type(self).__name__
+
+    def key(self):
+        return ("G", self.kind, self.d, self.m, self.source)
+
+    def column(self, k, y, t):
+        return np.asarray(self(y, t))[:, k]
+
+    def columns(self):
+        """The m column callables g_k(y, t) -> (d,) (integrate.py:330-334)."""
+        return [DiffusionColumn(self, k) for k in range(self.m)]
+
+
+class DiffusionColumn:
+    """Column k of a DiffusionOp; a list of these is recognised by the shim as
+    the list-of-columns form of the same device operator."""
+
+    def __init__(self, parent, k):
+        self.parent = parent
+        self.k = int(k)
+        self.__name__ = "%s_col%d" % (type(parent).__name__, k)
+
+    def __call__(self, y, t):
+        return self.parent.column(self.k, y, t)
+
+
+# ---- built-ins -----------------------------------------------------------------------
+
+class LinearDrift(DriftOp):
+    """f(y, t) = A y."""
+    kind = DRIFT_LINEAR
+
+    def __init__(self, A):
+        A = np.atleast_2d(np.asarray(A, dtype=np.float64))
+        if A.ndim != 2 or A.shape[0] != A.shape[1]:
+            raise ValueError("LinearDrift needs a square matrix A")
+        self.A = np.ascontiguousarray(A)
+        self.d = A.shape[0]
+        self.params = self.A.reshape(-1).copy()
+
+    def __call__(self, y, t):
+        if _is_scalar(y) and self.d == 1:
+            return float(self.A[0, 0]) * y
+        return self.A.dot(y)
+
+
+class ConstDiffusion(DiffusionOp):
+    """G(y, t) = B (additive noise)."""
+    kind = DIFF_CONST
+
+    def __init__(self, B):
+        B = np.asarray(B, dtype=np.float64)
+        if B.ndim == 0:
+            B = B.reshape(1, 1)
+        if B.ndim != 2:
+            raise ValueError("ConstDiffusion needs a (d, m) matrix B")
+        self.B = np.ascontiguousarray(B)
+        self.d, self.m = B.shape
+        self.params = self.B.reshape(-1).copy()
+
+    def __call__(self, y, t):
+        if _is_scalar(y) and self.d == 1 and self.m == 1:
+            return float(self.B[0, 0])
+        return self.B.copy()
+
+    def column(self, k, y, t):
+        return self.B[:, k].copy()
+
+
+class LinearDiffusion(DiffusionOp):
+    """g_k(y, t) = B_k y for k = 0..m-1, B of shape (m, d, d)."""
+    kind = DIFF_LINEAR_COLS
+
+    def __init__(self, B):
+        B = np.asarray(B, dtype=np.float64)
+        if B.ndim != 3 or B.shape[1] != B.shape[2]:
+            raise ValueError("LinearDiffusion needs B of shape (m, d, d)")
+        self.B = np.ascontiguousarray(B)
+        self.m, self.d = B.shape[0], B.shape[1]
+        self.params = self.B.reshape(-1).copy()
+
+    def __call__(self, y, t):
+        if _is_scalar(y) and self.d == 1 and self.m == 1:
+            return float(self.B[0, 0, 0]) * y
+        return np.dot(self.B, y).T
+
+    def column(self, k, y, t):
+        return self.B[k].dot(y)
+
+
+class KP4446Drift(DriftOp):
+    """Kloeden & Platen (4.46) drift, sdeint/tests/test_integrate.py:93-99.
+    Ito: -(a + y b^2)(1 - y^2); Stratonovich: -a (1 - y^2)."""
+    kind = DRIFT_KP4446
+    d = 1
+
+    def __init__(self, a=1.0, b=0.8, stratonovich=False):
+        self.a, self.b, self.stratonovich = float(a), float(b), bool(stratonovich)
+        c = 0.0 if stratonovich else self.b ** 2
+        self.params = np.array([self.a, c], dtype=np.float64)
+
+    def __call__(self, y, t):
+        a, c = self.params
+        return -(a + y * c) * (1 - y ** 2)
+
+
+class KP4446Diffusion(DiffusionOp):
+    """G = b (1 - y^2), test_integrate.py:95-96."""
+    kind = DIFF_KP4446
+    d = 1
+    m = 1
+
+    def __init__(self, b=0.8):
+        self.b = float(b)
+        self.params = np.array([self.b], dtype=np.float64)
+
+    def __call__(self, y, t):
+        if _is_scalar(y):
+            return self.b * (1 - y ** 2)
+        return (self.b * (1 - np.asarray(y) ** 2)).reshape(1, 1)
+
+    def column(self, k, y, t):
+        return self.b * (1 - np.asarray(y) ** 2)
+
+
+class KPS445Drift(DriftOp):
+    """Kloeden, Platen & Schurz (4.5) drift, test_integrate.py:263-269."""
+    kind = DRIFT_KPS445
+    d = 1
+
+    def __init__(self, stratonovich=False):
+        self.stratonovich = bool(stratonovich)
+        self.params = np.array([1.0 if stratonovich else 0.0], dtype=np.float64)
+
+    def __call__(self, y, t):
+        out = -np.sin(2 * y) - 0.25 * np.sin(4 * y)
+        if self.stratonovich:
+            out = out + 2.0 * np.sin(y) * np.cos(y) ** 3
+        return out
+
+
+class KPS445Diffusion(DiffusionOp):
+    """G = sqrt(2) cos^2 y, test_integrate.py:265-266."""
+    kind = DIFF_KPS445
+    d = 1
+    m = 1
+
+    def __init__(self):
+        self.params = np.array([np.sqrt(2.0)], dtype=np.float64)
+
+    def __call__(self, y, t):
+        if _is_scalar(y):
+            return np.sqrt(2.0) * np.cos(y) ** 2
+        return (np.sqrt(2.0) * np.cos(np.asarray(y)) ** 2).reshape(1, 1)
+
+    def column(self, k, y, t):
+        return np.sqrt(2.0) * np.cos(np.asarray(y)) ** 2
+
+
+# ---- user CUDA source (NVRTC) --------------------------------------------------------
+
+class CudaDrift(DriftOp):
+    """Drift given as CUDA source.  The source must define
+
+        __device__ void sde_drift(const double* y, double t,
+                                  const double* p, double* out);   // out[d]
+
+    `params` are passed as `p`.  `host` is an optional Python callable with the
+    reference's signature, used only for argument validation and tests."""
+    kind = DRIFT_USER
+
+    def __init__(self, source, d, params=(), host=None):
+        self.source = str(source)
+        self.d = int(d)
+        self.params = np.asarray(params, dtype=np.float64).reshape(-1).copy()
+        self.host = host
+
+    def __call__(self, y, t):
+        if self.host is None:
+            return np.zeros(self.d)        # shape probe only
+        return self.host(y, t)
+
+
+class CudaDiffusion(DiffusionOp):
+    """Diffusion given as CUDA source.  The source must define
+
+        __device__ void sde_diffusion_col(int k, const double* y, double t,
+                                          const double* p, double* out);  // out[d]
+
+    i.e. column k of G (the integrators only ever need single columns,
+    integrate.py:516-521)."""
+    kind = DIFF_USER
+
+    def __init__(self, source, d, m, params=(), host=None):
+        self.source = str(source)
+        self.d, self.m = int(d), int(m)
+        self.params = np.asarray(params, dtype=np.float64).reshape(-1).copy()
+        self.host = host
+
+    def __call__(self, y, t):
+        if self.host is None:
+            return np.zeros((self.d, self.m))
+        return self.host(y, t)
+
+
+# ---- named systems of SURVEY.md 8(d) --------------------------------------------------
+
+def sys_lin(d, m):
+    """SYS_LIN(d, m): non-commutative linear system generalising Roessler (7.4).
+    A[i,i] = -1.5, A[i,j] = 0.5/d; B_k = (0.5/sqrt m)(1 + 0.5 R_k / sqrt d),
+    R_k = default_rng(7000+k).standard_normal((d,d)); y0 = ones(d)."""
+    A = np.full((d, d), 0.5 / d)
+    np.fill_diagonal(A, -1.5)
+    B = np.empty((m, d, d))
+    for k in range(m):
+        R = np.random.default_rng(7000 + k).standard_normal((d, d))
+        B[k] = (0.5 / np.sqrt(m)) * (np.eye(d) + 0.5 * R / np.sqrt(d))
+    return LinearDrift(A), LinearDiffusion(B), np.ones(d)
+
+
+def sys_lin2():
+    """README 2-d linear Ito SDE (README.rst:83-95)."""
+    A = np.array([[-0.5, -2.0], [2.0, -1.0]])
+    B = np.diag([0.5, 0.5])
+    return LinearDrift(A), ConstDiffusion(B), np.array([3.0, 3.0])
+
+
+def sys_kp4446(stratonovich=False, a=1.0, b=0.8):
+    """README scalar SDE / KP (4.46) (README.rst:60-69)."""
+    return KP4446Drift(a, b, stratonovich), KP4446Diffusion(b), 0.1
+
+
+def sys_kp4459(stratonovich=False):
+    """KP (4.59): d=1, m=2 geometric Brownian motion (test_integrate.py:170-199)."""
+    a, b1, b2 = -0.02, 1.0, 2.0
+    coef = a - (b1 ** 2 + b2 ** 2) / 2.0 if stratonovich else a
+    return (LinearDrift([[coef]]), LinearDiffusion(np.array([[[b1]], [[b2]]])),
+            np.array([1.0]))
+
+
+def sys_kps445(stratonovich=False):
+    return KPS445Drift(stratonovich), KPS445Diffusion(), 1.0
+
+
+def sys_r74(stratonovich=False):
+    """Roessler (7.4): d=5, m=4 linear system (test_integrate.py:350-375)."""
+    d, m = 5, 4
+    A = np.full((d, d), 0.05)
+    B0 = np.full((d, d), 0.01)
+    np.fill_diagonal(A, -1.5)
+    np.fill_diagonal(B0, 0.2)
+    if stratonovich:
+        S = np.full((d, d), -0.0086)
+        np.fill_diagonal(S, -0.0808)
+        A = A + S
+    return LinearDrift(A), LinearDiffusion(np.stack([B0] * m)), np.ones(d)
+
+
+def sys_ou(theta=1.0, sigma=0.2):
+    """1-d Ornstein-Uhlenbeck, dy = -theta y dt + sigma dW (test_integrate.py:37-54)."""
+    return LinearDrift([[-theta]]), ConstDiffusion([[sigma]]), 0.0
