@@ -1,0 +1,150 @@
+/* sdb.h -- C ABI of libsdb.so, the B200 (sm_100a) ensemble SDE integrator.
+ *
+ * The reference (mattja/sdeint, pure Python) has no FFI: its only boundary is
+ * the Python function API of sdeint/__init__.py:3-5.  This header is the
+ * boundary a maintainer of the reference would bind with ctypes to replace the
+ * hot path (the per-step loops of sdeint/integrate.py and the noise
+ * construction of sdeint/wiener.py); INTEGRATION.md shows that binding and
+ * sdeint_b200/_lib.py is the one this repository ships.
+ *
+ * Conventions
+ *   - every entry point returns 0 on success, non-zero on error; the message is
+ *     available from sdb_last_error() (thread-local);
+ *   - pointers named d_* are DEVICE pointers, h_* are HOST pointers; the caller
+ *     owns every buffer (the Python shim allocates them as torch tensors);
+ *   - `stream` is a cudaStream_t passed as void*; launches are asynchronous;
+ *   - arrays are addressed through explicit element strides (in doubles) so the
+ *     same kernels serve the reference's per-path (N, .) layout and the
+ *     path-minor ensemble layout [time][component][path] used for coalescing;
+ *   - no torch types, no C++ types.
+ */
+#ifndef SDB_H
+#define SDB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDB_VERSION 100
+
+/* ---- schemes: the integrators of sdeint/integrate.py ------------------------------- */
+#define SDB_SCHEME_EULER 0 /* itoEuler    integrate.py:190-240 */
+#define SDB_SCHEME_HEUN 1  /* stratHeun   integrate.py:243-303 */
+#define SDB_SCHEME_SRK2 2  /* itoSRI2 / stratSRS2 = _Roessler2010_SRK2, integrate.py:436-523 */
+#define SDB_SCHEME_KP2IS 3 /* stratKP2iS  integrate.py:526-646 */
+
+/* ---- drift / diffusion operator kinds (sdeint_b200/ops.py) ------------------------- */
+#define SDB_DRIFT_LINEAR 0 /* params A[d][d]               f = A y */
+#define SDB_DRIFT_KP4446 1 /* params a, c                  f = -(a + c y)(1 - y^2) */
+#define SDB_DRIFT_KPS445 2 /* params s                     f = -sin 2y - sin 4y / 4 + 2 s sin y cos^3 y */
+#define SDB_DRIFT_USER 9   /* NVRTC: __device__ void sde_drift(const double* y, double t, const double* p, double* out) */
+#define SDB_DIFF_CONST 0       /* params B[d][m]           G = B */
+#define SDB_DIFF_LINEAR_COLS 1 /* params B[m][d][d]        g_k = B_k y */
+#define SDB_DIFF_KP4446 2      /* params b                 G = b (1 - y^2) */
+#define SDB_DIFF_KPS445 3      /* params sqrt2             G = sqrt2 cos^2 y */
+#define SDB_DIFF_USER 9 /* NVRTC: __device__ void sde_diffusion_col(int k, const double* y, double t, const double* p, double* out) */
+
+/* ---- where the noise comes from ------------------------------------------------------ */
+#define SDB_NOISE_HOST 0 /* dW (and I/J for SRK2, KP2iS) supplied by the caller (dW=, I=/J=) */
+#define SDB_NOISE_KPW 1  /* on-device Philox + Ikpw/Jkpw   wiener.py:77-131 */
+#define SDB_NOISE_WIK 2  /* on-device Philox + Iwik/Jwik   wiener.py:234-305 */
+
+/* ---- flags --------------------------------------------------------------------------- */
+#define SDB_FLAG_Y0_BROADCAST 1 /* d_y0 holds one state (d doubles) used by every path */
+#define SDB_FLAG_STRATONOVICH 2 /* device noise: build J = I + h/2 (Jkpw/Jwik) instead of I */
+
+typedef struct sdb_system sdb_system; /* opaque: drift + diffusion + compiled kernels */
+
+const char* sdb_last_error(void);
+int sdb_version(void);
+
+/* Number of kernels launched by this library in the calling process (bench "gpu_launches"). */
+uint64_t sdb_launch_count(void);
+
+/* A (drift, diffusion) pair of built-in kinds; parameters are copied.
+ * Replaces the callables f, G of every integrator (integrate.py:124-146). */
+int sdb_system_builtin(int drift_kind, const double* h_drift_params, int64_t n_drift,
+                       int diff_kind, const double* h_diff_params, int64_t n_diff,
+                       int d, int m, sdb_system** out);
+
+/* Same, with user CUDA source for the kinds given as *_USER (NVRTC, sm_100a). `src` must
+ * define sde_drift and/or sde_diffusion_col (see the kind comments above). */
+int sdb_system_nvrtc(const char* src, int drift_kind, const double* h_drift_params,
+                     int64_t n_drift, int diff_kind, const double* h_diff_params,
+                     int64_t n_diff, int d, int m, sdb_system** out);
+
+int sdb_system_destroy(sdb_system* sys);
+
+/* Ensemble integration arguments.  Strides are in elements (doubles). */
+typedef struct sdb_integrate_args {
+  int scheme;          /* SDB_SCHEME_* */
+  int noise;           /* SDB_NOISE_* */
+  int flags;           /* SDB_FLAG_* */
+  int n_terms;         /* series terms n of Ikpw/Iwik (default 5, wiener.py:77) */
+  int64_t paths;       /* P: sample paths in this call */
+  int64_t path_id0;    /* global id of the first path (Philox counter; rank offset) */
+  uint64_t seed;       /* Philox key */
+  int N;               /* len(tspan) */
+  int save_every;      /* store y at steps 0, save_every, 2 save_every, ... */
+  const double* h_tspan; /* HOST [N], equally spaced (checked by the caller) */
+  const double* d_y0;  /* [d] if Y0_BROADCAST else strided */
+  int64_t y0_stride_comp, y0_stride_path;
+  double* d_y;         /* output, n_saved = (N-1)/save_every + 1 points */
+  int64_t y_stride_save, y_stride_comp, y_stride_path;
+  const double* d_dW;  /* NOISE_HOST: [N-1][m][P] through strides; else NULL */
+  int64_t dW_stride_step, dW_stride_comp, dW_stride_path;
+  const double* d_IJ;  /* NOISE_HOST, SRK2/KP2IS: [N-1][m][m][P] through strides */
+  int64_t IJ_stride_step, IJ_stride_row, IJ_stride_col, IJ_stride_path;
+  const double* h_kp2is; /* KP2IS: HOST [3*d] = gam, al1, al2 (integrate.py:587-592) */
+  double rtol;         /* KP2IS: tolerance of the implicit solve (integrate.py:527) */
+  int64_t* d_status;   /* [4]: #non-finite paths, first such path, #unconverged solves, first such step */
+  void* stream;
+} sdb_integrate_args;
+
+/* The per-step loops of integrate.py:235-239, :292-302, :494-522, :613-645 over P paths. */
+int sdb_integrate(sdb_system* sys, const sdb_integrate_args* args);
+
+/* deltaW (wiener.py:36-52) for P paths: out[step][comp][path] through strides. */
+int sdb_delta_w(int64_t steps, int m, double h, int64_t paths, int64_t path_id0, uint64_t seed,
+                double* d_out, int64_t stride_step, int64_t stride_comp, int64_t stride_path,
+                void* stream);
+
+/* Ikpw/Jkpw/Iwik/Jwik (wiener.py:77-131, :234-305) for P paths x `steps` intervals.
+ * method: SDB_NOISE_KPW or SDB_NOISE_WIK; stratonovich: 0 -> I, 1 -> J.
+ * d_X, d_Y ([n][step][comp][path]) and d_Gt ([step][pair][path]) are OPTIONAL caller-supplied
+ * standard normals (construction parity with the reference's draws); when NULL they come
+ * from Philox(seed, path_id0 + p, step).  d_A receives A (KPW: m x m) or Atilde (WIK: M). */
+typedef struct sdb_repint_args {
+  int method, stratonovich, n_terms, m;
+  int64_t steps, paths, path_id0;
+  uint64_t seed;
+  double h;
+  const double* d_dW; int64_t dW_stride_step, dW_stride_comp, dW_stride_path;
+  const double* d_X;  const double* d_Y;
+  int64_t XY_stride_term, XY_stride_step, XY_stride_comp, XY_stride_path;
+  const double* d_Gt; int64_t Gt_stride_step, Gt_stride_pair, Gt_stride_path;
+  double* d_A;  int64_t A_stride_step, A_stride_elem, A_stride_path;
+  double* d_IJ; int64_t IJ_stride_step, IJ_stride_row, IJ_stride_col, IJ_stride_path;
+  void* stream;
+} sdb_repint_args;
+int sdb_repeated_integrals(const sdb_repint_args* args);
+
+/* Ensemble moments and histograms of saved states y[save][comp][path] (path stride 1):
+ * d_sums[save][comp][2] += (sum y, sum y^2) in a fixed, partition-independent order per
+ * block of 4096 paths; d_hist[save][comp][bins] += counts on [lo, hi) (NULL to skip). */
+int sdb_moments(const double* d_y, int64_t n_saved, int d, int64_t paths, double* d_sums,
+                unsigned long long* d_hist, int bins, double lo, double hi, void* stream);
+
+/* Measured peak of the FP64 pipe: runs a register-resident DFMA chain on every SM and
+ * returns TFLOP/s (roofline denominator of bench.py). */
+int sdb_fp64_peak(int iters, double* tflops_out, void* stream);
+
+/* Raw generator access (tests): Philox4x32-10 block for (seed, path, step, slot). */
+int sdb_philox_block(uint64_t seed, uint64_t path, uint32_t step, uint32_t slot, uint32_t out[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDB_H */

@@ -1,0 +1,84 @@
+"""Numpy restatement of the on-device noise source (TEST INFRASTRUCTURE).
+
+Philox4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11; Random123 v1.14 `philox.h`): not part of
+the reference (which uses numpy's PCG64) -- it is this repository's own generator, so the
+oracle restates the PUBLISHED algorithm and is pinned by Random123's known-answer vectors
+(`kat_vectors`: three philox4x32 10-round entries, checked in tests/test_philox.py).
+
+Normal transform (sdeint_b200/csrc/sdb_kernels.cuh, SdbStream::pair): one 128-bit block ->
+u1 = ((w0<<32|w1)>>11 + 1) 2^-53 in (0,1], u2 = ((w2<<32|w3)>>11) 2^-52 in [0,2),
+z0 = sqrt(-2 ln u1) cos(pi u2), z1 = sqrt(-2 ln u1) sin(pi u2).
+Normal number q of (path, step) is element q&1 of the block with counter
+(path_lo, path_hi, step, q>>1) and key (seed_lo, seed_hi).
+"""
+import numpy as np
+
+M0 = np.uint64(0xD2511F53)
+M1 = np.uint64(0xCD9E8D57)
+W0 = 0x9E3779B9
+W1 = 0xBB67AE85
+MASK = np.uint64(0xFFFFFFFF)
+
+
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Vectorised over numpy arrays of uint32-valued integers."""
+    c0, c1, c2, c3 = (np.asarray(c, dtype=np.uint64) & MASK for c in (c0, c1, c2, c3))
+    k0 = int(k0) & 0xFFFFFFFF
+    k1 = int(k1) & 0xFFFFFFFF
+    for _ in range(10):
+        p0 = M0 * c0
+        p1 = M1 * c2
+        n0 = ((p1 >> np.uint64(32)) ^ c1 ^ np.uint64(k0)) & MASK
+        n1 = p1 & MASK
+        n2 = ((p0 >> np.uint64(32)) ^ c3 ^ np.uint64(k1)) & MASK
+        n3 = p0 & MASK
+        c0, c1, c2, c3 = n0, n1, n2, n3
+        k0 = (k0 + W0) & 0xFFFFFFFF
+        k1 = (k1 + W1) & 0xFFFFFFFF
+    return c0, c1, c2, c3
+
+
+def normal_pairs(seed, path, step, slot):
+    """(z0, z1) for broadcastable integer arrays path, step, slot."""
+    path = np.asarray(path, dtype=np.uint64)
+    r0, r1, r2, r3 = philox4x32_10(path & MASK, path >> np.uint64(32), step, slot,
+                                   seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    a = ((r0 << np.uint64(32)) | r1) >> np.uint64(11)
+    b = ((r2 << np.uint64(32)) | r3) >> np.uint64(11)
+    u1 = (a + np.uint64(1)).astype(np.float64) * 2.0 ** -53
+    u2 = b.astype(np.float64) * 2.0 ** -52
+    rad = np.sqrt(-2.0 * np.log(u1))
+    return rad * np.cos(np.pi * u2), rad * np.sin(np.pi * u2)
+
+
+def normals(seed, path, step, q):
+    """Standard normal number q (array) of (path, step)."""
+    q = np.asarray(q, dtype=np.int64)
+    z0, z1 = normal_pairs(seed, path, step, q >> 1)
+    return np.where((q & 1) == 0, z0, z1)
+
+
+def delta_w(steps, m, h, paths, seed, path_id0=0):
+    """dW[p, n, j] as sdb_delta_w / the fused kernels generate it."""
+    p = (np.arange(paths, dtype=np.uint64) + np.uint64(path_id0))[:, None, None]
+    n = np.arange(steps)[None, :, None]
+    j = np.arange(m)[None, None, :]
+    return np.sqrt(h) * normals(seed, p, n, j)
+
+
+def kpw_normals(steps, m, n_terms, paths, seed, path_id0=0):
+    """X[k], Y[k] (n, P, N, m) as the device draws them for Ikpw/Iwik."""
+    p = (np.arange(paths, dtype=np.uint64) + np.uint64(path_id0))[:, None, None]
+    n = np.arange(steps)[None, :, None]
+    j = np.arange(m)[None, None, :]
+    X = np.stack([normals(seed, p, n, m + 2 * k * m + j) for k in range(n_terms)])
+    Y = np.stack([normals(seed, p, n, m + (2 * k + 1) * m + j) for k in range(n_terms)])
+    return X, Y
+
+
+def wik_tail_normals(steps, m, n_terms, paths, seed, path_id0=0):
+    M = m * (m - 1) // 2
+    p = (np.arange(paths, dtype=np.uint64) + np.uint64(path_id0))[:, None, None]
+    n = np.arange(steps)[None, :, None]
+    r = np.arange(M)[None, None, :]
+    return normals(seed, p, n, m + 2 * n_terms * m + r)

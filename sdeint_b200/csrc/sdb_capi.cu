@@ -1,0 +1,608 @@
+// sdb_capi.cu -- the C ABI of libsdb.so (include/sdb.h): system objects, kernel lookup
+// (ahead-of-time table, else NVRTC), launches.  No CPU fallback: every entry point that
+// computes launches a CUDA kernel or fails with an error.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#define SDB_DEFINE_STANDALONE 1
+#include "../../include/sdb.h"
+#include "sdb_host.h"
+#include "sdb_kernels.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// errors, counters
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static std::atomic<uint64_t> g_launches{0};
+
+static int fail(const std::string& msg) {
+  g_err = msg;
+  return 1;
+}
+#define SDB_CUDA(call)                                                                  \
+  do {                                                                                  \
+    cudaError_t e__ = (call);                                                           \
+    if (e__ != cudaSuccess)                                                             \
+      return fail(std::string(#call) + ": " + cudaGetErrorString(e__));                 \
+  } while (0)
+
+extern "C" const char* sdb_last_error(void) { return g_err.c_str(); }
+extern "C" int sdb_version(void) { return SDB_VERSION; }
+extern "C" uint64_t sdb_launch_count(void) { return g_launches.load(); }
+
+std::vector<SdbAotEntry>& sdb_aot_registry() {
+  static std::vector<SdbAotEntry> reg;
+  return reg;
+}
+
+std::string sdb_loop_key(int scheme, int fk, int gk, int d, int m, int noise, bool inl) {
+  char buf[128];
+  snprintf(buf, sizeof buf, "loop|s%d|f%d|g%d|d%d|m%d|n%d|p%c", scheme, fk, gk, d, m, noise,
+           inl ? 'i' : 'g');
+  return buf;
+}
+
+static const void* aot_lookup(const std::string& key) {
+  for (const auto& e : sdb_aot_registry())
+    if (e.key == key) return e.fn;
+  return nullptr;
+}
+
+static int launch(const void* fn, dim3 grid, dim3 block, void** args, cudaStream_t st) {
+  SDB_CUDA(cudaLaunchKernel(fn, grid, block, args, 0, st));
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// NVRTC (loaded lazily with dlopen so that libsdb.so itself loads on machines without it)
+// ---------------------------------------------------------------------------------------------
+static const char* kKernelHeader =
+#include "sdb_kernels_embed.inc"
+    ;
+
+typedef struct _nvrtcProgram* nvrtcProgram;
+struct Nvrtc {
+  void* lib = nullptr;
+  int (*CreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*,
+                       const char* const*) = nullptr;
+  int (*CompileProgram)(nvrtcProgram, int, const char* const*) = nullptr;
+  int (*GetProgramLogSize)(nvrtcProgram, size_t*) = nullptr;
+  int (*GetProgramLog)(nvrtcProgram, char*) = nullptr;
+  int (*GetCUBINSize)(nvrtcProgram, size_t*) = nullptr;
+  int (*GetCUBIN)(nvrtcProgram, char*) = nullptr;
+  int (*DestroyProgram)(nvrtcProgram*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+
+static int nvrtc_load(Nvrtc** out) {
+  static Nvrtc rt;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  if (!rt.lib) {
+    const char* env = getenv("SDB_NVRTC_PATH");
+    const char* names[] = {env, "libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12",
+                           "libnvrtc.so"};
+    for (const char* n : names) {
+      if (!n) continue;
+      rt.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (rt.lib) break;
+    }
+    if (!rt.lib) return fail("NVRTC (libnvrtc.so.12) not found; set SDB_NVRTC_PATH");
+#define SDB_SYM(name)                                                              \
+  *(void**)(&rt.name) = dlsym(rt.lib, "nvrtc" #name);                              \
+  if (!rt.name) return fail("NVRTC symbol nvrtc" #name " missing");
+    SDB_SYM(CreateProgram) SDB_SYM(CompileProgram) SDB_SYM(GetProgramLogSize)
+    SDB_SYM(GetProgramLog) SDB_SYM(GetCUBINSize) SDB_SYM(GetCUBIN) SDB_SYM(DestroyProgram)
+    SDB_SYM(GetErrorString)
+#undef SDB_SYM
+  }
+  *out = &rt;
+  return 0;
+}
+
+struct JitKernel {
+  cudaLibrary_t lib = nullptr;
+  cudaKernel_t kern = nullptr;
+};
+
+static int jit_compile(const std::string& source, const char* kernel_name, JitKernel* out) {
+  Nvrtc* rt;
+  if (nvrtc_load(&rt)) return 1;
+  nvrtcProgram prog;
+  const char* hdr_src[] = {kKernelHeader};
+  const char* hdr_name[] = {"sdb_kernels.cuh"};
+  int rc = rt->CreateProgram(&prog, source.c_str(), "sdb_jit.cu", 1, hdr_src, hdr_name);
+  if (rc) return fail(std::string("nvrtcCreateProgram: ") + rt->GetErrorString(rc));
+  const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo",
+                        "--fmad=true"};
+  rc = rt->CompileProgram(prog, 4, opts);
+  if (rc) {
+    size_t n = 0;
+    rt->GetProgramLogSize(prog, &n);
+    std::string log(n, '\0');
+    if (n) rt->GetProgramLog(prog, &log[0]);
+    rt->DestroyProgram(&prog);
+    return fail("NVRTC compile failed:\n" + log);
+  }
+  size_t sz = 0;
+  rt->GetCUBINSize(prog, &sz);
+  std::vector<char> cubin(sz);
+  rt->GetCUBIN(prog, cubin.data());
+  rt->DestroyProgram(&prog);
+  SDB_CUDA(cudaLibraryLoadData(&out->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+  SDB_CUDA(cudaLibraryGetKernel(&out->kern, out->lib, kernel_name));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// systems
+// ---------------------------------------------------------------------------------------------
+struct sdb_system {
+  int fk, gk, d, m;
+  std::vector<double> fp, gp;
+  std::string src;           // user CUDA source (may be empty)
+  double* d_fp = nullptr;    // device copies (PGlobal mode / user operators)
+  double* d_gp = nullptr;
+  bool inline_params = true;
+  std::map<std::string, JitKernel> jit;
+  std::mutex mu;
+};
+
+static const size_t kParamSpace = 32764;
+
+static int expected_params(int kind, bool drift, int d, int m, int64_t* n) {
+  if (drift) {
+    switch (kind) {
+      case SDB_DRIFT_LINEAR: *n = (int64_t)d * d; return 0;
+      case SDB_DRIFT_KP4446: *n = 2; return d == 1 ? 0 : 1;
+      case SDB_DRIFT_KPS445: *n = 1; return d == 1 ? 0 : 1;
+      case SDB_DRIFT_USER: *n = -1; return 0;
+    }
+  } else {
+    switch (kind) {
+      case SDB_DIFF_CONST: *n = (int64_t)d * m; return 0;
+      case SDB_DIFF_LINEAR_COLS: *n = (int64_t)m * d * d; return 0;
+      case SDB_DIFF_KP4446: *n = 1; return (d == 1 && m == 1) ? 0 : 1;
+      case SDB_DIFF_KPS445: *n = 1; return (d == 1 && m == 1) ? 0 : 1;
+      case SDB_DIFF_USER: *n = -1; return 0;
+    }
+  }
+  return 1;
+}
+
+static int system_create(const char* src, int fk, const double* fpar, int64_t nf, int gk,
+                         const double* gpar, int64_t ng, int d, int m, sdb_system** out) {
+  if (!out) return fail("sdb_system: out is NULL");
+  if (d < 1 || m < 1 || d > 64 || m > 64) return fail("sdb_system: need 1 <= d, m <= 64");
+  int64_t ef = 0, eg = 0;
+  if (expected_params(fk, true, d, m, &ef)) return fail("sdb_system: bad drift kind / dimension");
+  if (expected_params(gk, false, d, m, &eg)) return fail("sdb_system: bad diffusion kind / dimension");
+  if (ef >= 0 && nf != ef) return fail("sdb_system: wrong number of drift parameters");
+  if (eg >= 0 && ng != eg) return fail("sdb_system: wrong number of diffusion parameters");
+  if ((fk == SDB_DRIFT_USER || gk == SDB_DIFF_USER) && (!src || !*src))
+    return fail("sdb_system: user operator kinds need CUDA source");
+  if (nf < 0 || ng < 0 || (nf > 0 && !fpar) || (ng > 0 && !gpar))
+    return fail("sdb_system: parameter pointer is NULL");
+  sdb_system* s = new sdb_system();
+  s->fk = fk; s->gk = gk; s->d = d; s->m = m;
+  s->fp.assign(fpar, fpar + nf);
+  s->gp.assign(gpar, gpar + ng);
+  if (s->fp.empty()) s->fp.push_back(0.0);
+  if (s->gp.empty()) s->gp.push_back(0.0);
+  if (src) s->src = src;
+  s->inline_params =
+      (s->fp.size() + s->gp.size()) * sizeof(double) + sizeof(SdbLoopArgs) + 64 <= kParamSpace;
+  if (!s->inline_params) {
+    cudaError_t e = cudaMalloc(&s->d_fp, s->fp.size() * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_gp, s->gp.size() * sizeof(double));
+    if (e == cudaSuccess)
+      e = cudaMemcpy(s->d_fp, s->fp.data(), s->fp.size() * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess)
+      e = cudaMemcpy(s->d_gp, s->gp.data(), s->gp.size() * sizeof(double), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      delete s;
+      return fail(std::string("sdb_system: device parameter upload: ") + cudaGetErrorString(e));
+    }
+  }
+  *out = s;
+  return 0;
+}
+
+extern "C" int sdb_system_builtin(int fk, const double* fpar, int64_t nf, int gk,
+                                  const double* gpar, int64_t ng, int d, int m,
+                                  sdb_system** out) {
+  if (fk == SDB_DRIFT_USER || gk == SDB_DIFF_USER)
+    return fail("sdb_system_builtin: user kinds need sdb_system_nvrtc");
+  return system_create(nullptr, fk, fpar, nf, gk, gpar, ng, d, m, out);
+}
+
+extern "C" int sdb_system_nvrtc(const char* src, int fk, const double* fpar, int64_t nf, int gk,
+                                const double* gpar, int64_t ng, int d, int m, sdb_system** out) {
+  return system_create(src, fk, fpar, nf, gk, gpar, ng, d, m, out);
+}
+
+extern "C" int sdb_system_destroy(sdb_system* s) {
+  if (!s) return 0;
+  for (auto& kv : s->jit)
+    if (kv.second.lib) cudaLibraryUnload(kv.second.lib);
+  if (s->d_fp) cudaFree(s->d_fp);
+  if (s->d_gp) cudaFree(s->d_gp);
+  delete s;
+  return 0;
+}
+
+static std::string type_of(const sdb_system* s, bool drift) {
+  std::ostringstream o;
+  const std::string ps_f =
+      s->inline_params ? "PInline<" + std::to_string(s->fp.size()) + ">" : "PGlobal";
+  const std::string ps_g =
+      s->inline_params ? "PInline<" + std::to_string(s->gp.size()) + ">" : "PGlobal";
+  if (drift) {
+    switch (s->fk) {
+      case SDB_DRIFT_LINEAR: o << "DriftLinear<" << s->d << ", " << ps_f << ">"; break;
+      case SDB_DRIFT_KP4446: o << "DriftKP4446<" << ps_f << ">"; break;
+      case SDB_DRIFT_KPS445: o << "DriftKPS445<" << ps_f << ">"; break;
+      default: o << "DriftUser<" << s->d << ", " << ps_f << ">";
+    }
+  } else {
+    switch (s->gk) {
+      case SDB_DIFF_CONST: o << "DiffConst<" << s->d << ", " << s->m << ", " << ps_g << ">"; break;
+      case SDB_DIFF_LINEAR_COLS:
+        o << "DiffLinearCols<" << s->d << ", " << s->m << ", " << ps_g << ">"; break;
+      case SDB_DIFF_KP4446: o << "DiffKP4446<" << ps_g << ">"; break;
+      case SDB_DIFF_KPS445: o << "DiffKPS445<" << ps_g << ">"; break;
+      default: o << "DiffUser<" << s->d << ", " << s->m << ", " << ps_g << ">";
+    }
+  }
+  return o.str();
+}
+
+// Find (AOT) or build (NVRTC) the loop kernel for this system / scheme / noise source.
+static int loop_kernel(sdb_system* s, int scheme, int noise, const void** fn) {
+  const std::string key = sdb_loop_key(scheme, s->fk, s->gk, s->d, s->m, noise, s->inline_params);
+  const bool user = (s->fk == SDB_DRIFT_USER || s->gk == SDB_DIFF_USER);
+  if (!user) {
+    if (const void* f = aot_lookup(key)) { *fn = f; return 0; }
+  }
+  std::lock_guard<std::mutex> lk(s->mu);
+  auto it = s->jit.find(key);
+  if (it == s->jit.end()) {
+    std::ostringstream src;
+    if (s->fk == SDB_DRIFT_USER) src << "#define SDB_USER_DRIFT 1\n";
+    if (s->gk == SDB_DIFF_USER) src << "#define SDB_USER_DIFF 1\n";
+    src << "#include \"sdb_kernels.cuh\"\n";
+    if (user) src << "#line 1 \"user_source.cu\"\n" << s->src << "\n";
+    src << "typedef " << type_of(s, true) << " F_jit;\n";
+    src << "typedef " << type_of(s, false) << " G_jit;\n";
+    src << "SDB_LOOP_KERNEL(sdb_jit_loop, " << scheme << ", F_jit, G_jit, " << noise << ")\n";
+    JitKernel k;
+    if (jit_compile(src.str(), "sdb_jit_loop", &k)) return 1;
+    it = s->jit.emplace(key, k).first;
+  }
+  *fn = (const void*)it->second.kern;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// sdb_integrate
+// ---------------------------------------------------------------------------------------------
+__global__ void sdb_k_status_init(int64_t* st) {
+  st[0] = 0; st[1] = 0x7fffffffffffffffll; st[2] = 0; st[3] = 0x7fffffffffffffffll;
+}
+
+extern "C" int sdb_integrate(sdb_system* s, const sdb_integrate_args* a) {
+  if (!s || !a) return fail("sdb_integrate: NULL argument");
+  if (a->scheme < SDB_SCHEME_EULER || a->scheme > SDB_SCHEME_KP2IS)
+    return fail("sdb_integrate: unknown scheme");
+  if (a->noise < SDB_NOISE_HOST || a->noise > SDB_NOISE_WIK)
+    return fail("sdb_integrate: unknown noise source");
+  if (a->N < 2) return fail("sdb_integrate: need at least two time points");
+  if (a->paths < 1) return fail("sdb_integrate: need at least one path");
+  if (a->save_every < 1) return fail("sdb_integrate: save_every must be >= 1");
+  if (!a->h_tspan || !a->d_y0 || !a->d_y) return fail("sdb_integrate: NULL buffer");
+  const bool need_ij = a->scheme == SDB_SCHEME_SRK2 || a->scheme == SDB_SCHEME_KP2IS;
+  if (a->noise == SDB_NOISE_HOST && (!a->d_dW || (need_ij && !a->d_IJ)))
+    return fail("sdb_integrate: NOISE_HOST needs dW (and I/J for SRK2, KP2iS)");
+  if (a->noise != SDB_NOISE_HOST && a->n_terms < 1)
+    return fail("sdb_integrate: n_terms must be >= 1");
+  if (a->scheme == SDB_SCHEME_KP2IS && !a->h_kp2is)
+    return fail("sdb_integrate: KP2iS needs gam, al1, al2");
+  cudaStream_t st = (cudaStream_t)a->stream;
+
+  int noise = a->noise;
+  if (!need_ij && noise == SDB_NOISE_WIK) noise = SDB_NOISE_KPW;  // only dW is drawn
+  const void* fn = nullptr;
+  if (loop_kernel(s, a->scheme, noise, &fn)) return 1;
+
+  // tspan (+ KP2iS coefficients) to the device, stream-ordered
+  const size_t nt = (size_t)a->N, nk = a->scheme == SDB_SCHEME_KP2IS ? 3 * (size_t)s->d : 0;
+  double* d_aux = nullptr;
+  SDB_CUDA(cudaMallocAsync(&d_aux, (nt + nk) * sizeof(double), st));
+  SDB_CUDA(cudaMemcpyAsync(d_aux, a->h_tspan, nt * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (nk)
+    SDB_CUDA(cudaMemcpyAsync(d_aux + nt, a->h_kp2is, nk * sizeof(double), cudaMemcpyHostToDevice, st));
+
+  SdbLoopArgs k;
+  memset(&k, 0, sizeof k);
+  k.P = a->paths; k.path_id0 = a->path_id0; k.seed = a->seed;
+  k.N = a->N; k.save_every = a->save_every; k.n_terms = a->n_terms; k.flags = a->flags;
+  k.h_global = (a->h_tspan[a->N - 1] - a->h_tspan[0]) / (double)(a->N - 1);
+  k.rtol = a->rtol;
+  k.tspan = d_aux;
+  k.y0 = a->d_y0; k.y0_sI = a->y0_stride_comp; k.y0_sP = a->y0_stride_path;
+  k.y = a->d_y; k.y_sS = a->y_stride_save; k.y_sI = a->y_stride_comp; k.y_sP = a->y_stride_path;
+  k.dW = a->d_dW; k.dW_sN = a->dW_stride_step; k.dW_sJ = a->dW_stride_comp; k.dW_sP = a->dW_stride_path;
+  k.IJ = a->d_IJ; k.IJ_sN = a->IJ_stride_step; k.IJ_sR = a->IJ_stride_row;
+  k.IJ_sC = a->IJ_stride_col; k.IJ_sP = a->IJ_stride_path;
+  k.kp = nk ? d_aux + nt : nullptr;
+  k.status = a->d_status;
+  if (a->d_status) {
+    sdb_k_status_init<<<1, 1, 0, st>>>(a->d_status);
+    g_launches.fetch_add(1);
+  }
+
+  PGlobal gf{s->d_fp}, gg{s->d_gp};
+  void* args[3];
+  args[0] = &k;
+  args[1] = s->inline_params ? (void*)s->fp.data() : (void*)&gf;
+  args[2] = s->inline_params ? (void*)s->gp.data() : (void*)&gg;
+  const unsigned block = SDB_BLOCK;
+  const unsigned grid = (unsigned)((a->paths + block - 1) / block);
+  if (launch(fn, dim3(grid), dim3(block), args, st)) return 1;
+  SDB_CUDA(cudaFreeAsync(d_aux, st));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// deltaW, repeated integrals
+// ---------------------------------------------------------------------------------------------
+extern "C" int sdb_delta_w(int64_t steps, int m, double h, int64_t paths, int64_t path_id0,
+                           uint64_t seed, double* d_out, int64_t sN, int64_t sJ, int64_t sP,
+                           void* stream) {
+  if (steps < 0 || paths < 1 || m < 1 || !d_out) return fail("sdb_delta_w: bad argument");
+  if (!(h > 0.0)) return fail("sdb_delta_w: h must be positive");
+  if (steps == 0) return 0;
+  SdbDeltaWArgs a{steps, paths, path_id0, seed, m, sqrt(h), d_out, sN, sJ, sP};
+  void* args[1] = {&a};
+  const int64_t total = steps * paths;
+  return launch((const void*)sdb_k_delta_w, dim3((unsigned)((total + 255) / 256)), dim3(256), args,
+                (cudaStream_t)stream);
+}
+
+SDB_REPINT_KERNEL(sdb_k_repint_1, 1)
+SDB_REPINT_KERNEL(sdb_k_repint_2, 2)
+SDB_REPINT_KERNEL(sdb_k_repint_3, 3)
+SDB_REPINT_KERNEL(sdb_k_repint_4, 4)
+SDB_REPINT_KERNEL(sdb_k_repint_5, 5)
+SDB_REPINT_KERNEL(sdb_k_repint_6, 6)
+SDB_REPINT_KERNEL(sdb_k_repint_7, 7)
+SDB_REPINT_KERNEL(sdb_k_repint_8, 8)
+SDB_REPINT_KERNEL(sdb_k_repint_9, 9)
+SDB_REPINT_KERNEL(sdb_k_repint_10, 10)
+SDB_REPINT_KERNEL(sdb_k_repint_20, 20)
+
+static std::map<int, JitKernel> g_repint_jit;
+static std::mutex g_repint_mu;
+
+static int repint_kernel(int m, const void** fn) {
+  switch (m) {
+    case 1: *fn = (const void*)sdb_k_repint_1; return 0;
+    case 2: *fn = (const void*)sdb_k_repint_2; return 0;
+    case 3: *fn = (const void*)sdb_k_repint_3; return 0;
+    case 4: *fn = (const void*)sdb_k_repint_4; return 0;
+    case 5: *fn = (const void*)sdb_k_repint_5; return 0;
+    case 6: *fn = (const void*)sdb_k_repint_6; return 0;
+    case 7: *fn = (const void*)sdb_k_repint_7; return 0;
+    case 8: *fn = (const void*)sdb_k_repint_8; return 0;
+    case 9: *fn = (const void*)sdb_k_repint_9; return 0;
+    case 10: *fn = (const void*)sdb_k_repint_10; return 0;
+    case 20: *fn = (const void*)sdb_k_repint_20; return 0;
+  }
+  std::lock_guard<std::mutex> lk(g_repint_mu);
+  auto it = g_repint_jit.find(m);
+  if (it == g_repint_jit.end()) {
+    std::ostringstream src;
+    src << "#include \"sdb_kernels.cuh\"\nSDB_REPINT_KERNEL(sdb_jit_repint, " << m << ")\n";
+    JitKernel k;
+    if (jit_compile(src.str(), "sdb_jit_repint", &k)) return 1;
+    it = g_repint_jit.emplace(m, k).first;
+  }
+  *fn = (const void*)it->second.kern;
+  return 0;
+}
+
+extern "C" int sdb_repeated_integrals(const sdb_repint_args* a) {
+  if (!a) return fail("sdb_repeated_integrals: NULL argument");
+  if (a->method != SDB_NOISE_KPW && a->method != SDB_NOISE_WIK)
+    return fail("sdb_repeated_integrals: method must be KPW or WIK");
+  if (a->m < 1 || a->m > 64) return fail("sdb_repeated_integrals: need 1 <= m <= 64");
+  if (a->n_terms < 1) return fail("sdb_repeated_integrals: n_terms must be >= 1");
+  if (a->steps < 0 || a->paths < 1) return fail("sdb_repeated_integrals: bad sizes");
+  if (!(a->h > 0.0)) return fail("sdb_repeated_integrals: h must be positive");
+  if (!a->d_dW || !a->d_IJ) return fail("sdb_repeated_integrals: NULL buffer");
+  if ((a->d_X == nullptr) != (a->d_Y == nullptr))
+    return fail("sdb_repeated_integrals: X and Y must be given together");
+  if (a->d_X && a->method == SDB_NOISE_WIK && a->m > 1 && !a->d_Gt)
+    return fail("sdb_repeated_integrals: host normals for WIK also need Gt");
+  if (a->steps == 0) return 0;
+  const void* fn = nullptr;
+  if (repint_kernel(a->m, &fn)) return 1;
+  SdbRepintArgs k;
+  memset(&k, 0, sizeof k);
+  k.method = a->method; k.stratonovich = a->stratonovich; k.n_terms = a->n_terms; k.m = a->m;
+  k.steps = a->steps; k.paths = a->paths; k.path_id0 = a->path_id0; k.seed = a->seed; k.h = a->h;
+  k.dW = a->d_dW; k.dW_sN = a->dW_stride_step; k.dW_sJ = a->dW_stride_comp; k.dW_sP = a->dW_stride_path;
+  k.X = a->d_X; k.Y = a->d_Y;
+  k.XY_sT = a->XY_stride_term; k.XY_sN = a->XY_stride_step; k.XY_sJ = a->XY_stride_comp;
+  k.XY_sP = a->XY_stride_path;
+  k.Gt = a->d_Gt; k.Gt_sN = a->Gt_stride_step; k.Gt_sR = a->Gt_stride_pair; k.Gt_sP = a->Gt_stride_path;
+  k.A = a->d_A; k.A_sN = a->A_stride_step; k.A_sE = a->A_stride_elem; k.A_sP = a->A_stride_path;
+  k.IJ = a->d_IJ; k.IJ_sN = a->IJ_stride_step; k.IJ_sR = a->IJ_stride_row;
+  k.IJ_sC = a->IJ_stride_col; k.IJ_sP = a->IJ_stride_path;
+  void* args[1] = {&k};
+  const int64_t total = a->steps * a->paths;
+  return launch(fn, dim3((unsigned)((total + 127) / 128)), dim3(128), args, (cudaStream_t)a->stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// moments / histograms
+// ---------------------------------------------------------------------------------------------
+#define SDB_MOM_CHUNK 4096
+#define SDB_MOM_BLOCK 256
+
+// partial[row][chunk] = (sum, sumsq) of 4096 consecutive paths, fixed tree order.
+__global__ void __launch_bounds__(SDB_MOM_BLOCK)
+sdb_k_moments_partial(const double* __restrict__ y, int64_t paths, int64_t nchunks,
+                      double2* __restrict__ partial, unsigned long long* __restrict__ hist,
+                      int bins, double lo, double inv_w) {
+  extern __shared__ unsigned int sh_hist[];
+  __shared__ double sh_s[SDB_MOM_BLOCK / 32], sh_q[SDB_MOM_BLOCK / 32];
+  const int64_t row = blockIdx.y;
+  const int64_t chunk = blockIdx.x;
+  const double* src = y + row * paths;
+  if (hist)
+    for (int b = threadIdx.x; b < bins; b += blockDim.x) sh_hist[b] = 0u;
+  __syncthreads();
+  double s = 0.0, q = 0.0;
+  const int64_t base = chunk * SDB_MOM_CHUNK;
+#pragma unroll 4
+  for (int i = 0; i < SDB_MOM_CHUNK / SDB_MOM_BLOCK; ++i) {
+    const int64_t p = base + (int64_t)i * SDB_MOM_BLOCK + threadIdx.x;
+    if (p < paths) {
+      const double v = src[p];
+      s += v;
+      q = fma(v, v, q);
+      if (hist) {
+        const double f = (v - lo) * inv_w;
+        if (f >= 0.0 && f < (double)bins) atomicAdd(&sh_hist[(int)f], 1u);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_down_sync(0xffffffffu, s, o);
+    q += __shfl_down_sync(0xffffffffu, q, o);
+  }
+  if ((threadIdx.x & 31) == 0) { sh_s[threadIdx.x >> 5] = s; sh_q[threadIdx.x >> 5] = q; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ts = 0.0, tq = 0.0;
+#pragma unroll
+    for (int w = 0; w < SDB_MOM_BLOCK / 32; ++w) { ts += sh_s[w]; tq += sh_q[w]; }
+    partial[row * nchunks + chunk] = make_double2(ts, tq);
+  }
+  if (hist)
+    for (int b = threadIdx.x; b < bins; b += blockDim.x)
+      if (sh_hist[b]) atomicAdd(&hist[row * bins + b], (unsigned long long)sh_hist[b]);
+}
+
+// sums[row] += sum over chunks in chunk order (one thread per row: deterministic).
+__global__ void sdb_k_moments_final(const double2* __restrict__ partial, int64_t rows,
+                                    int64_t nchunks, double* __restrict__ sums) {
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  double s = 0.0, q = 0.0;
+  for (int64_t c = 0; c < nchunks; ++c) {
+    const double2 v = partial[row * nchunks + c];
+    s += v.x;
+    q += v.y;
+  }
+  sums[2 * row] += s;
+  sums[2 * row + 1] += q;
+}
+
+extern "C" int sdb_moments(const double* d_y, int64_t n_saved, int d, int64_t paths, double* d_sums,
+                           unsigned long long* d_hist, int bins, double lo, double hi,
+                           void* stream) {
+  if (!d_y || !d_sums || n_saved < 1 || d < 1 || paths < 1) return fail("sdb_moments: bad argument");
+  if (d_hist && (bins < 1 || bins > 8192 || !(hi > lo))) return fail("sdb_moments: bad histogram spec");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t rows = n_saved * d;
+  const int64_t nchunks = (paths + SDB_MOM_CHUNK - 1) / SDB_MOM_CHUNK;
+  if (rows > 65535) return fail("sdb_moments: too many (saved point, component) rows");
+  double2* partial = nullptr;
+  SDB_CUDA(cudaMallocAsync(&partial, rows * nchunks * sizeof(double2), st));
+  const double inv_w = d_hist ? (double)bins / (hi - lo) : 0.0;
+  const size_t shm = d_hist ? bins * sizeof(unsigned int) : 0;
+  sdb_k_moments_partial<<<dim3((unsigned)nchunks, (unsigned)rows), SDB_MOM_BLOCK, shm, st>>>(
+      d_y, paths, nchunks, partial, d_hist, bins, lo, inv_w);
+  SDB_CUDA(cudaGetLastError());
+  sdb_k_moments_final<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(partial, rows, nchunks, d_sums);
+  SDB_CUDA(cudaGetLastError());
+  g_launches.fetch_add(2);
+  SDB_CUDA(cudaFreeAsync(partial, st));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// FP64 pipe peak (roofline denominator)
+// ---------------------------------------------------------------------------------------------
+#define SDB_PROBE_CHAINS 8
+__global__ void __launch_bounds__(256) sdb_k_fp64_probe(int iters, double seed, double* sink) {
+  double acc[SDB_PROBE_CHAINS];
+  const double a = 1.0 + 1e-9 * seed, b = 1e-12 * (threadIdx.x + 1);
+#pragma unroll
+  for (int c = 0; c < SDB_PROBE_CHAINS; ++c) acc[c] = seed + c;
+#pragma unroll 1
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+      for (int c = 0; c < SDB_PROBE_CHAINS; ++c) acc[c] = fma(acc[c], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int c = 0; c < SDB_PROBE_CHAINS; ++c) s += acc[c];
+  if (s == 123.456) sink[0] = s;  // never true; keeps the chain alive
+}
+
+extern "C" int sdb_fp64_peak(int iters, double* tflops_out, void* stream) {
+  if (!tflops_out || iters < 1) return fail("sdb_fp64_peak: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev = 0, sms = 0;
+  SDB_CUDA(cudaGetDevice(&dev));
+  SDB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  double* sink = nullptr;
+  SDB_CUDA(cudaMalloc(&sink, sizeof(double)));
+  cudaEvent_t e0, e1;
+  SDB_CUDA(cudaEventCreate(&e0));
+  SDB_CUDA(cudaEventCreate(&e1));
+  const int blocks = sms * 8;
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {  // rep 0 warms up
+    SDB_CUDA(cudaEventRecord(e0, st));
+    sdb_k_fp64_probe<<<blocks, 256, 0, st>>>(iters, 1.0, sink);
+    SDB_CUDA(cudaEventRecord(e1, st));
+    SDB_CUDA(cudaEventSynchronize(e1));
+    g_launches.fetch_add(1);
+    float ms = 0.f;
+    SDB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 2.0 * 8.0 * SDB_PROBE_CHAINS * (double)iters * 256.0 * blocks;
+    const double tf = flops / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  *tflops_out = best;
+  return 0;
+}
+
+extern "C" int sdb_philox_block(uint64_t seed, uint64_t path, uint32_t step, uint32_t slot,
+                                uint32_t out[4]) {
+  uint32_t r[4];
+  sdb_philox4x32_10((uint32_t)path, (uint32_t)(path >> 32), step, slot, (uint32_t)seed,
+                    (uint32_t)(seed >> 32), r);
+  for (int i = 0; i < 4; ++i) out[i] = r[i];
+  return 0;
+}

@@ -1,0 +1,24 @@
+// sdb_host.h -- host-side internals shared by sdb_capi.cu and the AOT translation units.
+#pragma once
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+// One ahead-of-time compiled kernel.  `key` encodes what it was instantiated for:
+//   loop|s<scheme>|f<drift kind>|g<diff kind>|d<D>|m<M>|n<noise>|p<i|g>
+//   repint|m<M>
+struct SdbAotEntry {
+  std::string key;
+  const void* fn;
+};
+
+std::vector<SdbAotEntry>& sdb_aot_registry();
+
+struct SdbAotRegistrar {
+  SdbAotRegistrar(const std::string& key, const void* fn) {
+    sdb_aot_registry().push_back(SdbAotEntry{key, fn});
+  }
+};
+
+std::string sdb_loop_key(int scheme, int fk, int gk, int d, int m, int noise, bool inline_params);

@@ -1,0 +1,833 @@
+// sdb_kernels.cuh -- device code of libsdb (sm_100a).  One header, compiled two ways:
+//   * ahead of time by nvcc into libsdb.so for the named configurations (sdb_aot.cu);
+//   * at run time by NVRTC for any other (drift, diffusion, d, m) and for user CUDA source
+//     (sdb_capi.cu embeds this file verbatim).
+// It therefore includes no host headers.
+//
+// Work decomposition: ONE THREAD PER SAMPLE PATH.  A path's state, its Wiener increments and
+// its repeated integrals live in that thread's registers (local arrays, fully unrolled for
+// small d, m); consecutive threads own consecutive paths so every global access -- the
+// decimated trajectory stores, host-supplied dW / I loads -- is unit-stride across a warp.
+// Operator parameters (A, B_k) are passed BY VALUE as __grid_constant__ kernel parameters
+// when they fit in the 32 KB parameter space: fully unrolled loops then address them with
+// compile-time offsets and ptxas folds them into DFMA constant-bank operands, so the matrix
+// never costs a load instruction.
+#pragma once
+
+#ifdef __CUDACC_RTC__
+typedef unsigned int uint32_t;
+typedef unsigned long long uint64_t;
+typedef long long int64_t;
+#else
+#include <stdint.h>
+#endif
+
+#define SDB_DEV __device__ __forceinline__
+#define SDB_HD __host__ __device__ __forceinline__
+
+#ifndef SDB_BLOCK
+#define SDB_BLOCK 128
+#endif
+
+// ---- ids shared with include/sdb.h --------------------------------------------------------
+#define SDB_SCHEME_EULER 0
+#define SDB_SCHEME_HEUN 1
+#define SDB_SCHEME_SRK2 2
+#define SDB_SCHEME_KP2IS 3
+#define SDB_NOISE_HOST 0
+#define SDB_NOISE_KPW 1
+#define SDB_NOISE_WIK 2
+#define SDB_FLAG_Y0_BROADCAST 1
+#define SDB_FLAG_STRATONOVICH 2
+
+// ---- kernel argument block (plain data; mirrored by the host in sdb_capi.cu) ---------------
+struct SdbLoopArgs {
+  int64_t P;
+  int64_t path_id0;
+  uint64_t seed;
+  int N;
+  int save_every;
+  int n_terms;
+  int flags;
+  double h_global;  // (t[N-1]-t[0])/(N-1): integrate.py:228,285,480,594
+  double rtol;      // KP2iS implicit-solve tolerance
+  const double* tspan;  // device [N]
+  const double* y0;
+  int64_t y0_sI, y0_sP;
+  double* y;
+  int64_t y_sS, y_sI, y_sP;
+  const double* dW;
+  int64_t dW_sN, dW_sJ, dW_sP;
+  const double* IJ;
+  int64_t IJ_sN, IJ_sR, IJ_sC, IJ_sP;
+  const double* kp;  // device [3*D]: gam, al1, al2
+  int64_t* status;   // [4]
+};
+
+struct SdbRepintArgs {
+  int method, stratonovich, n_terms, m;
+  int64_t steps, paths, path_id0;
+  uint64_t seed;
+  double h;
+  const double* dW; int64_t dW_sN, dW_sJ, dW_sP;
+  const double* X; const double* Y; int64_t XY_sT, XY_sN, XY_sJ, XY_sP;
+  const double* Gt; int64_t Gt_sN, Gt_sR, Gt_sP;
+  double* A; int64_t A_sN, A_sE, A_sP;
+  double* IJ; int64_t IJ_sN, IJ_sR, IJ_sC, IJ_sP;
+};
+
+// ---- parameter stores --------------------------------------------------------------------
+template <int NP>
+struct PInline {  // by value in the kernel parameter space (constant bank)
+  double v[NP > 0 ? NP : 1];
+  SDB_DEV double operator[](int i) const { return v[i]; }
+  SDB_DEV const double* ptr() const { return v; }
+};
+struct PGlobal {  // too large for the parameter space: read through the L1/L2 hierarchy
+  const double* v;
+  SDB_DEV double operator[](int i) const { return __ldg(v + i); }
+  SDB_DEV const double* ptr() const { return v; }
+};
+
+// ---- Philox4x32-10 (Salmon et al. 2011) and the normal transform -------------------------
+#define SDB_PHILOX_M0 0xD2511F53u
+#define SDB_PHILOX_M1 0xCD9E8D57u
+#define SDB_PHILOX_W0 0x9E3779B9u
+#define SDB_PHILOX_W1 0xBB67AE85u
+
+SDB_HD void sdb_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                              uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)SDB_PHILOX_M0 * c0;
+    const uint64_t p1 = (uint64_t)SDB_PHILOX_M1 * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+    const uint32_t n1 = (uint32_t)p1;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    const uint32_t n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += SDB_PHILOX_W0;
+    k1 += SDB_PHILOX_W1;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// Counter layout: (path low, path high, step, slot); key = seed.  One block yields one
+// Box-Muller pair: u1 in (0,1] from words 0,1 (53 bits), u2 in [0,1) from words 2,3.
+// Normal number q of a path-step is element (q & 1) of slot (q >> 1):
+//   dW_j -> q = j;  X_k[j] -> m + 2(k-1)m + j;  Y_k[j] -> m + (2(k-1)+1)m + j;  Gtail_r -> m + 2nm + r.
+struct SdbStream {
+  uint32_t p_lo, p_hi, step, k0, k1;
+  SDB_DEV SdbStream(uint64_t seed, uint64_t path, uint32_t step_)
+      : p_lo((uint32_t)path), p_hi((uint32_t)(path >> 32)), step(step_), k0((uint32_t)seed),
+        k1((uint32_t)(seed >> 32)) {}
+  SDB_DEV void pair(uint32_t slot, double& z0, double& z1) const {
+    uint32_t r[4];
+    sdb_philox4x32_10(p_lo, p_hi, step, slot, k0, k1, r);
+    const uint64_t a = (((uint64_t)r[0] << 32) | r[1]) >> 11;
+    const uint64_t b = (((uint64_t)r[2] << 32) | r[3]) >> 11;
+    const double u1 = (double)(a + 1ull) * 1.1102230246251565e-16;  // 2^-53, (0,1]
+    const double u2 = (double)b * 2.2204460492503131e-16;           // 2^-52 -> 2*u in [0,2)
+    const double rad = sqrt(-2.0 * log(u1));
+    double s, c;
+    sincospi(u2, &s, &c);
+    z0 = rad * c;
+    z1 = rad * s;
+  }
+};
+
+// Sequential reader of normals q0, q0+1, ... (keeps the odd element of a pair for the next call).
+struct SdbNormalSeq {
+  const SdbStream& st;
+  uint32_t q;
+  double spare;
+  SDB_DEV SdbNormalSeq(const SdbStream& s, uint32_t q0) : st(s), q(q0), spare(0.0) {
+    if (q & 1u) { double z0; st.pair(q >> 1, z0, spare); }
+  }
+  SDB_DEV double next() {
+    double z;
+    if (q & 1u) {
+      z = spare;
+    } else {
+      st.pair(q >> 1, z, spare);
+    }
+    ++q;
+    return z;
+  }
+};
+
+// ---- repeated integrals, elementwise (oracle/sde_oracle.py: ikpw_from_normals,
+// iwik_from_normals; reference sdeint/wiener.py:67-106 and :206-282) ---------------------------
+#define SDB_INV_2PI 0.15915494309189535
+
+SDB_DEV double sdb_a_tail(int n) {  // wiener.py:229-231
+  double s = 0.0;
+  for (int k = 1; k <= n; ++k) s += 1.0 / ((double)k * (double)k);
+  return 1.6449340668482264 - s;  // pi^2/6
+}
+
+// Accumulate the Levy-area series term k into the strict upper triangle At (K_m row order).
+template <int M>
+SDB_DEV void sdb_levy_accumulate(const double (&X)[M], const double (&Z)[M], double inv_k,
+                                 double (&At)[M * (M - 1) / 2 + 1]) {
+  int r = 0;
+#pragma unroll
+  for (int i = 0; i < M; ++i) {
+#pragma unroll
+    for (int j = i + 1; j < M; ++j) {
+      At[r] = fma(X[i] * Z[j] - Z[i] * X[j], inv_k, At[r]);
+      ++r;
+    }
+  }
+}
+
+// Source of the standard normals: Philox stream or caller-supplied arrays.
+template <int M>
+struct SdbNormalsPhilox {
+  const SdbStream& st;
+  int n_terms;
+  SDB_DEV void xk(int k, double (&X)[M]) const {  // k = 1..n
+    SdbNormalSeq s(st, (uint32_t)(M + 2 * (k - 1) * M));
+#pragma unroll
+    for (int j = 0; j < M; ++j) X[j] = s.next();
+  }
+  SDB_DEV void yk(int k, double (&Y)[M]) const {
+    SdbNormalSeq s(st, (uint32_t)(M + (2 * (k - 1) + 1) * M));
+#pragma unroll
+    for (int j = 0; j < M; ++j) Y[j] = s.next();
+  }
+  SDB_DEV void tail(double (&G)[M * (M - 1) / 2 + 1]) const {
+    SdbNormalSeq s(st, (uint32_t)(M + 2 * n_terms * M));
+#pragma unroll 1
+    for (int r = 0; r < M * (M - 1) / 2; ++r) G[r] = s.next();
+  }
+};
+
+template <int M>
+struct SdbNormalsHost {
+  const double* X; const double* Y; int64_t sT, sJ;  // already offset to (step, path)
+  const double* Gt; int64_t sR;
+  SDB_DEV void xk(int k, double (&Xo)[M]) const {
+#pragma unroll
+    for (int j = 0; j < M; ++j) Xo[j] = X[(k - 1) * sT + j * sJ];
+  }
+  SDB_DEV void yk(int k, double (&Yo)[M]) const {
+#pragma unroll
+    for (int j = 0; j < M; ++j) Yo[j] = Y[(k - 1) * sT + j * sJ];
+  }
+  SDB_DEV void tail(double (&G)[M * (M - 1) / 2 + 1]) const {
+#pragma unroll 1
+    for (int r = 0; r < M * (M - 1) / 2; ++r) G[r] = Gt[r * sR];
+  }
+};
+
+// Kloeden-Platen-Wright series: At = (h/2pi) sum_k (X_k[i] Z_k[j] - Z_k[i] X_k[j]) / k, i<j.
+template <int M, class NS>
+SDB_DEV void sdb_levy_series(const double (&dW)[M], double h, int n_terms, const NS& ns,
+                             double (&At)[M * (M - 1) / 2 + 1]) {
+  constexpr int MM = M * (M - 1) / 2;
+#pragma unroll
+  for (int r = 0; r < MM + 1; ++r) At[r] = 0.0;
+  const double c = sqrt(2.0 / h);
+#pragma unroll 1
+  for (int k = 1; k <= n_terms; ++k) {
+    double X[M], Z[M];
+    ns.xk(k, X);
+    ns.yk(k, Z);
+#pragma unroll
+    for (int j = 0; j < M; ++j) Z[j] = fma(c, dW[j], Z[j]);
+    sdb_levy_accumulate<M>(X, Z, 1.0 / (double)k, At);
+  }
+  const double s = h * SDB_INV_2PI;
+#pragma unroll
+  for (int r = 0; r < MM; ++r) At[r] *= s;
+}
+
+// Wiktorsson tail correction applied in O(m^2): At += (h/2pi) sqrt(a_n) sqrtSigma g.
+template <int M, class NS>
+SDB_DEV void sdb_wik_tail(const double (&dW)[M], double h, int n_terms, const NS& ns,
+                          double (&At)[M * (M - 1) / 2 + 1]) {
+  constexpr int MM = M * (M - 1) / 2;
+  double G[MM + 1];
+  ns.tail(G);
+  double nrm = 0.0;
+#pragma unroll
+  for (int j = 0; j < M; ++j) nrm = fma(dW[j], dW[j], nrm);
+  const double rad = sqrt(1.0 + nrm / h);
+  double u[M];
+#pragma unroll
+  for (int j = 0; j < M; ++j) u[j] = 0.0;
+  {
+    int r = 0;
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+#pragma unroll
+      for (int j = i + 1; j < M; ++j) {
+        u[i] = fma(G[r], dW[j], u[i]);
+        u[j] = fma(-G[r], dW[i], u[j]);
+        ++r;
+      }
+    }
+  }
+  const double scale = h * SDB_INV_2PI * sqrt(sdb_a_tail(n_terms));
+  const double den = 1.0 / (1.4142135623730951 * (1.0 + rad));
+  const double two_h = 2.0 / h;
+  {
+    int r = 0;
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+#pragma unroll
+      for (int j = i + 1; j < M; ++j) {
+        const double sig = fma(two_h, dW[j] * u[i] - dW[i] * u[j], 2.0 * G[r]);
+        const double root = fma(2.0 * rad, G[r], sig) * den;
+        At[r] = fma(scale, root, At[r]);
+        ++r;
+      }
+    }
+  }
+}
+
+// Assemble I (or J) from dW and the area vector.  KPW places +A above the diagonal
+// (I[i][j] = dWi dWj/2 + A_ij, wiener.py:106); Wiktorsson's column-major unvec places it BELOW
+// (I[j][i] = dWi dWj/2 + Atilde_ij, wiener.py:278-280).
+template <int M>
+SDB_DEV void sdb_assemble_IJ(const double (&dW)[M], double h, const double (&At)[M * (M - 1) / 2 + 1],
+                             bool wik, bool strat, double (&IJ)[M][M]) {
+  int r = 0;
+#pragma unroll
+  for (int i = 0; i < M; ++i) {
+    IJ[i][i] = strat ? 0.5 * dW[i] * dW[i] : 0.5 * (dW[i] * dW[i] - h);
+#pragma unroll
+    for (int j = i + 1; j < M; ++j) {
+      const double sym = 0.5 * dW[i] * dW[j];
+      const double a = wik ? -At[r] : At[r];
+      IJ[i][j] = sym + a;
+      IJ[j][i] = sym - a;
+      ++r;
+    }
+  }
+}
+
+template <int M, class NS>
+SDB_DEV void sdb_repeated_integrals(const double (&dW)[M], double h, int n_terms, int method,
+                                    bool strat, const NS& ns, double (&At)[M * (M - 1) / 2 + 1],
+                                    double (&IJ)[M][M]) {
+  if (M == 1) {
+    At[0] = 0.0;
+    if (method == SDB_NOISE_KPW) {  // Ikpw still draws its 2n normals; A == 0
+      IJ[0][0] = strat ? 0.5 * dW[0] * dW[0] : 0.5 * (dW[0] * dW[0] - h);
+    } else {                         // Iwik shortcut, wiener.py:259-260
+      IJ[0][0] = strat ? (dW[0] * dW[0] - h) / 2.0 + 0.5 * h : (dW[0] * dW[0] - h) / 2.0;
+    }
+    return;
+  }
+  sdb_levy_series<M>(dW, h, n_terms, ns, At);
+  if (method == SDB_NOISE_WIK) sdb_wik_tail<M>(dW, h, n_terms, ns, At);
+  sdb_assemble_IJ<M>(dW, h, At, method == SDB_NOISE_WIK, strat, IJ);
+}
+
+// ---- drift / diffusion operators -------------------------------------------------------------
+// Interface:  Drift::eval(params, y[D], t, out[D]);  Diff::col(params, k, y[D], t, out[D]).
+template <int D_, class PS>
+struct DriftLinear {
+  static constexpr int D = D_;
+  typedef PS Params;
+  static SDB_DEV void eval(const PS& p, const double (&y)[D], double, double (&out)[D]) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      double acc = p[i * D] * y[0];
+#pragma unroll
+      for (int j = 1; j < D; ++j) acc = fma(p[i * D + j], y[j], acc);
+      out[i] = acc;
+    }
+  }
+};
+
+template <class PS>
+struct DriftKP4446 {  // -(a + c y)(1 - y^2), sdeint/tests/test_integrate.py:93-99
+  static constexpr int D = 1;
+  typedef PS Params;
+  static SDB_DEV void eval(const PS& p, const double (&y)[1], double, double (&out)[1]) {
+    out[0] = -(p[0] + y[0] * p[1]) * (1.0 - y[0] * y[0]);
+  }
+};
+
+template <class PS>
+struct DriftKPS445 {  // test_integrate.py:263-269
+  static constexpr int D = 1;
+  typedef PS Params;
+  static SDB_DEV void eval(const PS& p, const double (&y)[1], double, double (&out)[1]) {
+    double s, c;
+    sincos(y[0], &s, &c);
+    out[0] = -sin(2.0 * y[0]) - 0.25 * sin(4.0 * y[0]) + p[0] * 2.0 * s * c * c * c;
+  }
+};
+
+template <int D_, int M_, class PS>
+struct DiffConst {
+  static constexpr int D = D_, M = M_;
+  typedef PS Params;
+  static SDB_DEV void col(const PS& p, int k, const double (&)[D], double, double (&out)[D]) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) out[i] = p[i * M + k];
+  }
+};
+
+template <int D_, int M_, class PS>
+struct DiffLinearCols {  // g_k = B_k y
+  static constexpr int D = D_, M = M_;
+  typedef PS Params;
+  static SDB_DEV void col(const PS& p, int k, const double (&y)[D], double, double (&out)[D]) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      double acc = p[(k * D + i) * D] * y[0];
+#pragma unroll
+      for (int j = 1; j < D; ++j) acc = fma(p[(k * D + i) * D + j], y[j], acc);
+      out[i] = acc;
+    }
+  }
+};
+
+template <class PS>
+struct DiffKP4446 {
+  static constexpr int D = 1, M = 1;
+  typedef PS Params;
+  static SDB_DEV void col(const PS& p, int, const double (&y)[1], double, double (&out)[1]) {
+    out[0] = p[0] * (1.0 - y[0] * y[0]);
+  }
+};
+
+template <class PS>
+struct DiffKPS445 {
+  static constexpr int D = 1, M = 1;
+  typedef PS Params;
+  static SDB_DEV void col(const PS& p, int, const double (&y)[1], double, double (&out)[1]) {
+    const double c = cos(y[0]);
+    out[0] = p[0] * c * c;
+  }
+};
+
+#ifdef SDB_USER_DRIFT
+__device__ void sde_drift(const double* y, double t, const double* p, double* out);
+template <int D_, class PS>
+struct DriftUser {
+  static constexpr int D = D_;
+  typedef PS Params;
+  static SDB_DEV void eval(const PS& p, const double (&y)[D], double t, double (&out)[D]) {
+    sde_drift(y, t, p.ptr(), out);
+  }
+};
+#endif
+#ifdef SDB_USER_DIFF
+__device__ void sde_diffusion_col(int k, const double* y, double t, const double* p, double* out);
+template <int D_, int M_, class PS>
+struct DiffUser {
+  static constexpr int D = D_, M = M_;
+  typedef PS Params;
+  static SDB_DEV void col(const PS& p, int k, const double (&y)[D], double t, double (&out)[D]) {
+    sde_diffusion_col(k, y, t, p.ptr(), out);
+  }
+};
+#endif
+
+// ---- per-step noise for the loop kernels ---------------------------------------------------------
+template <int M, int NOISE, bool NEED_IJ>
+SDB_DEV void sdb_step_noise(const SdbLoopArgs& a, int64_t p, int n, double (&dW)[M],
+                            double (&IJ)[M][M]) {
+  if (NOISE == SDB_NOISE_HOST) {
+    const double* w = a.dW + (int64_t)n * a.dW_sN + p * a.dW_sP;
+#pragma unroll
+    for (int j = 0; j < M; ++j) dW[j] = w[j * a.dW_sJ];
+    if (NEED_IJ) {
+      const double* q = a.IJ + (int64_t)n * a.IJ_sN + p * a.IJ_sP;
+#pragma unroll
+      for (int j = 0; j < M; ++j)
+#pragma unroll
+        for (int k = 0; k < M; ++k) IJ[j][k] = q[j * a.IJ_sR + k * a.IJ_sC];
+    }
+  } else {
+    const SdbStream st(a.seed, (uint64_t)(a.path_id0 + p), (uint32_t)n);
+    const double rh = sqrt(a.h_global);  // deltaW(N-1, m, h_global): integrate.py:483
+    SdbNormalSeq s(st, 0u);
+#pragma unroll
+    for (int j = 0; j < M; ++j) dW[j] = rh * s.next();
+    if (NEED_IJ) {
+      double At[M * (M - 1) / 2 + 1];
+      const SdbNormalsPhilox<M> ns{st, a.n_terms};
+      sdb_repeated_integrals<M>(dW, a.h_global, a.n_terms, NOISE,
+                                (a.flags & SDB_FLAG_STRATONOVICH) != 0, ns, At, IJ);
+    }
+  }
+}
+
+template <int D>
+SDB_DEV void sdb_store(const SdbLoopArgs& a, int64_t p, int64_t s, const double (&Y)[D]) {
+  double* o = a.y + s * a.y_sS + p * a.y_sP;
+#pragma unroll
+  for (int i = 0; i < D; ++i) o[i * a.y_sI] = Y[i];
+}
+
+template <int D>
+SDB_DEV void sdb_finish(const SdbLoopArgs& a, int64_t p, const double (&Y)[D]) {
+  bool ok = true;
+#pragma unroll
+  for (int i = 0; i < D; ++i) ok = ok && isfinite(Y[i]);
+  if (!ok && a.status) {
+    atomicAdd((unsigned long long*)&a.status[0], 1ull);
+    atomicMin((long long*)&a.status[1], (long long)(a.path_id0 + p));
+  }
+}
+
+// Small dense solve J x = b with partial pivoting (KP2iS Newton step); J is destroyed.
+template <int D>
+SDB_DEV bool sdb_solve(double (&J)[D][D], double (&b)[D]) {
+#pragma unroll 1
+  for (int c = 0; c < D; ++c) {
+    int piv = c;
+    double best = fabs(J[c][c]);
+    for (int r = c + 1; r < D; ++r) {
+      const double v = fabs(J[r][c]);
+      if (v > best) { best = v; piv = r; }
+    }
+    if (best == 0.0) return false;
+    if (piv != c) {
+      for (int k = 0; k < D; ++k) { const double t = J[c][k]; J[c][k] = J[piv][k]; J[piv][k] = t; }
+      const double t = b[c]; b[c] = b[piv]; b[piv] = t;
+    }
+    const double inv = 1.0 / J[c][c];
+    for (int r = c + 1; r < D; ++r) {
+      const double f = J[r][c] * inv;
+      for (int k = c; k < D; ++k) J[r][k] = fma(-f, J[c][k], J[r][k]);
+      b[r] = fma(-f, b[c], b[r]);
+    }
+  }
+  for (int r = D - 1; r >= 0; --r) {
+    double acc = b[r];
+    for (int k = r + 1; k < D; ++k) acc = fma(-J[r][k], b[k], acc);
+    b[r] = acc / J[r][r];
+  }
+  return true;
+}
+
+// ---- the step loops ---------------------------------------------------------------------------------
+// SCHEME_EULER : integrate.py:235-239      SCHEME_HEUN : integrate.py:292-302
+// SCHEME_SRK2  : integrate.py:494-522      SCHEME_KP2IS: integrate.py:613-645
+template <int SCHEME, class F, class G, int NOISE>
+SDB_DEV void sdb_loop_body(const SdbLoopArgs& a, const typename F::Params& fp,
+                           const typename G::Params& gp) {
+  constexpr int D = G::D;
+  constexpr int M = G::M;
+  static_assert(F::D == G::D, "drift and diffusion disagree on d");
+  constexpr bool SMALL = (D * M <= 36);
+  constexpr bool NEED_IJ = (SCHEME == SDB_SCHEME_SRK2 || SCHEME == SDB_SCHEME_KP2IS);
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= a.P) return;
+
+  double Y[D];
+  if (a.flags & SDB_FLAG_Y0_BROADCAST) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) Y[i] = a.y0[i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < D; ++i) Y[i] = a.y0[i * a.y0_sI + p * a.y0_sP];
+  }
+  sdb_store<D>(a, p, 0, Y);
+
+  // KP2iS keeps the previous state, drift and noise term (integrate.py:621,628,635)
+  double Ym1[SCHEME == SDB_SCHEME_KP2IS ? D : 1], fm1[SCHEME == SDB_SCHEME_KP2IS ? D : 1],
+      Vm1[SCHEME == SDB_SCHEME_KP2IS ? D : 1];
+  int64_t bad_solve = -1;
+
+  const int steps = a.N - 1;
+  int next_save = a.save_every;
+  int64_t slot = 1;
+#pragma unroll 1
+  for (int n = 0; n < steps; ++n) {
+    const double t0 = a.tspan[n];
+    const double t1 = a.tspan[n + 1];
+    double dW[M];
+    double IJ[M][M];  // dead (and removed by the compiler) for Euler / Heun
+    sdb_step_noise<M, NOISE, NEED_IJ>(a, p, n, dW, IJ);
+
+    if (SCHEME == SDB_SCHEME_EULER) {
+      const double h = a.h_global;
+      double f0[D], Yn[D];
+      F::eval(fp, Y, t0, f0);
+#pragma unroll
+      for (int i = 0; i < D; ++i) Yn[i] = fma(f0[i], h, Y[i]);
+#pragma unroll(SMALL ? M : 1)
+      for (int k = 0; k < M; ++k) {
+        double g[D];
+        G::col(gp, k, Y, t0, g);
+#pragma unroll
+        for (int i = 0; i < D; ++i) Yn[i] = fma(g[i], dW[k], Yn[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < D; ++i) Y[i] = Yn[i];
+    } else if (SCHEME == SDB_SCHEME_HEUN) {
+      const double h = a.h_global;
+      double f0[D], Gw[D], Yb[D];
+      F::eval(fp, Y, t0, f0);
+#pragma unroll
+      for (int i = 0; i < D; ++i) Gw[i] = 0.0;
+#pragma unroll(SMALL ? M : 1)
+      for (int k = 0; k < M; ++k) {
+        double g[D];
+        G::col(gp, k, Y, t0, g);
+#pragma unroll
+        for (int i = 0; i < D; ++i) Gw[i] = fma(g[i], dW[k], Gw[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < D; ++i) Yb[i] = fma(f0[i], h, Y[i]) + Gw[i];
+      double f1[D], Gw1[D];
+      F::eval(fp, Yb, t1, f1);
+#pragma unroll
+      for (int i = 0; i < D; ++i) Gw1[i] = 0.0;
+#pragma unroll(SMALL ? M : 1)
+      for (int k = 0; k < M; ++k) {
+        double g[D];
+        G::col(gp, k, Yb, t1, g);
+#pragma unroll
+        for (int i = 0; i < D; ++i) Gw1[i] = fma(g[i], dW[k], Gw1[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+        Y[i] = Y[i] + 0.5 * (f0[i] + f1[i]) * h + 0.5 * (Gw[i] + Gw1[i]);
+    } else if (SCHEME == SDB_SCHEME_SRK2) {
+      const double h = t1 - t0;  // per-step h: integrate.py:497
+      const double rh = sqrt(h);
+      const double inv_rh = 1.0 / rh;
+      double f0h[D], base[D], f1h[D], Yn[D];
+      double Gn[D][M];
+      F::eval(fp, Y, t0, f0h);
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        f0h[i] *= h;
+        base[i] = Y[i] + f0h[i];
+      }
+      F::eval(fp, base, t1, f1h);
+#pragma unroll
+      for (int i = 0; i < D; ++i) Yn[i] = Y[i] + 0.5 * fma(f1h[i], h, f0h[i]);
+#pragma unroll(SMALL ? M : 1)
+      for (int k = 0; k < M; ++k) {
+        double g[D];
+        G::col(gp, k, Y, t0, g);
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+          Gn[i][k] = g[i];
+          Yn[i] = fma(g[i], dW[k], Yn[i]);
+        }
+      }
+      const double half_rh = 0.5 * rh;
+#pragma unroll(SMALL ? M : 1)
+      for (int k = 0; k < M; ++k) {
+        double up[D], dn[D], gu[D], gd[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+          double s = Gn[i][0] * IJ[0][k];
+#pragma unroll
+          for (int j = 1; j < M; ++j) s = fma(Gn[i][j], IJ[j][k], s);
+          s *= inv_rh;
+          up[i] = base[i] + s;
+          dn[i] = base[i] - s;
+        }
+        G::col(gp, k, up, t1, gu);
+        G::col(gp, k, dn, t1, gd);
+#pragma unroll
+        for (int i = 0; i < D; ++i) Yn[i] = fma(half_rh, gu[i] - gd[i], Yn[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < D; ++i) Y[i] = Yn[i];
+    } else {  // KP2IS
+      const double h = t1 - t0;
+      const double rh = sqrt(h);
+      double f0[D], V[D], acc[D];
+      double Gn[D][M];
+      F::eval(fp, Y, t0, f0);
+#pragma unroll
+      for (int i = 0; i < D; ++i) { V[i] = 0.0; acc[i] = 0.0; }
+#pragma unroll(SMALL ? M : 1)
+      for (int k = 0; k < M; ++k) {
+        double g[D];
+        G::col(gp, k, Y, t0, g);
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+          Gn[i][k] = g[i];
+          V[i] = fma(g[i], dW[k], V[i]);
+        }
+      }
+#pragma unroll 1
+      for (int j1 = 0; j1 < M; ++j1) {
+        double yb[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) yb[i] = fma(Gn[i][j1], rh, fma(f0[i], h, Y[i]));
+#pragma unroll(SMALL ? M : 1)
+        for (int k = 0; k < M; ++k) {
+          double g[D];
+          G::col(gp, k, yb, t0, g);  // G(Ybar[:,j1], tn): integrate.py:627
+#pragma unroll
+          for (int i = 0; i < D; ++i) acc[i] = fma(g[i] - Gn[i][k], IJ[j1][k], acc[i]);
+        }
+      }
+      const double inv_rh = 1.0 / rh;
+#pragma unroll
+      for (int i = 0; i < D; ++i) V[i] = fma(acc[i], inv_rh, V[i]);
+      double Ynew[D];
+      if (n == 0) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) Ynew[i] = fma(f0[i], h, Y[i]) + V[i];  // integrate.py:632
+      } else {
+        double cst[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+          const double gam = a.kp[i], al1 = a.kp[D + i], al2 = a.kp[2 * D + i];
+          cst[i] = (1.0 - gam) * Y[i] + gam * Ym1[i] +
+                   ((gam * al1 + (1.0 - al2)) * f0[i] + gam * (1.0 - al1) * fm1[i]) * h + V[i] +
+                   gam * Vm1[i];
+        }
+        // Newton on r(x) = cst + al2 h f(x, t1) - x with a forward-difference Jacobian; the
+        // reference hands the same residual to MINPACK hybrd (integrate.py:603-609,638).
+#pragma unroll
+        for (int i = 0; i < D; ++i) Ynew[i] = Y[i];
+        bool conv = false;
+#pragma unroll 1
+        for (int it = 0; it < 50 && !conv; ++it) {
+          double fx[D], r[D];
+          double Jm[D][D];
+          F::eval(fp, Ynew, t1, fx);
+#pragma unroll
+          for (int i = 0; i < D; ++i) r[i] = fma(a.kp[2 * D + i] * h, fx[i], cst[i]) - Ynew[i];
+#pragma unroll 1
+          for (int j = 0; j < D; ++j) {
+            double xp[D], fxp[D];
+            double step = 1.4901161193847656e-08 * fabs(Ynew[j]);
+            if (step == 0.0) step = 1.4901161193847656e-08;
+#pragma unroll
+            for (int i = 0; i < D; ++i) xp[i] = Ynew[i];
+            xp[j] += step;
+            step = xp[j] - Ynew[j];
+            F::eval(fp, xp, t1, fxp);
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+              Jm[i][j] = a.kp[2 * D + i] * h * (fxp[i] - fx[i]) / step - (i == j ? 1.0 : 0.0);
+          }
+#pragma unroll
+          for (int i = 0; i < D; ++i) r[i] = -r[i];
+          if (!sdb_solve<D>(Jm, r)) break;
+          double nd = 0.0, nx = 0.0;
+#pragma unroll
+          for (int i = 0; i < D; ++i) {
+            Ynew[i] += r[i];
+            nd = fma(r[i], r[i], nd);
+            nx = fma(Ynew[i], Ynew[i], nx);
+          }
+          conv = (nd <= a.rtol * a.rtol * nx) || nd == 0.0;
+        }
+        if (!conv && bad_solve < 0) bad_solve = n;
+      }
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        Ym1[i] = Y[i];
+        fm1[i] = f0[i];
+        Vm1[i] = V[i];
+        Y[i] = Ynew[i];
+      }
+    }
+
+    if (n + 1 == next_save) {
+      sdb_store<D>(a, p, slot, Y);
+      ++slot;
+      next_save += a.save_every;
+    }
+  }
+  sdb_finish<D>(a, p, Y);
+  if (SCHEME == SDB_SCHEME_KP2IS && bad_solve >= 0 && a.status) {
+    atomicAdd((unsigned long long*)&a.status[2], 1ull);
+    atomicMin((long long*)&a.status[3], (long long)bad_solve);
+  }
+}
+
+#define SDB_LOOP_KERNEL(NAME, SCHEME, F, G, NOISE)                                              \
+  extern "C" __global__ void __launch_bounds__(SDB_BLOCK)                                       \
+      NAME(const __grid_constant__ SdbLoopArgs a, const __grid_constant__ F::Params fp,         \
+           const __grid_constant__ G::Params gp) {                                              \
+    sdb_loop_body<SCHEME, F, G, NOISE>(a, fp, gp);                                              \
+  }
+
+// ---- standalone noise kernels ---------------------------------------------------------------------------
+// deltaW (wiener.py:52): out[step][comp][path] = sqrt(h) * z, one thread per (path, step).
+struct SdbDeltaWArgs {
+  int64_t steps, paths, path_id0;
+  uint64_t seed;
+  int m;
+  double sqrt_h;
+  double* out; int64_t sN, sJ, sP;
+};
+
+#ifdef SDB_DEFINE_STANDALONE
+extern "C" __global__ void __launch_bounds__(256) sdb_k_delta_w(const SdbDeltaWArgs a) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= a.steps * a.paths) return;
+  const int64_t n = idx / a.paths;
+  const int64_t p = idx - n * a.paths;
+  const SdbStream st(a.seed, (uint64_t)(a.path_id0 + p), (uint32_t)n);
+  SdbNormalSeq s(st, 0u);
+  double* o = a.out + n * a.sN + p * a.sP;
+  for (int j = 0; j < a.m; ++j) o[j * a.sJ] = a.sqrt_h * s.next();
+}
+#endif
+
+// Ikpw/Jkpw/Iwik/Jwik for every (path, step): one thread each.
+template <int M>
+SDB_DEV void sdb_repint_body(const SdbRepintArgs& a) {
+  constexpr int MM = M * (M - 1) / 2;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= a.steps * a.paths) return;
+  const int64_t n = idx / a.paths;
+  const int64_t p = idx - n * a.paths;
+  double dW[M];
+  const double* w = a.dW + n * a.dW_sN + p * a.dW_sP;
+#pragma unroll
+  for (int j = 0; j < M; ++j) dW[j] = w[j * a.dW_sJ];
+  double At[MM + 1];
+  double IJ[M][M];
+  if (a.X != nullptr) {
+    const SdbNormalsHost<M> ns{a.X + n * a.XY_sN + p * a.XY_sP, a.Y + n * a.XY_sN + p * a.XY_sP,
+                               a.XY_sT, a.XY_sJ,
+                               a.Gt ? a.Gt + n * a.Gt_sN + p * a.Gt_sP : nullptr, a.Gt_sR};
+    sdb_repeated_integrals<M>(dW, a.h, a.n_terms, a.method, a.stratonovich != 0, ns, At, IJ);
+  } else {
+    const SdbStream st(a.seed, (uint64_t)(a.path_id0 + p), (uint32_t)n);
+    const SdbNormalsPhilox<M> ns{st, a.n_terms};
+    sdb_repeated_integrals<M>(dW, a.h, a.n_terms, a.method, a.stratonovich != 0, ns, At, IJ);
+  }
+  if (a.A != nullptr) {
+    double* o = a.A + n * a.A_sN + p * a.A_sP;
+    if (a.method == SDB_NOISE_KPW) {  // full antisymmetric m x m matrix A
+      int r = 0;
+#pragma unroll
+      for (int i = 0; i < M; ++i) {
+        o[(i * M + i) * a.A_sE] = 0.0;
+#pragma unroll
+        for (int j = i + 1; j < M; ++j) {
+          o[(i * M + j) * a.A_sE] = At[r];
+          o[(j * M + i) * a.A_sE] = -At[r];
+          ++r;
+        }
+      }
+    } else {  // Atilde, length M(M-1)/2 (at least one entry: zeros((N,1,1)) for m == 1)
+#pragma unroll 1
+      for (int r = 0; r < (MM > 0 ? MM : 1); ++r) o[r * a.A_sE] = At[r];
+    }
+  }
+  double* q = a.IJ + n * a.IJ_sN + p * a.IJ_sP;
+#pragma unroll
+  for (int i = 0; i < M; ++i)
+#pragma unroll
+    for (int j = 0; j < M; ++j) q[i * a.IJ_sR + j * a.IJ_sC] = IJ[i][j];
+}
+
+#define SDB_REPINT_KERNEL(NAME, M)                                                   \
+  extern "C" __global__ void __launch_bounds__(128) NAME(const SdbRepintArgs a) {    \
+    sdb_repint_body<M>(a);                                                           \
+  }

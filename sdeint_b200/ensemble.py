@@ -1,0 +1,74 @@
+"""Ensemble statistics and multi-GPU sharding.
+
+Paths are independent (sdeint/integrate.py:494-522 reads only a path's own state and noise),
+so an ensemble shards across ranks with no exchange during stepping: rank r of R integrates
+global path ids [r*P/R, (r+1)*P/R) and Philox counters are keyed by the GLOBAL path id, so the
+trajectory of path p is identical for any R.  The only collective is one all-reduce (NCCL
+over NVLink through torch.distributed) of the moment sums and histogram counts."""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _device as dev
+from . import _lib
+
+
+def shard_paths(paths, rank, world_size):
+    """Contiguous block partition of global path ids: returns (path_id0, count)."""
+    paths, rank, world_size = int(paths), int(rank), int(world_size)
+    if not (0 <= rank < world_size):
+        raise ValueError("rank out of range")
+    base, rem = divmod(paths, world_size)
+    count = base + (1 if rank < rem else 0)
+    start = rank * base + min(rank, rem)
+    return start, count
+
+
+def moments(y_dev, hist=None):
+    """Per (saved point, component): sum y, sum y^2 (and optional histogram counts) of a
+    device trajectory tensor in path-minor layout (n_saved, d, P).
+
+    hist = (bins, lo, hi).  Returns (sums (n_saved, d, 2) float64 tensor,
+    counts (n_saved, d, bins) int64 tensor or None), both on the device."""
+    torch = dev.torch_mod()
+    if y_dev.dim() != 3 or y_dev.dtype != torch.float64 or not y_dev.is_contiguous():
+        raise ValueError("moments: need a contiguous float64 tensor (n_saved, d, P)")
+    S, d, P = y_dev.shape
+    with torch.cuda.device(y_dev.device):
+        sums = torch.zeros((S, d, 2), dtype=torch.float64, device=y_dev.device)
+        counts = None
+        bins, lo, hi = 0, 0.0, 1.0
+        if hist is not None:
+            bins, lo, hi = int(hist[0]), float(hist[1]), float(hist[2])
+            counts = torch.zeros((S, d, bins), dtype=torch.int64, device=y_dev.device)
+        _lib.check(_lib.load().sdb_moments(dev.ptr(y_dev), S, d, P, dev.ptr(sums),
+                                           dev.ptr(counts), bins, lo, hi, dev.stream_ptr()))
+    return sums, counts
+
+
+def allreduce_moments(sums, counts=None, group=None):
+    """Sum the per-rank partials over all ranks (torch.distributed; NCCL on GPUs)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+        if counts is not None:
+            dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+    return sums, counts
+
+
+def mean_var(sums, paths):
+    """Ensemble mean and (population) variance from (sum, sum of squares)."""
+    s = sums[..., 0] / paths
+    q = sums[..., 1] / paths
+    return s, q - s * s
+
+
+def merge_moments_host(partials):
+    """Fixed-order merge of per-rank (count, sums) partials on the host (numpy): the
+    reference semantics of the all-reduce, used by the CPU tests."""
+    total = 0
+    acc = None
+    for count, sums in partials:
+        total += int(count)
+        acc = np.array(sums, dtype=np.float64) if acc is None else acc + sums
+    return total, acc

@@ -1,0 +1,344 @@
+"""The integrators of sdeint/integrate.py with the same names, argument order and keyword
+names, running on the GPU.
+
+    itoint(f, G, y0, tspan, generator=None)                          integrate.py:124
+    stratint(f, G, y0, tspan, generator=None)                        integrate.py:157
+    itoEuler(f, G, y0, tspan, dW=None, generator=None)               integrate.py:190
+    stratHeun(f, G, y0, tspan, dW=None, generator=None)              integrate.py:243
+    itoSRI2(f, G, y0, tspan, Imethod=Ikpw, dW=None, I=None, generator=None)   :306
+    stratSRS2(f, G, y0, tspan, Jmethod=Jkpw, dW=None, J=None, generator=None) :371
+    stratKP2iS(f, G, y0, tspan, Jmethod=Jkpw, gam=None, al1=None, al2=None,
+               rtol=1e-4, dW=None, J=None, generator=None)           integrate.py:526
+
+Differences from the reference, all forced by "the loop runs in a CUDA kernel":
+  * `f` and `G` are operator objects from `sdeint_b200.ops` (built-in families or NVRTC
+    source), not arbitrary Python callables; `G` may also be the list `G.columns()`.
+  * fp64 only (the north-star scope); other dtypes raise SDEValueError.
+  * noise that the reference would draw from numpy's generator is drawn by an on-device
+    Philox generator (see sdeint_b200/wiener.py); results on host-supplied `dW`, `I`/`J`
+    match the reference to <= 1e-12 relative.
+Keyword-only ENSEMBLE extensions: `paths=P` integrates P independent sample paths in one
+launch (returns (P, n_saved, d)); `seed`, `path_id0` select the Philox streams; `save_every`
+decimates the stored trajectory; `out="torch"` leaves the result on the device in the
+path-minor layout (n_saved, d, P).  `dW` / `I` / `J` may then carry a leading path axis.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import numbers
+
+import numpy as np
+
+from . import _device as dev
+from . import _lib, ops
+from . import wiener
+from .wiener import Ikpw, Iwik, Jkpw, Jwik, deltaW  # noqa: F401  (re-exported like the reference)
+
+SCHEME_EULER, SCHEME_HEUN, SCHEME_SRK2, SCHEME_KP2IS = 0, 1, 2, 3
+NOISE_HOST, NOISE_KPW, NOISE_WIK = 0, 1, 2
+FLAG_Y0_BROADCAST, FLAG_STRATONOVICH = 1, 2
+
+
+class Error(Exception):
+    pass
+
+
+class SDEValueError(Error):
+    """Thrown if integration arguments fail some basic sanity checks"""
+    pass
+
+
+_last_status = None
+
+
+def last_status():
+    """(non-finite paths, first such path id, unconverged implicit solves, first such step)
+    of the most recent integration, or None."""
+    return _last_status
+
+
+def _check_args(f, G, y0, tspan, dW=None, IJ=None):
+    """Validation common to all algorithms; finds d and m.  Mirrors the checks of
+    sdeint/integrate.py:47-121 (equal spacing, scalar promotion, int -> float64, shape of
+    f(y0), G as one (d, m) operator or a list of m columns, shapes of dW and I/J), with an
+    optional leading path axis on dW / IJ.  Returns (d, m, f, Gop, y0, tspan, dW, IJ)."""
+    tspan = np.asarray(tspan, dtype=np.float64)
+    if tspan.ndim != 1 or tspan.shape[0] < 2:
+        raise SDEValueError('tspan must be a 1-d sequence of at least two time points.')
+    steps = np.diff(tspan)
+    if not np.isclose(steps.min(), steps.max()):
+        raise SDEValueError('Currently time steps must be equally spaced.')
+    if isinstance(y0, numbers.Number):
+        if isinstance(y0, numbers.Complex) and not isinstance(y0, numbers.Real):
+            raise SDEValueError('sdeint_b200 integrates real float64 systems only.')
+        if isinstance(y0, np.floating) and y0.dtype != np.float64:
+            raise SDEValueError('sdeint_b200 integrates float64 systems only (got %s).' % y0.dtype)
+        y0 = np.array([float(y0)], dtype=np.float64)
+    else:
+        y0 = np.array(y0)
+        if y0.dtype.kind in 'iub':
+            y0 = y0.astype(np.float64)
+        if y0.dtype != np.float64:
+            raise SDEValueError('sdeint_b200 integrates float64 systems only (got %s).' % y0.dtype)
+        if y0.ndim != 1:
+            raise SDEValueError('y0 must be a scalar or a 1-d array of length d.')
+    d = len(y0)
+    if not isinstance(f, ops.DriftOp):
+        raise SDEValueError(
+            'f must be a drift operator from sdeint_b200.ops (LinearDrift, KP4446Drift, ..., '
+            'or CudaDrift with NVRTC source): a Python callable cannot run inside a CUDA '
+            'kernel and this package has no CPU fallback.')
+    if f.d != d:
+        raise SDEValueError('y0 and f have incompatible shapes.')
+    message = ("y0 has length %d. So G must either be a single diffusion operator of shape "
+               "(%d, m), or else the list of its m columns (G.columns()), each of shape (%d,)"
+               % (d, d, d))
+    if isinstance(G, ops.DiffusionOp):
+        Gop = G
+    elif isinstance(G, (list, tuple)) and len(G) > 0:
+        cols = tuple(G)
+        if not all(isinstance(c, ops.DiffusionColumn) for c in cols):
+            raise SDEValueError(message)
+        Gop = cols[0].parent
+        if (len(cols) != Gop.m or any(c.parent is not Gop for c in cols)
+                or [c.k for c in cols] != list(range(Gop.m))):
+            raise SDEValueError('a list G must be exactly G.columns() of one diffusion operator.')
+    else:
+        raise SDEValueError(
+            'G must be a diffusion operator from sdeint_b200.ops (or its .columns() list): '
+            'a Python callable cannot run inside a CUDA kernel.')
+    if Gop.d != d:
+        raise SDEValueError(message)
+    m = Gop.m
+    N = len(tspan)
+    if dW is not None:
+        if not hasattr(dW, 'shape') or tuple(dW.shape[-2:]) != (N - 1, m) or len(dW.shape) > 3:
+            raise SDEValueError(
+                "From function G, it seems m==%d. If present, the optional parameter dW must "
+                "be an array of shape (len(tspan)-1, m) [or (paths, len(tspan)-1, m)] giving m "
+                "independent Wiener increments for each time interval." % m)
+    if IJ is not None:
+        if not hasattr(IJ, 'shape') or tuple(IJ.shape[-3:]) != (N - 1, m, m) or len(IJ.shape) > 4:
+            raise SDEValueError(
+                "From function G, it seems m==%d. If present, the optional parameter I or J "
+                "must be an array of shape (len(tspan)-1, m, m) [or (paths, len(tspan)-1, m, m)] "
+                "giving an m x m matrix of repeated integral values for each time interval." % m)
+    return (d, m, f, Gop, y0, tspan, dW, IJ)
+
+
+def _method_id(method, strat):
+    table = ({Jkpw: NOISE_KPW, Jwik: NOISE_WIK} if strat else {Ikpw: NOISE_KPW, Iwik: NOISE_WIK})
+    if method in table:
+        return table[method]
+    names = "Jkpw or Jwik" if strat else "Ikpw or Iwik"
+    raise SDEValueError("the repeated-integral method must be sdeint_b200.%s" % names)
+
+
+def _resolve_paths(paths, dW, IJ):
+    """Ensemble size: explicit `paths`, else the leading axis of a 3-d dW / 4-d IJ, else one
+    path returned in the reference's (N, d) layout."""
+    lead = []
+    if dW is not None and len(dW.shape) == 3:
+        lead.append(int(dW.shape[0]))
+    if IJ is not None and len(IJ.shape) == 4:
+        lead.append(int(IJ.shape[0]))
+    if paths is not None:
+        P = int(paths)
+        if P < 1:
+            raise SDEValueError('paths must be >= 1')
+        if any(p != P for p in lead):
+            raise SDEValueError('dW / I / J path axis does not match paths=%d' % P)
+        return P, True
+    if lead:
+        if any(p != lead[0] for p in lead):
+            raise SDEValueError('dW and I / J disagree on the number of paths')
+        return lead[0], True
+    return 1, False
+
+
+def _run(scheme, f, G, y0, tspan, dW, IJ, strat, method, generator, kp2is, paths, seed,
+         path_id0, save_every, n_terms, device, out, y0_paths=None):
+    global _last_status
+    (d, m, f, Gop, y0, tspan, dW, IJ) = _check_args(f, G, y0, tspan, dW, IJ)
+    P, ensemble = _resolve_paths(paths, dW, IJ)
+    need_ij = scheme in (SCHEME_SRK2, SCHEME_KP2IS)
+    N = len(tspan)
+    save_every = int(save_every)
+    if save_every < 1:
+        raise SDEValueError('save_every must be >= 1')
+    n_saved = (N - 1) // save_every + 1
+    h = (tspan[N - 1] - tspan[0]) / (N - 1)
+    method_id = _method_id(method, strat) if need_ij else NOISE_KPW
+    device = dev.require_cuda(device)
+    torch = dev.torch_mod()
+    lib = _lib.load()
+    have_dW, have_IJ = dW is not None, (IJ is not None or not need_ij)
+    key = 0
+    if not (have_dW and have_IJ):
+        key = wiener._derive_seed(seed, generator)
+
+    with torch.cuda.device(device):
+        system = dev.get_system(f, Gop, device)
+        a = _lib.IntegrateArgs()
+        keep = []
+        # --- noise --------------------------------------------------------------------
+        if not have_dW and not (need_ij and IJ is not None):
+            a.noise = method_id                         # everything drawn on the device, fused
+        else:
+            a.noise = NOISE_HOST
+            if have_dW:
+                dW_h = np.asarray(dW, dtype=np.float64)
+                if dW_h.ndim == 2:
+                    dW_h = np.broadcast_to(dW_h, (P,) + dW_h.shape) if P > 1 else dW_h[None]
+                d_dW = dev.to_device(dW_h, device)      # (P, N-1, m)
+                sW = (m, 1, (N - 1) * m)
+            else:                                        # I/J given, dW drawn (integrate.py:481-483)
+                d_dW = torch.empty((N - 1, m, P), dtype=torch.float64, device=device)
+                _lib.check(lib.sdb_delta_w(N - 1, m, float(h), P, int(path_id0), key,
+                                           dev.ptr(d_dW), m * P, P, 1, dev.stream_ptr()))
+                sW = (m * P, P, 1)
+            keep.append(d_dW)
+            a.d_dW = dev.ptr(d_dW)
+            a.dW_stride_step, a.dW_stride_comp, a.dW_stride_path = sW
+            if need_ij:
+                if IJ is not None:
+                    IJ_h = np.asarray(IJ, dtype=np.float64)
+                    if IJ_h.ndim == 3:
+                        IJ_h = np.broadcast_to(IJ_h, (P,) + IJ_h.shape) if P > 1 else IJ_h[None]
+                    d_IJ = dev.to_device(IJ_h, device)  # (P, N-1, m, m)
+                else:                                    # dW given, I/J drawn from it (:484-487)
+                    d_IJ = torch.empty((P, N - 1, m, m), dtype=torch.float64, device=device)
+                    r = _lib.RepintArgs()
+                    r.method, r.stratonovich, r.n_terms, r.m = method_id, int(strat), n_terms, m
+                    r.steps, r.paths, r.path_id0, r.seed, r.h = N - 1, P, int(path_id0), key, float(h)
+                    r.d_dW = a.d_dW
+                    r.dW_stride_step, r.dW_stride_comp, r.dW_stride_path = sW
+                    r.d_IJ = dev.ptr(d_IJ)
+                    r.IJ_stride_path, r.IJ_stride_step = (N - 1) * m * m, m * m
+                    r.IJ_stride_row, r.IJ_stride_col = m, 1
+                    r.stream = dev.stream_ptr()
+                    _lib.check(lib.sdb_repeated_integrals(C.byref(r)))
+                keep.append(d_IJ)
+                a.d_IJ = dev.ptr(d_IJ)
+                a.IJ_stride_path, a.IJ_stride_step = (N - 1) * m * m, m * m
+                a.IJ_stride_row, a.IJ_stride_col = m, 1
+        # --- state --------------------------------------------------------------------
+        if y0_paths is not None:
+            y0p = np.asarray(y0_paths, dtype=np.float64)
+            if y0p.shape != (P, d):
+                raise SDEValueError('y0_paths must have shape (paths, d)')
+            d_y0 = dev.to_device(y0p, device)
+            a.flags = 0
+            a.y0_stride_comp, a.y0_stride_path = 1, d
+        else:
+            d_y0 = dev.to_device(y0, device)
+            a.flags = FLAG_Y0_BROADCAST
+        if strat:
+            a.flags |= FLAG_STRATONOVICH
+        d_y = torch.empty((n_saved, d, P), dtype=torch.float64, device=device)
+        d_status = torch.empty(4, dtype=torch.int64, device=device)
+        a.scheme, a.n_terms = scheme, int(n_terms)
+        a.paths, a.path_id0, a.seed = P, int(path_id0), key
+        a.N, a.save_every = N, save_every
+        a.h_tspan = dev.host_ptr(tspan)
+        a.d_y0 = dev.ptr(d_y0)
+        a.d_y = dev.ptr(d_y)
+        a.y_stride_save, a.y_stride_comp, a.y_stride_path = d * P, P, 1
+        if kp2is is not None:
+            kp = np.ascontiguousarray(np.concatenate(kp2is[:3]), dtype=np.float64)
+            a.h_kp2is = dev.host_ptr(kp)
+            a.rtol = float(kp2is[3])
+        a.d_status = dev.ptr(d_status)
+        a.stream = dev.stream_ptr()
+        _lib.check(lib.sdb_integrate(system.handle, C.byref(a)))
+        status = tuple(int(v) for v in d_status.cpu().tolist())
+        _last_status = status
+        if scheme == SCHEME_KP2IS and status[2] > 0:
+            raise RuntimeError(
+                "At time t_n = %g Failed to solve for Y_{n+1}: the implicit equation did not "
+                "converge to rtol=%g on %d path(s)." % (tspan[status[3]], kp2is[3], status[2]))
+        if out == "torch":
+            return d_y
+        host = d_y.cpu().numpy()
+    if not ensemble:
+        return np.ascontiguousarray(host[:, :, 0])      # (N, d), y[0] == y0
+    return host.transpose(2, 0, 1)                       # (P, n_saved, d)
+
+
+_ENS = dict(paths=None, seed=None, path_id0=0, save_every=1, n_terms=5, device=None, out="numpy",
+            y0_paths=None)
+
+
+def itoEuler(f, G, y0, tspan, dW=None, generator=None, **ens):
+    """Euler-Maruyama for the Ito equation dy = f dt + G dW (integrate.py:190-240)."""
+    kw = _ens(ens)
+    if not isinstance(G, ops.DiffusionOp) and isinstance(G, (list, tuple)):
+        raise TypeError("'tuple' object is not callable")   # the reference's behaviour, App. B
+    return _run(SCHEME_EULER, f, G, y0, tspan, dW, None, False, None, generator, None, **kw)
+
+
+def stratHeun(f, G, y0, tspan, dW=None, generator=None, **ens):
+    """Stratonovich Heun (integrate.py:243-303)."""
+    kw = _ens(ens)
+    if not isinstance(G, ops.DiffusionOp) and isinstance(G, (list, tuple)):
+        raise TypeError("'tuple' object is not callable")
+    return _run(SCHEME_HEUN, f, G, y0, tspan, dW, None, True, None, generator, None, **kw)
+
+
+def itoSRI2(f, G, y0, tspan, Imethod=Ikpw, dW=None, I=None, generator=None, **ens):
+    """Roessler (2010) order 1.0 strong SRK scheme SRI2 for Ito equations
+    (integrate.py:306-368, loop at :494-522)."""
+    kw = _ens(ens)
+    return _run(SCHEME_SRK2, f, G, y0, tspan, dW, I, False, Imethod, generator, None, **kw)
+
+
+def stratSRS2(f, G, y0, tspan, Jmethod=Jkpw, dW=None, J=None, generator=None, **ens):
+    """Roessler (2010) SRS2 for Stratonovich equations (integrate.py:371-433)."""
+    kw = _ens(ens)
+    return _run(SCHEME_SRK2, f, G, y0, tspan, dW, J, True, Jmethod, generator, None, **kw)
+
+
+def stratKP2iS(f, G, y0, tspan, Jmethod=Jkpw, gam=None, al1=None, al2=None, rtol=1e-4, dW=None,
+               J=None, generator=None, **ens):
+    """Kloeden-Platen two-step implicit order 1.0 strong scheme (integrate.py:526-646).  The
+    implicit equation is solved per path by Newton iteration with a forward-difference
+    Jacobian to relative step tolerance `rtol` (the reference uses MINPACK hybrd with
+    xtol=rtol); RuntimeError if it does not converge."""
+    kw = _ens(ens)
+    if not isinstance(G, ops.DiffusionOp) and isinstance(G, (list, tuple)):
+        raise SDEValueError('G should be a function returning a d x m matrix.')
+    y0a = np.asarray(y0)
+    if np.iscomplexobj(y0a):
+        raise SDEValueError("stratKP2iS() can't yet handle complex variables.")
+    d = 1 if y0a.ndim == 0 else len(y0a)
+    pars = []
+    for v in (gam, al1, al2):
+        v = np.full(d, 0.5) if v is None else np.asarray(v, dtype=np.float64).reshape(-1)
+        if v.shape != (d,):
+            raise SDEValueError('gam, al1, al2 must have shape (d,)')
+        pars.append(v)
+    return _run(SCHEME_KP2IS, f, G, y0, tspan, dW, J, True, Jmethod, generator,
+                (pars[0], pars[1], pars[2], float(rtol)), **kw)
+
+
+def itoint(f, G, y0, tspan, generator=None, **ens):
+    """Integrate the Ito equation dy = f(y,t)dt + G(y,t)dW (integrate.py:124-154): currently
+    always itoSRI2, like the reference."""
+    _check_args(f, G, y0, tspan, None, None)
+    return itoSRI2(f, G, y0, tspan, generator=generator, **ens)
+
+
+def stratint(f, G, y0, tspan, generator=None, **ens):
+    """Integrate the Stratonovich equation dy = f dt + G o dW (integrate.py:157-187): always
+    stratSRS2, like the reference."""
+    _check_args(f, G, y0, tspan, None, None)
+    return stratSRS2(f, G, y0, tspan, generator=generator, **ens)
+
+
+def _ens(ens):
+    bad = set(ens) - set(_ENS)
+    if bad:
+        raise TypeError("unexpected keyword argument(s): %s" % ", ".join(sorted(bad)))
+    kw = dict(_ENS)
+    kw.update(ens)
+    return kw

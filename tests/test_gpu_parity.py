@@ -1,0 +1,364 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).  Everything here goes through
+the public shim -> ctypes -> C ABI (include/sdb.h) -> CUDA kernels, and is compared with
+(a) the committed outputs of the unmodified reference (tests/golden) and (b) the pinned
+oracle on seeded inputs.  Tolerance: 1e-12 relative (fp64), the north-star bound; the
+KP2iS scheme, whose implicit solve the reference delegates to MINPACK, gets 1e-10."""
+import numpy as np
+import pytest
+
+from conftest import SYSTEMS, load_golden, rel_err
+from oracle import philox_oracle as po
+from oracle import sde_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def sdb():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import sdeint_b200
+    sdeint_b200._lib.load()
+    return sdeint_b200
+
+
+# ---- integrators on host-supplied noise vs the reference's golden outputs ------------------
+
+@pytest.mark.parametrize("name", sorted(SYSTEMS))
+def test_integrators_vs_reference_golden(sdb, name):
+    g = load_golden("integrate_%s.npz" % name)
+    f_ito, G, _ = SYSTEMS[name](False)
+    f_str, _, _ = SYSTEMS[name](True)
+    tspan, dW, I, J, y0 = g["tspan"], g["dW"], g["I"], g["J"], g["y0"]
+    before = sdb.launch_count()
+    # ensemble form: all paths in one launch, (P, N, d)
+    assert rel_err(sdb.itoEuler(f_ito, G, y0, tspan, dW=dW), g["y_itoEuler"]) <= TOL
+    assert rel_err(sdb.stratHeun(f_str, G, y0, tspan, dW=dW), g["y_stratHeun"]) <= TOL
+    assert rel_err(sdb.itoSRI2(f_ito, G, y0, tspan, dW=dW, I=I), g["y_itoSRI2"]) <= TOL
+    assert rel_err(sdb.stratSRS2(f_str, G, y0, tspan, dW=dW, J=J), g["y_stratSRS2"]) <= TOL
+    if "y_itoSRI2_listG" in g:
+        y = sdb.itoSRI2(f_ito, G.columns(), y0, tspan, dW=dW, I=I)
+        assert rel_err(y, g["y_itoSRI2_listG"]) <= TOL
+    if "y_stratKP2iS" in g:
+        y = sdb.stratKP2iS(f_str, G, y0, tspan, dW=dW, J=J, rtol=1e-12)
+        assert rel_err(y, g["y_stratKP2iS"]) <= 1e-10
+    assert sdb.launch_count() > before          # kernels really launched
+    # single-path form: the reference's exact call and return layout (N, d)
+    y1 = sdb.itoSRI2(f_ito, G, y0, tspan, dW=dW[0], I=I[0])
+    assert y1.shape == g["y_itoSRI2"][0].shape and y1.dtype == np.float64
+    assert np.array_equal(y1[0], y0)
+    assert rel_err(y1, g["y_itoSRI2"][0]) <= TOL
+
+
+def test_scalar_y0_wrapping(sdb):
+    """Scalar y0 -> output (N, 1) (integrate.py:54-60); int -> float64."""
+    g = load_golden("integrate_kp4446.npz")
+    f, G, y0 = SYSTEMS["kp4446"](False)
+    assert np.ndim(y0) == 0
+    y = sdb.itoSRI2(f, G, y0, g["tspan"], dW=g["dW"][0], I=g["I"][0])
+    assert y.shape == (len(g["tspan"]), 1)
+    assert rel_err(y, g["y_itoSRI2"][0]) <= TOL
+    f2, G2, _ = SYSTEMS["ou"](False)
+    y = sdb.itoEuler(f2, G2, 1, np.linspace(0, 1, 11), dW=np.zeros((10, 1)))
+    assert y.dtype == np.float64 and y[0, 0] == 1.0
+
+
+# ---- repeated integrals: construction parity with host-supplied normals --------------------
+
+def test_repeated_integrals_vs_reference_golden(sdb):
+    g = load_golden("wiener.npz")
+    for ci, (m, n, N, h) in enumerate(g["cases"]):
+        m, n, N = int(m), int(n), int(N)
+        pre = "c%d_" % ci
+        dW, X, Y, Gt = g[pre + "dW"], g[pre + "X"], g[pre + "Y"], g[pre + "Gt"]
+        scale = np.max(np.abs(g[pre + "I_kpw"]))
+        A, I = sdb.Ikpw(dW, h, n=n, normals=(X, Y))
+        assert A.shape == g[pre + "A_kpw"].shape and I.shape == g[pre + "I_kpw"].shape
+        assert np.max(np.abs(A - g[pre + "A_kpw"])) <= TOL * scale
+        assert np.max(np.abs(I - g[pre + "I_kpw"])) <= TOL * scale
+        _, Jk = sdb.Jkpw(dW, h, n=n, normals=(X, Y))
+        assert np.max(np.abs(Jk - g[pre + "J_kpw"])) <= TOL * scale
+        At, Iw = sdb.Iwik(dW, h, n=n, normals=(X, Y, Gt))
+        assert At.shape == g[pre + "At_wik"].shape and Iw.shape == g[pre + "I_wik"].shape
+        assert np.max(np.abs(At - g[pre + "At_wik"])) <= TOL * scale
+        assert np.max(np.abs(Iw - g[pre + "I_wik"])) <= TOL * scale
+        _, Jw = sdb.Jwik(dW.reshape(N, m, 1), h, n=n, normals=(X, Y, Gt))   # (N, m, 1) accepted
+        assert np.max(np.abs(Jw - g[pre + "J_wik"])) <= TOL * scale
+
+
+def test_repeated_integrals_bad_shape(sdb):
+    with pytest.raises(ValueError):
+        sdb.Ikpw(np.zeros((4,)), 0.1)
+    with pytest.raises(ValueError):
+        sdb.Iwik(np.zeros((2, 3, 4, 5)), 0.1)
+
+
+def test_identities_on_device_noise(sdb):
+    """Wiktorsson (2.1) identities (test_wiener.py:94-130) on fully on-device output."""
+    N, h, m = 4000, 0.002, 8
+    dW = sdb.deltaW(N, m, h, seed=5)
+    assert dW.shape == (N, m)
+    outer = dW[:, :, None] * dW[:, None, :]
+    eye = np.eye(m)[None]
+    A, I = sdb.Ikpw(dW, h, seed=5)
+    assert A.shape == (N, m, m) and I.shape == (N, m, m)
+    assert np.allclose(I + I.transpose(0, 2, 1), outer - h * eye, atol=1e-15)
+    assert np.allclose(A, -A.transpose(0, 2, 1), atol=0)
+    assert np.allclose(2.0 * (I - A), outer - h * eye, atol=1e-15)
+    _, J = sdb.Jkpw(dW, h, seed=5)
+    assert np.allclose(J + J.transpose(0, 2, 1), outer, atol=1e-15)
+    At, Iw = sdb.Iwik(dW, h, seed=5)
+    M = m * (m - 1) // 2
+    assert At.shape == (N, M, 1)
+    assert np.allclose(Iw + Iw.transpose(0, 2, 1), outer - h * eye, atol=1e-15)
+    K0, P0 = orc.sel_K(m), orc.perm_P(m)
+    Afull = orc.unvec(np.einsum("ab,sbc->sac", (np.eye(m * m) - P0).dot(K0.T), At))
+    assert np.allclose(2.0 * (Iw - Afull), outer - h * eye, atol=1e-15)
+    # Levy area statistics: E A_ij = 0, Var A_ij (n=5 series) = h^2/(2 pi^2) sum_{k<=5} 1/k^2 * ...
+    a01 = A[:, 0, 1]
+    assert abs(a01.mean()) < 5 * a01.std() / np.sqrt(N)
+
+
+# ---- the on-device generator vs its numpy restatement ---------------------------------------
+
+def test_deltaW_matches_philox_oracle(sdb):
+    steps, m, h, P, seed = 37, 5, 0.01, 19, 987654321
+    dW = sdb.deltaW(steps, m, h, paths=P, seed=seed, path_id0=1000)
+    want = po.delta_w(steps, m, h, P, seed, path_id0=1000)
+    assert dW.shape == want.shape
+    assert np.max(np.abs(dW - want)) <= 1e-14
+    # rank invariance: a shard with a path offset reproduces the same paths
+    part = sdb.deltaW(steps, m, h, paths=7, seed=seed, path_id0=1005)
+    assert np.array_equal(part, dW[5:12])
+
+
+def test_device_Ikpw_matches_oracle_on_philox_normals(sdb):
+    steps, m, h, P, seed, n = 11, 6, 0.004, 5, 4242, 5
+    dW = sdb.deltaW(steps, m, h, paths=P, seed=seed)
+    X, Y = po.kpw_normals(steps, m, n, P, seed)
+    Gt = po.wik_tail_normals(steps, m, n, P, seed)
+    A, I = sdb.Ikpw(dW, h, n=n, seed=seed)
+    At, Jw = sdb.Jwik(dW, h, n=n, seed=seed)
+    for p in range(P):
+        A_o, I_o = orc.ikpw_from_normals(dW[p], h, X[:, p], Y[:, p])
+        At_o, Jw_o = orc.jwik_from_normals(dW[p], h, X[:, p], Y[:, p], Gt[p])
+        s = np.max(np.abs(I_o))
+        assert np.max(np.abs(A[p] - A_o)) <= 1e-12 * s
+        assert np.max(np.abs(I[p] - I_o)) <= 1e-12 * s
+        assert np.max(np.abs(At[p] - At_o)) <= 1e-12 * s
+        assert np.max(np.abs(Jw[p] - Jw_o)) <= 1e-12 * s
+
+
+def test_normals_distribution(sdb):
+    """Moments and a KS test of the device normals (2.4e6 draws)."""
+    from scipy import stats
+    z = sdb.deltaW(300, 8, 1.0, paths=1000, seed=77).reshape(-1)
+    n = z.size
+    assert abs(z.mean()) < 5 / np.sqrt(n)
+    assert abs(z.var() - 1.0) < 5 * np.sqrt(2.0 / n)
+    assert abs((z ** 3).mean()) < 5 * np.sqrt(15.0 / n)
+    assert abs((z ** 4).mean() - 3.0) < 5 * np.sqrt(96.0 / n)
+    assert stats.kstest(z[:200000], "norm").pvalue > 1e-3
+    # independence across paths and across steps
+    zz = z.reshape(1000, 300, 8)
+    assert abs(np.corrcoef(zz[:-1, :, 0].ravel(), zz[1:, :, 0].ravel())[0, 1]) < 0.01
+    assert abs(np.corrcoef(zz[:, :-1, 0].ravel(), zz[:, 1:, 0].ravel())[0, 1]) < 0.01
+    assert abs(np.corrcoef(zz[:, :, 0].ravel(), zz[:, :, 1].ravel())[0, 1]) < 0.01
+
+
+# ---- fused on-device noise path vs oracle on the noise the device generated ----------------
+
+@pytest.mark.parametrize("name,strat,method", [
+    ("lin10", False, "kpw"), ("lin10", True, "kpw"), ("lin10", False, "wik"),
+    ("r74", False, "kpw"), ("r74", True, "wik"), ("kp4459", False, "kpw"),
+    ("kp4446", False, "wik"), ("lin2", False, "kpw"),
+])
+def test_fused_device_noise_matches_oracle(sdb, name, strat, method):
+    f, G, y0 = SYSTEMS[name](strat)
+    y0v = np.atleast_1d(np.asarray(y0, dtype=float))
+    m = G.m
+    tspan = np.linspace(0.0, 0.2, 41)
+    N = len(tspan)
+    h = (tspan[-1] - tspan[0]) / (N - 1)
+    P, seed = 70, 31337
+    integ = sdb.stratSRS2 if strat else sdb.itoSRI2
+    rep = {(False, "kpw"): sdb.Ikpw, (False, "wik"): sdb.Iwik,
+           (True, "kpw"): sdb.Jkpw, (True, "wik"): sdb.Jwik}[(strat, method)]
+    y = integ(f, G, y0, tspan, rep, paths=P, seed=seed, path_id0=3)
+    assert y.shape == (P, N, len(y0v))
+    dW = sdb.deltaW(N - 1, m, h, paths=P, seed=seed, path_id0=3)
+    _, IJ = rep(dW, h, seed=seed, path_id0=3, ensemble=True)
+    for p in (0, 1, 33, P - 1):
+        ref = orc.srk2(f, G, y0v, tspan, dW[p], IJ[p])
+        assert rel_err(y[p], ref) <= TOL
+    # decimated storage returns the same states
+    yd = integ(f, G, y0, tspan, rep, paths=P, seed=seed, path_id0=3, save_every=10)
+    assert yd.shape == (P, 5, len(y0v))
+    assert np.array_equal(yd, y[:, ::10])
+    # unfused pipeline through the host-noise kernel agrees too
+    y2 = integ(f, G, y0, tspan, rep, dW=dW, **({"J": IJ} if strat else {"I": IJ}))
+    assert rel_err(y2, y) <= TOL
+
+
+def test_euler_heun_device_noise(sdb):
+    f, G, y0 = SYSTEMS["lin2"](False)
+    tspan = np.linspace(0.0, 1.0, 101)
+    h = 0.01
+    P, seed = 40, 99
+    dW = sdb.deltaW(100, 2, h, paths=P, seed=seed)
+    ye = sdb.itoEuler(f, G, y0, tspan, paths=P, seed=seed)
+    yh = sdb.stratHeun(f, G, y0, tspan, paths=P, seed=seed)
+    for p in (0, 17, P - 1):
+        assert rel_err(ye[p], orc.euler(f, G, y0, tspan, dW[p])) <= TOL
+        assert rel_err(yh[p], orc.heun(f, G, y0, tspan, dW[p])) <= TOL
+    # a seeded numpy generator gives reproducible results and is advanced
+    g1, g2 = np.random.default_rng(8), np.random.default_rng(8)
+    a = sdb.itoEuler(f, G, y0, tspan, generator=g1)
+    b = sdb.itoEuler(f, G, y0, tspan, generator=g2)
+    assert a.shape == (101, 2) and np.array_equal(a, b)
+    assert g1.integers(1 << 30) == g2.integers(1 << 30)
+    assert g1.integers(1 << 30) != np.random.default_rng(8).integers(1 << 30)
+
+
+def test_mixed_noise_inputs(sdb):
+    """Only one of dW / I supplied: the other is drawn on the device (integrate.py:481-489)."""
+    f, G, y0 = SYSTEMS["r74"](False)
+    tspan = np.linspace(0.0, 0.1, 21)
+    h = 0.005
+    dW = sdb.deltaW(20, 4, h, seed=3)
+    y = sdb.itoSRI2(f, G, y0, tspan, dW=dW, seed=11)
+    _, I = sdb.Ikpw(dW, h, seed=11)
+    assert rel_err(y, orc.srk2(f, G, y0, tspan, dW, I)) <= TOL
+    y = sdb.itoSRI2(f, G, y0, tspan, I=I, seed=12)
+    dW2 = sdb.deltaW(20, 4, h, seed=12)
+    assert rel_err(y, orc.srk2(f, G, y0, tspan, dW2, I)) <= TOL
+
+
+def test_kp2is_device_noise_and_params(sdb):
+    f, G, y0 = SYSTEMS["r74"](True)
+    tspan = np.linspace(0.0, 0.2, 41)
+    h = 0.005
+    P, seed = 6, 5150
+    gam, al1, al2 = np.full(5, 0.3), np.full(5, 0.6), np.full(5, 0.8)
+    y = sdb.stratKP2iS(f, G, y0, tspan, sdb.Jwik, gam=gam, al1=al1, al2=al2, rtol=1e-12,
+                       paths=P, seed=seed)
+    dW = sdb.deltaW(40, 4, h, paths=P, seed=seed)
+    _, J = sdb.Jwik(dW, h, seed=seed, ensemble=True)
+    for p in range(P):
+        ref = orc.kp2is(f, G, y0, tspan, dW[p], J[p], gam, al1, al2, rtol=1e-13, solver="newton")
+        assert rel_err(y[p], ref) <= 1e-10
+
+
+# ---- argument validation (integrate.py:47-121 semantics) ---------------------------------------
+
+def test_argument_validation(sdb):
+    f, G, y0 = SYSTEMS["r74"](False)
+    tspan = np.linspace(0.0, 0.1, 21)
+    with pytest.raises(sdb.SDEValueError):                       # unequal spacing
+        sdb.itoint(f, G, y0, np.array([0.0, 0.1, 0.3]))
+    with pytest.raises(sdb.SDEValueError):                       # y0 / f mismatch (test_mismatched_f)
+        sdb.itoint(f, G, np.zeros(3), tspan)
+    with pytest.raises(sdb.SDEValueError):                       # wrong dW shape
+        sdb.itoEuler(f, G, y0, tspan, dW=np.zeros((20, 3)))
+    with pytest.raises(sdb.SDEValueError):                       # nested list has no .shape
+        sdb.itoEuler(f, G, y0, tspan, dW=[[0.0] * 4] * 20)
+    with pytest.raises(sdb.SDEValueError):                       # wrong I shape
+        sdb.itoSRI2(f, G, y0, tspan, dW=np.zeros((20, 4)), I=np.zeros((20, 4, 3)))
+    with pytest.raises(sdb.SDEValueError):                       # Python callables cannot run
+        sdb.itoint(lambda y, t: -y, lambda y, t: np.eye(5), y0, tspan)
+    with pytest.raises(TypeError):                               # list-G only for SRI2/SRS2
+        sdb.itoEuler(f, G.columns(), y0, tspan)
+    with pytest.raises(sdb.SDEValueError):
+        sdb.stratKP2iS(f, G.columns(), y0, tspan)
+    with pytest.raises(sdb.SDEValueError):                       # fp64 only
+        sdb.itoint(f, G, np.ones(5, dtype=np.float32), tspan)
+    assert issubclass(sdb.SDEValueError, sdb.Error)
+
+
+# ---- moments / histogram kernels ----------------------------------------------------------------
+
+def test_moments_and_histogram(sdb):
+    import torch
+    rng = np.random.default_rng(0)
+    S, d, P = 3, 4, 10007
+    y = rng.normal(0.5, 1.0, (S, d, P))
+    yd = torch.from_numpy(y).cuda()
+    sums, counts = sdb.ensemble.moments(yd, hist=(32, -2.0, 3.0))
+    sums, counts = sums.cpu().numpy(), counts.cpu().numpy()
+    assert np.allclose(sums[..., 0], y.sum(-1), rtol=1e-12)
+    assert np.allclose(sums[..., 1], (y * y).sum(-1), rtol=1e-12)
+    for s in range(S):
+        for i in range(d):
+            want, _ = np.histogram(y[s, i], bins=32, range=(-2.0, 3.0))
+            inside = (y[s, i] >= -2.0) & (y[s, i] < 3.0)
+            assert counts[s, i].sum() == inside.sum()
+            assert np.abs(counts[s, i] - want).sum() <= 2     # edge rounding only
+    # deterministic: same input, same bits
+    sums2, _ = sdb.ensemble.moments(yd)
+    assert np.array_equal(sums2.cpu().numpy(), sums)
+
+
+# ---- NVRTC user operators ------------------------------------------------------------------------
+
+USER_SRC = r"""
+__device__ void sde_drift(const double* y, double t, const double* p, double* out) {
+  // damped oscillator with a time-dependent forcing: p = (k, c, amp)
+  out[0] = y[1];
+  out[1] = -p[0] * y[0] - p[1] * y[1] + p[2] * sin(t);
+}
+__device__ void sde_diffusion_col(int k, const double* y, double t, const double* p, double* out) {
+  // column 0: additive on velocity; column 1: multiplicative on both
+  if (k == 0) { out[0] = 0.0; out[1] = p[0]; }
+  else        { out[0] = p[1] * y[0]; out[1] = p[1] * y[1] * cos(t); }
+}
+"""
+
+
+def test_nvrtc_user_system(sdb):
+    kf = np.array([4.0, 0.3, 0.5])
+    kg = np.array([0.2, 0.1])
+
+    def f_host(y, t):
+        return np.array([y[1], -kf[0] * y[0] - kf[1] * y[1] + kf[2] * np.sin(t)])
+
+    def g_host(y, t):
+        return np.array([[0.0, kg[1] * y[0]], [kg[0], kg[1] * y[1] * np.cos(t)]])
+
+    f = sdb.ops.CudaDrift(USER_SRC, 2, kf, host=f_host)
+    G = sdb.ops.CudaDiffusion(USER_SRC, 2, 2, kg, host=g_host)
+    y0 = np.array([1.0, 0.0])
+    tspan = np.linspace(0.0, 1.0, 201)
+    rng = np.random.default_rng(1)
+    h = 0.005
+    dW = orc.delta_w(200, 2, h, rng)
+    _, I = orc.ikpw(dW, h, generator=rng)
+    _, J = orc.jkpw(dW, h, generator=rng)
+    assert rel_err(sdb.itoEuler(f, G, y0, tspan, dW=dW), orc.euler(f_host, g_host, y0, tspan, dW)) <= TOL
+    assert rel_err(sdb.stratHeun(f, G, y0, tspan, dW=dW), orc.heun(f_host, g_host, y0, tspan, dW)) <= TOL
+    assert rel_err(sdb.itoSRI2(f, G, y0, tspan, dW=dW, I=I), orc.srk2(f_host, g_host, y0, tspan, dW, I)) <= TOL
+    assert rel_err(sdb.stratSRS2(f, G, y0, tspan, dW=dW, J=J), orc.srk2(f_host, g_host, y0, tspan, dW, J)) <= TOL
+    yk = sdb.stratKP2iS(f, G, y0, tspan, dW=dW, J=J, rtol=1e-12)
+    assert rel_err(yk, orc.kp2is(f_host, g_host, y0, tspan, dW, J, rtol=1e-13, solver="newton")) <= 1e-10
+
+
+def test_jit_builtin_dimensions(sdb):
+    """A (d, m) with no ahead-of-time instantiation goes through NVRTC with the same header."""
+    rng = np.random.default_rng(3)
+    d, m = 3, 2
+    A = -np.eye(d) + 0.1 * rng.standard_normal((d, d))
+    B = 0.2 * rng.standard_normal((m, d, d))
+    f, G = sdb.ops.LinearDrift(A), sdb.ops.LinearDiffusion(B)
+    y0 = np.ones(d)
+    tspan = np.linspace(0, 0.5, 51)
+    dW = orc.delta_w(50, m, 0.01, rng)
+    _, I = orc.iwik(dW, 0.01, generator=rng)
+    assert rel_err(sdb.itoSRI2(f, G, y0, tspan, dW=dW, I=I), orc.srk2(f, G, y0, tspan, dW, I)) <= TOL
+    # repeated integrals for an m without an AOT kernel
+    dW13 = orc.delta_w(6, 13, 0.01, rng)
+    X, Y, Gt = orc.draw_wik_normals(np.random.default_rng(4), 6, 13, 4)
+    At, Iw = sdb.Iwik(dW13, 0.01, n=4, normals=(X, Y, Gt))
+    At_o, Iw_o = orc.iwik_from_normals(dW13, 0.01, X, Y, Gt)
+    assert np.max(np.abs(Iw - Iw_o)) <= 1e-12 * np.max(np.abs(Iw_o))
+    assert np.max(np.abs(At - At_o)) <= 1e-12 * np.max(np.abs(Iw_o))

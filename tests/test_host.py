@@ -1,0 +1,161 @@
+"""CPU tests: the C-ABI library loads and exports every symbol include/sdb.h declares, the
+host-side shim logic (argument validation, sharding, moment merging), and the product path
+fails loudly without a GPU (no CPU fallback)."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, SYSTEMS
+
+import sdeint_b200 as sdb
+from sdeint_b200 import _lib, integrate
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "sdb.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(sdb_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.sdb_version() == 100
+    # the built library really holds sm_100a code
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True)
+    if out.returncode == 0:
+        assert "sm_100a" in out.stdout
+
+
+def test_public_names_match_reference():
+    for name in ("deltaW", "Ikpw", "Jkpw", "Iwik", "Jwik", "SDEValueError", "itoint", "stratint",
+                 "itoEuler", "stratHeun", "itoSRI2", "stratSRS2", "stratKP2iS", "__version__"):
+        assert hasattr(sdb, name), name
+    import inspect
+    sig = inspect.signature
+    assert list(sig(sdb.itoint).parameters)[:5] == ["f", "G", "y0", "tspan", "generator"]
+    assert list(sig(sdb.itoEuler).parameters)[:6] == ["f", "G", "y0", "tspan", "dW", "generator"]
+    assert list(sig(sdb.itoSRI2).parameters)[:8] == ["f", "G", "y0", "tspan", "Imethod", "dW", "I",
+                                                     "generator"]
+    assert list(sig(sdb.stratSRS2).parameters)[:8] == ["f", "G", "y0", "tspan", "Jmethod", "dW", "J",
+                                                       "generator"]
+    assert list(sig(sdb.stratKP2iS).parameters)[:12] == [
+        "f", "G", "y0", "tspan", "Jmethod", "gam", "al1", "al2", "rtol", "dW", "J", "generator"]
+    assert sig(sdb.stratKP2iS).parameters["rtol"].default == 1e-4
+    assert sig(sdb.itoSRI2).parameters["Imethod"].default is sdb.Ikpw
+    assert sig(sdb.stratSRS2).parameters["Jmethod"].default is sdb.Jkpw
+    assert list(sig(sdb.deltaW).parameters)[:4] == ["N", "m", "h", "generator"]
+    assert list(sig(sdb.Iwik).parameters)[:4] == ["dW", "h", "n", "generator"]
+    assert sig(sdb.Ikpw).parameters["n"].default == 5
+
+
+def test_check_args_host_logic():
+    f, G, y0 = SYSTEMS["r74"](False)
+    tspan = np.linspace(0.0, 0.1, 21)
+    d, m, _, Gop, y0v, _, _, _ = integrate._check_args(f, G, y0, tspan)
+    assert (d, m) == (5, 4) and Gop is G
+    # list-of-columns form resolves to the same operator
+    assert integrate._check_args(f, G.columns(), y0, tspan)[3] is G
+    with pytest.raises(sdb.SDEValueError):
+        integrate._check_args(f, G.columns()[:-1], y0, tspan)
+    # scalar y0 -> length-1 float64 vector (integrate.py:54-60)
+    f1, G1, s0 = SYSTEMS["kp4446"](False)
+    assert integrate._check_args(f1, G1, s0, tspan)[4].shape == (1,)
+    assert integrate._check_args(f1, G1, 1, tspan)[4].dtype == np.float64
+    with pytest.raises(sdb.SDEValueError):
+        integrate._check_args(f, G, y0, np.array([0.0, 0.1, 0.3]))
+    with pytest.raises(sdb.SDEValueError):
+        integrate._check_args(f, G, np.zeros(3), tspan)
+    with pytest.raises(sdb.SDEValueError):
+        integrate._check_args(f, G, y0, tspan, dW=np.zeros((20, 3)))
+    with pytest.raises(sdb.SDEValueError):
+        integrate._check_args(f, G, y0, tspan, dW=np.zeros((20, 4)), IJ=np.zeros((20, 4, 3)))
+    integrate._check_args(f, G, y0, tspan, dW=np.zeros((7, 20, 4)), IJ=np.zeros((7, 20, 4, 4)))
+    assert integrate._resolve_paths(None, np.zeros((7, 20, 4)), None) == (7, True)
+    assert integrate._resolve_paths(None, np.zeros((20, 4)), None) == (1, False)
+    with pytest.raises(sdb.SDEValueError):
+        integrate._resolve_paths(3, np.zeros((7, 20, 4)), None)
+
+
+def test_ops_host_callables_follow_reference_conventions():
+    f, G, y0 = SYSTEMS["lin10"](False)
+    y = np.linspace(0.5, 1.5, 10)
+    assert f(y, 0.0).shape == (10,) and G(y, 0.0).shape == (10, 10)
+    cols = G.columns()
+    assert len(cols) == 10
+    for k in (0, 9):
+        assert np.allclose(cols[k](y, 0.0), G(y, 0.0)[:, k])
+    f1, G1, _ = SYSTEMS["kp4446"](False)
+    assert np.isscalar(f1(0.1, 0.0)) or np.ndim(f1(0.1, 0.0)) == 0
+    assert np.ndim(G1(0.1, 0.0)) == 0 and G1(np.array([0.1]), 0.0).shape == (1, 1)
+
+
+def test_shard_paths_partitions_exactly():
+    for P in (1, 7, 10 ** 8, 12345678):
+        for R in (1, 2, 4, 8):
+            if P < R:
+                continue
+            spans = [sdb.ensemble.shard_paths(P, r, R) for r in range(R)]
+            assert spans[0][0] == 0
+            for (s0, c0), (s1, _) in zip(spans, spans[1:]):
+                assert s0 + c0 == s1
+            assert spans[-1][0] + spans[-1][1] == P
+            assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
+
+
+@pytest.mark.skipif(__import__("torch").cuda.is_available(), reason="CPU-only check")
+def test_product_path_fails_loudly_without_gpu():
+    f, G, y0 = SYSTEMS["lin2"](False)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        sdb.itoEuler(f, G, y0, np.linspace(0, 1, 11), dW=np.zeros((10, 2)))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        sdb.deltaW(10, 2, 0.1)
+
+
+def test_product_package_never_imports_oracle():
+    pkg = os.path.join(ROOT, "sdeint_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, fn)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt, fn
+
+
+def test_gloo_world2_moment_allreduce(tmp_path):
+    """N>1 host path on CPU: two gloo ranks shard the path ids, build per-rank moment
+    partials and all-reduce them; the result equals the single-process sums."""
+    script = tmp_path / "w2.py"
+    script.write_text(r'''
+import os, sys
+sys.path.insert(0, %r)
+import numpy as np, torch, torch.distributed as dist
+import sdeint_b200 as sdb
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+P, S, d = 1001, 3, 2
+rng = np.random.default_rng(0)
+y = rng.standard_normal((S, d, P))                      # the "global" ensemble
+start, count = sdb.ensemble.shard_paths(P, rank, world)
+mine = y[:, :, start:start + count]
+sums = torch.from_numpy(np.stack([mine.sum(-1), (mine * mine).sum(-1)], axis=-1))
+counts = torch.from_numpy(np.stack([[np.histogram(mine[s, i], 8, (-2, 2))[0] for i in range(d)]
+                                    for s in range(S)]).astype(np.int64))
+sdb.ensemble.allreduce_moments(sums, counts)
+want = np.stack([y.sum(-1), (y * y).sum(-1)], axis=-1)
+assert np.allclose(sums.numpy(), want, rtol=1e-13), rank
+wc = np.stack([[np.histogram(y[s, i], 8, (-2, 2))[0] for i in range(d)] for s in range(S)])
+assert np.array_equal(counts.numpy(), wc), rank
+mean, var = sdb.ensemble.mean_var(sums, P)
+assert np.allclose(mean.numpy(), y.mean(-1)) and np.allclose(var.numpy(), y.var(-1))
+dist.destroy_process_group()
+print("rank", rank, "ok")
+''' % ROOT)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29617", str(script)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("ok") == 2
