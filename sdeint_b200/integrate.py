@@ -157,7 +157,7 @@ def _resolve_paths(paths, dW, IJ):
 
 
 def _run(scheme, f, G, y0, tspan, dW, IJ, strat, method, generator, kp2is, paths, seed,
-         path_id0, save_every, n_terms, device, out, y0_paths=None):
+         path_id0, save_every, n_terms, device, out, y0_paths=None, host_out=None):
     global _last_status
     (d, m, f, Gop, y0, tspan, dW, IJ) = _check_args(f, G, y0, tspan, dW, IJ)
     P, ensemble = _resolve_paths(paths, dW, IJ)
@@ -259,14 +259,23 @@ def _run(scheme, f, G, y0, tspan, dW, IJ, strat, method, generator, kp2is, paths
                 "converge to rtol=%g on %d path(s)." % (tspan[status[3]], kp2is[3], status[2]))
         if out == "torch":
             return d_y
-        host = d_y.cpu().numpy()
+        if host_out is not None:
+            # caller-owned (ideally pinned) host tensor in the device layout (n_saved, d, P)
+            if tuple(host_out.shape) != tuple(d_y.shape) or host_out.dtype != d_y.dtype:
+                raise SDEValueError('host_out must be a float64 tensor of shape %s'
+                                    % (tuple(d_y.shape),))
+            host_out.copy_(d_y, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            host = host_out.numpy()
+        else:
+            host = d_y.cpu().numpy()
     if not ensemble:
         return np.ascontiguousarray(host[:, :, 0])      # (N, d), y[0] == y0
     return host.transpose(2, 0, 1)                       # (P, n_saved, d)
 
 
 _ENS = dict(paths=None, seed=None, path_id0=0, save_every=1, n_terms=5, device=None, out="numpy",
-            y0_paths=None)
+            y0_paths=None, host_out=None)
 
 
 def itoEuler(f, G, y0, tspan, dW=None, generator=None, **ens):
