@@ -5,9 +5,11 @@ the reference (which uses numpy's PCG64) -- it is this repository's own generato
 oracle restates the PUBLISHED algorithm and is pinned by Random123's known-answer vectors
 (`kat_vectors`: three philox4x32 10-round entries, checked in tests/test_philox.py).
 
-Normal transform (sdeint_b200/csrc/sdb_kernels.cuh, SdbStream::pair): one 128-bit block ->
-u1 = ((w0<<32|w1)>>11 + 1) 2^-53 in (0,1], u2 = ((w2<<32|w3)>>11) 2^-52 in [0,2),
-z0 = sqrt(-2 ln u1) cos(pi u2), z1 = sqrt(-2 ln u1) sin(pi u2).
+Normal transform (sdeint_b200/csrc/sdb_kernels.cuh, sdb_normal_pair): one 128-bit block
+(w0..w3) -> hi = w0:w1, lo = w2:w3;  u1 = ((hi >> 11) | 1) 2^-53 in (0,1);  rad = sqrt(-2 ln u1);
+t = ((lo >> 9) mod 2^52) 2^-52 in [0,1);  (c, s) = (cos, sin)(pi t / 4);  o = lo >> 61;
+z0 = (o&2 ? -1 : 1) rad (o&1 ? s : c),  z1 = (o&4 ? -1 : 1) rad (o&1 ? c : s)
+(Box-Muller with the angle folded into one octant and unfolded by three random bits).
 Normal number q of (path, step) is element q&1 of the block with counter
 (path_lo, path_hi, step, q>>1) and key (seed_lo, seed_hi).
 """
@@ -39,16 +41,22 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
 
 
 def normal_pairs(seed, path, step, slot):
-    """(z0, z1) for broadcastable integer arrays path, step, slot."""
+    """(z0, z1) for broadcastable integer arrays path, step, slot (spec in the module doc)."""
     path = np.asarray(path, dtype=np.uint64)
     r0, r1, r2, r3 = philox4x32_10(path & MASK, path >> np.uint64(32), step, slot,
                                    seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
-    a = ((r0 << np.uint64(32)) | r1) >> np.uint64(11)
-    b = ((r2 << np.uint64(32)) | r3) >> np.uint64(11)
-    u1 = (a + np.uint64(1)).astype(np.float64) * 2.0 ** -53
-    u2 = b.astype(np.float64) * 2.0 ** -52
+    hi = (r0 << np.uint64(32)) | r1
+    lo = (r2 << np.uint64(32)) | r3
+    x = (hi >> np.uint64(11)) | np.uint64(1)                      # 53-bit odd integer
+    u1 = x.astype(np.float64) * 2.0 ** -53                        # exact, in (0, 1)
     rad = np.sqrt(-2.0 * np.log(u1))
-    return rad * np.cos(np.pi * u2), rad * np.sin(np.pi * u2)
+    t = ((lo >> np.uint64(9)) & np.uint64((1 << 52) - 1)).astype(np.float64) * 2.0 ** -52
+    c, s = np.cos(np.pi * t / 4), np.sin(np.pi * t / 4)
+    o = (lo >> np.uint64(61)).astype(np.int64)
+    swap, neg0, neg1 = (o & 1) == 1, (o & 2) != 0, (o & 4) != 0
+    a0 = np.where(swap, s, c)
+    b0 = np.where(swap, c, s)
+    return np.where(neg0, -rad * a0, rad * a0), np.where(neg1, -rad * b0, rad * b0)
 
 
 def normals(seed, path, step, q):

@@ -17,6 +17,10 @@
 #include "../../include/sdb.h"
 #include "sdb_host.h"
 #include "sdb_kernels.cuh"
+#include "sdb_fused.cuh"
+
+#include <math.h>
+#include <stdlib.h>
 
 // ---------------------------------------------------------------------------------------------
 // errors, counters
@@ -51,14 +55,26 @@ std::string sdb_loop_key(int scheme, int fk, int gk, int d, int m, int noise, bo
   return buf;
 }
 
-static const void* aot_lookup(const std::string& key) {
+std::string sdb_fused_key(int d, int m) {
+  char buf[64];
+  snprintf(buf, sizeof buf, "fused|srk2|kpw|d%d|m%d", d, m);
+  return buf;
+}
+
+static const SdbAotEntry* aot_entry(const std::string& key) {
   for (const auto& e : sdb_aot_registry())
-    if (e.key == key) return e.fn;
+    if (e.key == key) return &e;
   return nullptr;
 }
 
-static int launch(const void* fn, dim3 grid, dim3 block, void** args, cudaStream_t st) {
-  SDB_CUDA(cudaLaunchKernel(fn, grid, block, args, 0, st));
+static const void* aot_lookup(const std::string& key) {
+  const SdbAotEntry* e = aot_entry(key);
+  return e ? e->fn : nullptr;
+}
+
+static int launch(const void* fn, dim3 grid, dim3 block, void** args, cudaStream_t st,
+                  size_t smem = 0) {
+  SDB_CUDA(cudaLaunchKernel(fn, grid, block, args, smem, st));
   g_launches.fetch_add(1);
   return 0;
 }
@@ -66,9 +82,7 @@ static int launch(const void* fn, dim3 grid, dim3 block, void** args, cudaStream
 // ---------------------------------------------------------------------------------------------
 // NVRTC (loaded lazily with dlopen so that libsdb.so itself loads on machines without it)
 // ---------------------------------------------------------------------------------------------
-static const char* kKernelHeader =
-#include "sdb_kernels_embed.inc"
-    ;
+#include "sdb_kernels_embed.inc"  // kKernelHeader, kTablesHeader
 
 typedef struct _nvrtcProgram* nvrtcProgram;
 struct Nvrtc {
@@ -119,9 +133,9 @@ static int jit_compile(const std::string& source, const char* kernel_name, JitKe
   Nvrtc* rt;
   if (nvrtc_load(&rt)) return 1;
   nvrtcProgram prog;
-  const char* hdr_src[] = {kKernelHeader};
-  const char* hdr_name[] = {"sdb_kernels.cuh"};
-  int rc = rt->CreateProgram(&prog, source.c_str(), "sdb_jit.cu", 1, hdr_src, hdr_name);
+  const char* hdr_src[] = {kKernelHeader, kTablesHeader};
+  const char* hdr_name[] = {"sdb_kernels.cuh", "sdb_tables.cuh"};
+  int rc = rt->CreateProgram(&prog, source.c_str(), "sdb_jit.cu", 2, hdr_src, hdr_name);
   if (rc) return fail(std::string("nvrtcCreateProgram: ") + rt->GetErrorString(rc));
   const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo",
                         "--fmad=true"};
@@ -321,16 +335,45 @@ extern "C" int sdb_integrate(sdb_system* s, const sdb_integrate_args* a) {
 
   int noise = a->noise;
   if (!need_ij && noise == SDB_NOISE_WIK) noise = SDB_NOISE_KPW;  // only dW is drawn
+  // The production path: linear system, SRI2/SRS2, Philox + Ikpw/Jkpw -> fused kernel.
+  const SdbAotEntry* fused = nullptr;
+  if (a->scheme == SDB_SCHEME_SRK2 && noise == SDB_NOISE_KPW && s->fk == SDB_DRIFT_LINEAR &&
+      s->gk == SDB_DIFF_LINEAR_COLS && s->inline_params && a->n_terms <= SDB_FUSED_MAX_TERMS &&
+      !getenv("SDB_DISABLE_FUSED"))
+    fused = aot_entry(sdb_fused_key(s->d, s->m));
   const void* fn = nullptr;
-  if (loop_kernel(s, a->scheme, noise, &fn)) return 1;
+  if (fused) {
+    fn = fused->fn;
+    static std::mutex attr_mu;
+    static std::map<const void*, bool> attr_done;
+    std::lock_guard<std::mutex> lk(attr_mu);
+    if (!attr_done[fn]) {
+      SDB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)fused->smem));
+      attr_done[fn] = true;
+    }
+  } else if (loop_kernel(s, a->scheme, noise, &fn)) {
+    return 1;
+  }
 
-  // tspan (+ KP2iS coefficients) to the device, stream-ordered
-  const size_t nt = (size_t)a->N, nk = a->scheme == SDB_SCHEME_KP2IS ? 3 * (size_t)s->d : 0;
+  // tspan, the per-step h = t[n+1]-t[n] with its square root and reciprocal root (uniform over
+  // paths, so computed once here with IEEE sqrt / division) and the KP2iS coefficients go to
+  // the device in one stream-ordered copy.
+  const size_t nt = (size_t)a->N, ns = nt - 1;
+  const size_t nk = a->scheme == SDB_SCHEME_KP2IS ? 3 * (size_t)s->d : 0;
+  std::vector<double> aux(nt + 3 * ns + nk);
+  for (size_t i = 0; i < nt; ++i) aux[i] = a->h_tspan[i];
+  for (size_t i = 0; i < ns; ++i) {
+    const double h = a->h_tspan[i + 1] - a->h_tspan[i];
+    const double rh = sqrt(h);
+    aux[nt + i] = h;
+    aux[nt + ns + i] = rh;
+    aux[nt + 2 * ns + i] = 1.0 / rh;
+  }
+  for (size_t i = 0; i < nk; ++i) aux[nt + 3 * ns + i] = a->h_kp2is[i];
   double* d_aux = nullptr;
-  SDB_CUDA(cudaMallocAsync(&d_aux, (nt + nk) * sizeof(double), st));
-  SDB_CUDA(cudaMemcpyAsync(d_aux, a->h_tspan, nt * sizeof(double), cudaMemcpyHostToDevice, st));
-  if (nk)
-    SDB_CUDA(cudaMemcpyAsync(d_aux + nt, a->h_kp2is, nk * sizeof(double), cudaMemcpyHostToDevice, st));
+  SDB_CUDA(cudaMallocAsync(&d_aux, aux.size() * sizeof(double), st));
+  SDB_CUDA(cudaMemcpyAsync(d_aux, aux.data(), aux.size() * sizeof(double), cudaMemcpyHostToDevice, st));
 
   SdbLoopArgs k;
   memset(&k, 0, sizeof k);
@@ -344,7 +387,7 @@ extern "C" int sdb_integrate(sdb_system* s, const sdb_integrate_args* a) {
   k.dW = a->d_dW; k.dW_sN = a->dW_stride_step; k.dW_sJ = a->dW_stride_comp; k.dW_sP = a->dW_stride_path;
   k.IJ = a->d_IJ; k.IJ_sN = a->IJ_stride_step; k.IJ_sR = a->IJ_stride_row;
   k.IJ_sC = a->IJ_stride_col; k.IJ_sP = a->IJ_stride_path;
-  k.kp = nk ? d_aux + nt : nullptr;
+  k.kp = nk ? d_aux + nt + 3 * ns : nullptr;
   k.status = a->d_status;
   if (a->d_status) {
     sdb_k_status_init<<<1, 1, 0, st>>>(a->d_status);
@@ -356,9 +399,9 @@ extern "C" int sdb_integrate(sdb_system* s, const sdb_integrate_args* a) {
   args[0] = &k;
   args[1] = s->inline_params ? (void*)s->fp.data() : (void*)&gf;
   args[2] = s->inline_params ? (void*)s->gp.data() : (void*)&gg;
-  const unsigned block = SDB_BLOCK;
+  const unsigned block = fused ? SDB_FUSED_THREADS : SDB_BLOCK;
   const unsigned grid = (unsigned)((a->paths + block - 1) / block);
-  if (launch(fn, dim3(grid), dim3(block), args, st)) return 1;
+  if (launch(fn, dim3(grid), dim3(block), args, st, fused ? fused->smem : 0)) return 1;
   SDB_CUDA(cudaFreeAsync(d_aux, st));
   return 0;
 }

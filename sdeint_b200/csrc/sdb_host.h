@@ -11,14 +11,16 @@
 struct SdbAotEntry {
   std::string key;
   const void* fn;
+  size_t smem;  // dynamic shared memory the kernel needs (0 for the generic loops)
 };
 
 std::vector<SdbAotEntry>& sdb_aot_registry();
 
 struct SdbAotRegistrar {
-  SdbAotRegistrar(const std::string& key, const void* fn) {
-    sdb_aot_registry().push_back(SdbAotEntry{key, fn});
+  SdbAotRegistrar(const std::string& key, const void* fn, size_t smem = 0) {
+    sdb_aot_registry().push_back(SdbAotEntry{key, fn, smem});
   }
 };
 
 std::string sdb_loop_key(int scheme, int fk, int gk, int d, int m, int noise, bool inline_params);
+std::string sdb_fused_key(int d, int m);  // fused linear SRI2/SRS2 + Philox/KPW kernel

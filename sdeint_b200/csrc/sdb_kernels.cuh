@@ -22,6 +22,8 @@ typedef long long int64_t;
 #include <stdint.h>
 #endif
 
+#include "sdb_tables.cuh"
+
 #define SDB_DEV __device__ __forceinline__
 #define SDB_HD __host__ __device__ __forceinline__
 
@@ -112,27 +114,91 @@ SDB_HD void sdb_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-// Counter layout: (path low, path high, step, slot); key = seed.  One block yields one
-// Box-Muller pair: u1 in (0,1] from words 0,1 (53 bits), u2 in [0,1) from words 2,3.
+// Counter layout: (path low, path high, step, slot); key = seed.  One 128-bit block yields one
+// Box-Muller pair (spec restated in oracle/philox_oracle.py):
+//   hi = w0:w1, lo = w2:w3;  x = (hi >> 11) | 1 (53-bit odd integer), u1 = x 2^-53 in (0,1)
+//   rad = sqrt(-2 ln u1);  t = ((lo >> 9) & (2^52-1)) 2^-52 in [0,1);  (c, s) = cos, sin(pi t / 4)
+//   octant bits o = lo >> 61: swap = o&1, neg0 = o&2, neg1 = o&4
+//   z0 = +-rad * (swap ? s : c),  z1 = +-rad * (swap ? c : s)        -- a uniform angle, by symmetry
 // Normal number q of a path-step is element (q & 1) of slot (q >> 1):
 //   dW_j -> q = j;  X_k[j] -> m + 2(k-1)m + j;  Y_k[j] -> m + (2(k-1)+1)m + j;  Gtail_r -> m + 2nm + r.
+//
+// The transform is written for the FP64 pipe budget (32 DFMA-class instructions per pair, the
+// rest on the integer / XU pipes): ln u1 by a 128-entry table (1/c, -2 ln c) + degree-6 log1p,
+// sqrt by MUFU.RSQ64H + one Newton step + one residual correction, sin/cos by degree-6
+// polynomials in t^2.  Accuracy ~1e-16 relative (tests compare with numpy's libm).
+SDB_DEV double sdb_rsqrt_approx(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  return y;
+}
+
+SDB_DEV void sdb_normal_pair(const uint32_t (&w)[4], const double2* __restrict__ tab, double& z0,
+                             double& z1) {
+  // ---- radius -----------------------------------------------------------------------------------
+  const uint64_t hi = ((uint64_t)w[0] << 32) | w[1];
+  const uint64_t x = (hi >> 11) | 1ull;
+  const int lz = __clzll((long long)x);  // >= 11
+  const uint64_t mant = (x << (lz - 11)) & 0x000FFFFFFFFFFFFFull;
+  const uint64_t ix = ((uint64_t)(1033 - lz) << 52) | mant;  // bits of u1 = x 2^-53
+  const uint64_t tmp = ix - SDB_LOG_OFF;
+  const int i = (int)(tmp >> 45) & 127;
+  const int k = (int)((long long)tmp >> 52);
+  const double z = __longlong_as_double((long long)(ix - (tmp & 0xFFF0000000000000ull)));
+  const double2 tc = tab[i];  // {1/c, -2 ln c}
+  const double r = fma(z, tc.x, -1.0);
+  const double r2 = r * r;
+  double q = fma(r, 1.0 / 3.0, -0.4);
+  q = fma(r, q, 0.5);
+  q = fma(r, q, -2.0 / 3.0);
+  q = fma(r, q, 1.0);
+  double L = fma((double)k, SDB_M2LN2, tc.y);
+  L = fma(r, -2.0, L);
+  L = fma(r2, q, L);  // -2 ln u1 > 0
+  const double y = sdb_rsqrt_approx(L);
+  double g = L * y;
+  const double hh = 0.5 * y;
+  const double e = fma(-hh, g, 0.5);
+  g = fma(g, e, g);
+  const double rad = fma(fma(-g, g, L), hh, g);
+  // ---- angle ------------------------------------------------------------------------------------
+  const uint64_t lo = ((uint64_t)w[2] << 32) | w[3];
+  const double t =
+      __longlong_as_double((long long)(0x3FF0000000000000ull | ((lo >> 9) & 0x000FFFFFFFFFFFFFull))) - 1.0;
+  const double t2 = t * t;
+  double sn = fma(t2, SDB_SIN6, SDB_SIN5);
+  sn = fma(t2, sn, SDB_SIN4);
+  sn = fma(t2, sn, SDB_SIN3);
+  sn = fma(t2, sn, SDB_SIN2);
+  sn = fma(t2, sn, SDB_SIN1);
+  sn = fma(t2, sn, SDB_SIN0);
+  sn *= t;
+  double cs = fma(t2, SDB_COS6, SDB_COS5);
+  cs = fma(t2, cs, SDB_COS4);
+  cs = fma(t2, cs, SDB_COS3);
+  cs = fma(t2, cs, SDB_COS2);
+  cs = fma(t2, cs, SDB_COS1);
+  cs = fma(t2, cs, SDB_COS0);
+  const bool swap = (w[2] >> 29) & 1u;
+  const double a0 = swap ? sn : cs;
+  const double b0 = swap ? cs : sn;
+  const uint64_t s0 = (uint64_t)((w[2] >> 30) & 1u) << 63;
+  const uint64_t s1 = (uint64_t)(w[2] >> 31) << 63;
+  z0 = __longlong_as_double((long long)((uint64_t)__double_as_longlong(rad * a0) ^ s0));
+  z1 = __longlong_as_double((long long)((uint64_t)__double_as_longlong(rad * b0) ^ s1));
+}
+
 struct SdbStream {
   uint32_t p_lo, p_hi, step, k0, k1;
-  SDB_DEV SdbStream(uint64_t seed, uint64_t path, uint32_t step_)
+  const double2* tab;  // log table: global (sdb_logtab) or a shared-memory copy
+  SDB_DEV SdbStream(uint64_t seed, uint64_t path, uint32_t step_,
+                    const double2* tab_ = reinterpret_cast<const double2*>(sdb_logtab))
       : p_lo((uint32_t)path), p_hi((uint32_t)(path >> 32)), step(step_), k0((uint32_t)seed),
-        k1((uint32_t)(seed >> 32)) {}
+        k1((uint32_t)(seed >> 32)), tab(tab_) {}
   SDB_DEV void pair(uint32_t slot, double& z0, double& z1) const {
     uint32_t r[4];
     sdb_philox4x32_10(p_lo, p_hi, step, slot, k0, k1, r);
-    const uint64_t a = (((uint64_t)r[0] << 32) | r[1]) >> 11;
-    const uint64_t b = (((uint64_t)r[2] << 32) | r[3]) >> 11;
-    const double u1 = (double)(a + 1ull) * 1.1102230246251565e-16;  // 2^-53, (0,1]
-    const double u2 = (double)b * 2.2204460492503131e-16;           // 2^-52 -> 2*u in [0,2)
-    const double rad = sqrt(-2.0 * log(u1));
-    double s, c;
-    sincospi(u2, &s, &c);
-    z0 = rad * c;
-    z1 = rad * s;
+    sdb_normal_pair(r, tab, z0, z1);
   }
 };
 
