@@ -167,6 +167,7 @@ struct sdb_system {
   std::string src;           // user CUDA source (may be empty)
   double* d_fp = nullptr;    // device copies (PGlobal mode / user operators)
   double* d_gp = nullptr;
+  double* d_frag = nullptr;  // fused kernel: DMMA fragment tables
   bool inline_params = true;
   std::map<std::string, JitKernel> jit;
   std::mutex mu;
@@ -251,6 +252,7 @@ extern "C" int sdb_system_destroy(sdb_system* s) {
     if (kv.second.lib) cudaLibraryUnload(kv.second.lib);
   if (s->d_fp) cudaFree(s->d_fp);
   if (s->d_gp) cudaFree(s->d_gp);
+  if (s->d_frag) cudaFree(s->d_frag);
   delete s;
   return 0;
 }
@@ -336,21 +338,27 @@ extern "C" int sdb_integrate(sdb_system* s, const sdb_integrate_args* a) {
   int noise = a->noise;
   if (!need_ij && noise == SDB_NOISE_WIK) noise = SDB_NOISE_KPW;  // only dW is drawn
   // The production path: linear system, SRI2/SRS2, Philox + Ikpw/Jkpw -> fused kernel.
-  const SdbAotEntry* fused = nullptr;
+  const SdbFusedEntry* fused = nullptr;
   if (a->scheme == SDB_SCHEME_SRK2 && noise == SDB_NOISE_KPW && s->fk == SDB_DRIFT_LINEAR &&
-      s->gk == SDB_DIFF_LINEAR_COLS && s->inline_params && a->n_terms <= SDB_FUSED_MAX_TERMS &&
-      !getenv("SDB_DISABLE_FUSED"))
-    fused = aot_entry(sdb_fused_key(s->d, s->m));
+      s->gk == SDB_DIFF_LINEAR_COLS && a->n_terms <= SDB_FUSED_MAX_TERMS &&
+      !getenv("SDB_DISABLE_FUSED")) {
+    const char* vs = getenv("SDB_FUSED_VARIANT");
+    const int want = vs ? atoi(vs) : 0;
+    for (const auto& e : sdb_fused_registry())
+      if (e.d == s->d && e.m == s->m && (e.variant == want || (!fused && e.variant == 0))) fused = &e;
+  }
   const void* fn = nullptr;
   if (fused) {
     fn = fused->fn;
-    static std::mutex attr_mu;
-    static std::map<const void*, bool> attr_done;
-    std::lock_guard<std::mutex> lk(attr_mu);
-    if (!attr_done[fn]) {
+    std::lock_guard<std::mutex> lk(s->mu);
+    SDB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused->smem));
+    if (!s->d_frag) {  // DMMA fragment tables of (A, B_k), built once per system
+      std::vector<double> tab(fused->table_doubles);
+      fused->build(s->fp.data(), s->gp.data(), tab.data());
+      SDB_CUDA(cudaMalloc(&s->d_frag, tab.size() * sizeof(double)));
+      SDB_CUDA(cudaMemcpy(s->d_frag, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
       SDB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)fused->smem));
-      attr_done[fn] = true;
     }
   } else if (loop_kernel(s, a->scheme, noise, &fn)) {
     return 1;
@@ -399,6 +407,10 @@ extern "C" int sdb_integrate(sdb_system* s, const sdb_integrate_args* a) {
   args[0] = &k;
   args[1] = s->inline_params ? (void*)s->fp.data() : (void*)&gf;
   args[2] = s->inline_params ? (void*)s->gp.data() : (void*)&gg;
+  if (fused) {
+    args[1] = (void*)s->fp.data();
+    args[2] = (void*)&s->d_frag;
+  }
   const unsigned block = fused ? SDB_FUSED_THREADS : SDB_BLOCK;
   const unsigned grid = (unsigned)((a->paths + block - 1) / block);
   if (launch(fn, dim3(grid), dim3(block), args, st, fused ? fused->smem : 0)) return 1;
@@ -644,8 +656,7 @@ extern "C" int sdb_fp64_peak(int iters, double* tflops_out, void* stream) {
 extern "C" int sdb_philox_block(uint64_t seed, uint64_t path, uint32_t step, uint32_t slot,
                                 uint32_t out[4]) {
   uint32_t r[4];
-  sdb_philox4x32_10((uint32_t)path, (uint32_t)(path >> 32), step, slot, (uint32_t)seed,
-                    (uint32_t)(seed >> 32), r);
+  sdb_philox4x32_10((uint32_t)path, (uint32_t)(path >> 32), step, slot, SdbPhiloxKey(seed), r);
   for (int i = 0; i < 4; ++i) out[i] = r[i];
   return 0;
 }

@@ -1,159 +1,357 @@
-// sdb_fused.cuh -- the production SRI2/SRS2 kernel for linear systems f = A y, g_k = B_k y with
+// sdb_fused.cuh -- the production SRI2/SRS2 kernel for LINEAR systems f = A y, g_k = B_k y with
 // on-device Philox + Ikpw/Jkpw noise: the whole time loop of sdeint/integrate.py:494-522 plus
-// wiener.py:52 and :67-106 in ONE launch, one thread per sample path.
+// wiener.py:52 and :67-106 in ONE launch.  One lane per sample path, one warp per 32 paths.
 //
-// FP64-pipe budget per path-step at d = m = 10, n = 5 (DESIGN.md "fused SRK2 kernel"):
-//   55 Philox blocks -> 110 normals (32 FP64 ops per pair)            1760
-//   Levy-area series, 2 DFMA per (pair, term) + Z = Y + c dW            500
-//   drift twice, G_n (m matvecs), G_n I, H2/H3, 2m matvecs, updates    4900
-// against 5140 DFMA-equivalents (10 280 flop) of algorithmic work.
+// Why it looks the way it does (profiles/r01_microbench.md):
+//  * On sm_100a a DFMA cannot take a constant-bank operand, broadcast LDS delivers 8 B/clk/SM
+//    and LDCU-fed DFMAs are latency-bound, so "one uniform matrix element per DFMA" caps a
+//    thread-per-path kernel below 50 % of the FP64 peak.  All products with the SHARED matrices
+//    (G_n = [B_j y], f = A y, and the stage-2 sum) therefore run as FP64 tensor instructions
+//    (mma.sync m8n8k4 f64 -> DMMA.8x8x4): the matrix fragment is one register per lane and every
+//    instruction does 8 MACs per lane.  DMMA shares the FP64 pipe with DFMA (same 37 TFLOP/s peak),
+//    so this is about operand delivery, not extra flops.
+//  * Per-path products (the Levy-area series, G_n I) have no shared operand; they stay on DFMA with
+//    one lane per path and 4-10 DFMAs per loaded double.
+//  * g_k is linear, so the two stage-2 evaluations collapse exactly:
+//        (sqrt(h)/2) (g_k(H20 + s_k) - g_k(H20 - s_k)) = B_k (sqrt(h) s_k),   s_k = sum1[:,k]
+//    (integrate.py:509-521); sqrt(h) sum1 = G_n I is what the kernel accumulates.  The flop count
+//    used for the roofline is reduced accordingly (subtract 2md^2 + 2dm).
 //
-// Where the data lives.  A and B_k are kernel parameters (constant bank): every loop over
-// them is fully unrolled so each element is an immediate constant-bank operand of a DFMA.
-// Per-path state that does not fit the 255-register budget at once is staged in shared
-// memory, laid out [element][thread] so a warp's access is conflict-free:
-//   * the m(m-1)/2 Levy areas (read twice, once per row block of G_n I);
-//   * rows [0, d/2) of sum1 = G_n I (d/2 x m), while rows [d/2, d) stay in registers.
-// G_n itself is never stored: column j (half of its rows at a time) is produced, folded into
-// G_n dW and rank-1-accumulated into sum1, using
-//   I[j][k] = dW_j dW_k / 2 + A[j][k] - (h/2) delta_jk   (Ito; no delta term for Stratonovich)
-//   => sum1[:,k] sqrt(h) = (dW_k/2) (G_n dW) + sum_j G_n[:,j] (A[j][k] - (h/2) delta_jk).
-// 760 B of shared memory per thread at d = m = 10 -> 256 threads (8 warps, 2 per scheduler)
-// per SM.
+// Per step and per row block b (rows R_b of the state, 4 + 4 + 2 for d = 10):
+//   P1  DMMA   [B_j[R_b,:] ; A[R_b,:]] Y  -> shared staging (rows x 32 paths)
+//   P2  DFMA   s~[R_b,:] = G_n[R_b,:] I   (Levy areas from shared memory), G_n dW, drift
+//              bookkeeping; rows 8.. of the stage-2 sum on DFMA; s~ -> staging
+//   P3  DMMA   w[0:8] += [B_k[0:8, R_b]]_k vec(s~[R_b,:])
+// Shared memory per warp: staging 48 x 32, Levy areas 45 x 32, dW 10 x 32 doubles (26.4 KB).
 #pragma once
 #include "sdb_kernels.cuh"
 
+#ifdef __CUDACC__
+#define SDB_CX __host__ __device__ constexpr
+#else
+#define SDB_CX constexpr
+#endif
+
 #define SDB_FUSED_THREADS 256
+#define SDB_FUSED_WARPS (SDB_FUSED_THREADS / 32)
 #define SDB_FUSED_MAX_TERMS 64
+#ifndef SDB_FUSED_KUNROLL
+#define SDB_FUSED_KUNROLL 1  // unroll factor of the Levy-series loop over k
+#endif
 
 template <int D, int M>
 struct SdbFusedShape {
   static constexpr int MM = M * (M - 1) / 2;
-  static constexpr int D1 = D / 2;       // rows of sum1 staged in shared memory
-  static constexpr int D2 = D - D1;      // rows kept in registers
-  static constexpr int ROWS = MM + D1 * M;
-  static constexpr size_t smem_bytes() {
-    return (size_t)ROWS * SDB_FUSED_THREADS * sizeof(double) + 128 * sizeof(double2) +
-           (SDB_FUSED_MAX_TERMS + 1) * sizeof(double);
+  static constexpr int RB = 4;                        // rows per block
+  static constexpr int NB = (D + RB - 1) / RB;        // row blocks
+  static constexpr int LT = (D + 3) / 4;              // k-tiles over the state index l
+  static constexpr int IT = D / 8;                    // 8-row tiles of the stage-2 sum done by DMMA
+  static constexpr int IL = D - 8 * IT;               // leftover rows done by DFMA
+  static SDB_CX int rn(int b) { return b < NB - 1 ? RB : D - RB * (NB - 1); }
+  static SDB_CX int r0(int b) { return RB * b; }
+  static SDB_CX int nr(int b) { return (M + 1) * rn(b); }       // P1 rows: m columns + drift
+  static SDB_CX int t1(int b) { return (nr(b) + 7) / 8; }       // P1 row tiles
+  static SDB_CX int kt3(int b) { return (rn(b) * M + 3) / 4; }  // P3 k tiles
+  static SDB_CX int max2(int a, int b) { return a > b ? a : b; }
+  static SDB_CX int grows() {
+    int g = max2(8, D);
+    for (int b = 0; b < NB; ++b) g = max2(g, max2(8 * t1(b), 4 * kt3(b)));
+    return g;
+  }
+  static SDB_CX int p1_off(int b) {  // offset (in fragments) of block b in the P1 table
+    int o = 0;
+    for (int q = 0; q < b; ++q) o += t1(q) * LT;
+    return o;
+  }
+  static SDB_CX int p3_off(int b) {
+    int o = p1_off(NB);
+    for (int q = 0; q < b; ++q) o += kt3(q) * IT;
+    return o;
+  }
+  static SDB_CX int n_frags() { return p3_off(NB); }            // per-lane doubles
+  static SDB_CX int left_off(int b) {                            // leftover-row table offsets
+    int o = 0;
+    for (int q = 0; q < b; ++q) o += IL * rn(q) * M;
+    return o;
+  }
+  static SDB_CX int n_left() { return left_off(NB); }
+  static SDB_CX int warp_doubles() { return (grows() + M) * 32; }
+  static SDB_CX size_t smem_bytes() {
+    return ((size_t)MM * SDB_FUSED_THREADS + (size_t)warp_doubles() * SDB_FUSED_WARPS) * sizeof(double) +
+           128 * 16 + (SDB_FUSED_MAX_TERMS + 1 + n_left() + 1) * sizeof(double);
   }
 };
 
-// index of pair (i < j) in K_m row order
+// Host: lane-major fragment tables.  out[frag * 32 + lane]; then the leftover rows.
+template <int D, int M>
+inline void sdb_fused_build_tables(const double* A, const double* B, double* out) {
+  typedef SdbFusedShape<D, M> Sh;
+  for (int b = 0; b < Sh::NB; ++b) {
+    const int rn = Sh::rn(b), r0 = Sh::r0(b);
+    for (int t = 0; t < Sh::t1(b); ++t)
+      for (int lt = 0; lt < Sh::LT; ++lt)
+        for (int lane = 0; lane < 32; ++lane) {
+          const int n = 8 * t + (lane >> 2), l = 4 * lt + (lane & 3);
+          double v = 0.0;
+          if (l < D) {
+            if (n < M * rn) v = B[((n / rn) * D + r0 + n % rn) * D + l];       // B_j[r0+r][l]
+            else if (n < Sh::nr(b)) v = A[(r0 + n - M * rn) * D + l];          // drift rows
+          }
+          out[(size_t)(Sh::p1_off(b) + t * Sh::LT + lt) * 32 + lane] = v;
+        }
+    for (int kt = 0; kt < Sh::kt3(b); ++kt)
+      for (int it = 0; it < Sh::IT; ++it)
+        for (int lane = 0; lane < 32; ++lane) {
+          const int i = 8 * it + (lane >> 2), K = 4 * kt + (lane & 3);
+          double v = 0.0;
+          if (K < rn * M) v = B[((K % M) * D + i) * D + r0 + K / M];           // B_k[i][r0+r]
+          out[(size_t)(Sh::p3_off(b) + kt * Sh::IT + it) * 32 + lane] = v;
+        }
+  }
+  double* left = out + (size_t)Sh::n_frags() * 32;
+  for (int b = 0; b < Sh::NB; ++b)
+    for (int q = 0; q < Sh::IL; ++q)
+      for (int K = 0; K < Sh::rn(b) * M; ++K)
+        left[Sh::left_off(b) + q * Sh::rn(b) * M + K] =
+            B[((K % M) * D + 8 * Sh::IT + q) * D + Sh::r0(b) + K / M];
+}
+template <int D, int M>
+inline size_t sdb_fused_table_doubles() {
+  typedef SdbFusedShape<D, M> Sh;
+  return (size_t)Sh::n_frags() * 32 + Sh::n_left();
+}
+
+#ifdef __CUDACC__
+SDB_DEV void sdb_dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// column swizzle of the staging buffer: keeps every access pattern used below conflict-free
+SDB_DEV constexpr int sdb_swz(int row) { return (row & 1) | (((row >> 1) & 1) << 3); }
+
 template <int M>
-SDB_DEV constexpr int sdb_pair_index(int i, int j) {
+SDB_DEV constexpr int sdb_pair_index(int i, int j) {  // (i < j) in K_m row order
   return i * M - i * (i + 1) / 2 + (j - i - 1);
 }
 
-// One row block of   G_n dW   and   sum1 sqrt(h) = G_n I sqrt(h)   (rows R0 .. R0+RN-1).
-template <int D, int M, int R0, int RN>
-SDB_DEV void sdb_fused_rowblock(const PInline<M * D * D>& gp, const double (&Y)[D],
-                                const double (&dW)[M], const volatile double* sA, double dg,
-                                double (&Yn)[D], double (&s)[RN][M]) {
-  constexpr int NT = SDB_FUSED_THREADS;
-  double GdW[RN];
+template <int D, int M, int B_>
+struct SdbFusedBlock {
+  typedef SdbFusedShape<D, M> Sh;
+  static constexpr int RN = Sh::rn(B_), R0 = Sh::r0(B_), T1 = Sh::t1(B_), KT3 = Sh::kt3(B_);
+
+  // P1 + P2 + P3 for row block B_.
+  static SDB_DEV void run(const double* __restrict__ frag, const double* __restrict__ s_left,
+                          double* gbuf, const volatile double* sA, const volatile double* sW,
+                          const double (&Yf)[Sh::LT][4], double h, double dg, int lane,
+                          double (&H20)[D], double (&Yacc)[D], double (&w)[4][2],
+                          double (&wv)[Sh::IL > 0 ? Sh::IL : 1]) {
+    constexpr int LT = Sh::LT;
+    const int fr = lane >> 2, fc = lane & 3;
+    // ---- P1: staging[n][p] = sum_l Bmat[n][l] Y[l][p] -----------------------------------------
+    const double* f1 = frag + (size_t)Sh::p1_off(B_) * 32 + lane;
 #pragma unroll
-  for (int i = 0; i < RN; ++i) {
-    GdW[i] = 0.0;
+    for (int t = 0; t < T1; ++t) {
+      double a[LT];
 #pragma unroll
-    for (int k = 0; k < M; ++k) s[i][k] = 0.0;
-  }
+      for (int lt = 0; lt < LT; ++lt) a[lt] = __ldg(f1 + (t * LT + lt) * 32);
+      double c[4][2];
 #pragma unroll
-  for (int j = 0; j < M; ++j) {
-    double g[RN];
-#pragma unroll
-    for (int i = 0; i < RN; ++i) {
-      double acc = gp.v[(j * D + R0 + i) * D] * Y[0];
-#pragma unroll
-      for (int l = 1; l < D; ++l) acc = fma(gp.v[(j * D + R0 + i) * D + l], Y[l], acc);
-      g[i] = acc;
-      GdW[i] = fma(acc, dW[j], GdW[i]);
-    }
-#pragma unroll
-    for (int k = 0; k < M; ++k) {
-      double a;
-      if (k == j) {
-        a = dg;
-      } else if (j < k) {
-        a = sA[sdb_pair_index<M>(j, k) * NT];
-      } else {
-        a = -sA[sdb_pair_index<M>(k, j) * NT];
+      for (int pt = 0; pt < 4; ++pt) {
+        c[pt][0] = 0.0;
+        c[pt][1] = 0.0;
       }
 #pragma unroll
-      for (int i = 0; i < RN; ++i) s[i][k] = fma(g[i], a, s[i][k]);
+      for (int lt = 0; lt < LT; ++lt)  // consecutive DMMAs hit independent accumulators
+#pragma unroll
+        for (int pt = 0; pt < 4; ++pt) sdb_dmma(c[pt][0], c[pt][1], a[lt], Yf[lt][pt]);
+      double* row = gbuf + (8 * t + fr) * 32;
+      const int sw = sdb_swz(fr);  // (8t + fr) & 7 == fr
+#pragma unroll
+      for (int pt = 0; pt < 4; ++pt) {
+        row[(8 * pt + 2 * fc) ^ sw] = c[pt][0];
+        row[(8 * pt + 2 * fc + 1) ^ sw] = c[pt][1];
+      }
     }
+    __syncwarp();
+    // ---- P2: one lane per path ----------------------------------------------------------------
+    {
+      constexpr int NT = SDB_FUSED_THREADS;
+      const volatile double* g = gbuf;
+      double s[RN][M], GdW[RN];
+#pragma unroll
+      for (int r = 0; r < RN; ++r) {
+        GdW[r] = 0.0;
+#pragma unroll
+        for (int k = 0; k < M; ++k) s[r][k] = 0.0;
+      }
+#pragma unroll
+      for (int j = 0; j < M; ++j) {
+        double gj[RN];
+        const double dWj = sW[j * 32];
+#pragma unroll
+        for (int r = 0; r < RN; ++r) {
+          const int n = j * RN + r;
+          gj[r] = g[n * 32 + (lane ^ sdb_swz(n))];
+          GdW[r] = fma(gj[r], dWj, GdW[r]);
+        }
+#pragma unroll
+        for (int k = 0; k < M; ++k) {
+          double a;
+          if (k == j) {
+            a = dg;
+          } else if (j < k) {
+            a = sA[sdb_pair_index<M>(j, k) * NT];
+          } else {
+            a = -sA[sdb_pair_index<M>(k, j) * NT];
+          }
+#pragma unroll
+          for (int r = 0; r < RN; ++r) s[r][k] = fma(gj[r], a, s[r][k]);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < M; ++k) {
+        const double hd = 0.5 * sW[k * 32];
+#pragma unroll
+        for (int r = 0; r < RN; ++r) s[r][k] = fma(hd, GdW[r], s[r][k]);
+      }
+      // drift rows of this block: H20 = Y + f h (integrate.py:509), update without the f1 term
+#pragma unroll
+      for (int r = 0; r < RN; ++r) {
+        const int n = M * RN + r;
+        const double f0h = g[n * 32 + (lane ^ sdb_swz(n))] * h;
+        Yacc[R0 + r] = fma(-0.5, f0h, GdW[r]);
+        H20[R0 + r] += f0h;  // H20 held Y
+      }
+      // rows 8.. of the stage-2 sum on the FMA pipe (uniform operands from shared memory)
+      if (Sh::IL > 0) {
+#pragma unroll
+        for (int q = 0; q < Sh::IL; ++q) {
+          const double* bl = s_left + Sh::left_off(B_) + q * RN * M;
+          double acc = wv[q];
+#pragma unroll
+          for (int r = 0; r < RN; ++r)
+#pragma unroll
+            for (int k = 0; k < M; ++k) acc = fma(bl[r * M + k], s[r][k], acc);
+          wv[q] = acc;
+        }
+      }
+      __syncwarp();  // every lane has read its G_n entries: the staging rows may be overwritten
+#pragma unroll
+      for (int r = 0; r < RN; ++r)
+#pragma unroll
+        for (int k = 0; k < M; ++k) {
+          const int K = r * M + k;
+          gbuf[K * 32 + (lane ^ sdb_swz(K))] = s[r][k];
+        }
+    }
+    __syncwarp();
+    // ---- P3: w[i][p] += sum_K Bst[i][K] s~[K][p], rows i < 8 IT ------------------------------------
+    if (Sh::IT > 0) {
+      const double* f3 = frag + (size_t)Sh::p3_off(B_) * 32 + lane;
+#pragma unroll
+      for (int kt = 0; kt < KT3; ++kt) {
+        const double a = __ldg(f3 + kt * Sh::IT * 32);
+        const int K = 4 * kt + fc;
+        const double* row = gbuf + K * 32;
+        const int sw = sdb_swz(K);
+#pragma unroll
+        for (int pt = 0; pt < 4; ++pt) sdb_dmma(w[pt][0], w[pt][1], a, row[(8 * pt + fr) ^ sw]);
+      }
+    }
+    __syncwarp();
   }
-#pragma unroll
-  for (int k = 0; k < M; ++k) {
-    const double hd = 0.5 * dW[k];
-#pragma unroll
-    for (int i = 0; i < RN; ++i) s[i][k] = fma(hd, GdW[i], s[i][k]);
+};
+
+template <int D, int M, int B_>
+struct SdbFusedBlocks {
+  template <class... Args>
+  static SDB_DEV void run(Args&... args) {
+    SdbFusedBlocks<D, M, B_ - 1>::run(args...);
+    SdbFusedBlock<D, M, B_>::run(args...);
   }
-#pragma unroll
-  for (int i = 0; i < RN; ++i) Yn[R0 + i] += GdW[i];
-}
+};
+template <int D, int M>
+struct SdbFusedBlocks<D, M, -1> {
+  template <class... Args>
+  static SDB_DEV void run(Args&...) {}
+};
 
 template <int D, int M>
 SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * D>& fp,
-                                        const PInline<M * D * D>& gp, double* smem) {
+                                        const double* __restrict__ frag, double* smem) {
   typedef SdbFusedShape<D, M> Sh;
   constexpr int NT = SDB_FUSED_THREADS;
-  constexpr int MM = Sh::MM, D1 = Sh::D1, D2 = Sh::D2;
+  constexpr int MM = Sh::MM, LT = Sh::LT, GR = Sh::grows();
   static_assert(M % 2 == 0, "fused kernel needs an even number of Wiener processes");
-  const int tid = threadIdx.x;
+  static_assert(Sh::IT <= 1, "stage-2 DMMA tiles: d < 16 supported");
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  // shared: [ROWS][NT] per-thread staging | log table | h/(2 pi k)
-  double2* tab = reinterpret_cast<double2*>(smem + (size_t)Sh::ROWS * NT);
+  // shared: Levy areas [MM][NT] | per warp { staging [GR][32], dW [M][32] } | tables
+  double* warp_base = smem + (size_t)MM * NT + (size_t)warp * (GR + M) * 32;
+  double* gbuf = warp_base;
+  double2* tab =
+      reinterpret_cast<double2*>(smem + (size_t)MM * NT + (size_t)Sh::warp_doubles() * SDB_FUSED_WARPS);
   double* s_hk = reinterpret_cast<double*>(tab + 128);
+  double* s_left = s_hk + SDB_FUSED_MAX_TERMS + 1;
   if (tid < 128) tab[tid] = reinterpret_cast<const double2*>(sdb_logtab)[tid];
   if (tid <= SDB_FUSED_MAX_TERMS)
     s_hk[tid] = tid == 0 ? 0.0 : a.h_global * SDB_INV_2PI / (double)tid;
+  for (int i = tid; i < Sh::n_left(); i += NT) s_left[i] = frag[(size_t)Sh::n_frags() * 32 + i];
   __syncthreads();
+
   const int64_t p = (int64_t)blockIdx.x * NT + tid;
-  if (p >= a.P) return;
+  const bool active = p < a.P;  // idle lanes of the last warp still take part in the DMMAs
   double* sA = smem + tid;
-  double* sS = smem + (size_t)MM * NT + tid;
+  double* sW = warp_base + GR * 32 + lane;
 
   double Y[D];
-  if (a.flags & SDB_FLAG_Y0_BROADCAST) {
 #pragma unroll
-    for (int i = 0; i < D; ++i) Y[i] = a.y0[i];
-  } else {
+  for (int i = 0; i < D; ++i) Y[i] = 0.0;
+  if (active) {
+    if (a.flags & SDB_FLAG_Y0_BROADCAST) {
 #pragma unroll
-    for (int i = 0; i < D; ++i) Y[i] = a.y0[i * a.y0_sI + p * a.y0_sP];
+      for (int i = 0; i < D; ++i) Y[i] = a.y0[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < D; ++i) Y[i] = a.y0[i * a.y0_sI + p * a.y0_sP];
+    }
+    sdb_store<D>(a, p, 0, Y);
   }
-  sdb_store<D>(a, p, 0, Y);
 
   const double rh_g = sqrt(a.h_global);
   const double cz = sqrt(2.0 / a.h_global);
   const double dg = (a.flags & SDB_FLAG_STRATONOVICH) ? 0.0 : -0.5 * a.h_global;
   const uint64_t path = (uint64_t)(a.path_id0 + p);
+  const SdbPhiloxKey pkey(a.seed);
   const int steps = a.N - 1;
   const int n_terms = a.n_terms;
-  const double* __restrict__ hs = a.tspan + a.N;  // per-step h, sqrt(h), 1/sqrt(h) (host-built)
+  const double* __restrict__ hs = a.tspan + a.N;  // per-step h (host-built)
   int next_save = a.save_every;
   int64_t slot = 1;
+  const int fr = lane >> 2, fc = lane & 3;
 
 #pragma unroll 1
   for (int n = 0; n < steps; ++n) {
     const double h = hs[n];
-    const double rh = hs[steps + n];
-    const double inv_rh = hs[2 * steps + n];
 
-    // ---- noise: dW (wiener.py:52), Levy areas (wiener.py:67-74, :102-105) -------------------------
-    const SdbStream st(a.seed, path, (uint32_t)n, tab);
-    double dW[M];
-#pragma unroll
-    for (int s = 0; s < M / 2; ++s) {
-      double z0, z1;
-      st.pair((uint32_t)s, z0, z1);
-      dW[2 * s] = rh_g * z0;
-      dW[2 * s + 1] = rh_g * z1;
-    }
+    // ---- noise: dW (wiener.py:52), Levy areas (wiener.py:67-74, :102-105), one lane per path ------
     {
+      const SdbStream st(pkey, path, (uint32_t)n, tab);
+      double dW[M];
+#pragma unroll
+      for (int s = 0; s < M / 2; ++s) {
+        double z0, z1;
+        st.pair((uint32_t)s, z0, z1);
+        dW[2 * s] = rh_g * z0;
+        dW[2 * s + 1] = rh_g * z1;
+      }
+      constexpr int KU = SDB_FUSED_KUNROLL;
       double At[MM];
 #pragma unroll
       for (int r = 0; r < MM; ++r) At[r] = 0.0;
-#pragma unroll 1
+#pragma unroll(KU)
       for (int k = 1; k <= n_terms; ++k) {
         double X[M], Z[M];
         const uint32_t sx = (uint32_t)((M + 2 * (k - 1) * M) >> 1);
@@ -183,80 +381,87 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
       }
 #pragma unroll
       for (int r = 0; r < MM; ++r) sA[r * NT] = At[r];
+#pragma unroll
+      for (int j = 0; j < M; ++j) sW[j * 32] = dW[j];
     }
 
-    // ---- drift stages (integrate.py:502, :509, :514-515) --------------------------------------------
-    double H20[D], Yn[D];
+    // ---- P0: Y -> DMMA B-fragments Yf[lt][pt] = Y[4 lt + fc][path 8 pt + fr] ---------------------
+    double Yf[LT][4];
+#pragma unroll
+    for (int l = 0; l < D; ++l) gbuf[l * 32 + (lane ^ sdb_swz(l))] = Y[l];
+    __syncwarp();
+#pragma unroll
+    for (int lt = 0; lt < LT; ++lt) {
+      const int l = 4 * lt + fc;
+      const bool ok = (4 * lt + 3 < D) || (l < D);
+      const int lc = ok ? l : 0;
+#pragma unroll
+      for (int pt = 0; pt < 4; ++pt) {
+        const double v = gbuf[lc * 32 + ((8 * pt + fr) ^ sdb_swz(lc))];
+        Yf[lt][pt] = ok ? v : 0.0;
+      }
+    }
+    __syncwarp();
+
+    // ---- row blocks ----------------------------------------------------------------------------
+    double Yacc[D], w[4][2], wv[Sh::IL > 0 ? Sh::IL : 1];
+#pragma unroll
+    for (int pt = 0; pt < 4; ++pt) {
+      w[pt][0] = 0.0;
+      w[pt][1] = 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < (Sh::IL > 0 ? Sh::IL : 1); ++q) wv[q] = 0.0;
     {
-      double f0h[D];
-#pragma unroll
-      for (int i = 0; i < D; ++i) {
-        double acc = fp.v[i * D] * Y[0];
-#pragma unroll
-        for (int l = 1; l < D; ++l) acc = fma(fp.v[i * D + l], Y[l], acc);
-        f0h[i] = acc * h;
-        H20[i] = Y[i] + f0h[i];
-      }
-#pragma unroll
-      for (int i = 0; i < D; ++i) {
-        double acc = fp.v[i * D] * H20[0];
-#pragma unroll
-        for (int l = 1; l < D; ++l) acc = fma(fp.v[i * D + l], H20[l], acc);
-        Yn[i] = Y[i] + 0.5 * fma(acc, h, f0h[i]);
-      }
+      const double* s_left_c = s_left;
+      const volatile double* sAv = sA;
+      const volatile double* sWv = sW;
+      SdbFusedBlocks<D, M, Sh::NB - 1>::run(frag, s_left_c, gbuf, sAv, sWv, Yf, h, dg, lane, Y,
+                                            Yacc, w, wv);
     }
+    // Y now holds H20 = Y + f(Y) h
 
-    // ---- G_n dW and sum1 = G_n I (integrate.py:503-508), two row blocks -----------------------------
-    {
-      double s1[D1][M];
-      sdb_fused_rowblock<D, M, 0, D1>(gp, Y, dW, sA, dg, Yn, s1);
+    // ---- second drift evaluation f(H20, t_{n+1}) h (integrate.py:514) ----------------------------
 #pragma unroll
-      for (int i = 0; i < D1; ++i)
+    for (int i = 0; i < D; ++i) {
+      double acc = fp.v[i * D] * Y[0];
 #pragma unroll
-        for (int k = 0; k < M; ++k) sS[(i * M + k) * NT] = s1[i][k];
+      for (int l = 1; l < D; ++l) acc = fma(fp.v[i * D + l], Y[l], acc);
+      Yacc[i] = fma(0.5 * h, acc, Yacc[i]);
     }
-    double s2[D2][M];
-    sdb_fused_rowblock<D, M, D1, D2>(gp, Y, dW, sA, dg, Yn, s2);
-
-    // ---- stage-2 diffusion evaluations at H2_k, H3_k (integrate.py:509-521) -------------------------
-    const double half_rh = 0.5 * rh;
+    // ---- stage-2 sum back to one lane per path ---------------------------------------------------
+    if (Sh::IT > 0) {
+      double* row = gbuf + fr * 32;
+      const int sw = sdb_swz(fr);
 #pragma unroll
-    for (int k = 0; k < M; ++k) {
-      double H2[D], H3[D];
-#pragma unroll
-      for (int i = 0; i < D; ++i) {
-        const double sv = i < D1 ? sS[(i * M + k) * NT] : s2[i < D1 ? 0 : i - D1][k];
-        H2[i] = fma(sv, inv_rh, H20[i]);
-        H3[i] = fma(-sv, inv_rh, H20[i]);
+      for (int pt = 0; pt < 4; ++pt) {
+        row[(8 * pt + 2 * fc) ^ sw] = w[pt][0];
+        row[(8 * pt + 2 * fc + 1) ^ sw] = w[pt][1];
       }
+      __syncwarp();
 #pragma unroll
-      for (int i = 0; i < D; ++i) {
-        double u = gp.v[(k * D + i) * D] * H2[0];
-        double v = gp.v[(k * D + i) * D] * H3[0];
-#pragma unroll
-        for (int l = 1; l < D; ++l) {
-          u = fma(gp.v[(k * D + i) * D + l], H2[l], u);
-          v = fma(gp.v[(k * D + i) * D + l], H3[l], v);
-        }
-        Yn[i] = fma(half_rh, u - v, Yn[i]);
-      }
+      for (int i = 0; i < 8; ++i) Yacc[i] += gbuf[i * 32 + (lane ^ sdb_swz(i))];
+      __syncwarp();
     }
 #pragma unroll
-    for (int i = 0; i < D; ++i) Y[i] = Yn[i];
+    for (int q = 0; q < Sh::IL; ++q) Yacc[8 * Sh::IT + q] += wv[q];
+#pragma unroll
+    for (int i = 0; i < D; ++i) Y[i] += Yacc[i];  // Y_{n+1} = H20 - f0h/2 + f1h/2 + G dW + sum
 
     if (n + 1 == next_save) {
-      sdb_store<D>(a, p, slot, Y);
+      if (active) sdb_store<D>(a, p, slot, Y);
       ++slot;
       next_save += a.save_every;
     }
   }
-  sdb_finish<D>(a, p, Y);
+  if (active) sdb_finish<D>(a, p, Y);
 }
 
 #define SDB_FUSED_KERNEL(NAME, D, M)                                                          \
   extern "C" __global__ void __launch_bounds__(SDB_FUSED_THREADS, 1)                          \
       NAME(const __grid_constant__ SdbLoopArgs a, const __grid_constant__ PInline<D * D> fp,  \
-           const __grid_constant__ PInline<M * D * D> gp) {                                   \
+           const double* __restrict__ frag) {                                                 \
     extern __shared__ __align__(16) double sdb_fused_smem[];                                  \
-    sdb_srk2_fused_linear_body<D, M>(a, fp, gp, sdb_fused_smem);                              \
+    sdb_srk2_fused_linear_body<D, M>(a, fp, frag, sdb_fused_smem);                            \
   }
+#endif  // __CUDACC__

@@ -24,3 +24,17 @@ struct SdbAotRegistrar {
 
 std::string sdb_loop_key(int scheme, int fk, int gk, int d, int m, int noise, bool inline_params);
 std::string sdb_fused_key(int d, int m);  // fused linear SRI2/SRS2 + Philox/KPW kernel
+
+// The fused linear SRI2/SRS2 + Philox/KPW kernel (sdb_fused.cuh) for one (d, m).
+struct SdbFusedEntry {
+  int d, m;
+  int variant;                 // tuning variant (env SDB_FUSED_VARIANT; 0 = default)
+  const void* fn;
+  size_t smem;                 // dynamic shared memory
+  size_t table_doubles;        // size of the DMMA fragment table built from (A, B)
+  void (*build)(const double* A, const double* B, double* out);
+};
+std::vector<SdbFusedEntry>& sdb_fused_registry();
+struct SdbFusedRegistrar {
+  explicit SdbFusedRegistrar(const SdbFusedEntry& e) { sdb_fused_registry().push_back(e); }
+};

@@ -97,19 +97,30 @@ struct PGlobal {  // too large for the parameter space: read through the L1/L2 h
 #define SDB_PHILOX_W0 0x9E3779B9u
 #define SDB_PHILOX_W1 0xBB67AE85u
 
-SDB_HD void sdb_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
-                              uint32_t k1, uint32_t (&out)[4]) {
+// Round keys k + r W (warp-uniform): built once per kernel so they live in uniform registers and a
+// round is exactly 2 IMAD.WIDE + 2 LOP3.
+struct SdbPhiloxKey {
+  uint32_t a[10], b[10];
+  SDB_HD explicit SdbPhiloxKey(uint64_t seed) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      a[r] = (uint32_t)seed + (uint32_t)r * SDB_PHILOX_W0;
+      b[r] = (uint32_t)(seed >> 32) + (uint32_t)r * SDB_PHILOX_W1;
+    }
+  }
+};
+
+SDB_HD void sdb_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                              const SdbPhiloxKey& key, uint32_t (&out)[4]) {
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
     const uint64_t p0 = (uint64_t)SDB_PHILOX_M0 * c0;
     const uint64_t p1 = (uint64_t)SDB_PHILOX_M1 * c2;
-    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ key.a[r];
     const uint32_t n1 = (uint32_t)p1;
-    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ key.b[r];
     const uint32_t n3 = (uint32_t)p0;
     c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-    k0 += SDB_PHILOX_W0;
-    k1 += SDB_PHILOX_W1;
   }
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
@@ -136,15 +147,15 @@ SDB_DEV double sdb_rsqrt_approx(double x) {
 SDB_DEV void sdb_normal_pair(const uint32_t (&w)[4], const double2* __restrict__ tab, double& z0,
                              double& z1) {
   // ---- radius -----------------------------------------------------------------------------------
-  const uint64_t hi = ((uint64_t)w[0] << 32) | w[1];
-  const uint64_t x = (hi >> 11) | 1ull;
-  const int lz = __clzll((long long)x);  // >= 11
-  const uint64_t mant = (x << (lz - 11)) & 0x000FFFFFFFFFFFFFull;
-  const uint64_t ix = ((uint64_t)(1033 - lz) << 52) | mant;  // bits of u1 = x 2^-53
-  const uint64_t tmp = ix - SDB_LOG_OFF;
-  const int i = (int)(tmp >> 45) & 127;
-  const int k = (int)((long long)tmp >> 52);
-  const double z = __longlong_as_double((long long)(ix - (tmp & 0xFFF0000000000000ull)));
+  // x = 2 a + 1, a = (w0:w1) >> 12: 2^53 + 2a is exactly representable, and subtracting 2^53 - 1
+  // is exact, so one DADD converts and normalises; the rest works on the high word only.
+  const double x = __hiloint2double((int)(0x43400000u | (w[0] >> 12)),
+                                    (int)__funnelshift_r(w[1], w[0], 12)) - 9007199254740991.0;
+  const int xh = __double2hiint(x);
+  const int tmp = xh - 0x3FE60000;  // high word of SDB_LOG_OFF
+  const int i = (tmp >> 13) & 127;
+  const int k = (tmp >> 20) - 53;   // u1 = x 2^-53 = 2^k z,  z in [0.6875, 1.375)
+  const double z = __hiloint2double(xh - (tmp & (int)0xFFF00000), __double2loint(x));
   const double2 tc = tab[i];  // {1/c, -2 ln c}
   const double r = fma(z, tc.x, -1.0);
   const double r2 = r * r;
@@ -162,9 +173,8 @@ SDB_DEV void sdb_normal_pair(const uint32_t (&w)[4], const double2* __restrict__
   g = fma(g, e, g);
   const double rad = fma(fma(-g, g, L), hh, g);
   // ---- angle ------------------------------------------------------------------------------------
-  const uint64_t lo = ((uint64_t)w[2] << 32) | w[3];
-  const double t =
-      __longlong_as_double((long long)(0x3FF0000000000000ull | ((lo >> 9) & 0x000FFFFFFFFFFFFFull))) - 1.0;
+  const double t = __hiloint2double((int)(0x3FF00000u | ((w[2] >> 9) & 0x000FFFFFu)),
+                                    (int)__funnelshift_r(w[3], w[2], 9)) - 1.0;
   const double t2 = t * t;
   double sn = fma(t2, SDB_SIN6, SDB_SIN5);
   sn = fma(t2, sn, SDB_SIN4);
@@ -182,22 +192,23 @@ SDB_DEV void sdb_normal_pair(const uint32_t (&w)[4], const double2* __restrict__
   const bool swap = (w[2] >> 29) & 1u;
   const double a0 = swap ? sn : cs;
   const double b0 = swap ? cs : sn;
-  const uint64_t s0 = (uint64_t)((w[2] >> 30) & 1u) << 63;
-  const uint64_t s1 = (uint64_t)(w[2] >> 31) << 63;
-  z0 = __longlong_as_double((long long)((uint64_t)__double_as_longlong(rad * a0) ^ s0));
-  z1 = __longlong_as_double((long long)((uint64_t)__double_as_longlong(rad * b0) ^ s1));
+  const uint32_t s0 = (w[2] << 1) & 0x80000000u;  // bit 30 -> sign
+  const uint32_t s1 = w[2] & 0x80000000u;         // bit 31 -> sign
+  const double p0 = rad * a0, p1 = rad * b0;
+  z0 = __hiloint2double(__double2hiint(p0) ^ (int)s0, __double2loint(p0));
+  z1 = __hiloint2double(__double2hiint(p1) ^ (int)s1, __double2loint(p1));
 }
 
 struct SdbStream {
-  uint32_t p_lo, p_hi, step, k0, k1;
+  const SdbPhiloxKey& key;
+  uint32_t p_lo, p_hi, step;
   const double2* tab;  // log table: global (sdb_logtab) or a shared-memory copy
-  SDB_DEV SdbStream(uint64_t seed, uint64_t path, uint32_t step_,
+  SDB_DEV SdbStream(const SdbPhiloxKey& key_, uint64_t path, uint32_t step_,
                     const double2* tab_ = reinterpret_cast<const double2*>(sdb_logtab))
-      : p_lo((uint32_t)path), p_hi((uint32_t)(path >> 32)), step(step_), k0((uint32_t)seed),
-        k1((uint32_t)(seed >> 32)), tab(tab_) {}
+      : key(key_), p_lo((uint32_t)path), p_hi((uint32_t)(path >> 32)), step(step_), tab(tab_) {}
   SDB_DEV void pair(uint32_t slot, double& z0, double& z1) const {
     uint32_t r[4];
-    sdb_philox4x32_10(p_lo, p_hi, step, slot, k0, k1, r);
+    sdb_philox4x32_10(p_lo, p_hi, step, slot, key, r);
     sdb_normal_pair(r, tab, z0, z1);
   }
 };
@@ -512,7 +523,8 @@ SDB_DEV void sdb_step_noise(const SdbLoopArgs& a, int64_t p, int n, double (&dW)
         for (int k = 0; k < M; ++k) IJ[j][k] = q[j * a.IJ_sR + k * a.IJ_sC];
     }
   } else {
-    const SdbStream st(a.seed, (uint64_t)(a.path_id0 + p), (uint32_t)n);
+    const SdbPhiloxKey key(a.seed);
+    const SdbStream st(key, (uint64_t)(a.path_id0 + p), (uint32_t)n);
     const double rh = sqrt(a.h_global);  // deltaW(N-1, m, h_global): integrate.py:483
     SdbNormalSeq s(st, 0u);
 #pragma unroll
@@ -836,7 +848,8 @@ extern "C" __global__ void __launch_bounds__(256) sdb_k_delta_w(const SdbDeltaWA
   if (idx >= a.steps * a.paths) return;
   const int64_t n = idx / a.paths;
   const int64_t p = idx - n * a.paths;
-  const SdbStream st(a.seed, (uint64_t)(a.path_id0 + p), (uint32_t)n);
+  const SdbPhiloxKey key(a.seed);
+  const SdbStream st(key, (uint64_t)(a.path_id0 + p), (uint32_t)n);
   SdbNormalSeq s(st, 0u);
   double* o = a.out + n * a.sN + p * a.sP;
   for (int j = 0; j < a.m; ++j) o[j * a.sJ] = a.sqrt_h * s.next();
@@ -863,7 +876,8 @@ SDB_DEV void sdb_repint_body(const SdbRepintArgs& a) {
                                a.Gt ? a.Gt + n * a.Gt_sN + p * a.Gt_sP : nullptr, a.Gt_sR};
     sdb_repeated_integrals<M>(dW, a.h, a.n_terms, a.method, a.stratonovich != 0, ns, At, IJ);
   } else {
-    const SdbStream st(a.seed, (uint64_t)(a.path_id0 + p), (uint32_t)n);
+    const SdbPhiloxKey key(a.seed);
+    const SdbStream st(key, (uint64_t)(a.path_id0 + p), (uint32_t)n);
     const SdbNormalsPhilox<M> ns{st, a.n_terms};
     sdb_repeated_integrals<M>(dW, a.h, a.n_terms, a.method, a.stratonovich != 0, ns, At, IJ);
   }

@@ -362,3 +362,33 @@ def test_jit_builtin_dimensions(sdb):
     At_o, Iw_o = orc.iwik_from_normals(dW13, 0.01, X, Y, Gt)
     assert np.max(np.abs(Iw - Iw_o)) <= 1e-12 * np.max(np.abs(Iw_o))
     assert np.max(np.abs(At - At_o)) <= 1e-12 * np.max(np.abs(Iw_o))
+
+
+@pytest.mark.parametrize("d,m", [(10, 10), (4, 4), (8, 2), (5, 4)])
+@pytest.mark.parametrize("strat", [False, True])
+def test_fused_dmma_kernel_shapes(sdb, d, m, strat, monkeypatch):
+    """The fused linear SRI2/SRS2 kernel (DMMA products, exact linear collapse of the two
+    stage-2 evaluations) against the generic two-evaluation loop kernel and the oracle, for
+    every instantiated (d, m): DMMA tile / leftover-row / row-block edge cases, a partial last
+    warp (P not a multiple of 32) and per-path initial states."""
+    rng = np.random.default_rng(100 * d + m)
+    A = -1.2 * np.eye(d) + 0.3 * rng.standard_normal((d, d)) / np.sqrt(d)
+    B = 0.4 * rng.standard_normal((m, d, d)) / np.sqrt(d * m)
+    f, G = sdb.ops.LinearDrift(A), sdb.ops.LinearDiffusion(B)
+    y0 = rng.standard_normal(d)
+    tspan = np.linspace(0.0, 0.3, 31)
+    h = 0.01
+    P, seed = 77, 424242
+    integ = sdb.stratSRS2 if strat else sdb.itoSRI2
+    rep = sdb.Jkpw if strat else sdb.Ikpw
+    y0p = y0[None, :] + 0.1 * rng.standard_normal((P, d))
+    y_fused = integ(f, G, y0, tspan, paths=P, seed=seed, path_id0=11, y0_paths=y0p)
+    monkeypatch.setenv("SDB_DISABLE_FUSED", "1")
+    y_generic = integ(f, G, y0, tspan, paths=P, seed=seed, path_id0=11, y0_paths=y0p)
+    monkeypatch.delenv("SDB_DISABLE_FUSED")
+    assert rel_err(y_fused, y_generic) <= TOL
+    dW = sdb.deltaW(30, m, h, paths=P, seed=seed, path_id0=11)
+    _, IJ = rep(dW, h, seed=seed, path_id0=11, ensemble=True)
+    for p in (0, 31, 32, P - 1):
+        ref = orc.srk2(f, G, y0p[p], tspan, dW[p], IJ[p])
+        assert rel_err(y_fused[p], ref) <= TOL
