@@ -42,7 +42,10 @@ SEED = 20261019
 HIST = (64, -1.0, 3.0)
 FLOPS_SRK2 = 6 * M * D * D + 2 * D * M * M + 4 * D * D + 4 * D * M + 4 * D   # 8840
 FLOPS_IKPW = M * (N_TERMS + 4) + (M * (M - 1) // 2) * (5 * N_TERMS + 5)      # 1440
-FLOPS_PER_PATH_STEP = FLOPS_SRK2 + FLOPS_IKPW                                 # 10280
+FLOPS_REFERENCE_FORM = FLOPS_SRK2 + FLOPS_IKPW                                # 10280
+# The fused kernel collapses the two stage-2 evaluations of the LINEAR g_k into one product
+# B_k (sqrt(h) s_k): SURVEY 8d says to subtract 2md^2 + 2dm from the numerator in that case.
+FLOPS_PER_PATH_STEP = FLOPS_REFERENCE_FORM - (2 * M * D * D + 2 * D * M)      # 8080 executed
 BYTES_PER_PATH_STEP = 8.0 * D / SAVE_EVERY + 8.0 * D / (N_POINTS - 1)         # 0.88 B (stores)
 METRIC = "SRI2 path-steps/s (d=m=10, fp64)"
 UNIT = "path-steps/s"
@@ -267,8 +270,9 @@ def run_gpu(args):
 
     if rank == 0:
         import ctypes as C
-        peak = C.c_double()
-        sdb._lib.check(sdb._lib.load().sdb_fp64_peak(20000, C.byref(peak), None))
+        peak, peak_sus = C.c_double(), C.c_double()
+        sdb._lib.check(sdb._lib.load().sdb_fp64_peak(8000, C.byref(peak), None))       # ~4 ms launches
+        sdb._lib.check(sdb._lib.load().sdb_fp64_peak(400000, C.byref(peak_sus), None))  # ~0.2 s launches
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -280,11 +284,17 @@ def run_gpu(args):
             "bound": "fp64",
             "achieved": achieved_tf, "peak": float(peak.value), "unit": "TFLOP/s",
             "frac": achieved_tf / float(peak.value),
-            "peak_source": "measured live: sdb_fp64_peak DFMA chain on all SMs "
-                           "(MEASURED_PEAKS.json has no fp64 entry; nominal 37.2)",
+            "peak_source": "measured live: sdb_fp64_peak, register-resident DFMA chains on all "
+                           "SMs, burst (4 ms launches); MEASURED_PEAKS.json has no fp64 entry, "
+                           "nominal 37.2",
+            "peak_sustained": float(peak_sus.value),
             "kernel": "sdb fused SRI2 step loop (one launch per step)",
             "kernel_ms": ms_kernel,
             "flops_per_path_step": FLOPS_PER_PATH_STEP,
+            "flops_note": "executed flop: SURVEY 8d count 10280 minus 2md^2+2dm=2200 for the "
+                          "linear stage-2 collapse; normal transforms and Philox not counted",
+            "frac_reference_form": (FLOPS_REFERENCE_FORM * path_steps / (ms_kernel * 1e-3) / 1e12
+                                    / float(peak.value)),
             "traffic": None,
             "hbm": {"achieved": BYTES_PER_PATH_STEP * path_steps / (ms_kernel * 1e-3) / 1e9,
                     "peak": hbm_peak, "unit": "GB/s",

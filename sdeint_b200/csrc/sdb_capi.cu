@@ -602,8 +602,8 @@ extern "C" int sdb_moments(const double* d_y, int64_t n_saved, int d, int64_t pa
 // ---------------------------------------------------------------------------------------------
 // FP64 pipe peak (roofline denominator)
 // ---------------------------------------------------------------------------------------------
-#define SDB_PROBE_CHAINS 8
-__global__ void __launch_bounds__(256) sdb_k_fp64_probe(int iters, double seed, double* sink) {
+#define SDB_PROBE_CHAINS 16
+__global__ void __launch_bounds__(512) sdb_k_fp64_probe(int iters, double seed, double* sink) {
   double acc[SDB_PROBE_CHAINS];
   const double a = 1.0 + 1e-9 * seed, b = 1e-12 * (threadIdx.x + 1);
 #pragma unroll
@@ -621,6 +621,9 @@ __global__ void __launch_bounds__(256) sdb_k_fp64_probe(int iters, double seed, 
   if (s == 123.456) sink[0] = s;  // never true; keeps the chain alive
 }
 
+// One block of 512 threads per SM, 16 independent DFMA chains per thread (the configuration that
+// reached 64 DFMA/clk/SM in tools/micro/ubench.cu).  `iters` sets the length of one launch
+// (8 x 16 DFMAs per iteration): short launches give the burst figure, long ones the sustained one.
 extern "C" int sdb_fp64_peak(int iters, double* tflops_out, void* stream) {
   if (!tflops_out || iters < 1) return fail("sdb_fp64_peak: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
@@ -632,17 +635,16 @@ extern "C" int sdb_fp64_peak(int iters, double* tflops_out, void* stream) {
   cudaEvent_t e0, e1;
   SDB_CUDA(cudaEventCreate(&e0));
   SDB_CUDA(cudaEventCreate(&e1));
-  const int blocks = sms * 8;
   double best = 0.0;
   for (int rep = 0; rep < 4; ++rep) {  // rep 0 warms up
     SDB_CUDA(cudaEventRecord(e0, st));
-    sdb_k_fp64_probe<<<blocks, 256, 0, st>>>(iters, 1.0, sink);
+    sdb_k_fp64_probe<<<sms, 512, 0, st>>>(iters, 1.0, sink);
     SDB_CUDA(cudaEventRecord(e1, st));
     SDB_CUDA(cudaEventSynchronize(e1));
     g_launches.fetch_add(1);
     float ms = 0.f;
     SDB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-    const double flops = 2.0 * 8.0 * SDB_PROBE_CHAINS * (double)iters * 256.0 * blocks;
+    const double flops = 2.0 * 8.0 * SDB_PROBE_CHAINS * (double)iters * 512.0 * sms;
     const double tf = flops / (ms * 1e-3) / 1e12;
     if (rep > 0 && tf > best) best = tf;
   }

@@ -38,6 +38,17 @@
 #ifndef SDB_FUSED_KUNROLL
 #define SDB_FUSED_KUNROLL 1  // unroll factor of the Levy-series loop over k
 #endif
+#ifndef SDB_FUSED_VOL_MMA
+#define SDB_FUSED_VOL_MMA 1  // 1: asm volatile DMMA (strictly ordered), 0: plain asm (schedulable)
+#endif
+#ifndef SDB_FUSED_VOL_SMEM
+#define SDB_FUSED_VOL_SMEM 1  // 1: volatile shared-memory reads in P2, 0: plain reads between __syncwarp()s
+#endif
+#if SDB_FUSED_VOL_SMEM
+#define SDB_SMEM_CV const volatile
+#else
+#define SDB_SMEM_CV const
+#endif
 
 template <int D, int M>
 struct SdbFusedShape {
@@ -123,9 +134,14 @@ inline size_t sdb_fused_table_doubles() {
 
 #ifdef __CUDACC__
 SDB_DEV void sdb_dmma(double& c0, double& c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-               : "+d"(c0), "+d"(c1)
-               : "d"(a), "d"(b));
+#if SDB_FUSED_VOL_MMA
+  asm volatile(
+#else
+  asm(
+#endif
+      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
 }
 
 // column swizzle of the staging buffer: keeps every access pattern used below conflict-free
@@ -143,7 +159,7 @@ struct SdbFusedBlock {
 
   // P1 + P2 + P3 for row block B_.
   static SDB_DEV void run(const double* __restrict__ frag, const double* __restrict__ s_left,
-                          double* gbuf, const volatile double* sA, const volatile double* sW,
+                          double* gbuf, SDB_SMEM_CV double* sA, SDB_SMEM_CV double* sW,
                           const double (&Yf)[Sh::LT][4], double h, double dg, int lane,
                           double (&H20)[D], double (&Yacc)[D], double (&w)[4][2],
                           double (&wv)[Sh::IL > 0 ? Sh::IL : 1]) {
@@ -178,7 +194,7 @@ struct SdbFusedBlock {
     // ---- P2: one lane per path ----------------------------------------------------------------
     {
       constexpr int NT = SDB_FUSED_THREADS;
-      const volatile double* g = gbuf;
+      SDB_SMEM_CV double* g = gbuf;
       double s[RN][M], GdW[RN];
 #pragma unroll
       for (int r = 0; r < RN; ++r) {
@@ -414,8 +430,8 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
     for (int q = 0; q < (Sh::IL > 0 ? Sh::IL : 1); ++q) wv[q] = 0.0;
     {
       const double* s_left_c = s_left;
-      const volatile double* sAv = sA;
-      const volatile double* sWv = sW;
+      SDB_SMEM_CV double* sAv = sA;
+      SDB_SMEM_CV double* sWv = sW;
       SdbFusedBlocks<D, M, Sh::NB - 1>::run(frag, s_left_c, gbuf, sAv, sWv, Yf, h, dg, lane, Y,
                                             Yacc, w, wv);
     }
