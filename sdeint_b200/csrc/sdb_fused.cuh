@@ -44,6 +44,15 @@
 #ifndef SDB_FUSED_VOL_SMEM
 #define SDB_FUSED_VOL_SMEM 1  // 1: volatile shared-memory reads in P2, 0: plain reads between __syncwarp()s
 #endif
+#ifndef SDB_FUSED_BATCH
+#define SDB_FUSED_BATCH 0  // 1: Philox + normal transform of M/2 pairs in lock-step (explicit ILP)
+#endif
+#ifndef SDB_FUSED_PARK_Y
+#define SDB_FUSED_PARK_Y 0  // 1: the state waits in shared memory while the noise is generated
+#endif
+#ifndef SDB_FUSED_PARK_DW
+#define SDB_FUSED_PARK_DW 0  // 1: dW is re-read from shared memory inside the Levy loop
+#endif
 #if SDB_FUSED_VOL_SMEM
 #define SDB_SMEM_CV const volatile
 #else
@@ -150,6 +159,125 @@ SDB_DEV constexpr int sdb_swz(int row) { return (row & 1) | (((row >> 1) & 1) <<
 template <int M>
 SDB_DEV constexpr int sdb_pair_index(int i, int j) {  // (i < j) in K_m row order
   return i * M - i * (i + 1) / 2 + (j - i - 1);
+}
+
+
+// ---- lock-step generation of NB Box-Muller pairs (same arithmetic as sdb_normal_pair, written
+// stage by stage over the batch so that NB independent dependency chains are adjacent) ----------
+template <int NB>
+SDB_DEV void sdb_philox_batch(const SdbPhiloxKey& key, uint32_t p_lo, uint32_t p_hi, uint32_t step,
+                              uint32_t slot0, uint32_t (&w)[NB][4]) {
+  uint32_t c0[NB], c1[NB], c2[NB], c3[NB];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    c0[b] = p_lo; c1[b] = p_hi; c2[b] = step; c3[b] = slot0 + (uint32_t)b;
+  }
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      const uint64_t p0 = (uint64_t)SDB_PHILOX_M0 * c0[b];
+      const uint64_t p1 = (uint64_t)SDB_PHILOX_M1 * c2[b];
+      const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1[b] ^ key.a[r];
+      const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3[b] ^ key.b[r];
+      c1[b] = (uint32_t)p1; c3[b] = (uint32_t)p0; c0[b] = n0; c2[b] = n2;
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < NB; ++b) { w[b][0] = c0[b]; w[b][1] = c1[b]; w[b][2] = c2[b]; w[b][3] = c3[b]; }
+}
+
+// z[2b], z[2b+1] = scale * (normal pair b); SCALED = false skips the multiplication.
+template <int NB, bool SCALED>
+SDB_DEV void sdb_normal_batch(const uint32_t (&w)[NB][4], const double2* __restrict__ tab,
+                              double scale, double (&z)[2 * NB]) {
+  double x[NB], zz[NB], r[NB], r2[NB], q[NB], L[NB], t[NB], t2[NB], sn[NB], cs[NB], rad[NB];
+  double2 tc[NB];
+  int kk[NB];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    x[b] = __hiloint2double((int)(0x43400000u | (w[b][0] >> 12)),
+                            (int)__funnelshift_r(w[b][1], w[b][0], 12)) - 9007199254740991.0;
+    t[b] = __hiloint2double((int)(0x3FF00000u | ((w[b][2] >> 9) & 0x000FFFFFu)),
+                            (int)__funnelshift_r(w[b][3], w[b][2], 9)) - 1.0;
+  }
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    const int xh = __double2hiint(x[b]);
+    const int tmp = xh - 0x3FE60000;
+    kk[b] = (tmp >> 20) - 53;
+    zz[b] = __hiloint2double(xh - (tmp & (int)0xFFF00000), __double2loint(x[b]));
+    tc[b] = tab[(tmp >> 13) & 127];
+  }
+#pragma unroll
+  for (int b = 0; b < NB; ++b) { r[b] = fma(zz[b], tc[b].x, -1.0); t2[b] = t[b] * t[b]; }
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    r2[b] = r[b] * r[b];
+    q[b] = fma(r[b], 1.0 / 3.0, -0.4);
+    L[b] = fma((double)kk[b], SDB_M2LN2, tc[b].y);
+    sn[b] = fma(t2[b], SDB_SIN6, SDB_SIN5);
+    cs[b] = fma(t2[b], SDB_COS6, SDB_COS5);
+  }
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    q[b] = fma(r[b], q[b], 0.5);
+    L[b] = fma(r[b], -2.0, L[b]);
+    sn[b] = fma(t2[b], sn[b], SDB_SIN4);
+    cs[b] = fma(t2[b], cs[b], SDB_COS4);
+  }
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    q[b] = fma(r[b], q[b], -2.0 / 3.0);
+    sn[b] = fma(t2[b], sn[b], SDB_SIN3);
+    cs[b] = fma(t2[b], cs[b], SDB_COS3);
+  }
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    q[b] = fma(r[b], q[b], 1.0);
+    sn[b] = fma(t2[b], sn[b], SDB_SIN2);
+    cs[b] = fma(t2[b], cs[b], SDB_COS2);
+  }
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    L[b] = fma(r2[b], q[b], L[b]);  // -2 ln u1 > 0
+    sn[b] = fma(t2[b], sn[b], SDB_SIN1);
+    cs[b] = fma(t2[b], cs[b], SDB_COS1);
+  }
+  double y[NB], g[NB], hh[NB], e[NB];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    y[b] = sdb_rsqrt_approx(L[b]);
+    sn[b] = fma(t2[b], sn[b], SDB_SIN0);
+    cs[b] = fma(t2[b], cs[b], SDB_COS0);
+  }
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    g[b] = L[b] * y[b];
+    hh[b] = 0.5 * y[b];
+    sn[b] *= t[b];
+  }
+#pragma unroll
+  for (int b = 0; b < NB; ++b) e[b] = fma(-hh[b], g[b], 0.5);
+#pragma unroll
+  for (int b = 0; b < NB; ++b) g[b] = fma(g[b], e[b], g[b]);
+#pragma unroll
+  for (int b = 0; b < NB; ++b) rad[b] = fma(fma(-g[b], g[b], L[b]), hh[b], g[b]);
+  if (SCALED) {
+#pragma unroll
+    for (int b = 0; b < NB; ++b) rad[b] *= scale;
+  }
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    const bool swap = (w[b][2] >> 29) & 1u;
+    const double a0 = swap ? sn[b] : cs[b];
+    const double b0 = swap ? cs[b] : sn[b];
+    const uint32_t s0 = (w[b][2] << 1) & 0x80000000u;
+    const uint32_t s1 = w[b][2] & 0x80000000u;
+    const double p0 = rad[b] * a0, p1 = rad[b] * b0;
+    z[2 * b] = __hiloint2double(__double2hiint(p0) ^ (int)s0, __double2loint(p0));
+    z[2 * b + 1] = __hiloint2double(__double2hiint(p1) ^ (int)s1, __double2loint(p1));
+  }
 }
 
 template <int D, int M, int B_>
@@ -352,10 +480,24 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
   for (int n = 0; n < steps; ++n) {
     const double h = hs[n];
 
+#if SDB_FUSED_PARK_Y
+    // The state waits in the staging buffer (where P0 needs it anyway) while the noise is generated:
+    // 20 registers less across the register-hungry Levy loop.
+#pragma unroll
+    for (int l = 0; l < D; ++l) gbuf[l * 32 + (lane ^ sdb_swz(l))] = Y[l];
+    __syncwarp();
+#endif
     // ---- noise: dW (wiener.py:52), Levy areas (wiener.py:67-74, :102-105), one lane per path ------
     {
       const SdbStream st(pkey, path, (uint32_t)n, tab);
       double dW[M];
+#if SDB_FUSED_BATCH
+      {
+        uint32_t w[M / 2][4];
+        sdb_philox_batch<M / 2>(pkey, st.p_lo, st.p_hi, (uint32_t)n, 0u, w);
+        sdb_normal_batch<M / 2, true>(w, tab, rh_g, dW);
+      }
+#else
 #pragma unroll
       for (int s = 0; s < M / 2; ++s) {
         double z0, z1;
@@ -363,6 +505,11 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
         dW[2 * s] = rh_g * z0;
         dW[2 * s + 1] = rh_g * z1;
       }
+#endif
+#if SDB_FUSED_PARK_DW
+#pragma unroll
+      for (int j = 0; j < M; ++j) sW[j * 32] = dW[j];
+#endif
       constexpr int KU = SDB_FUSED_KUNROLL;
       double At[MM];
 #pragma unroll
@@ -372,6 +519,23 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
         double X[M], Z[M];
         const uint32_t sx = (uint32_t)((M + 2 * (k - 1) * M) >> 1);
         const double hk = s_hk[k];
+#if SDB_FUSED_BATCH
+        {
+          uint32_t w[M / 2][4];
+          sdb_philox_batch<M / 2>(pkey, st.p_lo, st.p_hi, (uint32_t)n, sx, w);
+          sdb_normal_batch<M / 2, true>(w, tab, hk, X);
+          sdb_philox_batch<M / 2>(pkey, st.p_lo, st.p_hi, (uint32_t)n, sx + M / 2, w);
+          sdb_normal_batch<M / 2, false>(w, tab, 1.0, Z);
+        }
+#pragma unroll
+        for (int j = 0; j < M; ++j) {
+#if SDB_FUSED_PARK_DW
+          Z[j] = fma(cz, ((const volatile double*)sW)[j * 32], Z[j]);
+#else
+          Z[j] = fma(cz, dW[j], Z[j]);
+#endif
+        }
+#else
 #pragma unroll
         for (int s = 0; s < M / 2; ++s) {
           double z0, z1;
@@ -383,9 +547,15 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
         for (int s = 0; s < M / 2; ++s) {
           double z0, z1;
           st.pair(sx + M / 2 + s, z0, z1);
+#if SDB_FUSED_PARK_DW
+          Z[2 * s] = fma(cz, ((const volatile double*)sW)[2 * s * 32], z0);
+          Z[2 * s + 1] = fma(cz, ((const volatile double*)sW)[(2 * s + 1) * 32], z1);
+#else
           Z[2 * s] = fma(cz, dW[2 * s], z0);
           Z[2 * s + 1] = fma(cz, dW[2 * s + 1], z1);
+#endif
         }
+#endif
 #pragma unroll
         for (int i = 0; i < M; ++i)
 #pragma unroll
@@ -397,15 +567,22 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
       }
 #pragma unroll
       for (int r = 0; r < MM; ++r) sA[r * NT] = At[r];
+#if !SDB_FUSED_PARK_DW
 #pragma unroll
       for (int j = 0; j < M; ++j) sW[j * 32] = dW[j];
+#endif
     }
 
     // ---- P0: Y -> DMMA B-fragments Yf[lt][pt] = Y[4 lt + fc][path 8 pt + fr] ---------------------
     double Yf[LT][4];
+#if SDB_FUSED_PARK_Y
+#pragma unroll
+    for (int l = 0; l < D; ++l) Y[l] = gbuf[l * 32 + (lane ^ sdb_swz(l))];
+#else
 #pragma unroll
     for (int l = 0; l < D; ++l) gbuf[l * 32 + (lane ^ sdb_swz(l))] = Y[l];
     __syncwarp();
+#endif
 #pragma unroll
     for (int lt = 0; lt < LT; ++lt) {
       const int l = 4 * lt + fc;

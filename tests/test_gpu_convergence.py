@@ -1,0 +1,140 @@
+"""GPU tests of what the integrators are FOR: pathwise closeness to exact solutions (the
+reference's own acceptance tests, sdeint/tests/test_integrate.py:117-422, batched over an
+ensemble), strong convergence orders on KP (4.46), the weak (ensemble
+mean) check of the headline system, and invariance of a path to the way the ensemble is
+sharded over ranks."""
+import numpy as np
+import pytest
+
+from conftest import SYSTEMS
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sdb():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import sdeint_b200
+    sdeint_b200._lib.load()
+    return sdeint_b200
+
+
+def _assert_close(approx, exact, rel_tol, abs_tol):
+    """The acceptance rule of test_integrate.py:58-78: every point within rel_tol OR abs_tol."""
+    abs_err = np.abs(approx - exact)
+    rel_err = abs_err / np.maximum(np.abs(exact), 1e-300)
+    bad = (abs_err > abs_tol) & (rel_err > rel_tol)
+    assert not bad.any(), "worst abs %.3g rel %.3g" % (abs_err[bad].max(), rel_err[bad].max())
+
+
+def _kp4446_exact(y0, a, b, t, W):
+    e = (1 + y0) * np.exp(-2.0 * a * t + 2.0 * b * W)
+    return (e + y0 - 1.0) / (e + 1.0 - y0)
+
+
+def test_exact_solution_kp4446_ensemble(sdb):
+    """test_integrate.py:82-153 on 64 device-generated Brownian paths at the reference's h."""
+    a, b, y0, h, P = 1.0, 0.8, 0.1, 0.0004, 64
+    tspan = np.arange(0.0, 2.0, h)
+    N = len(tspan)
+    f_ito, G, _ = SYSTEMS["kp4446"](False)
+    f_str, _, _ = SYSTEMS["kp4446"](True)
+    dW = sdb.deltaW(N - 1, 1, h, paths=P, seed=11)                    # (P, N-1, 1)
+    _, I = sdb.Iwik(dW, h, seed=11, ensemble=True)
+    J = I + 0.5 * h
+    W = np.concatenate([np.zeros((P, 1)), np.cumsum(dW[:, :, 0], axis=1)], axis=1)
+    exact = _kp4446_exact(y0, a, b, tspan[None, :], W)
+    _assert_close(sdb.itoEuler(f_ito, G, y0, tspan, dW=dW)[:, :, 0], exact, 1e-1, 1e-1)
+    _assert_close(sdb.itoSRI2(f_ito, G, y0, tspan, dW=dW, I=I)[:, :, 0], exact, 1e-2, 1e-2)
+    _assert_close(sdb.stratHeun(f_str, G, y0, tspan, dW=dW)[:, :, 0], exact, 1e-2, 1e-2)
+    _assert_close(sdb.stratSRS2(f_str, G, y0, tspan, dW=dW, J=J)[:, :, 0], exact, 1e-2, 1e-2)
+    _assert_close(sdb.stratKP2iS(f_str, G, y0, tspan, dW=dW, J=J)[:, :, 0], exact, 1e-1, 1e-1)
+
+
+def test_exact_solution_kp4459_ensemble(sdb):
+    """test_integrate.py:170-252: d=1, m=2 multiplicative (commutative) noise."""
+    a, b1, b2, h, P = -0.02, 1.0, 2.0, 0.0004, 32
+    tspan = np.arange(0.0, 1.0, h)
+    N = len(tspan)
+    f_ito, G, y0 = SYSTEMS["kp4459"](False)
+    f_str, _, _ = SYSTEMS["kp4459"](True)
+    dW = sdb.deltaW(N - 1, 2, h, paths=P, seed=12)
+    _, I = sdb.Iwik(dW, h, seed=12, ensemble=True)
+    J = I + 0.5 * h * np.eye(2)[None, None]
+    W = np.concatenate([np.zeros((P, 1, 2)), np.cumsum(dW, axis=1)], axis=1)
+    exact = float(y0[0]) * np.exp((a - (b1 ** 2 + b2 ** 2) / 2.0) * tspan[None, :]
+                                  + b1 * W[:, :, 0] + b2 * W[:, :, 1])
+    _assert_close(sdb.itoSRI2(f_ito, G, y0, tspan, dW=dW, I=I)[:, :, 0], exact, 1e-2, 1e-2)
+    _assert_close(sdb.stratSRS2(f_str, G, y0, tspan, dW=dW, J=J)[:, :, 0], exact, 1e-2, 1e-2)
+    _assert_close(sdb.stratHeun(f_str, G, y0, tspan, dW=dW)[:, :, 0], exact, 1e-1, 1e-1)
+
+
+def test_strong_orders_kp4446(sdb):
+    """E|y_T - y_exact| over h = 2^-5 .. 2^-9 on Brownian paths coarsened from 2^-12
+    (I = (dW^2 - h)/2 is exact for m = 1).  The reference delivers slopes 0.53 (itoEuler),
+    1.00 (stratHeun), 0.98 (itoSRI2), 1.00 (stratSRS2) [SURVEY.md A.7]."""
+    a, b, y0, T, P = 1.0, 0.8, 0.1, 1.0, 2000
+    fine = 12
+    hf = 2.0 ** -fine
+    dWf = sdb.deltaW(2 ** fine, 1, hf, paths=P, seed=2026)[:, :, 0]    # (P, 4096)
+    WT = dWf.sum(axis=1)
+    exact = _kp4446_exact(y0, a, b, T, WT)
+    f_ito, G, _ = SYSTEMS["kp4446"](False)
+    f_str, _, _ = SYSTEMS["kp4446"](True)
+    levels = [5, 6, 7, 8, 9]
+    errs = {k: [] for k in ("itoEuler", "stratHeun", "itoSRI2", "stratSRS2")}
+    for lv in levels:
+        n = 2 ** lv
+        h = T / n
+        dW = dWf.reshape(P, n, -1).sum(axis=2)[:, :, None]              # (P, n, 1)
+        I = (0.5 * (dW[:, :, 0] ** 2 - h))[:, :, None, None]
+        J = I + 0.5 * h
+        tspan = np.linspace(0.0, T, n + 1)
+        ends = {
+            "itoEuler": sdb.itoEuler(f_ito, G, y0, tspan, dW=dW)[:, -1, 0],
+            "stratHeun": sdb.stratHeun(f_str, G, y0, tspan, dW=dW)[:, -1, 0],
+            "itoSRI2": sdb.itoSRI2(f_ito, G, y0, tspan, dW=dW, I=I)[:, -1, 0],
+            "stratSRS2": sdb.stratSRS2(f_str, G, y0, tspan, dW=dW, J=J)[:, -1, 0],
+        }
+        for k, v in ends.items():
+            errs[k].append(np.mean(np.abs(v - exact)))
+    x = np.log2([T / 2 ** lv for lv in levels])
+    slopes = {k: np.polyfit(x, np.log2(v), 1)[0] for k, v in errs.items()}
+    assert 0.35 <= slopes["itoEuler"] <= 0.7, slopes
+    for k in ("stratHeun", "itoSRI2", "stratSRS2"):
+        assert 0.85 <= slopes[k] <= 1.15, slopes
+    # absolute level at h = 2^-9 (6.2e-3, 5.7e-4, 5.8e-4, 5.9e-4)
+    assert errs["itoEuler"][-1] < 1.2e-2 and errs["itoSRI2"][-1] < 1.2e-3
+
+
+def test_weak_mean_of_headline_system(sdb):
+    """Ito SYS_LIN(10,10): E y(T) = expm(A T) y0.  2e5 device-noise paths, fused
+    kernel; the statistical error of the mean is ~ 1e-3 sd / sqrt(P)."""
+    from scipy.linalg import expm
+    f, G, y0 = SYSTEMS["lin10"](False)
+    T, n, P = 0.5, 100, 200000
+    tspan = np.linspace(0.0, T, n + 1)
+    y = sdb.itoSRI2(f, G, y0, tspan, paths=P, seed=7, save_every=n, out="torch")  # (2, d, P)
+    sums, _ = sdb.ensemble.moments(y)
+    mean, var = sdb.ensemble.mean_var(sums, float(P))
+    mean, var = mean[-1].cpu().numpy(), var[-1].cpu().numpy()
+    want = expm(f.A * T).dot(y0)
+    tol = 5.0 * np.sqrt(var / P) + 2e-4
+    assert np.all(np.abs(mean - want) <= tol), (mean - want, tol)
+    assert np.all(var > 0)
+
+
+def test_paths_do_not_depend_on_sharding(sdb):
+    """Rank invariance: path p of the ensemble is bit-identical whether it is
+    integrated in one launch or as part of a shard with a path_id0 offset."""
+    f, G, y0 = SYSTEMS["lin10"](False)
+    tspan = np.linspace(0.0, 0.1, 41)
+    whole = sdb.itoSRI2(f, G, y0, tspan, paths=96, seed=99, save_every=8)
+    for rank, world in ((0, 2), (1, 2), (2, 3)):
+        start, count = sdb.ensemble.shard_paths(96, rank, world)
+        part = sdb.itoSRI2(f, G, y0, tspan, paths=count, seed=99, path_id0=start, save_every=8)
+        assert np.array_equal(part, whole[start:start + count])
+    # and a different seed gives different paths
+    other = sdb.itoSRI2(f, G, y0, tspan, paths=4, seed=100, save_every=8)
+    assert not np.array_equal(other, whole[:4])
