@@ -45,7 +45,10 @@
 #define SDB_FUSED_VOL_SMEM 1  // 1: volatile shared-memory reads in P2, 0: plain reads between __syncwarp()s
 #endif
 #ifndef SDB_FUSED_BATCH
-#define SDB_FUSED_BATCH 0  // 1: Philox + normal transform of M/2 pairs in lock-step (explicit ILP)
+#define SDB_FUSED_BATCH 1  // 1: Philox + normal transform of M/2 pairs in lock-step (explicit ILP)
+#endif
+#ifndef SDB_FUSED_RB
+#define SDB_FUSED_RB 4  // state rows per block of the P1/P2/P3 pipeline
 #endif
 #ifndef SDB_FUSED_PARK_Y
 #define SDB_FUSED_PARK_Y 0  // 1: the state waits in shared memory while the noise is generated
@@ -59,10 +62,20 @@
 #define SDB_SMEM_CV const
 #endif
 
+// Everything below depends on the tuning macros, so each variant's translation unit gets its own
+// namespace (host inline templates with identical names would otherwise be merged by the linker).
+#ifndef SDB_FUSED_VARIANT
+#define SDB_FUSED_VARIANT 0
+#endif
+#define SDB_FUSED_NS2(v) sdb_fused_v##v
+#define SDB_FUSED_NS1(v) SDB_FUSED_NS2(v)
+#define SDB_FUSED_NS SDB_FUSED_NS1(SDB_FUSED_VARIANT)
+namespace SDB_FUSED_NS {
+
 template <int D, int M>
 struct SdbFusedShape {
   static constexpr int MM = M * (M - 1) / 2;
-  static constexpr int RB = 4;                        // rows per block
+  static constexpr int RB = (SDB_FUSED_RB > 0 && D > SDB_FUSED_RB) ? SDB_FUSED_RB : 4;  // rows per block
   static constexpr int NB = (D + RB - 1) / RB;        // row blocks
   static constexpr int LT = (D + 3) / 4;              // k-tiles over the state index l
   static constexpr int IT = D / 8;                    // 8-row tiles of the stage-2 sum done by DMMA
@@ -650,6 +663,9 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
   if (active) sdb_finish<D>(a, p, Y);
 }
 
+}  // namespace SDB_FUSED_NS
+using namespace SDB_FUSED_NS;
+
 #define SDB_FUSED_KERNEL(NAME, D, M)                                                          \
   extern "C" __global__ void __launch_bounds__(SDB_FUSED_THREADS, 1)                          \
       NAME(const __grid_constant__ SdbLoopArgs a, const __grid_constant__ PInline<D * D> fp,  \
@@ -658,3 +674,7 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
     sdb_srk2_fused_linear_body<D, M>(a, fp, frag, sdb_fused_smem);                            \
   }
 #endif  // __CUDACC__
+#ifndef __CUDACC__
+}  // namespace SDB_FUSED_NS
+using namespace SDB_FUSED_NS;
+#endif
