@@ -47,6 +47,12 @@
 #ifndef SDB_FUSED_BATCH
 #define SDB_FUSED_BATCH 1  // 1: Philox + normal transform of M/2 pairs in lock-step (explicit ILP)
 #endif
+#ifndef SDB_FUSED_BATCH_ORDER
+#define SDB_FUSED_BATCH_ORDER 0  // 1: angle polynomials before the table-dependent log part
+#endif
+#ifndef SDB_FUSED_BATCH_XZ
+#define SDB_FUSED_BATCH_XZ 0  // 1: X_k and Y_k pairs of one series term in ONE lock-step batch of M
+#endif
 #ifndef SDB_FUSED_RB
 #define SDB_FUSED_RB 4  // state rows per block of the P1/P2/P3 pipeline
 #endif
@@ -222,6 +228,7 @@ SDB_DEV void sdb_normal_batch(const uint32_t (&w)[NB][4], const double2* __restr
     zz[b] = __hiloint2double(xh - (tmp & (int)0xFFF00000), __double2loint(x[b]));
     tc[b] = tab[(tmp >> 13) & 127];
   }
+#if SDB_FUSED_BATCH_ORDER == 0
 #pragma unroll
   for (int b = 0; b < NB; ++b) { r[b] = fma(zz[b], tc[b].x, -1.0); t2[b] = t[b] * t[b]; }
 #pragma unroll
@@ -257,6 +264,55 @@ SDB_DEV void sdb_normal_batch(const uint32_t (&w)[NB][4], const double2* __restr
     sn[b] = fma(t2[b], sn[b], SDB_SIN1);
     cs[b] = fma(t2[b], cs[b], SDB_COS1);
   }
+#else
+  // the angle polynomials first: they do not need the table entry, so they cover its latency
+#pragma unroll
+  for (int b = 0; b < NB; ++b) t2[b] = t[b] * t[b];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    sn[b] = fma(t2[b], SDB_SIN6, SDB_SIN5);
+    cs[b] = fma(t2[b], SDB_COS6, SDB_COS5);
+  }
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    sn[b] = fma(t2[b], sn[b], SDB_SIN4);
+    cs[b] = fma(t2[b], cs[b], SDB_COS4);
+  }
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    sn[b] = fma(t2[b], sn[b], SDB_SIN3);
+    cs[b] = fma(t2[b], cs[b], SDB_COS3);
+  }
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    sn[b] = fma(t2[b], sn[b], SDB_SIN2);
+    cs[b] = fma(t2[b], cs[b], SDB_COS2);
+  }
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    sn[b] = fma(t2[b], sn[b], SDB_SIN1);
+    cs[b] = fma(t2[b], cs[b], SDB_COS1);
+  }
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    r[b] = fma(zz[b], tc[b].x, -1.0);
+    L[b] = fma((double)kk[b], SDB_M2LN2, tc[b].y);
+  }
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    r2[b] = r[b] * r[b];
+    q[b] = fma(r[b], 1.0 / 3.0, -0.4);
+    L[b] = fma(r[b], -2.0, L[b]);
+  }
+#pragma unroll
+  for (int b = 0; b < NB; ++b) q[b] = fma(r[b], q[b], 0.5);
+#pragma unroll
+  for (int b = 0; b < NB; ++b) q[b] = fma(r[b], q[b], -2.0 / 3.0);
+#pragma unroll
+  for (int b = 0; b < NB; ++b) q[b] = fma(r[b], q[b], 1.0);
+#pragma unroll
+  for (int b = 0; b < NB; ++b) L[b] = fma(r2[b], q[b], L[b]);  // -2 ln u1 > 0
+#endif
   double y[NB], g[NB], hh[NB], e[NB];
 #pragma unroll
   for (int b = 0; b < NB; ++b) {
@@ -533,6 +589,19 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
         const uint32_t sx = (uint32_t)((M + 2 * (k - 1) * M) >> 1);
         const double hk = s_hk[k];
 #if SDB_FUSED_BATCH
+#if SDB_FUSED_BATCH_XZ
+        {
+          uint32_t w[M][4];
+          double xz[2 * M];
+          sdb_philox_batch<M>(pkey, st.p_lo, st.p_hi, (uint32_t)n, sx, w);
+          sdb_normal_batch<M, false>(w, tab, 1.0, xz);
+#pragma unroll
+          for (int j = 0; j < M; ++j) {
+            X[j] = hk * xz[j];
+            Z[j] = xz[M + j];
+          }
+        }
+#else
         {
           uint32_t w[M / 2][4];
           sdb_philox_batch<M / 2>(pkey, st.p_lo, st.p_hi, (uint32_t)n, sx, w);
@@ -540,6 +609,7 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
           sdb_philox_batch<M / 2>(pkey, st.p_lo, st.p_hi, (uint32_t)n, sx + M / 2, w);
           sdb_normal_batch<M / 2, false>(w, tab, 1.0, Z);
         }
+#endif
 #pragma unroll
         for (int j = 0; j < M; ++j) {
 #if SDB_FUSED_PARK_DW
