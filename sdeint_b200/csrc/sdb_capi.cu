@@ -411,8 +411,9 @@ extern "C" int sdb_integrate(sdb_system* s, const sdb_integrate_args* a) {
     args[1] = (void*)s->fp.data();
     args[2] = (void*)&s->d_frag;
   }
-  const unsigned block = fused ? SDB_FUSED_THREADS : SDB_BLOCK;
-  const unsigned grid = (unsigned)((a->paths + block - 1) / block);
+  const unsigned block = fused ? (unsigned)fused->threads : SDB_BLOCK;
+  const int64_t per_block = fused ? fused->paths_per_block : SDB_BLOCK;
+  const unsigned grid = (unsigned)((a->paths + per_block - 1) / per_block);
   if (launch(fn, dim3(grid), dim3(block), args, st, fused ? fused->smem : 0)) return 1;
   SDB_CUDA(cudaFreeAsync(d_aux, st));
   return 0;

@@ -33,6 +33,8 @@ struct SdbFusedEntry {
   size_t smem;                 // dynamic shared memory
   size_t table_doubles;        // size of the DMMA fragment table built from (A, B)
   void (*build)(const double* A, const double* B, double* out);
+  int threads;                 // block size
+  int paths_per_block;         // sample paths integrated by one block
 };
 std::vector<SdbFusedEntry>& sdb_fused_registry();
 struct SdbFusedRegistrar {
