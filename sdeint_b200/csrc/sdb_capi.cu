@@ -167,7 +167,7 @@ struct sdb_system {
   std::string src;           // user CUDA source (may be empty)
   double* d_fp = nullptr;    // device copies (PGlobal mode / user operators)
   double* d_gp = nullptr;
-  double* d_frag = nullptr;  // fused kernel: DMMA fragment tables
+  std::map<const void*, double*> d_frags;  // fused kernels: DMMA fragment tables, per kernel
   bool inline_params = true;
   std::map<std::string, JitKernel> jit;
   std::mutex mu;
@@ -252,7 +252,7 @@ extern "C" int sdb_system_destroy(sdb_system* s) {
     if (kv.second.lib) cudaLibraryUnload(kv.second.lib);
   if (s->d_fp) cudaFree(s->d_fp);
   if (s->d_gp) cudaFree(s->d_gp);
-  if (s->d_frag) cudaFree(s->d_frag);
+  for (auto& kv : s->d_frags) cudaFree(kv.second);
   delete s;
   return 0;
 }
@@ -337,29 +337,35 @@ extern "C" int sdb_integrate(sdb_system* s, const sdb_integrate_args* a) {
 
   int noise = a->noise;
   if (!need_ij && noise == SDB_NOISE_WIK) noise = SDB_NOISE_KPW;  // only dW is drawn
-  // The production path: linear system, SRI2/SRS2, Philox + Ikpw/Jkpw -> fused kernel.
+  // The production path: linear system, SRI2/SRS2, on-device Philox + Ikpw/Jkpw (or Iwik/Jwik)
+  // -> a fused kernel when one is instantiated for this (d, m, method).
   const SdbFusedEntry* fused = nullptr;
-  if (a->scheme == SDB_SCHEME_SRK2 && noise == SDB_NOISE_KPW && s->fk == SDB_DRIFT_LINEAR &&
+  if (a->scheme == SDB_SCHEME_SRK2 && noise != SDB_NOISE_HOST && s->fk == SDB_DRIFT_LINEAR &&
       s->gk == SDB_DIFF_LINEAR_COLS && a->n_terms <= SDB_FUSED_MAX_TERMS &&
       !getenv("SDB_DISABLE_FUSED")) {
     const char* vs = getenv("SDB_FUSED_VARIANT");
     const int want = vs ? atoi(vs) : 0;
     for (const auto& e : sdb_fused_registry())
-      if (e.d == s->d && e.m == s->m && (e.variant == want || (!fused && e.variant == 0))) fused = &e;
+      if (e.d == s->d && e.m == s->m && e.noise == noise &&
+          (e.variant == want || (!fused && e.variant == 0)))
+        fused = &e;
   }
   const void* fn = nullptr;
+  double* d_frag = nullptr;
   if (fused) {
     fn = fused->fn;
     std::lock_guard<std::mutex> lk(s->mu);
-    SDB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused->smem));
-    if (!s->d_frag) {  // DMMA fragment tables of (A, B_k), built once per system
+    auto it = s->d_frags.find(fn);
+    if (it == s->d_frags.end()) {  // DMMA fragment tables of (A, B_k), built once per system and kernel
+      SDB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused->smem));
       std::vector<double> tab(fused->table_doubles);
       fused->build(s->fp.data(), s->gp.data(), tab.data());
-      SDB_CUDA(cudaMalloc(&s->d_frag, tab.size() * sizeof(double)));
-      SDB_CUDA(cudaMemcpy(s->d_frag, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
-      SDB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)fused->smem));
+      double* d = nullptr;
+      SDB_CUDA(cudaMalloc(&d, tab.size() * sizeof(double)));
+      SDB_CUDA(cudaMemcpy(d, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+      it = s->d_frags.emplace(fn, d).first;
     }
+    d_frag = it->second;
   } else if (loop_kernel(s, a->scheme, noise, &fn)) {
     return 1;
   }
@@ -409,7 +415,7 @@ extern "C" int sdb_integrate(sdb_system* s, const sdb_integrate_args* a) {
   args[2] = s->inline_params ? (void*)s->gp.data() : (void*)&gg;
   if (fused) {
     args[1] = (void*)s->fp.data();
-    args[2] = (void*)&s->d_frag;
+    args[2] = (void*)&d_frag;
   }
   const unsigned block = fused ? (unsigned)fused->threads : SDB_BLOCK;
   const int64_t per_block = fused ? fused->paths_per_block : SDB_BLOCK;

@@ -35,6 +35,7 @@ struct SdbFusedEntry {
   void (*build)(const double* A, const double* B, double* out);
   int threads;                 // block size
   int paths_per_block;         // sample paths integrated by one block
+  int noise;                   // SDB_NOISE_KPW or SDB_NOISE_WIK: which repeated integrals it builds
 };
 std::vector<SdbFusedEntry>& sdb_fused_registry();
 struct SdbFusedRegistrar {

@@ -385,12 +385,24 @@ SDB_DEV void sdb_assemble_IJ(const double (&dW)[M], double h, const double (&At)
   }
 }
 
+// Levy areas only (series + optional Wiktorsson tail), K_m row order; At[0] = 0 for M == 1.
+template <int M, class NS>
+SDB_DEV void sdb_levy_areas(const double (&dW)[M], double h, int n_terms, int method, const NS& ns,
+                            double (&At)[M * (M - 1) / 2 + 1]) {
+  if (M == 1) {
+    At[0] = 0.0;
+    return;
+  }
+  sdb_levy_series<M>(dW, h, n_terms, ns, At);
+  if (method == SDB_NOISE_WIK) sdb_wik_tail<M>(dW, h, n_terms, ns, At);
+}
+
 template <int M, class NS>
 SDB_DEV void sdb_repeated_integrals(const double (&dW)[M], double h, int n_terms, int method,
                                     bool strat, const NS& ns, double (&At)[M * (M - 1) / 2 + 1],
                                     double (&IJ)[M][M]) {
+  sdb_levy_areas<M>(dW, h, n_terms, method, ns, At);
   if (M == 1) {
-    At[0] = 0.0;
     if (method == SDB_NOISE_KPW) {  // Ikpw still draws its 2n normals; A == 0
       IJ[0][0] = strat ? 0.5 * dW[0] * dW[0] : 0.5 * (dW[0] * dW[0] - h);
     } else {                         // Iwik shortcut, wiener.py:259-260
@@ -398,8 +410,6 @@ SDB_DEV void sdb_repeated_integrals(const double (&dW)[M], double h, int n_terms
     }
     return;
   }
-  sdb_levy_series<M>(dW, h, n_terms, ns, At);
-  if (method == SDB_NOISE_WIK) sdb_wik_tail<M>(dW, h, n_terms, ns, At);
   sdb_assemble_IJ<M>(dW, h, At, method == SDB_NOISE_WIK, strat, IJ);
 }
 
@@ -869,26 +879,25 @@ SDB_DEV void sdb_repint_body(const SdbRepintArgs& a) {
 #pragma unroll
   for (int j = 0; j < M; ++j) dW[j] = w[j * a.dW_sJ];
   double At[MM + 1];
-  double IJ[M][M];
   if (a.X != nullptr) {
     const SdbNormalsHost<M> ns{a.X + n * a.XY_sN + p * a.XY_sP, a.Y + n * a.XY_sN + p * a.XY_sP,
                                a.XY_sT, a.XY_sJ,
                                a.Gt ? a.Gt + n * a.Gt_sN + p * a.Gt_sP : nullptr, a.Gt_sR};
-    sdb_repeated_integrals<M>(dW, a.h, a.n_terms, a.method, a.stratonovich != 0, ns, At, IJ);
+    sdb_levy_areas<M>(dW, a.h, a.n_terms, a.method, ns, At);
   } else {
     const SdbPhiloxKey key(a.seed);
     const SdbStream st(key, (uint64_t)(a.path_id0 + p), (uint32_t)n);
     const SdbNormalsPhilox<M> ns{st, a.n_terms};
-    sdb_repeated_integrals<M>(dW, a.h, a.n_terms, a.method, a.stratonovich != 0, ns, At, IJ);
+    sdb_levy_areas<M>(dW, a.h, a.n_terms, a.method, ns, At);
   }
   if (a.A != nullptr) {
     double* o = a.A + n * a.A_sN + p * a.A_sP;
     if (a.method == SDB_NOISE_KPW) {  // full antisymmetric m x m matrix A
       int r = 0;
-#pragma unroll
+#pragma unroll 1
       for (int i = 0; i < M; ++i) {
         o[(i * M + i) * a.A_sE] = 0.0;
-#pragma unroll
+#pragma unroll 1
         for (int j = i + 1; j < M; ++j) {
           o[(i * M + j) * a.A_sE] = At[r];
           o[(j * M + i) * a.A_sE] = -At[r];
@@ -900,11 +909,29 @@ SDB_DEV void sdb_repint_body(const SdbRepintArgs& a) {
       for (int r = 0; r < (MM > 0 ? MM : 1); ++r) o[r * a.A_sE] = At[r];
     }
   }
+  // I (or J) assembled entry by entry from dW and the areas (no m x m temporary): KPW places +A
+  // above the diagonal (wiener.py:106), Wiktorsson's column-major unvec below (wiener.py:278-280).
   double* q = a.IJ + n * a.IJ_sN + p * a.IJ_sP;
-#pragma unroll
-  for (int i = 0; i < M; ++i)
-#pragma unroll
-    for (int j = 0; j < M; ++j) q[i * a.IJ_sR + j * a.IJ_sC] = IJ[i][j];
+  const bool strat = a.stratonovich != 0;
+  const double sg = a.method == SDB_NOISE_WIK ? -1.0 : 1.0;
+  int r = 0;
+#pragma unroll 1
+  for (int i = 0; i < M; ++i) {
+    double dii;
+    if (M == 1 && a.method == SDB_NOISE_WIK)  // Iwik shortcut, wiener.py:259-260
+      dii = strat ? (dW[i] * dW[i] - a.h) / 2.0 + 0.5 * a.h : (dW[i] * dW[i] - a.h) / 2.0;
+    else
+      dii = strat ? 0.5 * dW[i] * dW[i] : 0.5 * (dW[i] * dW[i] - a.h);
+    q[i * a.IJ_sR + i * a.IJ_sC] = dii;
+#pragma unroll 1
+    for (int j = i + 1; j < M; ++j) {
+      const double sym = 0.5 * dW[i] * dW[j];
+      const double av = sg * At[r];
+      q[i * a.IJ_sR + j * a.IJ_sC] = sym + av;
+      q[j * a.IJ_sR + i * a.IJ_sC] = sym - av;
+      ++r;
+    }
+  }
 }
 
 #define SDB_REPINT_KERNEL(NAME, M)                                                   \

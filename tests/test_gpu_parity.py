@@ -392,3 +392,54 @@ def test_fused_dmma_kernel_shapes(sdb, d, m, strat, monkeypatch):
     for p in (0, 31, 32, P - 1):
         ref = orc.srk2(f, G, y0p[p], tspan, dW[p], IJ[p])
         assert rel_err(y_fused[p], ref) <= TOL
+
+
+@pytest.mark.parametrize("variant", ["1", "10", "11"])
+def test_fused_tuning_variants_agree(sdb, variant, monkeypatch):
+    """The tuning variants of the headline kernel kept for A/B measurements -- pair-at-a-time
+    noise (1), warp-specialised with a tensor-memory ring (10), the same pipeline without helper
+    warps (11) -- integrate the same Philox streams: they must agree with the default kernel to
+    rounding and with the oracle to 1e-12."""
+    f, G, y0 = SYSTEMS["lin10"](False)
+    tspan = np.linspace(0.0, 0.25, 51)
+    h = 0.005
+    P, seed = 300, 777            # two blocks of the 256-path kernels, partial last warp
+    base = sdb.itoSRI2(f, G, y0, tspan, paths=P, seed=seed, save_every=5)
+    monkeypatch.setenv("SDB_FUSED_VARIANT", variant)
+    alt = sdb.itoSRI2(f, G, y0, tspan, paths=P, seed=seed, save_every=5)
+    alt_s = sdb.stratSRS2(f, G, y0, tspan, paths=P, seed=seed, save_every=5)
+    monkeypatch.delenv("SDB_FUSED_VARIANT")
+    base_s = sdb.stratSRS2(f, G, y0, tspan, paths=P, seed=seed, save_every=5)
+    assert rel_err(alt, base) <= TOL and rel_err(alt_s, base_s) <= TOL
+    dW = sdb.deltaW(50, 10, h, paths=P, seed=seed)
+    _, I = sdb.Ikpw(dW, h, seed=seed, ensemble=True)
+    for p in (0, 255, 256, P - 1):
+        ref = orc.srk2(f, G, y0, tspan, dW[p], I[p])
+        assert rel_err(alt[p], ref[::5]) <= TOL
+
+
+@pytest.mark.parametrize("strat,method", [(False, "kpw"), (True, "kpw"), (False, "wik"), (True, "wik")])
+def test_fused_tmem_kernel_d20(sdb, strat, method, monkeypatch):
+    """d = m = 20 (BASELINE configs[3]): the TMEM-resident fused kernel (sdb_fusedx.cuh: Levy areas
+    read-modify-written in tensor memory, two-pass Wiktorsson tail) against the generic loop kernel
+    and against the oracle on the noise the device generated."""
+    f, G, y0 = sdb.ops.sys_lin(20, 20)
+    tspan = np.linspace(0.0, 0.1, 21)
+    h = 0.005
+    P, seed = 70, 20262026
+    integ = sdb.stratSRS2 if strat else sdb.itoSRI2
+    rep = {(False, "kpw"): sdb.Ikpw, (False, "wik"): sdb.Iwik,
+           (True, "kpw"): sdb.Jkpw, (True, "wik"): sdb.Jwik}[(strat, method)]
+    y = integ(f, G, y0, tspan, rep, paths=P, seed=seed, path_id0=5)
+    assert y.shape == (P, 21, 20) and np.all(np.isfinite(y))
+    monkeypatch.setenv("SDB_DISABLE_FUSED", "1")
+    y_gen = integ(f, G, y0, tspan, rep, paths=P, seed=seed, path_id0=5)
+    monkeypatch.delenv("SDB_DISABLE_FUSED")
+    assert rel_err(y, y_gen) <= TOL
+    dW = sdb.deltaW(20, 20, h, paths=P, seed=seed, path_id0=5)
+    _, IJ = rep(dW, h, seed=seed, path_id0=5, ensemble=True)
+    for p in (0, 31, 32, P - 1):
+        ref = orc.srk2(f, G, y0, tspan, dW[p], IJ[p])
+        assert rel_err(y[p], ref) <= TOL
+    yd = integ(f, G, y0, tspan, rep, paths=P, seed=seed, path_id0=5, save_every=4)
+    assert np.array_equal(yd, y[:, ::4])
