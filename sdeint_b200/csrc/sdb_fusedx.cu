@@ -2,6 +2,7 @@
 // (BASELINE.json configs[3]) with Ikpw/Jkpw and Iwik/Jwik, and d = m = 10 with Iwik/Jwik.
 #define SDB_FUSED_VARIANT 20
 #define SDB_FUSED_RB 2
+#define SDB_FUSED_VOL_MMA 0   // one warp per sub-partition: let ptxas interleave the DMMA tiles
 #include "sdb_fusedx.cuh"
 #include "sdb_host.h"
 

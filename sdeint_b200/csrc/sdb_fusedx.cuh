@@ -210,24 +210,31 @@ SDB_DEV void sdb_srk2_fusedx_body(const SdbLoopArgs& a, const PInline<D * D>& fp
       const double c1 = den * (2.0 + 2.0 * rad);
       const double c2 = den * (2.0 / hg);
       const uint32_t st0 = (uint32_t)((M + 2 * n_terms * M) >> 1);
-      sdb_static_for<0, NCH>([&](auto cc) {
-        constexpr int c = decltype(cc)::value;
+      // pass 1: the generator code exists once (runtime loop); only the index-dependent FMAs of a
+      // chunk are selected by a warp-uniform jump (keeps the kernel inside the instruction cache)
+#pragma unroll 1
+      for (int c = 0; c < NCH; ++c) {
         double g[CH], At[CH];
         sdb_gen_pairs<CH / 2, 0, CH, false>(pkey, p_lo, p_hi, (uint32_t)n, st0 + (uint32_t)(c * CH / 2),
                                             tab, 1.0, g);
         sdb_tm_ld<CH>(tm + Xs::C_AT + 2 * CH * c, At);
-        sdb_static_for<0, CH>([&](auto ee) {
-          constexpr int e = decltype(ee)::value;
-          constexpr int idx = CH * c + e;
-          if constexpr (idx < MM) {
-            constexpr int i = sdb_pair_j<M>(idx), j = sdb_pair_k<M>(idx);
-            At[e] = fma(c1, g[e], At[e]);
-            u[i] = fma(g[e], dW[j], u[i]);
-            u[j] = fma(-g[e], dW[i], u[j]);
+        sdb_static_for<0, NCH>([&](auto cc) {
+          constexpr int c_ = decltype(cc)::value;
+          if (c == c_) {
+            sdb_static_for<0, CH>([&](auto ee) {
+              constexpr int e = decltype(ee)::value;
+              constexpr int idx = CH * c_ + e;
+              if constexpr (idx < MM) {
+                constexpr int i = sdb_pair_j<M>(idx), j = sdb_pair_k<M>(idx);
+                At[e] = fma(c1, g[e], At[e]);
+                u[i] = fma(g[e], dW[j], u[i]);
+                u[j] = fma(-g[e], dW[i], u[j]);
+              }
+            });
           }
         });
         sdb_tm_st<CH>(tm + Xs::C_AT + 2 * CH * c, At);
-      });
+      }
       sdb_tm_wait_st();
       sdb_static_for<0, NCH>([&](auto cc) {
         constexpr int c = decltype(cc)::value;
