@@ -295,7 +295,14 @@ def run_gpu(args):
                           "linear stage-2 collapse; normal transforms and Philox not counted",
             "frac_reference_form": (FLOPS_REFERENCE_FORM * path_steps / (ms_kernel * 1e-3) / 1e12
                                     / float(peak.value)),
-            "traffic": None,
+            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from one `ncu --set full`
+            # capture of a 10^6-path launch with the bench's tspan / save_every: 880.8 MB against
+            # 880.0 MB of algorithmic stores (profiles/r01_fused_v0_bench1e6_se100_ncu_summary.txt);
+            # the traffic is the decimated store and nothing else, so it scales with the paths.
+            "traffic": 880.82e6 * (P / 1e6),
+            "traffic_unit": "B per launch",
+            "traffic_source": "ncu --set full at 1e6 paths (37.7 MB read + 843.1 MB written), "
+                              "scaled linearly to this launch",
             "hbm": {"achieved": BYTES_PER_PATH_STEP * path_steps / (ms_kernel * 1e-3) / 1e9,
                     "peak": hbm_peak, "unit": "GB/s",
                     "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},

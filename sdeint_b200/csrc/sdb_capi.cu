@@ -326,7 +326,9 @@ extern "C" int sdb_integrate(sdb_system* s, const sdb_integrate_args* a) {
   if (a->paths < 1) return fail("sdb_integrate: need at least one path");
   if (a->save_every < 1) return fail("sdb_integrate: save_every must be >= 1");
   if (!a->h_tspan || !a->d_y0 || !a->d_y) return fail("sdb_integrate: NULL buffer");
-  const bool need_ij = a->scheme == SDB_SCHEME_SRK2 || a->scheme == SDB_SCHEME_KP2IS;
+  // additive noise never uses the repeated integrals (see NEED_IJ in sdb_kernels.cuh)
+  const bool need_ij = (a->scheme == SDB_SCHEME_SRK2 || a->scheme == SDB_SCHEME_KP2IS) &&
+                       s->gk != SDB_DIFF_CONST;
   if (a->noise == SDB_NOISE_HOST && (!a->d_dW || (need_ij && !a->d_IJ)))
     return fail("sdb_integrate: NOISE_HOST needs dW (and I/J for SRK2, KP2iS)");
   if (a->noise != SDB_NOISE_HOST && a->n_terms < 1)

@@ -451,8 +451,9 @@ struct DriftKPS445 {  // test_integrate.py:263-269
 };
 
 template <int D_, int M_, class PS>
-struct DiffConst {
+struct DiffConst {  // additive noise: G does not depend on y
   static constexpr int D = D_, M = M_;
+  static constexpr bool ADDITIVE = true;
   typedef PS Params;
   static SDB_DEV void col(const PS& p, int k, const double (&)[D], double, double (&out)[D]) {
 #pragma unroll
@@ -463,6 +464,7 @@ struct DiffConst {
 template <int D_, int M_, class PS>
 struct DiffLinearCols {  // g_k = B_k y
   static constexpr int D = D_, M = M_;
+  static constexpr bool ADDITIVE = false;
   typedef PS Params;
   static SDB_DEV void col(const PS& p, int k, const double (&y)[D], double, double (&out)[D]) {
 #pragma unroll
@@ -478,6 +480,7 @@ struct DiffLinearCols {  // g_k = B_k y
 template <class PS>
 struct DiffKP4446 {
   static constexpr int D = 1, M = 1;
+  static constexpr bool ADDITIVE = false;
   typedef PS Params;
   static SDB_DEV void col(const PS& p, int, const double (&y)[1], double, double (&out)[1]) {
     out[0] = p[0] * (1.0 - y[0] * y[0]);
@@ -487,6 +490,7 @@ struct DiffKP4446 {
 template <class PS>
 struct DiffKPS445 {
   static constexpr int D = 1, M = 1;
+  static constexpr bool ADDITIVE = false;
   typedef PS Params;
   static SDB_DEV void col(const PS& p, int, const double (&y)[1], double, double (&out)[1]) {
     const double c = cos(y[0]);
@@ -510,6 +514,7 @@ __device__ void sde_diffusion_col(int k, const double* y, double t, const double
 template <int D_, int M_, class PS>
 struct DiffUser {
   static constexpr int D = D_, M = M_;
+  static constexpr bool ADDITIVE = false;
   typedef PS Params;
   static SDB_DEV void col(const PS& p, int k, const double (&y)[D], double t, double (&out)[D]) {
     sde_diffusion_col(k, y, t, p.ptr(), out);
@@ -607,7 +612,12 @@ SDB_DEV void sdb_loop_body(const SdbLoopArgs& a, const typename F::Params& fp,
   constexpr int M = G::M;
   static_assert(F::D == G::D, "drift and diffusion disagree on d");
   constexpr bool SMALL = (D * M <= 36);
-  constexpr bool NEED_IJ = (SCHEME == SDB_SCHEME_SRK2 || SCHEME == SDB_SCHEME_KP2IS);
+  // Additive noise (G independent of y): the stage-2 differences g_k(H2) - g_k(H3) of SRK2 and the
+  // G(Ybar) - G_n of KP2iS are exactly zero, so the repeated integrals are never used and are neither
+  // generated nor read (bit-identical results; the first step of the reference's planned
+  // noise-structure dispatch, integrate.py:150-151, README.rst:130).
+  constexpr bool NEED_IJ =
+      (SCHEME == SDB_SCHEME_SRK2 || SCHEME == SDB_SCHEME_KP2IS) && !G::ADDITIVE;
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= a.P) return;
 
@@ -708,7 +718,7 @@ SDB_DEV void sdb_loop_body(const SdbLoopArgs& a, const typename F::Params& fp,
       }
       const double half_rh = 0.5 * rh;
 #pragma unroll(SMALL ? M : 1)
-      for (int k = 0; k < M; ++k) {
+      for (int k = 0; k < (NEED_IJ ? M : 0); ++k) {
         double up[D], dn[D], gu[D], gd[D];
 #pragma unroll
         for (int i = 0; i < D; ++i) {
@@ -745,7 +755,7 @@ SDB_DEV void sdb_loop_body(const SdbLoopArgs& a, const typename F::Params& fp,
         }
       }
 #pragma unroll 1
-      for (int j1 = 0; j1 < M; ++j1) {
+      for (int j1 = 0; j1 < (NEED_IJ ? M : 0); ++j1) {
         double yb[D];
 #pragma unroll
         for (int i = 0; i < D; ++i) yb[i] = fma(Gn[i][j1], rh, fma(f0[i], h, Y[i]));

@@ -161,7 +161,9 @@ def _run(scheme, f, G, y0, tspan, dW, IJ, strat, method, generator, kp2is, paths
     global _last_status
     (d, m, f, Gop, y0, tspan, dW, IJ) = _check_args(f, G, y0, tspan, dW, IJ)
     P, ensemble = _resolve_paths(paths, dW, IJ)
-    need_ij = scheme in (SCHEME_SRK2, SCHEME_KP2IS)
+    # additive noise (G independent of y): SRI2/SRS2/KP2iS never use the repeated integrals, so
+    # they are neither generated nor uploaded -- results are bit-identical (ops.ConstDiffusion)
+    need_ij = scheme in (SCHEME_SRK2, SCHEME_KP2IS) and Gop.kind != ops.DIFF_CONST
     N = len(tspan)
     save_every = int(save_every)
     if save_every < 1:

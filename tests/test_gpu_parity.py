@@ -443,3 +443,67 @@ def test_fused_tmem_kernel_d20(sdb, strat, method, monkeypatch):
         assert rel_err(y[p], ref) <= TOL
     yd = integ(f, G, y0, tspan, rep, paths=P, seed=seed, path_id0=5, save_every=4)
     assert np.array_equal(yd, y[:, ::4])
+
+
+def test_additive_noise_never_builds_repeated_integrals(sdb):
+    """Noise-structure dispatch, first case (integrate.py:150-151): for additive noise the stage-2
+    differences of SRI2/SRS2 and the G(Ybar) - G_n of KP2iS vanish identically, so I / J are neither
+    generated nor read -- and the results stay those of the reference."""
+    g = load_golden("integrate_lin2.npz")
+    f, G, y0 = SYSTEMS["lin2"](False)
+    tspan, dW, I, J = g["tspan"], g["dW"], g["I"], g["J"]
+    with_I = sdb.itoSRI2(f, G, y0, tspan, dW=dW, I=I)
+    n0 = sdb.launch_count()
+    without_I = sdb.itoSRI2(f, G, y0, tspan, dW=dW)
+    assert sdb.launch_count() - n0 == 2            # status init + the step loop: no repint kernel
+    assert np.array_equal(with_I, without_I)
+    assert rel_err(without_I, g["y_itoSRI2"]) <= TOL
+    assert rel_err(sdb.stratSRS2(f, G, y0, tspan, dW=dW), g["y_stratSRS2"]) <= TOL
+    if "y_stratKP2iS" in g:
+        assert rel_err(sdb.stratKP2iS(f, G, y0, tspan, dW=dW, rtol=1e-12), g["y_stratKP2iS"]) <= 1e-10
+    # on-device noise: only dW is drawn; any I gives the same oracle result
+    P, seed = 50, 606
+    y = sdb.itoSRI2(f, G, y0, tspan, paths=P, seed=seed)
+    h = (tspan[-1] - tspan[0]) / (len(tspan) - 1)
+    dWd = sdb.deltaW(len(tspan) - 1, 2, h, paths=P, seed=seed)
+    for p in (0, P - 1):
+        ref = orc.srk2(f, G, y0, tspan, dWd[p], np.zeros((len(tspan) - 1, 2, 2)))
+        assert rel_err(y[p], ref) <= TOL
+
+
+# ---- edge cases of the ensemble interface ---------------------------------------------------------
+
+@pytest.mark.parametrize("name", ["lin10", "r74", "lin2", "kp4446"])
+def test_edge_shapes(sdb, name):
+    """One step, one path, decimation that does not divide N-1 or exceeds it, path ids and seeds
+    beyond 32 bits, non-default series lengths: fused and generic kernels alike."""
+    f, G, y0 = SYSTEMS[name](False)
+    y0v = np.atleast_1d(np.asarray(y0, dtype=float))
+    m, d = G.m, len(y0v)
+    big_id, big_seed = (1 << 40) + 12345, (1 << 63) + 987654321
+    # N = 2: a single step, a single path
+    t2 = np.array([0.0, 0.01])
+    y = sdb.itoSRI2(f, G, y0, t2, paths=1, seed=big_seed, path_id0=big_id)
+    assert y.shape == (1, 2, d) and np.array_equal(y[0, 0], y0v)
+    dW = sdb.deltaW(1, m, 0.01, paths=1, seed=big_seed, path_id0=big_id)
+    _, I = sdb.Ikpw(dW, 0.01, seed=big_seed, path_id0=big_id, ensemble=True)
+    assert rel_err(y[0], orc.srk2(f, G, y0v, t2, dW[0], I[0])) <= TOL
+    # the high word of the path id matters
+    y_lo = sdb.itoSRI2(f, G, y0, t2, paths=1, seed=big_seed, path_id0=12345)
+    assert not np.array_equal(y_lo, y)
+    # save_every that does not divide N-1 / is larger than N-1
+    tspan = np.linspace(0.0, 0.17, 18)
+    full = sdb.itoSRI2(f, G, y0, tspan, paths=33, seed=5)
+    part = sdb.itoSRI2(f, G, y0, tspan, paths=33, seed=5, save_every=5)
+    assert part.shape == (33, 4, d) and np.array_equal(part, full[:, ::5])
+    only0 = sdb.itoSRI2(f, G, y0, tspan, paths=33, seed=5, save_every=100)
+    assert only0.shape == (33, 1, d) and np.array_equal(only0[:, 0], full[:, 0])
+    # series length n != 5 (Ikpw(dW, h, n)): the integrators use the default n = 5 like the
+    # reference; the standalone constructions take any n >= 1
+    h = 0.01
+    dW1 = sdb.deltaW(17, m, h, paths=2, seed=9)
+    for n in (1, 8):
+        A, I = sdb.Ikpw(dW1, h, n=n, seed=9, ensemble=True)
+        X, Y = po.kpw_normals(17, m, n, 2, 9)
+        _, I_o = orc.ikpw_from_normals(dW1[1], h, X[:, 1], Y[:, 1])
+        assert np.max(np.abs(I[1] - I_o)) <= 1e-12 * max(np.max(np.abs(I_o)), 1e-300)

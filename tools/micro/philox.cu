@@ -29,8 +29,11 @@ __global__ void k_philox(int iters, uint32_t k0, uint32_t k1, double a, double b
         if (MODE == 0) {
           const uint64_t p0 = (uint64_t)M0 * c0[q], p1 = (uint64_t)M1 * c2[q];
           h0 = (uint32_t)(p0 >> 32); l0 = (uint32_t)p0; h1 = (uint32_t)(p1 >> 32); l1 = (uint32_t)p1;
-        } else {
-          h0 = __umulhi(M0, c0[q]); l0 = M0 * c0[q]; h1 = __umulhi(M1, c2[q]); l1 = M1 * c2[q];
+        } else {  // separate high / low products (inline PTX so that they are not re-fused)
+          asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(h0) : "r"(c0[q]), "r"(M0));
+          asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(l0) : "r"(c0[q]), "r"(M0));
+          asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(h1) : "r"(c2[q]), "r"(M1));
+          asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(l1) : "r"(c2[q]), "r"(M1));
         }
         const uint32_t n0 = h1 ^ c1[q] ^ (k0 + r * W0), n2 = h0 ^ c3[q] ^ (k1 + r * W1);
         c1[q] = l1; c3[q] = l0; c0[q] = n0; c2[q] = n2;

@@ -13,6 +13,7 @@ import sdeint_b200 as sdb
 P = int(sys.argv[1]) if len(sys.argv) > 1 else 148 * 256 * 2
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 100
 R = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+SE = int(os.environ.get("SDB_PROF_SAVE_EVERY", T))
 f, G, y0 = sdb.ops.sys_lin(10, 10)
 tspan = np.linspace(0.0, T / 1000.0, T + 1)
 best = None
@@ -20,7 +21,7 @@ for rep in range(R):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
-    y = sdb.itoSRI2(f, G, y0, tspan, paths=P, seed=20261019, save_every=T, out="torch")
+    y = sdb.itoSRI2(f, G, y0, tspan, paths=P, seed=20261019, save_every=SE, out="torch")
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
