@@ -247,26 +247,29 @@ def run_gpu(args):
     mean_err = float(np.max(np.abs(mean[-1].cpu().numpy() - want)))
 
     # -- e2e: the public host-array call, copies inside the timed region ---------------------
-    e2e = None
-    host = torch.empty((n_saved, D, P), dtype=torch.float64).pin_memory()
+    # With several ranks on one host the pinned result buffers add up (8.8 GB per 10^7 paths and
+    # rank), so each call then integrates at most 2*10^6 paths; the rate is what is reported.
+    Pe = P if world == 1 else min(P, 2 * 10 ** 6)
+    host = torch.empty((n_saved, D, Pe), dtype=torch.float64).pin_memory()
     e2e_steps = max(1, min(args.steps, 3))
-    sdb.itoSRI2(f, G, y0, tspan, paths=P, seed=SEED, path_id0=path_id0, save_every=SAVE_EVERY,
+    sdb.itoSRI2(f, G, y0, tspan, paths=Pe, seed=SEED, path_id0=path_id0, save_every=SAVE_EVERY,
                 host_out=host)                                           # warm the path
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        yh = sdb.itoSRI2(f, G, y0, tspan, paths=P, seed=SEED, path_id0=path_id0,
+        yh = sdb.itoSRI2(f, G, y0, tspan, paths=Pe, seed=SEED, path_id0=path_id0,
                          save_every=SAVE_EVERY, host_out=host)
     barrier()
     wall = time.perf_counter() - t0
     tw = torch.tensor([wall], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tw, op=dist.ReduceOp.MAX)
-    e2e_val = world * path_steps * e2e_steps / float(tw.item())
+    e2e_val = world * float(Pe) * (N_POINTS - 1) * e2e_steps / float(tw.item())
     h2d = int(8 * (f.params.size + G.params.size + y0.size + tspan.size))
     d2h = int(host.numel() * 8 + 32)
     e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "steps": e2e_steps, "checksum": float(np.asarray(yh[0, -1]).sum())}
+           "steps": e2e_steps, "paths_per_call": Pe,
+           "checksum": float(np.asarray(yh[0, -1]).sum())}
 
     if rank == 0:
         import ctypes as C
@@ -308,6 +311,19 @@ def run_gpu(args):
                     "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
         }
         roofline["hbm"]["frac"] = roofline["hbm"]["achieved"] / hbm_peak
+        # What the FP64 number does not see (profiles/r01_microbench.md): the 20
+        # IMAD.WIDE of each Philox4x32-10 block issue at ~3.7 cycles each and do not overlap with
+        # DFMA/DMMA.  Per warp-step (32 path-steps) of a sub-partition: 4040 DFMA-class x 2
+        # + 280 DMMA x 16 = 12560 FP64-pipe cycles, + 55 Philox blocks x 74 = 4070 cycles.
+        sm_hz = 1e6 * float((clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0))
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        floor = sms * 4 * 32 * sm_hz / (12560.0 + 4070.0)
+        roofline["issue_model"] = {
+            "fp64_pipe_cycles_per_warp_step": 12560, "philox_cycles_per_warp_step": 4070,
+            "floor_path_steps_per_s": floor,
+            "frac_of_floor": (path_steps / (ms_kernel * 1e-3)) / floor,
+            "source": "SASS instruction counts (profiles/r01_fused_v0_bench1e6_ncu_summary.txt) "
+                      "x measured issue costs (tools/micro/philox.cu, coissue.cu)"}
         cpu_v, cores, sample = cpu_path_steps_per_s(4, 500) if world == 1 else (None, None, None)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,

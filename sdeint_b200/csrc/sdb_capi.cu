@@ -55,12 +55,6 @@ std::string sdb_loop_key(int scheme, int fk, int gk, int d, int m, int noise, bo
   return buf;
 }
 
-std::string sdb_fused_key(int d, int m) {
-  char buf[64];
-  snprintf(buf, sizeof buf, "fused|srk2|kpw|d%d|m%d", d, m);
-  return buf;
-}
-
 static const SdbAotEntry* aot_entry(const std::string& key) {
   for (const auto& e : sdb_aot_registry())
     if (e.key == key) return &e;
@@ -422,8 +416,10 @@ extern "C" int sdb_integrate(sdb_system* s, const sdb_integrate_args* a) {
   const unsigned block = fused ? (unsigned)fused->threads : SDB_BLOCK;
   const int64_t per_block = fused ? fused->paths_per_block : SDB_BLOCK;
   const unsigned grid = (unsigned)((a->paths + per_block - 1) / per_block);
-  if (launch(fn, dim3(grid), dim3(block), args, st, fused ? fused->smem : 0)) return 1;
-  SDB_CUDA(cudaFreeAsync(d_aux, st));
+  const int rc = launch(fn, dim3(grid), dim3(block), args, st, fused ? fused->smem : 0);
+  const cudaError_t fe = cudaFreeAsync(d_aux, st);  // stream-ordered: after the kernel has read it
+  if (rc) return 1;
+  if (fe != cudaSuccess) return fail(std::string("cudaFreeAsync: ") + cudaGetErrorString(fe));
   return 0;
 }
 

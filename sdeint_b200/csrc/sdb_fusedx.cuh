@@ -336,6 +336,12 @@ SDB_DEV void sdb_srk2_fusedx_body(const SdbLoopArgs& a, const PInline<D * D>& fp
             for (int r = 0; r < RN; ++r) s[r][k] = fma(hd, GdW[r], dg * g[r][k]);
           }
         }
+        double sj[2][RN];
+#pragma unroll
+        for (int r = 0; r < RN; ++r) {
+          sj[0][r] = 0.0;
+          sj[1][r] = 0.0;
+        }
         sdb_static_for<0, NCH>([&](auto cc) {
           constexpr int c = decltype(cc)::value;
           if constexpr (c + 1 < NCH) {
@@ -351,10 +357,21 @@ SDB_DEV void sdb_srk2_fusedx_body(const SdbLoopArgs& a, const PInline<D * D>& fp
               if constexpr (c & 1) av = cb.get(e);
               else av = ca.get(e);
               if (WIK) av = -av;  // column-major unvec: +Atilde goes BELOW the diagonal (wiener.py:278-280)
+              // the M-1-j updates of column j form one dependent chain per row: two partial sums
+              // (k - j odd / even) halve it -- with one warp per sub-partition latency is exposed
+              constexpr int par = (k - j) & 1;
 #pragma unroll
               for (int r = 0; r < RN; ++r) {
                 s[r][k] = fma(g[r][j], av, s[r][k]);
-                s[r][j] = fma(-g[r][k], av, s[r][j]);
+                sj[par][r] = fma(-g[r][k], av, sj[par][r]);
+              }
+              if constexpr (k == M - 1) {
+#pragma unroll
+                for (int r = 0; r < RN; ++r) {
+                  s[r][j] += sj[0][r] + sj[1][r];
+                  sj[0][r] = 0.0;
+                  sj[1][r] = 0.0;
+                }
               }
             }
           });

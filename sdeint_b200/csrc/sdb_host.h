@@ -23,7 +23,6 @@ struct SdbAotRegistrar {
 };
 
 std::string sdb_loop_key(int scheme, int fk, int gk, int d, int m, int noise, bool inline_params);
-std::string sdb_fused_key(int d, int m);  // fused linear SRI2/SRS2 + Philox/KPW kernel
 
 // The fused linear SRI2/SRS2 + Philox/KPW kernel (sdb_fused.cuh) for one (d, m).
 struct SdbFusedEntry {

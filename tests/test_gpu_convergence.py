@@ -125,6 +125,30 @@ def test_weak_mean_of_headline_system(sdb):
     assert np.all(var > 0)
 
 
+def test_second_moments_of_headline_system(sdb):
+    """E[y y^T](T) of the linear Ito system solves dP/dt = A P + P A^T + sum_k B_k P B_k^T; the
+    ensemble second moments (sum y^2 from the moments kernel) of 2e5 fused-kernel paths must agree
+    within the sampling error plus the O(h) weak bias of the scheme."""
+    from scipy.linalg import expm
+    f, G, y0 = SYSTEMS["lin10"](False)
+    d = len(y0)
+    T, n, P = 0.5, 200, 200000
+    tspan = np.linspace(0.0, T, n + 1)
+    y = sdb.itoSRI2(f, G, y0, tspan, paths=P, seed=11, save_every=n, out="torch")
+    sums, _ = sdb.ensemble.moments(y)
+    m2 = (sums[-1, :, 1] / P).cpu().numpy()
+    yy = y[-1].cpu().numpy()                                        # (d, P)
+    sd = np.sqrt(np.var(yy ** 2, axis=1) / P)
+    eye = np.eye(d)
+    L = np.kron(f.A, eye) + np.kron(eye, f.A) + sum(np.kron(Bk, Bk) for Bk in G.B)
+    Pm = expm(L * T).dot(np.outer(y0, y0).reshape(-1)).reshape(d, d)
+    want = np.diag(Pm)
+    assert np.all(np.abs(m2 - want) <= 5.0 * sd + 2e-3 * want), (m2 - want, sd)
+    # a cross moment too, straight from the trajectories
+    c01 = np.mean(yy[0] * yy[1])
+    assert abs(c01 - Pm[0, 1]) <= 5.0 * np.std(yy[0] * yy[1]) / np.sqrt(P) + 2e-3 * abs(Pm[0, 1])
+
+
 def test_paths_do_not_depend_on_sharding(sdb):
     """Rank invariance: path p of the ensemble is bit-identical whether it is
     integrated in one launch or as part of a shard with a path_id0 offset."""
