@@ -18,6 +18,7 @@
 #include "sdb_host.h"
 #include "sdb_kernels.cuh"
 #include "sdb_fused.cuh"
+#include "sdb_fused_rt.h"
 
 #include <math.h>
 #include <stdlib.h>
@@ -127,9 +128,9 @@ static int jit_compile(const std::string& source, const char* kernel_name, JitKe
   Nvrtc* rt;
   if (nvrtc_load(&rt)) return 1;
   nvrtcProgram prog;
-  const char* hdr_src[] = {kKernelHeader, kTablesHeader};
-  const char* hdr_name[] = {"sdb_kernels.cuh", "sdb_tables.cuh"};
-  int rc = rt->CreateProgram(&prog, source.c_str(), "sdb_jit.cu", 2, hdr_src, hdr_name);
+  const char* hdr_src[] = {kKernelHeader, kTablesHeader, kFusedHeader};
+  const char* hdr_name[] = {"sdb_kernels.cuh", "sdb_tables.cuh", "sdb_fused.cuh"};
+  int rc = rt->CreateProgram(&prog, source.c_str(), "sdb_jit.cu", 3, hdr_src, hdr_name);
   if (rc) return fail(std::string("nvrtcCreateProgram: ") + rt->GetErrorString(rc));
   const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo",
                         "--fmad=true"};
@@ -346,6 +347,30 @@ extern "C" int sdb_integrate(sdb_system* s, const sdb_integrate_args* a) {
           (e.variant == want || (!fused && e.variant == 0)))
         fused = &e;
   }
+  // No ahead-of-time instantiation for this (d, m): compile the fused kernel with NVRTC when the
+  // shape is one it supports (even m, d < 16, shared memory of one SM); else the generic loop kernel.
+  SdbFusedEntry jit_entry{};
+  if (!fused && a->scheme == SDB_SCHEME_SRK2 && noise == SDB_NOISE_KPW &&
+      s->fk == SDB_DRIFT_LINEAR && s->gk == SDB_DIFF_LINEAR_COLS &&
+      a->n_terms <= SDB_FUSED_MAX_TERMS && !getenv("SDB_DISABLE_FUSED") &&
+      !getenv("SDB_DISABLE_FUSED_JIT") && SdbFusedDims(s->d, s->m).supported() &&
+      s->d * s->m >= 16) {  // tiny systems are generator-bound: the high-occupancy loop kernel wins
+    const SdbFusedDims dims(s->d, s->m);
+    const std::string key = "fusedjit";
+    std::lock_guard<std::mutex> lk(s->mu);
+    auto it = s->jit.find(key);
+    if (it == s->jit.end()) {
+      std::ostringstream src;
+      src << "#include \"sdb_fused.cuh\"\nSDB_FUSED_KERNEL(sdb_jit_fused, " << s->d << ", " << s->m << ")\n";
+      JitKernel k;
+      if (jit_compile(src.str(), "sdb_jit_fused", &k)) return 1;
+      it = s->jit.emplace(key, k).first;
+    }
+    jit_entry = SdbFusedEntry{s->d, s->m, 0, (const void*)it->second.kern, dims.smem_bytes(),
+                              dims.table_doubles(), nullptr, SdbFusedDims::THREADS,
+                              SdbFusedDims::THREADS, SDB_NOISE_KPW};
+    fused = &jit_entry;
+  }
   const void* fn = nullptr;
   double* d_frag = nullptr;
   if (fused) {
@@ -355,7 +380,8 @@ extern "C" int sdb_integrate(sdb_system* s, const sdb_integrate_args* a) {
     if (it == s->d_frags.end()) {  // DMMA fragment tables of (A, B_k), built once per system and kernel
       SDB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused->smem));
       std::vector<double> tab(fused->table_doubles);
-      fused->build(s->fp.data(), s->gp.data(), tab.data());
+      if (fused->build) fused->build(s->fp.data(), s->gp.data(), tab.data());
+      else SdbFusedDims(s->d, s->m).build_tables(s->fp.data(), s->gp.data(), tab.data());
       double* d = nullptr;
       SDB_CUDA(cudaMalloc(&d, tab.size() * sizeof(double)));
       SDB_CUDA(cudaMemcpy(d, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));

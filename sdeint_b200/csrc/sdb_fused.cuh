@@ -121,6 +121,7 @@ struct SdbFusedShape {
   }
 };
 
+#ifndef __CUDACC_RTC__  // host functions are not allowed in NVRTC; sdb_fused_rt.h serves JIT shapes
 // Host: lane-major fragment tables.  out[frag * 32 + lane]; then the leftover rows.
 template <int D, int M>
 inline void sdb_fused_build_tables(const double* A, const double* B, double* out) {
@@ -159,6 +160,7 @@ inline size_t sdb_fused_table_doubles() {
   typedef SdbFusedShape<D, M> Sh;
   return (size_t)Sh::n_frags() * 32 + Sh::n_left();
 }
+#endif  // !__CUDACC_RTC__
 
 #ifdef __CUDACC__
 SDB_DEV void sdb_dmma(double& c0, double& c1, double a, double b) {

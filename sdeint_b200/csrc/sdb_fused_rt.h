@@ -1,0 +1,84 @@
+// sdb_fused_rt.h -- run-time mirror of SdbFusedShape / sdb_fused_build_tables (sdb_fused.cuh, default
+// tuning: 4-row blocks, 256 threads) for shapes that have no ahead-of-time instantiation: the fused
+// kernel is then compiled by NVRTC for the (d, m) at hand and this header sizes its shared memory
+// and builds its DMMA fragment tables.  sdb_fused.cu static_asserts that both agree.
+#pragma once
+#include <stddef.h>
+
+struct SdbFusedDims {
+  int D, M;
+  constexpr SdbFusedDims(int d, int m) : D(d), M(m) {}
+  static constexpr int RB = 4, THREADS = 256, WARPS = 8, MAX_TERMS = 64;
+  constexpr int MM() const { return M * (M - 1) / 2; }
+  constexpr int NB() const { return (D + RB - 1) / RB; }
+  constexpr int LT() const { return (D + 3) / 4; }
+  constexpr int IT() const { return D / 8; }
+  constexpr int IL() const { return D - 8 * IT(); }
+  constexpr int rn(int b) const { return b < NB() - 1 ? RB : D - RB * (NB() - 1); }
+  constexpr int r0(int b) const { return RB * b; }
+  constexpr int nr(int b) const { return (M + 1) * rn(b); }
+  constexpr int t1(int b) const { return (nr(b) + 7) / 8; }
+  constexpr int kt3(int b) const { return (rn(b) * M + 3) / 4; }
+  static constexpr int max2(int a, int b) { return a > b ? a : b; }
+  constexpr int grows() const {
+    int g = max2(8, D);
+    for (int b = 0; b < NB(); ++b) g = max2(g, max2(8 * t1(b), 4 * kt3(b)));
+    return g;
+  }
+  constexpr int p1_off(int b) const {
+    int o = 0;
+    for (int q = 0; q < b; ++q) o += t1(q) * LT();
+    return o;
+  }
+  constexpr int p3_off(int b) const {
+    int o = p1_off(NB());
+    for (int q = 0; q < b; ++q) o += kt3(q) * IT();
+    return o;
+  }
+  constexpr int n_frags() const { return p3_off(NB()); }
+  constexpr int left_off(int b) const {
+    int o = 0;
+    for (int q = 0; q < b; ++q) o += IL() * rn(q) * M;
+    return o;
+  }
+  constexpr int n_left() const { return left_off(NB()); }
+  constexpr size_t table_doubles() const { return (size_t)n_frags() * 32 + n_left(); }
+  constexpr size_t smem_bytes() const {
+    return ((size_t)MM() * THREADS + (size_t)(grows() + M) * 32 * WARPS) * sizeof(double) + 128 * 16 +
+           (MAX_TERMS + 1 + n_left() + 1) * sizeof(double);
+  }
+  // the kernel needs an even m, d < 16 (one DMMA tile of the stage-2 sum) and must fit an SM
+  constexpr bool supported() const {
+    return D >= 1 && M >= 2 && M % 2 == 0 && D < 16 && smem_bytes() <= 227u * 1024u;
+  }
+  // lane-major fragment tables: out[frag * 32 + lane], then the leftover rows (as sdb_fused_build_tables)
+  void build_tables(const double* A, const double* B, double* out) const {
+    for (int b = 0; b < NB(); ++b) {
+      const int rnb = rn(b), r0b = r0(b);
+      for (int t = 0; t < t1(b); ++t)
+        for (int lt = 0; lt < LT(); ++lt)
+          for (int lane = 0; lane < 32; ++lane) {
+            const int n = 8 * t + (lane >> 2), l = 4 * lt + (lane & 3);
+            double v = 0.0;
+            if (l < D) {
+              if (n < M * rnb) v = B[((n / rnb) * D + r0b + n % rnb) * D + l];
+              else if (n < nr(b)) v = A[(r0b + n - M * rnb) * D + l];
+            }
+            out[(size_t)(p1_off(b) + t * LT() + lt) * 32 + lane] = v;
+          }
+      for (int kt = 0; kt < kt3(b); ++kt)
+        for (int it = 0; it < IT(); ++it)
+          for (int lane = 0; lane < 32; ++lane) {
+            const int i = 8 * it + (lane >> 2), K = 4 * kt + (lane & 3);
+            double v = 0.0;
+            if (K < rnb * M) v = B[((K % M) * D + i) * D + r0b + K / M];
+            out[(size_t)(p3_off(b) + kt * IT() + it) * 32 + lane] = v;
+          }
+    }
+    double* left = out + (size_t)n_frags() * 32;
+    for (int b = 0; b < NB(); ++b)
+      for (int q = 0; q < IL(); ++q)
+        for (int K = 0; K < rn(b) * M; ++K)
+          left[left_off(b) + q * rn(b) * M + K] = B[((K % M) * D + 8 * IT() + q) * D + r0(b) + K / M];
+  }
+};

@@ -364,7 +364,8 @@ def test_jit_builtin_dimensions(sdb):
     assert np.max(np.abs(At - At_o)) <= 1e-12 * np.max(np.abs(Iw_o))
 
 
-@pytest.mark.parametrize("d,m", [(10, 10), (4, 4), (8, 2), (5, 4)])
+@pytest.mark.parametrize("d,m", [(10, 10), (4, 4), (8, 2), (5, 4),          # ahead-of-time kernels
+                                 (6, 4), (4, 6), (12, 6), (9, 10), (15, 8)])  # NVRTC-compiled fused kernel
 @pytest.mark.parametrize("strat", [False, True])
 def test_fused_dmma_kernel_shapes(sdb, d, m, strat, monkeypatch):
     """The fused linear SRI2/SRS2 kernel (DMMA products, exact linear collapse of the two
