@@ -44,7 +44,11 @@ extern "C" {
 #define SDB_DIFF_LINEAR_COLS 1 /* params B[m][d][d]        g_k = B_k y */
 #define SDB_DIFF_KP4446 2      /* params b                 G = b (1 - y^2) */
 #define SDB_DIFF_KPS445 3      /* params sqrt2             G = sqrt2 cos^2 y */
+#define SDB_DIFF_DIAG_LINEAR 4 /* params b[d]              g_k = b_k y_k e_k, m = d: DIAGONAL noise */
 #define SDB_DIFF_USER 9 /* NVRTC: __device__ void sde_diffusion_col(int k, const double* y, double t, const double* p, double* out) */
+#define SDB_DIFF_USER_DIAG 10 /* as SDB_DIFF_USER, and the caller guarantees diagonal noise (m = d, column k has
+                                 only component k and depends only on y_k): SRI2/SRS2 then need only the
+                                 diagonal I_kk = (dW_k^2 - h)/2, no Levy areas (README.rst:130 of the reference) */
 
 /* ---- where the noise comes from ------------------------------------------------------ */
 #define SDB_NOISE_HOST 0 /* dW (and I/J for SRK2, KP2iS) supplied by the caller (dW=, I=/J=) */

@@ -71,7 +71,7 @@ class System:
         fp = np.ascontiguousarray(f.params, dtype=np.float64)
         gp = np.ascontiguousarray(G.params, dtype=np.float64)
         handle = C.c_void_p()
-        user = f.kind == ops.DRIFT_USER or G.kind == ops.DIFF_USER
+        user = f.kind == ops.DRIFT_USER or G.kind in (ops.DIFF_USER, ops.DIFF_USER_DIAG)
         torch = torch_mod()
         with torch.cuda.device(device):
             if user:

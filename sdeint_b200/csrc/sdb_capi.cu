@@ -184,7 +184,9 @@ static int expected_params(int kind, bool drift, int d, int m, int64_t* n) {
       case SDB_DIFF_LINEAR_COLS: *n = (int64_t)m * d * d; return 0;
       case SDB_DIFF_KP4446: *n = 1; return (d == 1 && m == 1) ? 0 : 1;
       case SDB_DIFF_KPS445: *n = 1; return (d == 1 && m == 1) ? 0 : 1;
+      case SDB_DIFF_DIAG_LINEAR: *n = d; return d == m ? 0 : 1;
       case SDB_DIFF_USER: *n = -1; return 0;
+      case SDB_DIFF_USER_DIAG: *n = -1; return d == m ? 0 : 1;
     }
   }
   return 1;
@@ -199,7 +201,7 @@ static int system_create(const char* src, int fk, const double* fpar, int64_t nf
   if (expected_params(gk, false, d, m, &eg)) return fail("sdb_system: bad diffusion kind / dimension");
   if (ef >= 0 && nf != ef) return fail("sdb_system: wrong number of drift parameters");
   if (eg >= 0 && ng != eg) return fail("sdb_system: wrong number of diffusion parameters");
-  if ((fk == SDB_DRIFT_USER || gk == SDB_DIFF_USER) && (!src || !*src))
+  if ((fk == SDB_DRIFT_USER || gk == SDB_DIFF_USER || gk == SDB_DIFF_USER_DIAG) && (!src || !*src))
     return fail("sdb_system: user operator kinds need CUDA source");
   if (nf < 0 || ng < 0 || (nf > 0 && !fpar) || (ng > 0 && !gpar))
     return fail("sdb_system: parameter pointer is NULL");
@@ -231,7 +233,7 @@ static int system_create(const char* src, int fk, const double* fpar, int64_t nf
 extern "C" int sdb_system_builtin(int fk, const double* fpar, int64_t nf, int gk,
                                   const double* gpar, int64_t ng, int d, int m,
                                   sdb_system** out) {
-  if (fk == SDB_DRIFT_USER || gk == SDB_DIFF_USER)
+  if (fk == SDB_DRIFT_USER || gk == SDB_DIFF_USER || gk == SDB_DIFF_USER_DIAG)
     return fail("sdb_system_builtin: user kinds need sdb_system_nvrtc");
   return system_create(nullptr, fk, fpar, nf, gk, gpar, ng, d, m, out);
 }
@@ -272,6 +274,9 @@ static std::string type_of(const sdb_system* s, bool drift) {
         o << "DiffLinearCols<" << s->d << ", " << s->m << ", " << ps_g << ">"; break;
       case SDB_DIFF_KP4446: o << "DiffKP4446<" << ps_g << ">"; break;
       case SDB_DIFF_KPS445: o << "DiffKPS445<" << ps_g << ">"; break;
+      case SDB_DIFF_DIAG_LINEAR: o << "DiffDiagLinear<" << s->d << ", " << ps_g << ">"; break;
+      case SDB_DIFF_USER_DIAG:
+        o << "DiffUser<" << s->d << ", " << s->m << ", " << ps_g << ", true>"; break;
       default: o << "DiffUser<" << s->d << ", " << s->m << ", " << ps_g << ">";
     }
   }
@@ -281,7 +286,8 @@ static std::string type_of(const sdb_system* s, bool drift) {
 // Find (AOT) or build (NVRTC) the loop kernel for this system / scheme / noise source.
 static int loop_kernel(sdb_system* s, int scheme, int noise, const void** fn) {
   const std::string key = sdb_loop_key(scheme, s->fk, s->gk, s->d, s->m, noise, s->inline_params);
-  const bool user = (s->fk == SDB_DRIFT_USER || s->gk == SDB_DIFF_USER);
+  const bool user_g = s->gk == SDB_DIFF_USER || s->gk == SDB_DIFF_USER_DIAG;
+  const bool user = s->fk == SDB_DRIFT_USER || user_g;
   if (!user) {
     if (const void* f = aot_lookup(key)) { *fn = f; return 0; }
   }
@@ -290,7 +296,7 @@ static int loop_kernel(sdb_system* s, int scheme, int noise, const void** fn) {
   if (it == s->jit.end()) {
     std::ostringstream src;
     if (s->fk == SDB_DRIFT_USER) src << "#define SDB_USER_DRIFT 1\n";
-    if (s->gk == SDB_DIFF_USER) src << "#define SDB_USER_DIFF 1\n";
+    if (user_g) src << "#define SDB_USER_DIFF 1\n";
     src << "#include \"sdb_kernels.cuh\"\n";
     if (user) src << "#line 1 \"user_source.cu\"\n" << s->src << "\n";
     src << "typedef " << type_of(s, true) << " F_jit;\n";
@@ -324,7 +330,10 @@ extern "C" int sdb_integrate(sdb_system* s, const sdb_integrate_args* a) {
   // additive noise never uses the repeated integrals (see NEED_IJ in sdb_kernels.cuh)
   const bool need_ij = (a->scheme == SDB_SCHEME_SRK2 || a->scheme == SDB_SCHEME_KP2IS) &&
                        s->gk != SDB_DIFF_CONST;
-  if (a->noise == SDB_NOISE_HOST && (!a->d_dW || (need_ij && !a->d_IJ)))
+  // diagonal noise: I/J may be omitted, the kernel builds the diagonal from dW
+  const bool diag = (s->gk == SDB_DIFF_DIAG_LINEAR || s->gk == SDB_DIFF_USER_DIAG) &&
+                    a->scheme == SDB_SCHEME_SRK2;  // KP2iS does use the off-diagonal J
+  if (a->noise == SDB_NOISE_HOST && (!a->d_dW || (need_ij && !a->d_IJ && !diag)))
     return fail("sdb_integrate: NOISE_HOST needs dW (and I/J for SRK2, KP2iS)");
   if (a->noise != SDB_NOISE_HOST && a->n_terms < 1)
     return fail("sdb_integrate: n_terms must be >= 1");

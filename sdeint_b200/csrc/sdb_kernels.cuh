@@ -453,7 +453,7 @@ struct DriftKPS445 {  // test_integrate.py:263-269
 template <int D_, int M_, class PS>
 struct DiffConst {  // additive noise: G does not depend on y
   static constexpr int D = D_, M = M_;
-  static constexpr bool ADDITIVE = true;
+  static constexpr bool ADDITIVE = true, DIAGONAL = false;
   typedef PS Params;
   static SDB_DEV void col(const PS& p, int k, const double (&)[D], double, double (&out)[D]) {
 #pragma unroll
@@ -464,7 +464,7 @@ struct DiffConst {  // additive noise: G does not depend on y
 template <int D_, int M_, class PS>
 struct DiffLinearCols {  // g_k = B_k y
   static constexpr int D = D_, M = M_;
-  static constexpr bool ADDITIVE = false;
+  static constexpr bool ADDITIVE = false, DIAGONAL = false;
   typedef PS Params;
   static SDB_DEV void col(const PS& p, int k, const double (&y)[D], double, double (&out)[D]) {
 #pragma unroll
@@ -477,10 +477,21 @@ struct DiffLinearCols {  // g_k = B_k y
   }
 };
 
+template <int D_, class PS>
+struct DiffDiagLinear {  // g_k = b_k y_k e_k: diagonal noise (m = d)
+  static constexpr int D = D_, M = D_;
+  static constexpr bool ADDITIVE = false, DIAGONAL = true;
+  typedef PS Params;
+  static SDB_DEV void col(const PS& p, int k, const double (&y)[D], double, double (&out)[D]) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) out[i] = i == k ? p[i] * y[i] : 0.0;
+  }
+};
+
 template <class PS>
 struct DiffKP4446 {
   static constexpr int D = 1, M = 1;
-  static constexpr bool ADDITIVE = false;
+  static constexpr bool ADDITIVE = false, DIAGONAL = false;
   typedef PS Params;
   static SDB_DEV void col(const PS& p, int, const double (&y)[1], double, double (&out)[1]) {
     out[0] = p[0] * (1.0 - y[0] * y[0]);
@@ -490,7 +501,7 @@ struct DiffKP4446 {
 template <class PS>
 struct DiffKPS445 {
   static constexpr int D = 1, M = 1;
-  static constexpr bool ADDITIVE = false;
+  static constexpr bool ADDITIVE = false, DIAGONAL = false;
   typedef PS Params;
   static SDB_DEV void col(const PS& p, int, const double (&y)[1], double, double (&out)[1]) {
     const double c = cos(y[0]);
@@ -511,10 +522,10 @@ struct DriftUser {
 #endif
 #ifdef SDB_USER_DIFF
 __device__ void sde_diffusion_col(int k, const double* y, double t, const double* p, double* out);
-template <int D_, int M_, class PS>
+template <int D_, int M_, class PS, bool DIAG = false>
 struct DiffUser {
   static constexpr int D = D_, M = M_;
-  static constexpr bool ADDITIVE = false;
+  static constexpr bool ADDITIVE = false, DIAGONAL = DIAG;
   typedef PS Params;
   static SDB_DEV void col(const PS& p, int k, const double (&y)[D], double t, double (&out)[D]) {
     sde_diffusion_col(k, y, t, p.ptr(), out);
@@ -523,14 +534,27 @@ struct DiffUser {
 #endif
 
 // ---- per-step noise for the loop kernels ---------------------------------------------------------
-template <int M, int NOISE, bool NEED_IJ>
+// Diagonal noise: only I_kk = (dW_k^2 - h)/2 (J_kk = dW_k^2/2) enters the schemes; no Levy areas.
+template <int M>
+SDB_DEV void sdb_diag_IJ(const SdbLoopArgs& a, const double (&dW)[M], double (&IJ)[M][M]) {
+  const bool strat = (a.flags & SDB_FLAG_STRATONOVICH) != 0;
+#pragma unroll
+  for (int j = 0; j < M; ++j)
+#pragma unroll
+    for (int k = 0; k < M; ++k)
+      IJ[j][k] = j != k ? 0.0 : (strat ? 0.5 * dW[j] * dW[j] : 0.5 * (dW[j] * dW[j] - a.h_global));
+}
+
+template <int M, int NOISE, bool NEED_IJ, bool DIAG>
 SDB_DEV void sdb_step_noise(const SdbLoopArgs& a, int64_t p, int n, double (&dW)[M],
                             double (&IJ)[M][M]) {
   if (NOISE == SDB_NOISE_HOST) {
     const double* w = a.dW + (int64_t)n * a.dW_sN + p * a.dW_sP;
 #pragma unroll
     for (int j = 0; j < M; ++j) dW[j] = w[j * a.dW_sJ];
-    if (NEED_IJ) {
+    if (NEED_IJ && DIAG && a.IJ == nullptr) {
+      sdb_diag_IJ<M>(a, dW, IJ);
+    } else if (NEED_IJ) {
       const double* q = a.IJ + (int64_t)n * a.IJ_sN + p * a.IJ_sP;
 #pragma unroll
       for (int j = 0; j < M; ++j)
@@ -544,7 +568,9 @@ SDB_DEV void sdb_step_noise(const SdbLoopArgs& a, int64_t p, int n, double (&dW)
     SdbNormalSeq s(st, 0u);
 #pragma unroll
     for (int j = 0; j < M; ++j) dW[j] = rh * s.next();
-    if (NEED_IJ) {
+    if (NEED_IJ && DIAG) {
+      sdb_diag_IJ<M>(a, dW, IJ);
+    } else if (NEED_IJ) {
       double At[M * (M - 1) / 2 + 1];
       const SdbNormalsPhilox<M> ns{st, a.n_terms};
       sdb_repeated_integrals<M>(dW, a.h_global, a.n_terms, NOISE,
@@ -645,7 +671,7 @@ SDB_DEV void sdb_loop_body(const SdbLoopArgs& a, const typename F::Params& fp,
     const double t1 = a.tspan[n + 1];
     double dW[M];
     double IJ[M][M];  // dead (and removed by the compiler) for Euler / Heun
-    sdb_step_noise<M, NOISE, NEED_IJ>(a, p, n, dW, IJ);
+    sdb_step_noise<M, NOISE, NEED_IJ, (G::DIAGONAL && SCHEME == SDB_SCHEME_SRK2)>(a, p, n, dW, IJ);
 
     if (SCHEME == SDB_SCHEME_EULER) {
       const double h = a.h_global;

@@ -164,6 +164,11 @@ def _run(scheme, f, G, y0, tspan, dW, IJ, strat, method, generator, kp2is, paths
     # additive noise (G independent of y): SRI2/SRS2/KP2iS never use the repeated integrals, so
     # they are neither generated nor uploaded -- results are bit-identical (ops.ConstDiffusion)
     need_ij = scheme in (SCHEME_SRK2, SCHEME_KP2IS) and Gop.kind != ops.DIFF_CONST
+    # diagonal noise: only I_kk = (dW_k^2 - h)/2 enters; unless the caller supplies I/J the kernel
+    # builds that diagonal from dW and no Levy areas are generated at all
+    diag = Gop.kind in (ops.DIFF_DIAG_LINEAR, ops.DIFF_USER_DIAG)
+    if diag and IJ is None and scheme == SCHEME_SRK2:   # (KP2iS does use off-diagonal J)
+        need_ij = False
     N = len(tspan)
     save_every = int(save_every)
     if save_every < 1:

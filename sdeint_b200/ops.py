@@ -34,7 +34,9 @@ DIFF_CONST = 0        # params: B[d][m] row-major                      G = B
 DIFF_LINEAR_COLS = 1  # params: B[m][d][d]                             g_k = B_k y
 DIFF_KP4446 = 2       # params: b                                      G = b (1 - y^2)
 DIFF_KPS445 = 3       # params: (none; one dummy)                      G = sqrt2 cos^2 y
+DIFF_DIAG_LINEAR = 4  # params: b[d]                                   g_k = b_k y_k e_k (m = d)
 DIFF_USER = 9
+DIFF_USER_DIAG = 10   # NVRTC source, diagonal noise promised by the caller
 
 
 def _is_scalar(y):
@@ -156,6 +158,21 @@ class LinearDiffusion(DiffusionOp):
         return self.B[k].dot(y)
 
 
+class DiagLinearDiffusion(DiffusionOp):
+    """Diagonal multiplicative noise g_k(y, t) = b_k y_k e_k (m = d).  For diagonal noise
+    SRI2/SRS2/KP2iS need only I_kk = (dW_k^2 - h)/2, so no Levy areas are generated: the first
+    "fast path" of the reference's to-do list (README.rst:130, integrate.py:150-151)."""
+    kind = DIFF_DIAG_LINEAR
+
+    def __init__(self, b):
+        self.b = np.asarray(b, dtype=np.float64).reshape(-1).copy()
+        self.d = self.m = len(self.b)
+        self.params = self.b.copy()
+
+    def __call__(self, y, t):
+        return np.diag(self.b * np.asarray(y, dtype=np.float64))
+
+
 class KP4446Drift(DriftOp):
     """Kloeden & Platen (4.46) drift, sdeint/tests/test_integrate.py:93-99.
     Ito: -(a + y b^2)(1 - y^2); Stratonovich: -a (1 - y^2)."""
@@ -259,11 +276,15 @@ class CudaDiffusion(DiffusionOp):
     integrate.py:516-521)."""
     kind = DIFF_USER
 
-    def __init__(self, source, d, m, params=(), host=None):
+    def __init__(self, source, d, m, params=(), host=None, diagonal=False):
         self.source = str(source)
         self.d, self.m = int(d), int(m)
         self.params = np.asarray(params, dtype=np.float64).reshape(-1).copy()
         self.host = host
+        if diagonal:   # promise: column k has only component k and depends only on y_k
+            if self.d != self.m:
+                raise ValueError("diagonal noise needs m == d")
+            self.kind = DIFF_USER_DIAG
 
     def __call__(self, y, t):
         if self.host is None:

@@ -508,3 +508,66 @@ def test_edge_shapes(sdb, name):
         X, Y = po.kpw_normals(17, m, n, 2, 9)
         _, I_o = orc.ikpw_from_normals(dW1[1], h, X[:, 1], Y[:, 1])
         assert np.max(np.abs(I[1] - I_o)) <= 1e-12 * max(np.max(np.abs(I_o)), 1e-300)
+
+
+DIAG_SRC = r"""
+__device__ void sde_drift(const double* y, double t, const double* p, double* out) {
+  for (int i = 0; i < 4; ++i) out[i] = -p[0] * y[i] + p[1] * y[(i + 1) & 3];
+}
+__device__ void sde_diffusion_col(int k, const double* y, double t, const double* p, double* out) {
+  for (int i = 0; i < 4; ++i) out[i] = 0.0;
+  out[k] = p[0] * sin(y[k]) + p[1];        // column k: only component k, depends only on y_k
+}
+"""
+
+
+def test_diagonal_noise_needs_no_levy_areas(sdb):
+    """Noise-structure dispatch, second case: for diagonal noise SRI2/SRS2 depend on I only through
+    I_kk = (dW_k^2 - h)/2, so nothing but dW is generated (or read).  Checked against the oracle fed
+    with the FULL I of Ikpw (the reference's computation) and with the diagonal only."""
+    rng = np.random.default_rng(17)
+    d = 6
+    A = -np.eye(d) + 0.2 * rng.standard_normal((d, d))
+    b = 0.3 + 0.2 * rng.random(d)
+    f, G = sdb.ops.LinearDrift(A), sdb.ops.DiagLinearDiffusion(b)
+    y0 = 1.0 + rng.random(d)
+    tspan = np.linspace(0.0, 0.4, 81)
+    h = 0.005
+    dW = orc.delta_w(80, d, h, rng)
+    _, I_full = orc.ikpw(dW, h, generator=rng)
+    _, J_full = orc.jkpw(dW, h, generator=rng)
+    n0 = sdb.launch_count()
+    y = sdb.itoSRI2(f, G, y0, tspan, dW=dW)                           # no I: diagonal built on device
+    assert sdb.launch_count() - n0 == 2                               # no repeated-integral kernel
+    assert rel_err(y, orc.srk2(f, G, y0, tspan, dW, I_full)) <= TOL
+    assert rel_err(sdb.itoSRI2(f, G, y0, tspan, dW=dW, I=I_full), y) <= TOL
+    ys = sdb.stratSRS2(f, G, y0, tspan, dW=dW)
+    assert rel_err(ys, orc.srk2(f, G, y0, tspan, dW, J_full)) <= TOL
+    # on-device noise: only the m dW normals of each step are drawn
+    P, seed = 40, 2468
+    yp = sdb.itoSRI2(f, G, y0, tspan, paths=P, seed=seed)
+    dWd = sdb.deltaW(80, d, h, paths=P, seed=seed)
+    for p in (0, P - 1):
+        Idiag = np.zeros((80, d, d))
+        Idiag[:, np.arange(d), np.arange(d)] = 0.5 * (dWd[p] ** 2 - h)
+        assert rel_err(yp[p], orc.srk2(f, G, y0, tspan, dWd[p], Idiag)) <= TOL
+    # KP2iS does use off-diagonal J: it still gets the full construction
+    yk = sdb.stratKP2iS(f, G, y0, tspan, dW=dW, J=J_full, rtol=1e-12)
+    ref = orc.kp2is(f, G, y0, tspan, dW, J_full, rtol=1e-13, solver="newton")
+    assert rel_err(yk, ref) <= 1e-10
+    # user CUDA source with the diagonal promise
+    kf, kg = np.array([1.2, 0.3]), np.array([0.25, 0.1])
+
+    def f_host(yv, t):
+        return np.array([-kf[0] * yv[i] + kf[1] * yv[(i + 1) & 3] for i in range(4)])
+
+    def g_host(yv, t):
+        return np.diag(kg[0] * np.sin(yv) + kg[1])
+
+    fu = sdb.ops.CudaDrift(DIAG_SRC, 4, kf, host=f_host)
+    Gu = sdb.ops.CudaDiffusion(DIAG_SRC, 4, 4, kg, host=g_host, diagonal=True)
+    y0u = np.array([0.5, -0.2, 0.8, 0.1])
+    dWu = orc.delta_w(80, 4, h, rng)
+    _, Iu = orc.ikpw(dWu, h, generator=rng)
+    yu = sdb.itoSRI2(fu, Gu, y0u, tspan, dW=dWu)
+    assert rel_err(yu, orc.srk2(f_host, g_host, y0u, tspan, dWu, Iu)) <= TOL
