@@ -47,6 +47,7 @@ FLOPS_REFERENCE_FORM = FLOPS_SRK2 + FLOPS_IKPW                                # 
 # B_k (sqrt(h) s_k): SURVEY 8d says to subtract 2md^2 + 2dm from the numerator in that case.
 FLOPS_PER_PATH_STEP = FLOPS_REFERENCE_FORM - (2 * M * D * D + 2 * D * M)      # 8080 executed
 BYTES_PER_PATH_STEP = 8.0 * D / SAVE_EVERY + 8.0 * D / (N_POINTS - 1)         # 0.88 B (stores)
+CPU_PATHS, CPU_STEPS = 16, 1000   # CPU sample per worker: ~1.2 s each, ~20 core-seconds on 16 cores
 METRIC = "SRI2 path-steps/s (d=m=10, fp64)"
 UNIT = "path-steps/s"
 
@@ -98,14 +99,14 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     sample = ""
     for i in range(args.warmup + args.steps):
-        v, cores, sample = cpu_path_steps_per_s(4, 500, cores)
+        v, cores, sample = cpu_path_steps_per_s(CPU_PATHS, CPU_STEPS, cores)
         if i >= args.warmup:
             vals.append(v)
     value = float(np.mean(vals))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * cores * 4 * 500 / value, "higher_is_better": True,
+        "ms_per_step": 1e3 * cores * CPU_PATHS * CPU_STEPS / value, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
@@ -324,7 +325,8 @@ def run_gpu(args):
             "frac_of_floor": (path_steps / (ms_kernel * 1e-3)) / floor,
             "source": "SASS instruction counts (profiles/r01_fused_v0_bench1e6_ncu_summary.txt) "
                       "x measured issue costs (tools/micro/philox.cu, coissue.cu)"}
-        cpu_v, cores, sample = cpu_path_steps_per_s(4, 500) if world == 1 else (None, None, None)
+        cpu_v, cores, sample = (cpu_path_steps_per_s(CPU_PATHS, CPU_STEPS) if world == 1
+                                else (None, None, None))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,

@@ -13,7 +13,8 @@
   static SdbFusedRegistrar sdbreg_fusedx_d##D##_m##M##_##TAG(                                  \
       SdbFusedEntry{D, M, 0, (const void*)sdbk_fusedx_srk2_d##D##_m##M##_##TAG,                \
                     SdbXShape<D, M>::smem_bytes(), sdb_fused_table_doubles<D, M>(),            \
-                    &sdb_fused_build_tables<D, M>, SDB_X_THREADS, SDB_X_PATHS,                 \
+                    &sdb_fused_build_tables<D, M>, SdbXShape<D, M>::THREADS,                   \
+                    SdbXShape<D, M>::PATHS,                                                    \
                     WIK ? SDB_NOISE_WIK : SDB_NOISE_KPW});
 
 SDB_FUSEDX_AOT(20, 20, 0, kpw)

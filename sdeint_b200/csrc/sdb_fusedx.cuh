@@ -30,9 +30,6 @@
 #endif
 #include "sdb_fusedws.cuh"  // sdb_fused.cuh, sdb_tmem.cuh, sdb_static_for, sdb_pair_j/k
 
-#define SDB_X_THREADS 128
-#define SDB_X_WARPS 4
-#define SDB_X_PATHS (SDB_X_WARPS * 32)
 
 namespace SDB_FUSED_NS {
 
@@ -54,8 +51,13 @@ struct SdbXShape {
   static constexpr int GR = Sh::grows();
   static constexpr int R_Y = GR;                             // shared-memory rows of one warp
   static constexpr int WROWS = R_Y + D;
+  // warps per SM sub-partition: two when two warps' columns fit the 512 of a TMEM lane (and the
+  // register file: 2 x 255 registers per lane slot)
+  static constexpr int WPQ = 2 * C_END <= 512 ? 2 : 1;
+  static constexpr int WARPS = 4 * WPQ, THREADS = 32 * WARPS, PATHS = THREADS;
+  static constexpr int C_STRIDE = 512 / WPQ;                 // TMEM columns per warp
   static SDB_CX size_t smem_bytes() {
-    size_t b = (size_t)WROWS * 32 * 8 * SDB_X_WARPS + 128 * 16 +
+    size_t b = (size_t)WROWS * 32 * 8 * WARPS + 128 * 16 +
                (SDB_FUSED_MAX_TERMS + 1 + Sh::n_left() + 1) * sizeof(double) + 16;
     return b < 120 * 1024 ? 120 * 1024 : b;  // > half an SM: one block (one TMEM allocation) per SM
   }
@@ -90,20 +92,20 @@ SDB_DEV void sdb_srk2_fusedx_body(const SdbLoopArgs& a, const PInline<D * D>& fp
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int fr = lane >> 2, fc = lane & 3;
 
-  double2* tab = reinterpret_cast<double2*>(smem + (size_t)Xs::WROWS * 32 * SDB_X_WARPS);
+  double2* tab = reinterpret_cast<double2*>(smem + (size_t)Xs::WROWS * 32 * Xs::WARPS);
   double* s_hk = reinterpret_cast<double*>(tab + 128);
   double* s_left = s_hk + SDB_FUSED_MAX_TERMS + 1;
   uint32_t* tm_slot = reinterpret_cast<uint32_t*>(s_left + Sh::n_left() + 1);
   if (tid < 128) tab[tid] = reinterpret_cast<const double2*>(sdb_logtab)[tid];
   if (tid <= SDB_FUSED_MAX_TERMS)
     s_hk[tid] = tid == 0 ? 0.0 : a.h_global * SDB_INV_2PI / (double)tid;
-  for (int i = tid; i < Sh::n_left(); i += SDB_X_THREADS) s_left[i] = frag[(size_t)Sh::n_frags() * 32 + i];
+  for (int i = tid; i < Sh::n_left(); i += Xs::THREADS) s_left[i] = frag[(size_t)Sh::n_frags() * 32 + i];
   const uint32_t tm_base = sdb_tm_alloc512(tm_slot);  // contains a __syncthreads()
-  const uint32_t tm = tm_base + (((uint32_t)(warp & 3) * 32u) << 16);
+  const uint32_t tm = tm_base + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)((warp >> 2) * Xs::C_STRIDE);
 
   double* gbuf = smem + (size_t)warp * Xs::WROWS * 32;
   double* ybuf = gbuf + Xs::R_Y * 32;
-  const int64_t p = (int64_t)blockIdx.x * SDB_X_PATHS + tid;
+  const int64_t p = (int64_t)blockIdx.x * Xs::PATHS + tid;
   const bool active = p < a.P;  // idle lanes of the last warp still take part in the DMMAs
   {
     double Y[D];
@@ -499,7 +501,7 @@ SDB_DEV void sdb_srk2_fusedx_body(const SdbLoopArgs& a, const PInline<D * D>& fp
 using namespace SDB_FUSED_NS;
 
 #define SDB_FUSEDX_KERNEL(NAME, D, M, WIK)                                                    \
-  extern "C" __global__ void __launch_bounds__(SDB_X_THREADS, 1)                              \
+  extern "C" __global__ void __launch_bounds__((SdbXShape<D, M>::THREADS), 1)                 \
       NAME(const __grid_constant__ SdbLoopArgs a, const __grid_constant__ PInline<D * D> fp,  \
            const double* __restrict__ frag) {                                                 \
     extern __shared__ __align__(16) double sdb_fused_smem[];                                  \
