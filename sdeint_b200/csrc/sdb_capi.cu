@@ -128,13 +128,17 @@ static int jit_compile(const std::string& source, const char* kernel_name, JitKe
   Nvrtc* rt;
   if (nvrtc_load(&rt)) return 1;
   nvrtcProgram prog;
-  const char* hdr_src[] = {kKernelHeader, kTablesHeader, kFusedHeader};
-  const char* hdr_name[] = {"sdb_kernels.cuh", "sdb_tables.cuh", "sdb_fused.cuh"};
-  int rc = rt->CreateProgram(&prog, source.c_str(), "sdb_jit.cu", 3, hdr_src, hdr_name);
+  const char* hdr_src[] = {kKernelHeader, kTablesHeader, kFusedHeader, kTmemHeader, kFusedWsHeader,
+                           kFusedXHeader};
+  const char* hdr_name[] = {"sdb_kernels.cuh", "sdb_tables.cuh", "sdb_fused.cuh", "sdb_tmem.cuh",
+                            "sdb_fusedws.cuh", "sdb_fusedx.cuh"};
+  int rc = rt->CreateProgram(&prog, source.c_str(), "sdb_jit.cu", 6, hdr_src, hdr_name);
   if (rc) return fail(std::string("nvrtcCreateProgram: ") + rt->GetErrorString(rc));
+  // -default-device: un-annotated functions (the generic lambdas of the compile-time loops) are
+  // device functions in JIT mode
   const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo",
-                        "--fmad=true"};
-  rc = rt->CompileProgram(prog, 4, opts);
+                        "--fmad=true", "-default-device"};
+  rc = rt->CompileProgram(prog, 5, opts);
   if (rc) {
     size_t n = 0;
     rt->GetProgramLogSize(prog, &n);
@@ -356,29 +360,48 @@ extern "C" int sdb_integrate(sdb_system* s, const sdb_integrate_args* a) {
           (e.variant == want || (!fused && e.variant == 0)))
         fused = &e;
   }
-  // No ahead-of-time instantiation for this (d, m): compile the fused kernel with NVRTC when the
-  // shape is one it supports (even m, d < 16, shared memory of one SM); else the generic loop kernel.
+  // No ahead-of-time instantiation for this (d, m, method): compile a fused kernel with NVRTC when
+  // the shape is one it supports -- sdb_fused.cuh (8 warps per SM; Ikpw/Jkpw, even m <= 10, d < 16) or
+  // sdb_fusedx.cuh (Levy areas in tensor memory; Iwik/Jwik and larger shapes) -- else the generic loop.
   SdbFusedEntry jit_entry{};
-  if (!fused && a->scheme == SDB_SCHEME_SRK2 && noise == SDB_NOISE_KPW &&
+  int jit_rb = 4;
+  if (!fused && a->scheme == SDB_SCHEME_SRK2 && noise != SDB_NOISE_HOST &&
       s->fk == SDB_DRIFT_LINEAR && s->gk == SDB_DIFF_LINEAR_COLS &&
       a->n_terms <= SDB_FUSED_MAX_TERMS && !getenv("SDB_DISABLE_FUSED") &&
-      !getenv("SDB_DISABLE_FUSED_JIT") && SdbFusedDims(s->d, s->m).supported() &&
-      s->d * s->m >= 16) {  // tiny systems are generator-bound: the high-occupancy loop kernel wins
-    const SdbFusedDims dims(s->d, s->m);
-    const std::string key = "fusedjit";
-    std::lock_guard<std::mutex> lk(s->mu);
-    auto it = s->jit.find(key);
-    if (it == s->jit.end()) {
-      std::ostringstream src;
-      src << "#include \"sdb_fused.cuh\"\nSDB_FUSED_KERNEL(sdb_jit_fused, " << s->d << ", " << s->m << ")\n";
-      JitKernel k;
-      if (jit_compile(src.str(), "sdb_jit_fused", &k)) return 1;
-      it = s->jit.emplace(key, k).first;
+      !getenv("SDB_DISABLE_FUSED_JIT") && s->d * s->m >= 16) {  // tiny systems are generator-bound:
+    const SdbFusedDims dims(s->d, s->m);                        // the high-occupancy loop kernel wins
+    const SdbFusedXDims xdims(s->d, s->m);
+    const bool use_v0 = noise == SDB_NOISE_KPW && dims.supported();
+    const bool use_x = !use_v0 && xdims.supported();
+    if (use_v0 || use_x) {
+      const std::string key = use_v0 ? "fusedjit" : (noise == SDB_NOISE_WIK ? "fusedxjit|wik" : "fusedxjit|kpw");
+      std::lock_guard<std::mutex> lk(s->mu);
+      auto it = s->jit.find(key);
+      if (it == s->jit.end()) {
+        std::ostringstream src;
+        if (use_v0) {
+          src << "#include \"sdb_fused.cuh\"\nSDB_FUSED_KERNEL(sdb_jit_fused, " << s->d << ", " << s->m << ")\n";
+        } else {
+          src << "#define SDB_FUSED_RB 2\n#define SDB_FUSED_VOL_MMA 0\n#include \"sdb_fusedx.cuh\"\n"
+              << "SDB_FUSEDX_KERNEL(sdb_jit_fused, " << s->d << ", " << s->m << ", "
+              << (noise == SDB_NOISE_WIK ? 1 : 0) << ")\n";
+        }
+        JitKernel k;
+        if (jit_compile(src.str(), "sdb_jit_fused", &k)) return 1;
+        it = s->jit.emplace(key, k).first;
+      }
+      if (use_v0) {
+        jit_entry = SdbFusedEntry{s->d, s->m, 0, (const void*)it->second.kern, dims.smem_bytes(),
+                                  dims.table_doubles(), nullptr, SdbFusedDims::THREADS,
+                                  SdbFusedDims::THREADS, SDB_NOISE_KPW};
+      } else {
+        jit_rb = 2;
+        jit_entry = SdbFusedEntry{s->d, s->m, 0, (const void*)it->second.kern, xdims.smem_bytes(),
+                                  xdims.sh.table_doubles(), nullptr, xdims.threads(),
+                                  xdims.threads(), noise};
+      }
+      fused = &jit_entry;
     }
-    jit_entry = SdbFusedEntry{s->d, s->m, 0, (const void*)it->second.kern, dims.smem_bytes(),
-                              dims.table_doubles(), nullptr, SdbFusedDims::THREADS,
-                              SdbFusedDims::THREADS, SDB_NOISE_KPW};
-    fused = &jit_entry;
   }
   const void* fn = nullptr;
   double* d_frag = nullptr;
@@ -390,7 +413,7 @@ extern "C" int sdb_integrate(sdb_system* s, const sdb_integrate_args* a) {
       SDB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused->smem));
       std::vector<double> tab(fused->table_doubles);
       if (fused->build) fused->build(s->fp.data(), s->gp.data(), tab.data());
-      else SdbFusedDims(s->d, s->m).build_tables(s->fp.data(), s->gp.data(), tab.data());
+      else SdbFusedDims(s->d, s->m, jit_rb).build_tables(s->fp.data(), s->gp.data(), tab.data());
       double* d = nullptr;
       SDB_CUDA(cudaMalloc(&d, tab.size() * sizeof(double)));
       SDB_CUDA(cudaMemcpy(d, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));

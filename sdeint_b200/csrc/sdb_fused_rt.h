@@ -6,9 +6,9 @@
 #include <stddef.h>
 
 struct SdbFusedDims {
-  int D, M;
-  constexpr SdbFusedDims(int d, int m) : D(d), M(m) {}
-  static constexpr int RB = 4, THREADS = 256, WARPS = 8, MAX_TERMS = 64;
+  int D, M, RB;  // RB: state rows per block (4: sdb_fused.cuh default; 2: sdb_fusedx.cuh)
+  constexpr SdbFusedDims(int d, int m, int rb = 4) : D(d), M(m), RB(d > rb ? rb : 4) {}
+  static constexpr int THREADS = 256, WARPS = 8, MAX_TERMS = 64;
   constexpr int MM() const { return M * (M - 1) / 2; }
   constexpr int NB() const { return (D + RB - 1) / RB; }
   constexpr int LT() const { return (D + 3) / 4; }
@@ -80,5 +80,27 @@ struct SdbFusedDims {
       for (int q = 0; q < IL(); ++q)
         for (int K = 0; K < rn(b) * M; ++K)
           left[left_off(b) + q * rn(b) * M + K] = B[((K % M) * D + 8 * IT() + q) * D + r0(b) + K / M];
+  }
+};
+
+// Run-time mirror of SdbXShape (sdb_fusedx.cuh): the TMEM-resident kernel, 2-row blocks.
+struct SdbFusedXDims {
+  SdbFusedDims sh;
+  constexpr SdbFusedXDims(int d, int m) : sh(d, m, 2) {}
+  constexpr int MM() const { return sh.MM(); }
+  constexpr int MMP() const { return (MM() + 15) / 16 * 16; }
+  constexpr int C_END() const { return 2 * MMP() + (2 * sh.M + 7) / 8 * 8 + 4 * sh.D; }
+  constexpr int WPQ() const { return 2 * C_END() <= 512 ? 2 : 1; }
+  constexpr int threads() const { return 128 * WPQ(); }
+  constexpr size_t smem_bytes() const {
+    const size_t b = (size_t)(sh.grows() + sh.D) * 32 * 8 * 4 * WPQ() + 128 * 16 +
+                     (SdbFusedDims::MAX_TERMS + 1 + sh.n_left() + 1) * sizeof(double) + 16;
+    return b < 120u * 1024u ? 120u * 1024u : b;
+  }
+  // even m; uniform 2-row blocks (even d > 2); the areas, dW and row pieces of a path within the 512
+  // columns of a TMEM lane; at most 3 DMMA row tiles of the stage-2 sum; one SM's shared memory
+  constexpr bool supported() const {
+    return sh.M >= 2 && sh.M % 2 == 0 && sh.D > 2 && sh.D % 2 == 0 && sh.D <= 24 && C_END() <= 512 &&
+           smem_bytes() <= 227u * 1024u;
   }
 };

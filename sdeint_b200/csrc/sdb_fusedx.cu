@@ -20,3 +20,15 @@
 SDB_FUSEDX_AOT(20, 20, 0, kpw)
 SDB_FUSEDX_AOT(20, 20, 1, wik)
 SDB_FUSEDX_AOT(10, 10, 1, wik)
+
+// The run-time mirror used for NVRTC-compiled shapes (sdb_fused_rt.h) must agree with the templates.
+#include "sdb_fused_rt.h"
+#define SDB_CHECK_XDIMS(D, M)                                                                   \
+  static_assert(SdbFusedXDims(D, M).smem_bytes() == SdbXShape<D, M>::smem_bytes() &&            \
+                    SdbFusedXDims(D, M).C_END() == SdbXShape<D, M>::C_END &&                    \
+                    SdbFusedXDims(D, M).threads() == SdbXShape<D, M>::THREADS &&                \
+                    SdbFusedXDims(D, M).sh.n_frags() == SdbFusedShape<D, M>::n_frags() &&       \
+                    SdbFusedXDims(D, M).sh.n_left() == SdbFusedShape<D, M>::n_left(),           \
+                "sdb_fused_rt.h disagrees with SdbXShape");
+SDB_CHECK_XDIMS(20, 20) SDB_CHECK_XDIMS(10, 10) SDB_CHECK_XDIMS(16, 12) SDB_CHECK_XDIMS(4, 6)
+SDB_CHECK_XDIMS(12, 14) SDB_CHECK_XDIMS(6, 4)

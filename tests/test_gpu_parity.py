@@ -571,3 +571,32 @@ def test_diagonal_noise_needs_no_levy_areas(sdb):
     _, Iu = orc.ikpw(dWu, h, generator=rng)
     yu = sdb.itoSRI2(fu, Gu, y0u, tspan, dW=dWu)
     assert rel_err(yu, orc.srk2(f_host, g_host, y0u, tspan, dWu, Iu)) <= TOL
+
+
+@pytest.mark.parametrize("d,m,method,strat", [(6, 4, "wik", False), (12, 8, "wik", True),
+                                              (16, 12, "kpw", False), (14, 14, "wik", False)])
+def test_fused_tmem_kernel_jit_shapes(sdb, d, m, method, strat, monkeypatch):
+    """Shapes / methods without an ahead-of-time kernel: sdb_fusedx.cuh compiled by NVRTC (run-time
+    shape mirror in sdb_fused_rt.h) against the generic loop kernel and the oracle."""
+    rng = np.random.default_rng(1000 * d + m)
+    A = -1.1 * np.eye(d) + 0.3 * rng.standard_normal((d, d)) / np.sqrt(d)
+    B = 0.4 * rng.standard_normal((m, d, d)) / np.sqrt(d * m)
+    f, G = sdb.ops.LinearDrift(A), sdb.ops.LinearDiffusion(B)
+    y0 = rng.standard_normal(d)
+    tspan = np.linspace(0.0, 0.12, 25)
+    h = 0.005
+    P, seed = 45, 90210
+    integ = sdb.stratSRS2 if strat else sdb.itoSRI2
+    rep = {(False, "kpw"): sdb.Ikpw, (False, "wik"): sdb.Iwik,
+           (True, "kpw"): sdb.Jkpw, (True, "wik"): sdb.Jwik}[(strat, method)]
+    n0 = sdb.launch_count()
+    y = integ(f, G, y0, tspan, rep, paths=P, seed=seed, path_id0=2)
+    assert sdb.launch_count() - n0 == 2
+    monkeypatch.setenv("SDB_DISABLE_FUSED", "1")
+    y_gen = integ(f, G, y0, tspan, rep, paths=P, seed=seed, path_id0=2)
+    monkeypatch.delenv("SDB_DISABLE_FUSED")
+    assert rel_err(y, y_gen) <= TOL
+    dW = sdb.deltaW(24, m, h, paths=P, seed=seed, path_id0=2)
+    _, IJ = rep(dW, h, seed=seed, path_id0=2, ensemble=True)
+    for p in (0, 32, P - 1):
+        assert rel_err(y[p], orc.srk2(f, G, y0, tspan, dW[p], IJ[p])) <= TOL
