@@ -11,7 +11,8 @@
 #define W1 0xBB67AE85u
 
 template <int NB, int MODE, int NF>
-__global__ void k_philox(int iters, uint32_t k0, uint32_t k1, double a, double b, uint32_t* sink) {
+__global__ void k_philox(int iters, uint32_t k0, uint32_t k1, double a, double b, uint32_t* sink,
+                         uint32_t rm0, uint32_t rm1) {
   uint32_t acc = 0;
   double f[NF > 0 ? NF : 1];
 #pragma unroll
@@ -28,6 +29,9 @@ __global__ void k_philox(int iters, uint32_t k0, uint32_t k1, double a, double b
         uint32_t h0, l0, h1, l1;
         if (MODE == 0) {
           const uint64_t p0 = (uint64_t)M0 * c0[q], p1 = (uint64_t)M1 * c2[q];
+          h0 = (uint32_t)(p0 >> 32); l0 = (uint32_t)p0; h1 = (uint32_t)(p1 >> 32); l1 = (uint32_t)p1;
+        } else if (MODE == 2) {  // multipliers in registers (not immediates)
+          const uint64_t p0 = (uint64_t)rm0 * c0[q], p1 = (uint64_t)rm1 * c2[q];
           h0 = (uint32_t)(p0 >> 32); l0 = (uint32_t)p0; h1 = (uint32_t)(p1 >> 32); l1 = (uint32_t)p1;
         } else {  // separate high / low products (inline PTX so that they are not re-fused)
           asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(h0) : "r"(c0[q]), "r"(M0));
@@ -70,16 +74,16 @@ int main() {
   uint32_t* sink;
   cudaMalloc(&sink, 8);
   const int iters = 4000, sms = 148;
-  printf("mode(0=IMAD.WIDE,1=HI+LO),blocks_in_flight,dfma_chains,warps_per_smsp,cycles_per_philox_block_per_smsp,dfma_cycles_alone\n");
+  printf("mode(0=IMAD.WIDE imm,2=IMAD.WIDE reg),blocks_in_flight,dfma_chains,warps_per_smsp,cycles_per_philox_block_per_smsp,dfma_cycles_alone\n");
 #define RUN(NB, MODE, NF, W)                                                                       \
   {                                                                                                 \
-    float ms = timeit([&] { k_philox<NB, MODE, NF><<<sms, W * 128>>>(iters, 123u, 456u, 1.0000001, 1e-9, sink); }); \
+    float ms = timeit([&] { k_philox<NB, MODE, NF><<<sms, W * 128>>>(iters, 123u, 456u, 1.0000001, 1e-9, sink, M0, M1); }); \
     printf("%d,%d,%d,%d,%.1f,%.1f\n", MODE, NB, NF, W, ms * 1e-3 * 1.965e9 / iters / (NB * W), 20.0 * NF * 2 / NB); \
   }
 #define SET(MODE)                                                                                   \
   RUN(5, MODE, 0, 1) RUN(5, MODE, 0, 2) RUN(5, MODE, 0, 4) RUN(10, MODE, 0, 1) RUN(10, MODE, 0, 2)  \
   RUN(5, MODE, 4, 1) RUN(5, MODE, 4, 2) RUN(5, MODE, 4, 4) RUN(5, MODE, 8, 1) RUN(5, MODE, 8, 2)
-  SET(0) SET(1)
+  SET(0) SET(2)
   cudaError_t e = cudaDeviceSynchronize();
   printf("status: %s\n", cudaGetErrorString(e));
   return e != cudaSuccess;

@@ -1,5 +1,6 @@
+"""Timing of itoSRI2 d=m=10 with Iwik (TMEM-resident fused kernel) next to Ikpw: python tools/prof_wik10.py"""
 import os, sys, numpy as np
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, sdeint_b200 as sdb
 f, G, y0 = sdb.ops.sys_lin(10, 10)
 T, P = 200, 2000000
