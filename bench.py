@@ -246,6 +246,12 @@ def run_gpu(args):
     from scipy.linalg import expm
     want = expm(f.A * 1.0).dot(y0)
     mean_err = float(np.max(np.abs(mean[-1].cpu().numpy() - want)))
+    # and E y_i(1)^2 from dP/dt = A P + P A^T + sum_k B_k P B_k^T, P(0) = y0 y0^T
+    eye = np.eye(D)
+    Lop = np.kron(f.A, eye) + np.kron(eye, f.A) + sum(np.kron(Bk, Bk) for Bk in G.B)
+    P2 = expm(Lop).dot(np.outer(y0, y0).reshape(-1)).reshape(D, D)
+    m2 = (sums[-1, :, 1] / float(P * world)).cpu().numpy()
+    m2_err = float(np.max(np.abs(m2 - np.diag(P2)) / np.diag(P2)))
 
     # -- e2e: the public host-array call, copies inside the timed region ---------------------
     # With several ranks on one host the pinned result buffers add up (8.8 GB per 10^7 paths and
@@ -333,7 +339,8 @@ def run_gpu(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(args), "clocks": clocks,
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "check": {"max_abs_err_of_ensemble_mean_vs_expm": mean_err},
+            "check": {"max_abs_err_of_ensemble_mean_vs_expm": mean_err,
+                      "max_rel_err_of_second_moment_vs_moment_ode": m2_err},
         }
         if cpu_v is not None:
             line["cpu_baseline"] = {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port",

@@ -195,10 +195,9 @@ def _run(scheme, f, G, y0, tspan, dW, IJ, strat, method, generator, kp2is, paths
             a.noise = NOISE_HOST
             if have_dW:
                 dW_h = np.asarray(dW, dtype=np.float64)
-                if dW_h.ndim == 2:
-                    dW_h = np.broadcast_to(dW_h, (P,) + dW_h.shape) if P > 1 else dW_h[None]
-                d_dW = dev.to_device(dW_h, device)      # (P, N-1, m)
-                sW = (m, 1, (N - 1) * m)
+                # (N-1, m): one realisation shared by every path -> path stride 0, no replication
+                sW = (m, 1, (N - 1) * m if dW_h.ndim == 3 else 0)
+                d_dW = dev.to_device(dW_h, device)      # (P, N-1, m) or (N-1, m)
             else:                                        # I/J given, dW drawn (integrate.py:481-483)
                 d_dW = torch.empty((N - 1, m, P), dtype=torch.float64, device=device)
                 _lib.check(lib.sdb_delta_w(N - 1, m, float(h), P, int(path_id0), key,
@@ -210,10 +209,10 @@ def _run(scheme, f, G, y0, tspan, dW, IJ, strat, method, generator, kp2is, paths
             if need_ij:
                 if IJ is not None:
                     IJ_h = np.asarray(IJ, dtype=np.float64)
-                    if IJ_h.ndim == 3:
-                        IJ_h = np.broadcast_to(IJ_h, (P,) + IJ_h.shape) if P > 1 else IJ_h[None]
-                    d_IJ = dev.to_device(IJ_h, device)  # (P, N-1, m, m)
+                    ij_path = (N - 1) * m * m if IJ_h.ndim == 4 else 0
+                    d_IJ = dev.to_device(IJ_h, device)  # (P, N-1, m, m) or (N-1, m, m)
                 else:                                    # dW given, I/J drawn from it (:484-487)
+                    ij_path = (N - 1) * m * m
                     d_IJ = torch.empty((P, N - 1, m, m), dtype=torch.float64, device=device)
                     r = _lib.RepintArgs()
                     r.method, r.stratonovich, r.n_terms, r.m = method_id, int(strat), n_terms, m
@@ -227,7 +226,7 @@ def _run(scheme, f, G, y0, tspan, dW, IJ, strat, method, generator, kp2is, paths
                     _lib.check(lib.sdb_repeated_integrals(C.byref(r)))
                 keep.append(d_IJ)
                 a.d_IJ = dev.ptr(d_IJ)
-                a.IJ_stride_path, a.IJ_stride_step = (N - 1) * m * m, m * m
+                a.IJ_stride_path, a.IJ_stride_step = ij_path, m * m
                 a.IJ_stride_row, a.IJ_stride_col = m, 1
         # --- state --------------------------------------------------------------------
         if y0_paths is not None:

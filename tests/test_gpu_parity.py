@@ -600,3 +600,19 @@ def test_fused_tmem_kernel_jit_shapes(sdb, d, m, method, strat, monkeypatch):
     _, IJ = rep(dW, h, seed=seed, path_id0=2, ensemble=True)
     for p in (0, 32, P - 1):
         assert rel_err(y[p], orc.srk2(f, G, y0, tspan, dW[p], IJ[p])) <= TOL
+
+
+def test_shared_noise_is_broadcast_not_replicated(sdb):
+    """A 2-d dW / 3-d I with paths=P is ONE realisation shared by all paths (path stride 0 at the
+    C ABI): with per-path initial states the paths differ, with equal ones they coincide."""
+    g = load_golden("integrate_r74.npz")
+    f, G, y0 = SYSTEMS["r74"](False)
+    tspan, dW, I = g["tspan"], g["dW"][0], g["I"][0]
+    one = sdb.itoSRI2(f, G, y0, tspan, dW=dW, I=I)
+    many = sdb.itoSRI2(f, G, y0, tspan, dW=dW, I=I, paths=37)
+    assert many.shape == (37,) + one.shape
+    assert all(np.array_equal(many[p], one) for p in range(37))
+    y0p = np.asarray(y0)[None, :] * (1.0 + 0.01 * np.arange(37))[:, None]
+    spread = sdb.itoSRI2(f, G, y0, tspan, dW=dW, I=I, paths=37, y0_paths=y0p)
+    assert rel_err(spread[0], one) <= TOL and not np.array_equal(spread[5], one)
+    assert rel_err(spread[5], orc.srk2(f, G, y0p[5], tspan, dW, I)) <= TOL
