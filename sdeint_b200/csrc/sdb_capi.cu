@@ -129,10 +129,10 @@ static int jit_compile(const std::string& source, const char* kernel_name, JitKe
   if (nvrtc_load(&rt)) return 1;
   nvrtcProgram prog;
   const char* hdr_src[] = {kKernelHeader, kTablesHeader, kFusedHeader, kTmemHeader, kFusedWsHeader,
-                           kFusedXHeader};
+                           kFusedXHeader, kRepintXHeader};
   const char* hdr_name[] = {"sdb_kernels.cuh", "sdb_tables.cuh", "sdb_fused.cuh", "sdb_tmem.cuh",
-                            "sdb_fusedws.cuh", "sdb_fusedx.cuh"};
-  int rc = rt->CreateProgram(&prog, source.c_str(), "sdb_jit.cu", 6, hdr_src, hdr_name);
+                            "sdb_fusedws.cuh", "sdb_fusedx.cuh", "sdb_repintx.cuh"};
+  int rc = rt->CreateProgram(&prog, source.c_str(), "sdb_jit.cu", 7, hdr_src, hdr_name);
   if (rc) return fail(std::string("nvrtcCreateProgram: ") + rt->GetErrorString(rc));
   // -default-device: un-annotated functions (the generic lambdas of the compile-time loops) are
   // device functions in JIT mode
@@ -510,6 +510,7 @@ SDB_REPINT_KERNEL(sdb_k_repint_10, 10)
 SDB_REPINT_KERNEL(sdb_k_repint_20, 20)
 
 static std::map<int, JitKernel> g_repint_jit;
+static std::map<int, JitKernel> g_repintx_jit;  // key: 4 m + method
 static std::mutex g_repint_mu;
 
 static int repint_kernel(int m, const void** fn) {
@@ -553,8 +554,34 @@ extern "C" int sdb_repeated_integrals(const sdb_repint_args* a) {
   if (a->d_X && a->method == SDB_NOISE_WIK && a->m > 1 && !a->d_Gt)
     return fail("sdb_repeated_integrals: host normals for WIK also need Gt");
   if (a->steps == 0) return 0;
+  // Philox normals and a large even m: the TMEM-resident kernel (ahead of time for m = 20, else NVRTC)
   const void* fn = nullptr;
-  if (repint_kernel(a->m, &fn)) return 1;
+  size_t smem = 0;
+  unsigned block = 128;
+  if (!a->d_X && a->m >= 12 && SdbRepintXDims(a->m).supported() && !getenv("SDB_DISABLE_FUSED")) {
+    for (const auto& e : sdb_repintx_registry())
+      if (e.m == a->m && e.noise == a->method) { fn = e.fn; smem = e.smem; block = (unsigned)e.threads; }
+    if (!fn) {
+      const int key = a->m * 4 + a->method;
+      std::lock_guard<std::mutex> lk(g_repint_mu);
+      auto it = g_repintx_jit.find(key);
+      if (it == g_repintx_jit.end()) {
+        std::ostringstream src;
+        src << "#define SDB_FUSED_RB 2\n#define SDB_FUSED_VOL_MMA 0\n#include \"sdb_repintx.cuh\"\n"
+            << "SDB_REPINTX_KERNEL(sdb_jit_repintx, " << a->m << ", " << (a->method == SDB_NOISE_WIK ? 1 : 0)
+            << ")\n";
+        JitKernel jk;
+        if (jit_compile(src.str(), "sdb_jit_repintx", &jk)) return 1;
+        it = g_repintx_jit.emplace(key, jk).first;
+      }
+      fn = (const void*)it->second.kern;
+      smem = SdbRepintXDims(a->m).smem_bytes();
+      block = (unsigned)SdbRepintXDims(a->m).threads();
+    }
+    SDB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  } else if (repint_kernel(a->m, &fn)) {
+    return 1;
+  }
   SdbRepintArgs k;
   memset(&k, 0, sizeof k);
   k.method = a->method; k.stratonovich = a->stratonovich; k.n_terms = a->n_terms; k.m = a->m;
@@ -569,7 +596,8 @@ extern "C" int sdb_repeated_integrals(const sdb_repint_args* a) {
   k.IJ_sC = a->IJ_stride_col; k.IJ_sP = a->IJ_stride_path;
   void* args[1] = {&k};
   const int64_t total = a->steps * a->paths;
-  return launch(fn, dim3((unsigned)((total + 127) / 128)), dim3(128), args, (cudaStream_t)a->stream);
+  return launch(fn, dim3((unsigned)((total + block - 1) / block)), dim3(block), args,
+                (cudaStream_t)a->stream, smem);
 }
 
 // ---------------------------------------------------------------------------------------------

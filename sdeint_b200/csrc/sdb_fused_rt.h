@@ -104,3 +104,13 @@ struct SdbFusedXDims {
            smem_bytes() <= 227u * 1024u;
   }
 };
+
+// Run-time mirror of SdbRxShape (sdb_repintx.cuh).
+struct SdbRepintXDims {
+  int M;
+  constexpr explicit SdbRepintXDims(int m) : M(m) {}
+  constexpr int C_END() const { return 2 * ((M * (M - 1) / 2 + 15) / 16 * 16) + (2 * M + 7) / 8 * 8; }
+  constexpr int threads() const { return 2 * C_END() <= 512 ? 256 : 128; }
+  constexpr size_t smem_bytes() const { return 120u * 1024u; }
+  constexpr bool supported() const { return M >= 2 && M % 2 == 0 && C_END() <= 512; }
+};

@@ -81,6 +81,118 @@ SDB_DEV void sdb_gen_pairs(const SdbPhiloxKey& key, uint32_t p_lo, uint32_t p_hi
   }
 }
 
+// Levy areas of one (path, step) in TENSOR MEMORY: the Kloeden-Platen-Wright series (wiener.py:67-74,
+// :102-105 / :264-267) read-modify-written chunk by chunk at columns tm_at (which must hold zeros on
+// entry), plus Wiktorsson's tail when WIK.  dW is read from columns tm_dw.  X_k is pre-scaled by
+// s_hk[k] = h / (2 pi k).  Used by the fused step kernel below and by the standalone
+// Ikpw/Jkpw/Iwik/Jwik kernel (sdb_repintx.cuh).
+template <int M, int WIK>
+SDB_DEV void sdb_x_levy_areas(const SdbPhiloxKey& pkey, uint32_t p_lo, uint32_t p_hi, uint32_t step,
+                              const double2* __restrict__ tab, const double* __restrict__ s_hk,
+                              double hg, double cz, double tail_scale, int n_terms, uint32_t tm_at,
+                              uint32_t tm_dw) {
+  constexpr int MM = M * (M - 1) / 2, CH = 16, NCH = (MM + CH - 1) / CH;
+  // ---- Levy-area series (wiener.py:67-74, :102-105 / :264-267) ------------------------------------
+#pragma unroll 1
+  for (int k = 1; k <= n_terms; ++k) {
+    double X[M], Z[M];
+    const uint32_t sx = (uint32_t)((M + 2 * (k - 1) * M) >> 1);
+    sdb_gen_pairs<M / 2, 0, M, true>(pkey, p_lo, p_hi, step, sx, tab, s_hk[k], X);
+    sdb_gen_pairs<M / 2, 0, M, false>(pkey, p_lo, p_hi, step, sx + M / 2, tab, 1.0, Z);
+    {
+      double dW[M];
+      sdb_tm_ld<M>(tm_dw, dW);
+#pragma unroll
+      for (int j = 0; j < M; ++j) Z[j] = fma(cz, dW[j], Z[j]);
+    }
+    SdbTmLoad<CH> ca, cb;
+    ca.issue(tm_at);
+    ca.wait();
+    sdb_static_for<0, NCH>([&](auto cc) {
+      constexpr int c = decltype(cc)::value;
+      if constexpr (c + 1 < NCH) {
+        if constexpr (c & 1) ca.issue(tm_at + 2 * CH * (c + 1));
+        else cb.issue(tm_at + 2 * CH * (c + 1));
+      }
+      double At[CH];
+#pragma unroll
+      for (int e = 0; e < CH; ++e) At[e] = (c & 1) ? cb.get(e) : ca.get(e);
+      sdb_static_for<0, CH>([&](auto ee) {
+        constexpr int e = decltype(ee)::value;
+        constexpr int idx = CH * c + e;
+        if constexpr (idx < MM) {
+          constexpr int i = sdb_pair_j<M>(idx), j = sdb_pair_k<M>(idx);
+          At[e] = fma(X[i], Z[j], At[e]);
+          At[e] = fma(-Z[i], X[j], At[e]);
+        }
+      });
+      sdb_tm_st<CH>(tm_at + 2 * CH * c, At);
+      if constexpr (c + 1 < NCH) {
+        if constexpr (c & 1) ca.wait();
+        else cb.wait();
+      }
+    });
+    sdb_tm_wait_st();
+  }
+  // ---- Wiktorsson's tail (wiener.py:269-277), O(m^2), no storage for the tail normals ----------------
+  if (WIK) {
+    double dW[M], u[M];
+    sdb_tm_ld<M>(tm_dw, dW);
+    double nrm = 0.0;
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+      nrm = fma(dW[j], dW[j], nrm);
+      u[j] = 0.0;
+    }
+    const double rad = sqrt(1.0 + nrm / hg);
+    const double den = tail_scale / (1.4142135623730951 * (1.0 + rad));
+    const double c1 = den * (2.0 + 2.0 * rad);
+    const double c2 = den * (2.0 / hg);
+    const uint32_t st0 = (uint32_t)((M + 2 * n_terms * M) >> 1);
+    // pass 1: the generator code exists once (runtime loop); only the index-dependent FMAs of a
+    // chunk are selected by a warp-uniform jump (keeps the kernel inside the instruction cache)
+#pragma unroll 1
+    for (int c = 0; c < NCH; ++c) {
+      double g[CH], At[CH];
+      sdb_gen_pairs<CH / 2, 0, CH, false>(pkey, p_lo, p_hi, step, st0 + (uint32_t)(c * CH / 2),
+                                          tab, 1.0, g);
+      sdb_tm_ld<CH>(tm_at + 2 * CH * c, At);
+      sdb_static_for<0, NCH>([&](auto cc) {
+        constexpr int c_ = decltype(cc)::value;
+        if (c == c_) {
+          sdb_static_for<0, CH>([&](auto ee) {
+            constexpr int e = decltype(ee)::value;
+            constexpr int idx = CH * c_ + e;
+            if constexpr (idx < MM) {
+              constexpr int i = sdb_pair_j<M>(idx), j = sdb_pair_k<M>(idx);
+              At[e] = fma(c1, g[e], At[e]);
+              u[i] = fma(g[e], dW[j], u[i]);
+              u[j] = fma(-g[e], dW[i], u[j]);
+            }
+          });
+        }
+      });
+      sdb_tm_st<CH>(tm_at + 2 * CH * c, At);
+    }
+    sdb_tm_wait_st();
+    sdb_static_for<0, NCH>([&](auto cc) {
+      constexpr int c = decltype(cc)::value;
+      double At[CH];
+      sdb_tm_ld<CH>(tm_at + 2 * CH * c, At);
+      sdb_static_for<0, CH>([&](auto ee) {
+        constexpr int e = decltype(ee)::value;
+        constexpr int idx = CH * c + e;
+        if constexpr (idx < MM) {
+          constexpr int i = sdb_pair_j<M>(idx), j = sdb_pair_k<M>(idx);
+          At[e] = fma(c2, fma(dW[j], u[i], -dW[i] * u[j]), At[e]);
+        }
+      });
+      sdb_tm_st<CH>(tm_at + 2 * CH * c, At);
+    });
+    sdb_tm_wait_st();
+  }
+}
+
 template <int D, int M, int WIK>
 SDB_DEV void sdb_srk2_fusedx_body(const SdbLoopArgs& a, const PInline<D * D>& fp,
                                   const double* __restrict__ frag, double* smem) {
@@ -155,105 +267,9 @@ SDB_DEV void sdb_srk2_fusedx_body(const SdbLoopArgs& a, const PInline<D * D>& fp
       for (int c = 0; c < NCH; ++c) sdb_tm_st<CH>(tm + Xs::C_AT + 2 * CH * c, zero);
       sdb_tm_wait_st();
     }
-    // ---- Levy-area series (wiener.py:67-74, :102-105 / :264-267) ------------------------------------
-#pragma unroll 1
-    for (int k = 1; k <= n_terms; ++k) {
-      double X[M], Z[M];
-      const uint32_t sx = (uint32_t)((M + 2 * (k - 1) * M) >> 1);
-      sdb_gen_pairs<M / 2, 0, M, true>(pkey, p_lo, p_hi, (uint32_t)n, sx, tab, s_hk[k], X);
-      sdb_gen_pairs<M / 2, 0, M, false>(pkey, p_lo, p_hi, (uint32_t)n, sx + M / 2, tab, 1.0, Z);
-      {
-        double dW[M];
-        sdb_tm_ld<M>(tm + Xs::C_DW, dW);
-#pragma unroll
-        for (int j = 0; j < M; ++j) Z[j] = fma(cz, dW[j], Z[j]);
-      }
-      SdbTmLoad<CH> ca, cb;
-      ca.issue(tm + Xs::C_AT);
-      ca.wait();
-      sdb_static_for<0, NCH>([&](auto cc) {
-        constexpr int c = decltype(cc)::value;
-        if constexpr (c + 1 < NCH) {
-          if constexpr (c & 1) ca.issue(tm + Xs::C_AT + 2 * CH * (c + 1));
-          else cb.issue(tm + Xs::C_AT + 2 * CH * (c + 1));
-        }
-        double At[CH];
-#pragma unroll
-        for (int e = 0; e < CH; ++e) At[e] = (c & 1) ? cb.get(e) : ca.get(e);
-        sdb_static_for<0, CH>([&](auto ee) {
-          constexpr int e = decltype(ee)::value;
-          constexpr int idx = CH * c + e;
-          if constexpr (idx < MM) {
-            constexpr int i = sdb_pair_j<M>(idx), j = sdb_pair_k<M>(idx);
-            At[e] = fma(X[i], Z[j], At[e]);
-            At[e] = fma(-Z[i], X[j], At[e]);
-          }
-        });
-        sdb_tm_st<CH>(tm + Xs::C_AT + 2 * CH * c, At);
-        if constexpr (c + 1 < NCH) {
-          if constexpr (c & 1) ca.wait();
-          else cb.wait();
-        }
-      });
-      sdb_tm_wait_st();
-    }
-    // ---- Wiktorsson's tail (wiener.py:269-277), O(m^2), no storage for the tail normals ----------------
-    if (WIK) {
-      double dW[M], u[M];
-      sdb_tm_ld<M>(tm + Xs::C_DW, dW);
-      double nrm = 0.0;
-#pragma unroll
-      for (int j = 0; j < M; ++j) {
-        nrm = fma(dW[j], dW[j], nrm);
-        u[j] = 0.0;
-      }
-      const double rad = sqrt(1.0 + nrm / hg);
-      const double den = tail_scale / (1.4142135623730951 * (1.0 + rad));
-      const double c1 = den * (2.0 + 2.0 * rad);
-      const double c2 = den * (2.0 / hg);
-      const uint32_t st0 = (uint32_t)((M + 2 * n_terms * M) >> 1);
-      // pass 1: the generator code exists once (runtime loop); only the index-dependent FMAs of a
-      // chunk are selected by a warp-uniform jump (keeps the kernel inside the instruction cache)
-#pragma unroll 1
-      for (int c = 0; c < NCH; ++c) {
-        double g[CH], At[CH];
-        sdb_gen_pairs<CH / 2, 0, CH, false>(pkey, p_lo, p_hi, (uint32_t)n, st0 + (uint32_t)(c * CH / 2),
-                                            tab, 1.0, g);
-        sdb_tm_ld<CH>(tm + Xs::C_AT + 2 * CH * c, At);
-        sdb_static_for<0, NCH>([&](auto cc) {
-          constexpr int c_ = decltype(cc)::value;
-          if (c == c_) {
-            sdb_static_for<0, CH>([&](auto ee) {
-              constexpr int e = decltype(ee)::value;
-              constexpr int idx = CH * c_ + e;
-              if constexpr (idx < MM) {
-                constexpr int i = sdb_pair_j<M>(idx), j = sdb_pair_k<M>(idx);
-                At[e] = fma(c1, g[e], At[e]);
-                u[i] = fma(g[e], dW[j], u[i]);
-                u[j] = fma(-g[e], dW[i], u[j]);
-              }
-            });
-          }
-        });
-        sdb_tm_st<CH>(tm + Xs::C_AT + 2 * CH * c, At);
-      }
-      sdb_tm_wait_st();
-      sdb_static_for<0, NCH>([&](auto cc) {
-        constexpr int c = decltype(cc)::value;
-        double At[CH];
-        sdb_tm_ld<CH>(tm + Xs::C_AT + 2 * CH * c, At);
-        sdb_static_for<0, CH>([&](auto ee) {
-          constexpr int e = decltype(ee)::value;
-          constexpr int idx = CH * c + e;
-          if constexpr (idx < MM) {
-            constexpr int i = sdb_pair_j<M>(idx), j = sdb_pair_k<M>(idx);
-            At[e] = fma(c2, fma(dW[j], u[i], -dW[i] * u[j]), At[e]);
-          }
-        });
-        sdb_tm_st<CH>(tm + Xs::C_AT + 2 * CH * c, At);
-      });
-      sdb_tm_wait_st();
-    }
+    // ---- Levy areas (series + Wiktorsson tail) into tensor memory ------------------------------------
+    sdb_x_levy_areas<M, WIK>(pkey, p_lo, p_hi, (uint32_t)n, tab, s_hk, hg, cz, tail_scale, n_terms,
+                             tm + Xs::C_AT, tm + Xs::C_DW);
 
     // ---- row blocks (runtime loop: every block has RN rows) ------------------------------------------
     double w[IT > 0 ? IT : 1][4][2], wv[IL > 0 ? IL : 1];

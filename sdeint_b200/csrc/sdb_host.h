@@ -40,3 +40,15 @@ std::vector<SdbFusedEntry>& sdb_fused_registry();
 struct SdbFusedRegistrar {
   explicit SdbFusedRegistrar(const SdbFusedEntry& e) { sdb_fused_registry().push_back(e); }
 };
+
+// The TMEM-resident standalone repeated-integral kernel (sdb_repintx.cuh) for one (m, method).
+struct SdbRepintXEntry {
+  int m, noise;
+  const void* fn;
+  size_t smem;
+  int threads;
+};
+std::vector<SdbRepintXEntry>& sdb_repintx_registry();
+struct SdbRepintXRegistrar {
+  explicit SdbRepintXRegistrar(const SdbRepintXEntry& e) { sdb_repintx_registry().push_back(e); }
+};

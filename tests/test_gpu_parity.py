@@ -616,3 +616,32 @@ def test_shared_noise_is_broadcast_not_replicated(sdb):
     spread = sdb.itoSRI2(f, G, y0, tspan, dW=dW, I=I, paths=37, y0_paths=y0p)
     assert rel_err(spread[0], one) <= TOL and not np.array_equal(spread[5], one)
     assert rel_err(spread[5], orc.srk2(f, G, y0p[5], tspan, dW, I)) <= TOL
+
+
+@pytest.mark.parametrize("m", [12, 16, 20])
+def test_standalone_repeated_integrals_large_m(sdb, m):
+    """Ikpw/Jkpw/Iwik/Jwik with on-device normals at large m go through the TMEM-resident kernel
+    (sdb_repintx.cuh; m = 20 ahead of time, others NVRTC): checked against the oracle on the replayed
+    Philox normals, for a partial last block, and against the generic kernel."""
+    steps, h, P, seed, n = 3, 0.005, 75, 4242, 5
+    dW = sdb.deltaW(steps, m, h, paths=P, seed=seed, path_id0=9)
+    X, Y = po.kpw_normals(steps, m, n, P, seed, path_id0=9)
+    Gt = po.wik_tail_normals(steps, m, n, P, seed, path_id0=9)
+    A, I = sdb.Ikpw(dW, h, n=n, seed=seed, path_id0=9, ensemble=True)
+    _, J = sdb.Jkpw(dW, h, n=n, seed=seed, path_id0=9, ensemble=True)
+    At, Iw = sdb.Iwik(dW, h, n=n, seed=seed, path_id0=9, ensemble=True)
+    _, Jw = sdb.Jwik(dW, h, n=n, seed=seed, path_id0=9, ensemble=True)
+    M = m * (m - 1) // 2
+    assert A.shape == (P, steps, m, m) and At.shape == (P, steps, M, 1)
+    for p in (0, 31, 32, P - 1):
+        A_o, I_o = orc.ikpw_from_normals(dW[p], h, X[:, p], Y[:, p])
+        At_o, Iw_o = orc.iwik_from_normals(dW[p], h, X[:, p], Y[:, p], Gt[p])
+        s = np.max(np.abs(I_o))
+        assert np.max(np.abs(A[p] - A_o)) <= 1e-12 * s and np.max(np.abs(I[p] - I_o)) <= 1e-12 * s
+        assert np.max(np.abs(At[p] - At_o)) <= 1e-12 * s and np.max(np.abs(Iw[p] - Iw_o)) <= 1e-12 * s
+        eye = 0.5 * h * np.eye(m)[None]
+        assert np.max(np.abs(J[p] - I_o - eye)) <= 1e-12 * s
+        assert np.max(np.abs(Jw[p] - Iw_o - eye)) <= 1e-12 * s
+    # single-path call in the reference's layout
+    A1, I1 = sdb.Ikpw(dW[0], h, n=n, seed=seed, path_id0=9)
+    assert A1.shape == (steps, m, m) and np.array_equal(I1, I[0])
