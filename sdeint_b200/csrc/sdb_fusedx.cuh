@@ -53,9 +53,14 @@ struct SdbXShape {
   static constexpr int WROWS = R_Y + D;
   // warps per SM sub-partition: two when two warps' columns fit the 512 of a TMEM lane (and the
   // register file: 2 x 255 registers per lane slot)
+#ifdef SDB_X_WPQ
+  static constexpr int WPQ = SDB_X_WPQ;                      // tuning override (3: 168 registers/thread)
+#else
   static constexpr int WPQ = 2 * C_END <= 512 ? 2 : 1;
+#endif
   static constexpr int WARPS = 4 * WPQ, THREADS = 32 * WARPS, PATHS = THREADS;
-  static constexpr int C_STRIDE = 512 / WPQ;                 // TMEM columns per warp
+  static constexpr int C_STRIDE = (512 / WPQ) / 8 * 8;       // TMEM columns per warp
+  static_assert(C_STRIDE >= C_END, "tensor-memory columns of a lane exceeded");
   static SDB_CX size_t smem_bytes() {
     size_t b = (size_t)WROWS * 32 * 8 * WARPS + 128 * 16 +
                (SDB_FUSED_MAX_TERMS + 1 + Sh::n_left() + 1) * sizeof(double) + 16;

@@ -395,11 +395,11 @@ def test_fused_dmma_kernel_shapes(sdb, d, m, strat, monkeypatch):
         assert rel_err(y_fused[p], ref) <= TOL
 
 
-@pytest.mark.parametrize("variant", ["1", "10", "11"])
+@pytest.mark.parametrize("variant", ["1", "10", "11", "13"])
 def test_fused_tuning_variants_agree(sdb, variant, monkeypatch):
     """The tuning variants of the headline kernel kept for A/B measurements -- pair-at-a-time
     noise (1), warp-specialised with a tensor-memory ring (10), the same pipeline without helper
-    warps (11) -- integrate the same Philox streams: they must agree with the default kernel to
+    warps (11), the TMEM-resident pipeline with 12 warps per SM at 168 registers (13) -- integrate the same Philox streams: they must agree with the default kernel to
     rounding and with the oracle to 1e-12."""
     f, G, y0 = SYSTEMS["lin10"](False)
     tspan = np.linspace(0.0, 0.25, 51)
