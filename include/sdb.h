@@ -141,6 +141,12 @@ int sdb_repeated_integrals(const sdb_repint_args* args);
 int sdb_moments(const double* d_y, int64_t n_saved, int d, int64_t paths, double* d_sums,
                 unsigned long long* d_hist, int bins, double lo, double hi, void* stream);
 
+/* Strided device -> host copy on `stream` (cudaMemcpy2DAsync): `height` rows of `width_bytes`,
+ * row pitches in bytes.  The shim uses it to stream chunks of a path-minor trajectory buffer
+ * into the caller's (pinned) result array while the next chunk of paths is being integrated. */
+int sdb_copy2d_d2h_async(void* h_dst, int64_t dst_pitch_bytes, const void* d_src,
+                         int64_t src_pitch_bytes, int64_t width_bytes, int64_t height, void* stream);
+
 /* Measured peak of the FP64 pipe: runs a register-resident DFMA chain on every SM and
  * returns TFLOP/s (roofline denominator of bench.py). */
 int sdb_fp64_peak(int iters, double* tflops_out, void* stream);

@@ -690,6 +690,16 @@ extern "C" int sdb_moments(const double* d_y, int64_t n_saved, int d, int64_t pa
   return 0;
 }
 
+extern "C" int sdb_copy2d_d2h_async(void* h_dst, int64_t dpitch, const void* d_src, int64_t spitch,
+                                    int64_t width, int64_t height, void* stream) {
+  if (!h_dst || !d_src || width < 0 || height < 0 || dpitch < width || spitch < width)
+    return fail("sdb_copy2d_d2h_async: bad argument");
+  if (width == 0 || height == 0) return 0;
+  SDB_CUDA(cudaMemcpy2DAsync(h_dst, (size_t)dpitch, d_src, (size_t)spitch, (size_t)width,
+                             (size_t)height, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // FP64 pipe peak (roofline denominator)
 // ---------------------------------------------------------------------------------------------

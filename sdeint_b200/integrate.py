@@ -241,19 +241,37 @@ def _run(scheme, f, G, y0, tspan, dW, IJ, strat, method, generator, kp2is, paths
             a.flags = FLAG_Y0_BROADCAST
         if strat:
             a.flags |= FLAG_STRATONOVICH
-        d_y = torch.empty((n_saved, d, P), dtype=torch.float64, device=device)
-        d_status = torch.empty(4, dtype=torch.int64, device=device)
         a.scheme, a.n_terms = scheme, int(n_terms)
-        a.paths, a.path_id0, a.seed = P, int(path_id0), key
-        a.N, a.save_every = N, save_every
+        a.N, a.save_every, a.seed = N, save_every, key
         a.h_tspan = dev.host_ptr(tspan)
         a.d_y0 = dev.ptr(d_y0)
-        a.d_y = dev.ptr(d_y)
-        a.y_stride_save, a.y_stride_comp, a.y_stride_path = d * P, P, 1
         if kp2is is not None:
             kp = np.ascontiguousarray(np.concatenate(kp2is[:3]), dtype=np.float64)
             a.h_kp2is = dev.host_ptr(kp)
             a.rtol = float(kp2is[3])
+        if (host_out is not None and out != "torch" and a.noise != NOISE_HOST and y0_paths is None
+                and P >= _PIPELINE_MIN_PATHS):
+            # Large ensemble, on-device noise, caller-owned host result: integrate the paths in chunks
+            # and copy chunk c to the host while chunk c+1 is being integrated (two device buffers).
+            if tuple(host_out.shape) != (n_saved, d, P) or host_out.dtype != torch.float64 \
+                    or not host_out.is_contiguous():
+                raise SDEValueError('host_out must be a contiguous float64 tensor of shape %s'
+                                    % ((n_saved, d, P),))
+            status = _run_pipelined(lib, system, a, host_out, P, int(path_id0), n_saved, d, device)
+            _last_status = status
+            if scheme == SCHEME_KP2IS and status[2] > 0:
+                raise RuntimeError(
+                    "At time t_n = %g Failed to solve for Y_{n+1}: the implicit equation did not "
+                    "converge to rtol=%g on %d path(s)." % (tspan[status[3]], kp2is[3], status[2]))
+            host = host_out.numpy()
+            if not ensemble:
+                return np.ascontiguousarray(host[:, :, 0])
+            return host.transpose(2, 0, 1)
+        d_y = torch.empty((n_saved, d, P), dtype=torch.float64, device=device)
+        d_status = torch.empty(4, dtype=torch.int64, device=device)
+        a.paths, a.path_id0 = P, int(path_id0)
+        a.d_y = dev.ptr(d_y)
+        a.y_stride_save, a.y_stride_comp, a.y_stride_path = d * P, P, 1
         a.d_status = dev.ptr(d_status)
         a.stream = dev.stream_ptr()
         _lib.check(lib.sdb_integrate(system.handle, C.byref(a)))
@@ -278,6 +296,51 @@ def _run(scheme, f, G, y0, tspan, dW, IJ, strat, method, generator, kp2is, paths
     if not ensemble:
         return np.ascontiguousarray(host[:, :, 0])      # (N, d), y[0] == y0
     return host.transpose(2, 0, 1)                       # (P, n_saved, d)
+
+
+_PIPELINE_MIN_PATHS = 1 << 19
+_PIPELINE_CHUNKS = 8
+
+
+def _run_pipelined(lib, system, a, host_out, P, path_id0, n_saved, d, device):
+    """Chunked integration with overlapped device -> host copies; returns the merged status."""
+    torch = dev.torch_mod()
+    # chunk = a whole number of waves of the fused kernels (one 256-path block per SM), so that only
+    # the last chunk has a partial wave -- exactly like the single launch it replaces
+    wave = 256 * torch.cuda.get_device_properties(device).multi_processor_count
+    chunks = min(_PIPELINE_CHUNKS, max(2, P >> 18))
+    Pc = max(wave, (P // chunks) // wave * wave)
+    chunks = -(-P // Pc)
+    compute = torch.cuda.current_stream()
+    copier = torch.cuda.Stream(device=device)
+    bufs = [torch.empty((n_saved, d, Pc), dtype=torch.float64, device=device) for _ in range(2)]
+    stats = torch.empty((chunks, 4), dtype=torch.int64, device=device)
+    copied = [None, None]
+    base = host_out.data_ptr()
+    for c in range(chunks):
+        p0 = c * Pc
+        n = min(Pc, P - p0)
+        buf = bufs[c & 1]
+        if copied[c & 1] is not None:
+            compute.wait_event(copied[c & 1])     # the copy of chunk c-2 has left this buffer
+        a.paths, a.path_id0 = n, path_id0 + p0
+        a.d_y = dev.ptr(buf)
+        a.y_stride_save, a.y_stride_comp, a.y_stride_path = d * Pc, Pc, 1
+        a.d_status = C.c_void_p(stats[c].data_ptr())
+        a.stream = C.c_void_p(compute.cuda_stream)
+        _lib.check(lib.sdb_integrate(system.handle, C.byref(a)))
+        done = torch.cuda.Event()
+        done.record(compute)
+        copier.wait_event(done)
+        _lib.check(lib.sdb_copy2d_d2h_async(C.c_void_p(base + 8 * p0), 8 * P, dev.ptr(buf), 8 * Pc,
+                                            8 * n, n_saved * d, C.c_void_p(copier.cuda_stream)))
+        ev = torch.cuda.Event()
+        ev.record(copier)
+        copied[c & 1] = ev
+    copier.synchronize()
+    compute.wait_stream(copier)
+    st = stats.cpu().numpy()
+    return (int(st[:, 0].sum()), int(st[:, 1].min()), int(st[:, 2].sum()), int(st[:, 3].min()))
 
 
 _ENS = dict(paths=None, seed=None, path_id0=0, save_every=1, n_terms=5, device=None, out="numpy",

@@ -645,3 +645,25 @@ def test_standalone_repeated_integrals_large_m(sdb, m):
     # single-path call in the reference's layout
     A1, I1 = sdb.Ikpw(dW[0], h, n=n, seed=seed, path_id0=9)
     assert A1.shape == (steps, m, m) and np.array_equal(I1, I[0])
+
+
+def test_pipelined_host_output_matches_single_launch(sdb):
+    """Large ensembles written to a caller-owned pinned host array are integrated in chunks with the
+    device -> host copies overlapped (sdb_copy2d_d2h_async): same bits as one launch, because the
+    Philox streams are keyed by the global path id."""
+    import torch
+    P = (1 << 19) + 777
+    f, G, y0 = SYSTEMS["lin10"](False)
+    tspan = np.linspace(0.0, 0.01, 11)
+    ref = sdb.itoSRI2(f, G, y0, tspan, paths=P, seed=3, path_id0=10, save_every=5, out="torch").cpu().numpy()
+    host = torch.empty((3, 10, P), dtype=torch.float64).pin_memory()
+    n0 = sdb.launch_count()
+    y = sdb.itoSRI2(f, G, y0, tspan, paths=P, seed=3, path_id0=10, save_every=5, host_out=host)
+    assert sdb.launch_count() - n0 >= 4                       # more than one chunk
+    assert y.shape == (P, 3, 10) and np.array_equal(y, ref.transpose(2, 0, 1))
+    assert sdb.last_status()[0] == 0
+    f2, G2, y02 = SYSTEMS["lin2"](False)
+    host2 = torch.empty((2, 2, P), dtype=torch.float64).pin_memory()
+    y2 = sdb.itoEuler(f2, G2, y02, tspan, paths=P, seed=4, save_every=10, host_out=host2)
+    ref2 = sdb.itoEuler(f2, G2, y02, tspan, paths=P, seed=4, save_every=10, out="torch").cpu().numpy()
+    assert np.array_equal(y2, ref2.transpose(2, 0, 1))
