@@ -17,6 +17,11 @@
 //    (integrate.py:509-521); sqrt(h) sum1 = G_n I is what the kernel accumulates.  The flop count
 //    used for the roofline is reduced accordingly (subtract 2md^2 + 2dm).
 //
+//  * What bounds it (tools/micro/philox.cu): the FP64 pipe PLUS the 20 IMAD.WIDE of
+//    every Philox4x32-10 block, which issue at ~3.7 cycles each and do not overlap with DFMA/DMMA.
+//    Per warp-step: 12 560 FP64 cycles + 4070 Philox cycles; the kernel runs at 82 % of that floor,
+//    and neither more resident warps (variants 10, 13) nor deeper software ILP move it further.
+//
 // Per step and per row block b (rows R_b of the state, 4 + 4 + 2 for d = 10):
 //   P1  DMMA   [B_j[R_b,:] ; A[R_b,:]] Y  -> shared staging (rows x 32 paths)
 //   P2  DFMA   s~[R_b,:] = G_n[R_b,:] I   (Levy areas from shared memory), G_n dW, drift
