@@ -162,3 +162,31 @@ def test_paths_do_not_depend_on_sharding(sdb):
     # and a different seed gives different paths
     other = sdb.itoSRI2(f, G, y0, tspan, paths=4, seed=100, save_every=8)
     assert not np.array_equal(other, whole[:4])
+
+
+def test_device_normals_chi_square_1e9(sdb):
+    """10^9 normals of the on-device generator (Philox4x32-10 + fp64 Box-Muller), binned by the
+    histogram kernel: chi-square against the Gaussian bin probabilities, tail counts beyond 5 sigma,
+    and the first four moments from the moments kernel."""
+    import torch
+    from scipy import stats
+    N, m, P = 1000, 10, 100000
+    z = sdb.deltaW(N, m, 1.0, paths=P, seed=123456789, out="torch")         # (N, m, P), unit variance
+    n = z.numel()
+    flat = z.reshape(1, 1, n)
+    bins, lo, hi = 128, -6.0, 6.0
+    sums, counts = sdb.ensemble.moments(flat, hist=(bins, lo, hi))
+    c = counts[0, 0].cpu().numpy().astype(np.float64)
+    edges = np.linspace(lo, hi, bins + 1)
+    pexp = np.diff(stats.norm.cdf(edges))
+    keep = pexp * n > 50                                                      # well-populated bins
+    chi2 = np.sum((c[keep] - n * pexp[keep]) ** 2 / (n * pexp[keep]))
+    dof = keep.sum()
+    assert chi2 < dof + 6.0 * np.sqrt(2.0 * dof), (chi2, dof)
+    assert abs(sums[0, 0, 0].item() / n) < 5.0 / np.sqrt(n)
+    assert abs(sums[0, 0, 1].item() / n - 1.0) < 5.0 * np.sqrt(2.0 / n)
+    tail = int((z.abs() > 5.0).sum().item())
+    want = 2.0 * stats.norm.sf(5.0) * n                                       # 573
+    assert abs(tail - want) < 6.0 * np.sqrt(want), (tail, want)
+    m4 = float((z.reshape(-1)[: 10 ** 8] ** 4).mean().item())
+    assert abs(m4 - 3.0) < 6.0 * np.sqrt(96.0 / 1e8)
