@@ -141,6 +141,14 @@ int sdb_repeated_integrals(const sdb_repint_args* args);
 int sdb_moments(const double* d_y, int64_t n_saved, int d, int64_t paths, double* d_sums,
                 unsigned long long* d_hist, int bins, double lo, double hi, void* stream);
 
+/* Ensemble second moments of saved states y[save][comp][path] (path stride 1):
+ * d_out[save][i][j] += sum_p y_i y_j (full symmetric d x d matrix, d <= 16), summed per chunk of
+ * 4096 paths and then over chunks in a fixed order (deterministic, partition-independent per chunk).
+ * With sdb_moments this gives the ensemble covariance at every saved time; like the moment sums it
+ * is all-reduced over ranks by the caller. */
+int sdb_cross_moments(const double* d_y, int64_t n_saved, int d, int64_t paths, double* d_out,
+                      void* stream);
+
 /* Strided device -> host copy on `stream` (cudaMemcpy2DAsync): `height` rows of `width_bytes`,
  * row pitches in bytes.  The shim uses it to stream chunks of a path-minor trajectory buffer
  * into the caller's (pinned) result array while the next chunk of paths is being integrated. */

@@ -690,6 +690,68 @@ extern "C" int sdb_moments(const double* d_y, int64_t n_saved, int d, int64_t pa
   return 0;
 }
 
+// cross[save][chunk][i*d+j] = sum over the 4096 paths of the chunk of y_i y_j: the chunk is staged
+// through shared memory 256 paths at a time, thread t < d*d owns the pair (t / d, t % d).
+__global__ void __launch_bounds__(256)
+sdb_k_cross_partial(const double* __restrict__ y, int d, int64_t paths, int64_t nchunks,
+                    double* __restrict__ partial) {
+  extern __shared__ double tile[];  // [d][256]
+  const int64_t save = blockIdx.y, chunk = blockIdx.x;
+  const double* src = y + save * d * paths;
+  const int t = threadIdx.x, i = t / d, j = t % d;
+  const bool owner = t < d * d;
+  double acc = 0.0;
+  for (int b = 0; b < SDB_MOM_CHUNK / 256; ++b) {
+    const int64_t p = chunk * SDB_MOM_CHUNK + (int64_t)b * 256 + t;
+    for (int c = 0; c < d; ++c) tile[c * 256 + t] = p < paths ? src[c * paths + p] : 0.0;
+    __syncthreads();
+    if (owner) {
+      const double* a = tile + i * 256;
+      const double* bb = tile + j * 256;
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;  // fixed association: deterministic
+      for (int q = 0; q < 256; q += 4) {
+        s0 = fma(a[q], bb[q], s0);
+        s1 = fma(a[q + 1], bb[q + 1], s1);
+        s2 = fma(a[q + 2], bb[q + 2], s2);
+        s3 = fma(a[q + 3], bb[q + 3], s3);
+      }
+      acc += (s0 + s1) + (s2 + s3);
+    }
+    __syncthreads();
+  }
+  if (owner) partial[(save * nchunks + chunk) * d * d + t] = acc;
+}
+
+__global__ void sdb_k_cross_final(const double* __restrict__ partial, int64_t n_saved, int dd,
+                                  int64_t nchunks, double* __restrict__ out) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_saved * dd) return;
+  const int64_t save = e / dd, t = e % dd;
+  double s = 0.0;
+  for (int64_t c = 0; c < nchunks; ++c) s += partial[(save * nchunks + c) * dd + t];
+  out[e] += s;
+}
+
+extern "C" int sdb_cross_moments(const double* d_y, int64_t n_saved, int d, int64_t paths,
+                                 double* d_out, void* stream) {
+  if (!d_y || !d_out || n_saved < 1 || paths < 1) return fail("sdb_cross_moments: bad argument");
+  if (d < 1 || d > 16) return fail("sdb_cross_moments: need 1 <= d <= 16");
+  if (n_saved > 65535) return fail("sdb_cross_moments: too many saved points");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t nchunks = (paths + SDB_MOM_CHUNK - 1) / SDB_MOM_CHUNK;
+  double* partial = nullptr;
+  SDB_CUDA(cudaMallocAsync(&partial, (size_t)n_saved * nchunks * d * d * sizeof(double), st));
+  sdb_k_cross_partial<<<dim3((unsigned)nchunks, (unsigned)n_saved), 256, (size_t)d * 256 * sizeof(double), st>>>(
+      d_y, d, paths, nchunks, partial);
+  SDB_CUDA(cudaGetLastError());
+  const int64_t total = n_saved * d * d;
+  sdb_k_cross_final<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(partial, n_saved, d * d, nchunks, d_out);
+  SDB_CUDA(cudaGetLastError());
+  g_launches.fetch_add(2);
+  SDB_CUDA(cudaFreeAsync(partial, st));
+  return 0;
+}
+
 extern "C" int sdb_copy2d_d2h_async(void* h_dst, int64_t dpitch, const void* d_src, int64_t spitch,
                                     int64_t width, int64_t height, void* stream) {
   if (!h_dst || !d_src || width < 0 || height < 0 || dpitch < width || spitch < width)

@@ -46,6 +46,45 @@ def moments(y_dev, hist=None):
     return sums, counts
 
 
+def second_moments(y_dev):
+    """sum_p y_i y_j at every saved point of a device trajectory tensor (n_saved, d, P), d <= 16:
+    returns a float64 device tensor (n_saved, d, d) (deterministic; all-reduce it like the sums)."""
+    torch = dev.torch_mod()
+    if y_dev.dim() != 3 or y_dev.dtype != torch.float64 or not y_dev.is_contiguous():
+        raise ValueError("second_moments: need a contiguous float64 tensor (n_saved, d, P)")
+    S, d, P = y_dev.shape
+    with torch.cuda.device(y_dev.device):
+        out = torch.zeros((S, d, d), dtype=torch.float64, device=y_dev.device)
+        _lib.check(_lib.load().sdb_cross_moments(dev.ptr(y_dev), S, d, P, dev.ptr(out), dev.stream_ptr()))
+    return out
+
+
+def covariance(sums, cross, paths):
+    """Ensemble covariance matrices (n_saved, d, d) from the moment sums and the second moments."""
+    mean = sums[..., 0] / paths
+    return cross / paths - mean[..., :, None] * mean[..., None, :]
+
+
+def quantiles(counts, lo, hi, q):
+    """Quantiles from the on-device histograms (n_saved, d, bins) on [lo, hi): linear interpolation of
+    the empirical CDF inside the bin (resolution = the bin width).  q: scalar or sequence in (0, 1)."""
+    c = np.asarray(counts.cpu() if hasattr(counts, "cpu") else counts, dtype=np.float64)
+    q = np.atleast_1d(np.asarray(q, dtype=np.float64))
+    bins = c.shape[-1]
+    width = (hi - lo) / bins
+    cdf = np.cumsum(c, axis=-1)
+    total = cdf[..., -1:]
+    out = np.empty(c.shape[:-1] + (q.size,))
+    for k, qq in enumerate(q):
+        target = qq * total[..., 0]
+        idx = np.minimum((cdf < target[..., None]).sum(axis=-1), bins - 1)
+        below = np.where(idx > 0, np.take_along_axis(cdf, np.maximum(idx - 1, 0)[..., None], -1)[..., 0], 0.0)
+        inbin = np.take_along_axis(c, idx[..., None], -1)[..., 0]
+        frac = np.where(inbin > 0, (target - below) / np.where(inbin > 0, inbin, 1.0), 0.5)
+        out[..., k] = lo + (idx + np.clip(frac, 0.0, 1.0)) * width
+    return out
+
+
 def allreduce_moments(sums, counts=None, group=None):
     """Sum the per-rank partials over all ranks (torch.distributed; NCCL on GPUs)."""
     import torch.distributed as dist

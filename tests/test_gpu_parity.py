@@ -667,3 +667,27 @@ def test_pipelined_host_output_matches_single_launch(sdb):
     y2 = sdb.itoEuler(f2, G2, y02, tspan, paths=P, seed=4, save_every=10, host_out=host2)
     ref2 = sdb.itoEuler(f2, G2, y02, tspan, paths=P, seed=4, save_every=10, out="torch").cpu().numpy()
     assert np.array_equal(y2, ref2.transpose(2, 0, 1))
+
+
+def test_second_moments_covariance_quantiles(sdb):
+    """Ensemble analysis beyond mean/variance: sum_p y_i y_j per saved point on the
+    device (deterministic), covariance, and quantiles from the on-device histograms."""
+    import torch
+    rng = np.random.default_rng(5)
+    S, d, P = 3, 7, 20011
+    L = rng.standard_normal((d, d)) * 0.4 + np.eye(d)
+    y = np.einsum("ij,sjp->sip", L, rng.standard_normal((S, d, P))) + 0.3
+    yd = torch.from_numpy(y).cuda()
+    cross = sdb.ensemble.second_moments(yd)
+    want = np.einsum("sip,sjp->sij", y, y)
+    assert np.allclose(cross.cpu().numpy(), want, rtol=1e-12, atol=1e-9)
+    assert np.array_equal(sdb.ensemble.second_moments(yd).cpu().numpy(), cross.cpu().numpy())
+    sums, counts = sdb.ensemble.moments(yd, hist=(400, -8.0, 8.0))
+    cov = sdb.ensemble.covariance(sums, cross, float(P)).cpu().numpy()
+    for s in range(S):
+        assert np.allclose(cov[s], np.cov(y[s], bias=True), rtol=1e-9, atol=1e-10)
+    qs = sdb.ensemble.quantiles(counts, -8.0, 8.0, [0.1, 0.5, 0.9])
+    ref = np.quantile(y, [0.1, 0.5, 0.9], axis=-1).transpose(1, 2, 0)
+    assert np.max(np.abs(qs - ref)) < 2 * 16.0 / 400
+    with pytest.raises(sdb._lib.SdbError):
+        sdb.ensemble.second_moments(torch.zeros((1, 17, 8), dtype=torch.float64, device="cuda"))
