@@ -17,10 +17,16 @@ Differences from the reference, all forced by "the loop runs in a CUDA kernel":
   * noise that the reference would draw from numpy's generator is drawn by an on-device
     Philox generator (see sdeint_b200/wiener.py); results on host-supplied `dW`, `I`/`J`
     match the reference to <= 1e-12 relative.
+Noise structure is exploited where the result is unchanged: additive noise (ops.ConstDiffusion)
+never builds I/J, diagonal noise (ops.DiagLinearDiffusion, CudaDiffusion(diagonal=True)) builds only
+I_kk = (dW_k^2 - h)/2 for SRI2/SRS2, scalar noise draws nothing beyond dW with Iwik -- the first items
+of the reference's own to-do list (integrate.py:150-151, README.rst:130).
 Keyword-only ENSEMBLE extensions: `paths=P` integrates P independent sample paths in one
 launch (returns (P, n_saved, d)); `seed`, `path_id0` select the Philox streams; `save_every`
 decimates the stored trajectory; `out="torch"` leaves the result on the device in the
-path-minor layout (n_saved, d, P).  `dW` / `I` / `J` may then carry a leading path axis.
+path-minor layout (n_saved, d, P); `host_out=` (a pinned torch tensor (n_saved, d, P)) receives
+large results chunk by chunk while the next chunk of paths is integrated.  `dW` / `I` / `J` may
+then carry a leading path axis (without it, one realisation is shared by all paths).
 """
 from __future__ import annotations
 
