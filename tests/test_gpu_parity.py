@@ -691,3 +691,24 @@ def test_second_moments_covariance_quantiles(sdb):
     assert np.max(np.abs(qs - ref)) < 2 * 16.0 / 400
     with pytest.raises(sdb._lib.SdbError):
         sdb.ensemble.second_moments(torch.zeros((1, 17, 8), dtype=torch.float64, device="cuda"))
+
+
+@pytest.mark.parametrize("name,n", [("lin10", 1), ("lin10", 8), ("r74", 3), ("lin10", 70)])
+def test_series_length_in_integrators(sdb, name, n):
+    """`n_terms` (the series length n of Ikpw/Iwik, default 5 like the reference) is honoured by the
+    fused and the generic kernels alike; n > 64 leaves the fused kernels for the generic loop."""
+    f, G, y0 = SYSTEMS[name](False)
+    m = G.m
+    tspan = np.linspace(0.0, 0.05, 11)
+    h = 0.005
+    P, seed = 34, 1212
+    y = sdb.itoSRI2(f, G, y0, tspan, paths=P, seed=seed, n_terms=n)
+    dW = sdb.deltaW(10, m, h, paths=P, seed=seed)
+    X, Y = po.kpw_normals(10, m, n, P, seed)
+    for p in (0, P - 1):
+        _, I = orc.ikpw_from_normals(dW[p], h, X[:, p], Y[:, p])
+        assert rel_err(y[p], orc.srk2(f, G, np.atleast_1d(y0), tspan, dW[p], I)) <= TOL
+    yw = sdb.itoSRI2(f, G, y0, tspan, sdb.Iwik, paths=P, seed=seed, n_terms=n)
+    Gt = po.wik_tail_normals(10, m, n, P, seed)
+    _, Iw = orc.iwik_from_normals(dW[0], h, X[:, 0], Y[:, 0], Gt[0])
+    assert rel_err(yw[0], orc.srk2(f, G, np.atleast_1d(y0), tspan, dW[0], Iw)) <= TOL
