@@ -418,7 +418,9 @@ SDB_DEV void sdb_repeated_integrals(const double (&dW)[M], double h, int n_terms
 template <int D_, class PS>
 struct DriftLinear {
   static constexpr int D = D_;
+  static constexpr bool LINEAR = true;  // the Jacobian is A: KP2iS needs no finite differences
   typedef PS Params;
+  static SDB_DEV double jac(const PS& p, int i, int j) { return p[i * D + j]; }
   static SDB_DEV void eval(const PS& p, const double (&y)[D], double, double (&out)[D]) {
 #pragma unroll
     for (int i = 0; i < D; ++i) {
@@ -433,6 +435,7 @@ struct DriftLinear {
 template <class PS>
 struct DriftKP4446 {  // -(a + c y)(1 - y^2), sdeint/tests/test_integrate.py:93-99
   static constexpr int D = 1;
+  static constexpr bool LINEAR = false;
   typedef PS Params;
   static SDB_DEV void eval(const PS& p, const double (&y)[1], double, double (&out)[1]) {
     out[0] = -(p[0] + y[0] * p[1]) * (1.0 - y[0] * y[0]);
@@ -442,6 +445,7 @@ struct DriftKP4446 {  // -(a + c y)(1 - y^2), sdeint/tests/test_integrate.py:93-
 template <class PS>
 struct DriftKPS445 {  // test_integrate.py:263-269
   static constexpr int D = 1;
+  static constexpr bool LINEAR = false;
   typedef PS Params;
   static SDB_DEV void eval(const PS& p, const double (&y)[1], double, double (&out)[1]) {
     double s, c;
@@ -514,6 +518,7 @@ __device__ void sde_drift(const double* y, double t, const double* p, double* ou
 template <int D_, class PS>
 struct DriftUser {
   static constexpr int D = D_;
+  static constexpr bool LINEAR = false;
   typedef PS Params;
   static SDB_DEV void eval(const PS& p, const double (&y)[D], double t, double (&out)[D]) {
     sde_drift(y, t, p.ptr(), out);
@@ -821,19 +826,27 @@ SDB_DEV void sdb_loop_body(const SdbLoopArgs& a, const typename F::Params& fp,
           F::eval(fp, Ynew, t1, fx);
 #pragma unroll
           for (int i = 0; i < D; ++i) r[i] = fma(a.kp[2 * D + i] * h, fx[i], cst[i]) - Ynew[i];
+          if constexpr (F::LINEAR) {  // d r / d x = al2 h A - 1, exactly
 #pragma unroll 1
-          for (int j = 0; j < D; ++j) {
-            double xp[D], fxp[D];
-            double step = 1.4901161193847656e-08 * fabs(Ynew[j]);
-            if (step == 0.0) step = 1.4901161193847656e-08;
+            for (int j = 0; j < D; ++j)
 #pragma unroll
-            for (int i = 0; i < D; ++i) xp[i] = Ynew[i];
-            xp[j] += step;
-            step = xp[j] - Ynew[j];
-            F::eval(fp, xp, t1, fxp);
+              for (int i = 0; i < D; ++i)
+                Jm[i][j] = a.kp[2 * D + i] * h * F::jac(fp, i, j) - (i == j ? 1.0 : 0.0);
+          } else {
+#pragma unroll 1
+            for (int j = 0; j < D; ++j) {
+              double xp[D], fxp[D];
+              double step = 1.4901161193847656e-08 * fabs(Ynew[j]);
+              if (step == 0.0) step = 1.4901161193847656e-08;
 #pragma unroll
-            for (int i = 0; i < D; ++i)
-              Jm[i][j] = a.kp[2 * D + i] * h * (fxp[i] - fx[i]) / step - (i == j ? 1.0 : 0.0);
+              for (int i = 0; i < D; ++i) xp[i] = Ynew[i];
+              xp[j] += step;
+              step = xp[j] - Ynew[j];
+              F::eval(fp, xp, t1, fxp);
+#pragma unroll
+              for (int i = 0; i < D; ++i)
+                Jm[i][j] = a.kp[2 * D + i] * h * (fxp[i] - fx[i]) / step - (i == j ? 1.0 : 0.0);
+            }
           }
 #pragma unroll
           for (int i = 0; i < D; ++i) r[i] = -r[i];
