@@ -159,3 +159,17 @@ print("rank", rank, "ok")
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("ok") == 2
+
+
+def test_quantiles_from_histogram_counts():
+    """ensemble.quantiles is host-side arithmetic on the on-device histogram counts."""
+    from sdeint_b200 import ensemble
+    rng = np.random.default_rng(0)
+    x = rng.normal(0.3, 1.2, (2, 3, 50000))
+    bins, lo, hi = 200, -6.0, 6.0
+    counts = np.stack([[np.histogram(x[s, i], bins=bins, range=(lo, hi))[0] for i in range(3)]
+                       for s in range(2)])
+    q = ensemble.quantiles(counts, lo, hi, [0.05, 0.5, 0.95])
+    ref = np.quantile(x, [0.05, 0.5, 0.95], axis=-1).transpose(1, 2, 0)
+    assert q.shape == (2, 3, 3) and np.max(np.abs(q - ref)) < 2 * (hi - lo) / bins
+    assert ensemble.quantiles(counts, lo, hi, 0.5).shape == (2, 3, 1)
