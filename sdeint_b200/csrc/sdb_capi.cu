@@ -129,10 +129,10 @@ static int jit_compile(const std::string& source, const char* kernel_name, JitKe
   if (nvrtc_load(&rt)) return 1;
   nvrtcProgram prog;
   const char* hdr_src[] = {kKernelHeader, kTablesHeader, kFusedHeader, kTmemHeader, kFusedWsHeader,
-                           kFusedXHeader, kRepintXHeader};
+                           kFusedXHeader, kRepintXHeader, kFusedEhHeader};
   const char* hdr_name[] = {"sdb_kernels.cuh", "sdb_tables.cuh", "sdb_fused.cuh", "sdb_tmem.cuh",
-                            "sdb_fusedws.cuh", "sdb_fusedx.cuh", "sdb_repintx.cuh"};
-  int rc = rt->CreateProgram(&prog, source.c_str(), "sdb_jit.cu", 7, hdr_src, hdr_name);
+                            "sdb_fusedws.cuh", "sdb_fusedx.cuh", "sdb_repintx.cuh", "sdb_fusedeh.cuh"};
+  int rc = rt->CreateProgram(&prog, source.c_str(), "sdb_jit.cu", 8, hdr_src, hdr_name);
   if (rc) return fail(std::string("nvrtcCreateProgram: ") + rt->GetErrorString(rc));
   // -default-device: un-annotated functions (the generic lambdas of the compile-time loops) are
   // device functions in JIT mode
@@ -350,13 +350,14 @@ extern "C" int sdb_integrate(sdb_system* s, const sdb_integrate_args* a) {
   // The production path: linear system, SRI2/SRS2, on-device Philox + Ikpw/Jkpw (or Iwik/Jwik)
   // -> a fused kernel when one is instantiated for this (d, m, method).
   const SdbFusedEntry* fused = nullptr;
-  if (a->scheme == SDB_SCHEME_SRK2 && noise != SDB_NOISE_HOST && s->fk == SDB_DRIFT_LINEAR &&
-      s->gk == SDB_DIFF_LINEAR_COLS && a->n_terms <= SDB_FUSED_MAX_TERMS &&
-      !getenv("SDB_DISABLE_FUSED")) {
+  const bool explicit_em = a->scheme == SDB_SCHEME_EULER || a->scheme == SDB_SCHEME_HEUN;
+  if ((a->scheme == SDB_SCHEME_SRK2 || explicit_em) && noise != SDB_NOISE_HOST &&
+      s->fk == SDB_DRIFT_LINEAR && s->gk == SDB_DIFF_LINEAR_COLS &&
+      a->n_terms <= SDB_FUSED_MAX_TERMS && !getenv("SDB_DISABLE_FUSED")) {
     const char* vs = getenv("SDB_FUSED_VARIANT");
     const int want = vs ? atoi(vs) : 0;
     for (const auto& e : sdb_fused_registry())
-      if (e.d == s->d && e.m == s->m && e.noise == noise &&
+      if (e.d == s->d && e.m == s->m && e.noise == noise && e.scheme == a->scheme &&
           (e.variant == want || (!fused && e.variant == 0)))
         fused = &e;
   }
@@ -365,6 +366,31 @@ extern "C" int sdb_integrate(sdb_system* s, const sdb_integrate_args* a) {
   // sdb_fusedx.cuh (Levy areas in tensor memory; Iwik/Jwik and larger shapes) -- else the generic loop.
   SdbFusedEntry jit_entry{};
   int jit_rb = 4;
+  if (!fused && explicit_em && noise != SDB_NOISE_HOST && s->fk == SDB_DRIFT_LINEAR &&
+      s->gk == SDB_DIFF_LINEAR_COLS && !getenv("SDB_DISABLE_FUSED") &&
+      !getenv("SDB_DISABLE_FUSED_JIT") &&
+      // measured crossover against the high-occupancy loop kernel (tools/bench_crossover.py):
+      // Heun wins from d m ~ 48 (2.4x at (8,6)), Euler only for the largest shapes (1.5x at (10,10))
+      s->d * s->m >= (a->scheme == SDB_SCHEME_HEUN ? 48 : 96) &&
+      SdbFusedEhDims(s->d, s->m, a->scheme == SDB_SCHEME_HEUN).supported()) {
+    const bool heun = a->scheme == SDB_SCHEME_HEUN;
+    const SdbFusedEhDims edims(s->d, s->m, heun);
+    const std::string key = heun ? "fusedehjit|heun" : "fusedehjit|euler";
+    std::lock_guard<std::mutex> lk(s->mu);
+    auto it = s->jit.find(key);
+    if (it == s->jit.end()) {
+      std::ostringstream src;
+      src << "#include \"sdb_fusedeh.cuh\"\nSDB_FUSEDEH_KERNEL(sdb_jit_fused, " << s->d << ", " << s->m
+          << ", " << (heun ? 1 : 0) << ")\n";
+      JitKernel k;
+      if (jit_compile(src.str(), "sdb_jit_fused", &k)) return 1;
+      it = s->jit.emplace(key, k).first;
+    }
+    jit_entry = SdbFusedEntry{s->d, s->m, 0, (const void*)it->second.kern, edims.smem_bytes(),
+                              edims.sh.table_doubles(), nullptr, edims.threads(), edims.threads(),
+                              SDB_NOISE_KPW, a->scheme};
+    fused = &jit_entry;
+  }
   if (!fused && a->scheme == SDB_SCHEME_SRK2 && noise != SDB_NOISE_HOST &&
       s->fk == SDB_DRIFT_LINEAR && s->gk == SDB_DIFF_LINEAR_COLS &&
       a->n_terms <= SDB_FUSED_MAX_TERMS && !getenv("SDB_DISABLE_FUSED") &&
@@ -393,12 +419,12 @@ extern "C" int sdb_integrate(sdb_system* s, const sdb_integrate_args* a) {
       if (use_v0) {
         jit_entry = SdbFusedEntry{s->d, s->m, 0, (const void*)it->second.kern, dims.smem_bytes(),
                                   dims.table_doubles(), nullptr, SdbFusedDims::THREADS,
-                                  SdbFusedDims::THREADS, SDB_NOISE_KPW};
+                                  SdbFusedDims::THREADS, SDB_NOISE_KPW, SDB_SCHEME_SRK2};
       } else {
         jit_rb = 2;
         jit_entry = SdbFusedEntry{s->d, s->m, 0, (const void*)it->second.kern, xdims.smem_bytes(),
                                   xdims.sh.table_doubles(), nullptr, xdims.threads(),
-                                  xdims.threads(), noise};
+                                  xdims.threads(), noise, SDB_SCHEME_SRK2};
       }
       fused = &jit_entry;
     }
@@ -468,8 +494,12 @@ extern "C" int sdb_integrate(sdb_system* s, const sdb_integrate_args* a) {
   args[1] = s->inline_params ? (void*)s->fp.data() : (void*)&gf;
   args[2] = s->inline_params ? (void*)s->gp.data() : (void*)&gg;
   if (fused) {
-    args[1] = (void*)s->fp.data();
-    args[2] = (void*)&d_frag;
+    if (fused->scheme == SDB_SCHEME_SRK2) {
+      args[1] = (void*)s->fp.data();
+      args[2] = (void*)&d_frag;
+    } else {  // fused Euler / Heun: (a, frag)
+      args[1] = (void*)&d_frag;
+    }
   }
   const unsigned block = fused ? (unsigned)fused->threads : SDB_BLOCK;
   const int64_t per_block = fused ? fused->paths_per_block : SDB_BLOCK;

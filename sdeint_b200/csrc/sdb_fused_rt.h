@@ -114,3 +114,20 @@ struct SdbRepintXDims {
   constexpr size_t smem_bytes() const { return 120u * 1024u; }
   constexpr bool supported() const { return M >= 2 && M % 2 == 0 && C_END() <= 512; }
 };
+
+// Run-time mirror of SdbEhShape (sdb_fusedeh.cuh): fused Euler (12 warps per SM) / Heun (8 warps).
+struct SdbFusedEhDims {
+  SdbFusedDims sh;
+  int heun;
+  constexpr SdbFusedEhDims(int d, int m, int heun_) : sh(d, m, 4), heun(heun_) {}
+  constexpr int threads() const { return heun ? 256 : 384; }
+  constexpr int grows() const {
+    int g = SdbFusedDims::max2(8, sh.D);
+    for (int b = 0; b < sh.NB(); ++b) g = SdbFusedDims::max2(g, 8 * sh.t1(b));
+    return g;
+  }
+  constexpr size_t smem_bytes() const { return (size_t)grows() * 32 * 8 * (threads() / 32) + 128 * 16; }
+  constexpr bool supported() const {
+    return sh.M >= 2 && sh.M % 2 == 0 && sh.D >= 1 && sh.D <= 16 && smem_bytes() <= 227u * 1024u;
+  }
+};

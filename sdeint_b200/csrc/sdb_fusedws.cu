@@ -14,6 +14,6 @@
   static SdbFusedRegistrar sdbreg_fusedws_d##D##_m##M(                                         \
       SdbFusedEntry{D, M, SDB_FUSED_VARIANT, (const void*)sdbk_fusedws_srk2_d##D##_m##M,       \
                     SdbWsShape<D, M>::smem_bytes(), sdb_fused_table_doubles<D, M>(),           \
-                    &sdb_fused_build_tables<D, M>, SDB_WS_THREADS, SDB_WS_PATHS, SDB_NOISE_KPW});
+                    &sdb_fused_build_tables<D, M>, SDB_WS_THREADS, SDB_WS_PATHS, SDB_NOISE_KPW, SDB_SCHEME_SRK2});
 
 SDB_FUSEDWS_AOT(10, 10)

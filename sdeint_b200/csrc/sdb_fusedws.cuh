@@ -89,31 +89,6 @@ SDB_DEV void sdb_mbar_wait(uint64_t* bar, uint32_t parity) {
   } while (!done);
 }
 
-// Compile-time loop and the inverse of sdb_pair_index.
-template <int I>
-struct SdbInt { static constexpr int value = I; };
-template <int I, int N, class F>
-SDB_DEV void sdb_static_for(F&& f) {
-  if constexpr (I < N) {
-    f(SdbInt<I>{});
-    sdb_static_for<I + 1, N>(f);
-  }
-}
-template <int M>
-SDB_CX int sdb_pair_j(int idx) {
-  int j = 0, base = 0;
-  while (idx >= base + (M - 1 - j)) {
-    base += M - 1 - j;
-    ++j;
-  }
-  return j;
-}
-template <int M>
-SDB_CX int sdb_pair_k(int idx) {
-  const int j = sdb_pair_j<M>(idx);
-  return idx - (j * M - j * (j + 1) / 2) + j + 1;
-}
-
 // Ring position shared by producer and consumer code.
 struct SdbRing {
   int slot;

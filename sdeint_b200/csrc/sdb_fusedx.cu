@@ -15,7 +15,7 @@
                     SdbXShape<D, M>::smem_bytes(), sdb_fused_table_doubles<D, M>(),            \
                     &sdb_fused_build_tables<D, M>, SdbXShape<D, M>::THREADS,                   \
                     SdbXShape<D, M>::PATHS,                                                    \
-                    WIK ? SDB_NOISE_WIK : SDB_NOISE_KPW});
+                    WIK ? SDB_NOISE_WIK : SDB_NOISE_KPW, SDB_SCHEME_SRK2});
 
 SDB_FUSEDX_AOT(20, 20, 0, kpw)
 SDB_FUSEDX_AOT(20, 20, 1, wik)

@@ -35,6 +35,7 @@ struct SdbFusedEntry {
   int threads;                 // block size
   int paths_per_block;         // sample paths integrated by one block
   int noise;                   // SDB_NOISE_KPW or SDB_NOISE_WIK: which repeated integrals it builds
+  int scheme;                  // SDB_SCHEME_SRK2 (args: a, A, frag) or EULER / HEUN (args: a, frag)
 };
 std::vector<SdbFusedEntry>& sdb_fused_registry();
 struct SdbFusedRegistrar {

@@ -712,3 +712,30 @@ def test_series_length_in_integrators(sdb, name, n):
     Gt = po.wik_tail_normals(10, m, n, P, seed)
     _, Iw = orc.iwik_from_normals(dW[0], h, X[:, 0], Y[:, 0], Gt[0])
     assert rel_err(yw[0], orc.srk2(f, G, np.atleast_1d(y0), tspan, dW[0], Iw)) <= TOL
+
+
+@pytest.mark.parametrize("d,m", [(10, 10), (8, 6), (12, 8)])
+def test_fused_euler_heun_linear(sdb, d, m, monkeypatch):
+    """itoEuler / stratHeun for linear multiplicative systems on device noise: the DMMA kernel of
+    sdb_fusedeh.cuh ((10,10) ahead of time, other shapes NVRTC) against the generic loop kernel and
+    the oracle, with a partial last warp and per-path initial states."""
+    rng = np.random.default_rng(77 * d + m)
+    A = -1.0 * np.eye(d) + 0.3 * rng.standard_normal((d, d)) / np.sqrt(d)
+    B = 0.4 * rng.standard_normal((m, d, d)) / np.sqrt(d * m)
+    f, G = sdb.ops.LinearDrift(A), sdb.ops.LinearDiffusion(B)
+    y0 = rng.standard_normal(d)
+    tspan = np.linspace(0.0, 0.5, 51)
+    h = 0.01
+    P, seed = 77, 5151
+    y0p = y0[None, :] + 0.1 * rng.standard_normal((P, d))
+    dW = sdb.deltaW(50, m, h, paths=P, seed=seed, path_id0=4)
+    for integ, ofn in ((sdb.itoEuler, orc.euler), (sdb.stratHeun, orc.heun)):
+        y = integ(f, G, y0, tspan, paths=P, seed=seed, path_id0=4, y0_paths=y0p)
+        monkeypatch.setenv("SDB_DISABLE_FUSED", "1")
+        y_gen = integ(f, G, y0, tspan, paths=P, seed=seed, path_id0=4, y0_paths=y0p)
+        monkeypatch.delenv("SDB_DISABLE_FUSED")
+        assert rel_err(y, y_gen) <= TOL
+        for p in (0, 31, 32, P - 1):
+            assert rel_err(y[p], ofn(f, G, y0p[p], tspan, dW[p])) <= TOL
+        yd = integ(f, G, y0, tspan, paths=P, seed=seed, path_id0=4, y0_paths=y0p, save_every=7)
+        assert np.array_equal(yd, y[:, ::7])

@@ -1,13 +1,14 @@
-"""Throughput of stratKP2iS / stratSRS2 / stratHeun on two linear systems: python tools/bench_schemes.py"""
+"""Throughput of stratKP2iS / stratSRS2 / stratHeun / itoEuler on two linear systems: python tools/bench_schemes.py"""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, sdeint_b200 as sdb
 for name, mk in (("r74 d=5 m=4", lambda: sdb.ops.sys_r74(True)), ("lin10 d=m=10", lambda: sdb.ops.sys_lin(10, 10))):
     f, G, y0 = mk()
-    T, P = 200, 200000
+    T, P = 200, 2000000
     tspan = np.linspace(0.0, T / 1000.0, T + 1)
-    for sch, fn in (("stratKP2iS", sdb.stratKP2iS), ("stratSRS2", sdb.stratSRS2), ("stratHeun", sdb.stratHeun)):
+    for sch, fn in (("stratKP2iS", sdb.stratKP2iS), ("stratSRS2", sdb.stratSRS2), ("stratHeun", sdb.stratHeun),
+                    ("itoEuler", sdb.itoEuler)):
         best = None
         for rep in range(3):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
