@@ -67,6 +67,25 @@ static const void* aot_lookup(const std::string& key) {
   return e ? e->fn : nullptr;
 }
 
+// The small stream-ordered scratch buffers (tspan / h tables, moment partials) come from the device's
+// default memory pool.  Its default release threshold is 0, i.e. the pool hands everything back to
+// the driver at every synchronisation and the next cudaMallocAsync pays for a fresh allocation;
+// keep the pool's memory instead (set once per device).
+static void keep_pool_memory() {
+  static std::mutex mu;
+  static bool done[64] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+  std::lock_guard<std::mutex> lk(mu);
+  if (done[dev]) return;
+  done[dev] = true;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    uint64_t keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+}
+
 static int launch(const void* fn, dim3 grid, dim3 block, void** args, cudaStream_t st,
                   size_t smem = 0) {
   SDB_CUDA(cudaLaunchKernel(fn, grid, block, args, smem, st));
@@ -466,6 +485,7 @@ extern "C" int sdb_integrate(sdb_system* s, const sdb_integrate_args* a) {
   }
   for (size_t i = 0; i < nk; ++i) aux[nt + 3 * ns + i] = a->h_kp2is[i];
   double* d_aux = nullptr;
+  keep_pool_memory();
   SDB_CUDA(cudaMallocAsync(&d_aux, aux.size() * sizeof(double), st));
   SDB_CUDA(cudaMemcpyAsync(d_aux, aux.data(), aux.size() * sizeof(double), cudaMemcpyHostToDevice, st));
 
@@ -707,6 +727,7 @@ extern "C" int sdb_moments(const double* d_y, int64_t n_saved, int d, int64_t pa
   const int64_t nchunks = (paths + SDB_MOM_CHUNK - 1) / SDB_MOM_CHUNK;
   if (rows > 65535) return fail("sdb_moments: too many (saved point, component) rows");
   double2* partial = nullptr;
+  keep_pool_memory();
   SDB_CUDA(cudaMallocAsync(&partial, rows * nchunks * sizeof(double2), st));
   const double inv_w = d_hist ? (double)bins / (hi - lo) : 0.0;
   const size_t shm = d_hist ? bins * sizeof(unsigned int) : 0;
@@ -770,6 +791,7 @@ extern "C" int sdb_cross_moments(const double* d_y, int64_t n_saved, int d, int6
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t nchunks = (paths + SDB_MOM_CHUNK - 1) / SDB_MOM_CHUNK;
   double* partial = nullptr;
+  keep_pool_memory();
   SDB_CUDA(cudaMallocAsync(&partial, (size_t)n_saved * nchunks * d * d * sizeof(double), st));
   sdb_k_cross_partial<<<dim3((unsigned)nchunks, (unsigned)n_saved), 256, (size_t)d * 256 * sizeof(double), st>>>(
       d_y, d, paths, nchunks, partial);
