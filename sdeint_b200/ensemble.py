@@ -85,11 +85,25 @@ def quantiles(counts, lo, hi, q):
     return out
 
 
-def allreduce_moments(sums, counts=None, group=None):
-    """Sum the per-rank partials over all ranks (torch.distributed; NCCL on GPUs)."""
+def allreduce_moments(sums, counts=None, group=None, deterministic=False):
+    """Sum the per-rank partials over all ranks (torch.distributed; NCCL on GPUs), in place.
+
+    The floating-point sums of an all-reduce depend on the reduction order the collective picks.
+    `deterministic=True` all-gathers the per-rank partials instead and adds them in rank order, so
+    the result is bit-reproducible for a given number of ranks; the integer histogram
+    counts are exact either way."""
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+        if deterministic:
+            torch = dev.torch_mod()
+            parts = [torch.empty_like(sums) for _ in range(dist.get_world_size(group))]
+            dist.all_gather(parts, sums.contiguous(), group=group)
+            total = parts[0].clone()
+            for part in parts[1:]:
+                total += part
+            sums.copy_(total)
+        else:
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
         if counts is not None:
             dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
     return sums, counts

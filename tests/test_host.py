@@ -151,6 +151,15 @@ wc = np.stack([[np.histogram(y[s, i], 8, (-2, 2))[0] for i in range(d)] for s in
 assert np.array_equal(counts.numpy(), wc), rank
 mean, var = sdb.ensemble.mean_var(sums, P)
 assert np.allclose(mean.numpy(), y.mean(-1)) and np.allclose(var.numpy(), y.var(-1))
+# rank-ordered (bit-reproducible) merge: every rank gets the same bits, equal to sum_0 + sum_1
+mine2 = torch.from_numpy(np.stack([mine.sum(-1), (mine * mine).sum(-1)], axis=-1))
+sdb.ensemble.allreduce_moments(mine2, deterministic=True)
+parts = []
+for r in range(world):
+    s0, c0 = sdb.ensemble.shard_paths(P, r, world)
+    part = y[:, :, s0:s0 + c0]
+    parts.append(np.stack([part.sum(-1), (part * part).sum(-1)], axis=-1))
+assert np.array_equal(mine2.numpy(), parts[0] + parts[1]), rank
 dist.destroy_process_group()
 print("rank", rank, "ok")
 ''' % ROOT)
