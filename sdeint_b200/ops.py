@@ -292,6 +292,97 @@ class CudaDiffusion(DiffusionOp):
         return self.host(y, t)
 
 
+# ---- drift / diffusion from arithmetic expressions -------------------------------------
+# The reference takes Python callables; a CUDA kernel cannot.  For the common case of closed-form
+# f and G these two classes take the formulas as strings -- one per component, in the state
+# y[0..d-1], the time t and the parameters p[0..] with + - * / and sin cos tan exp log sqrt pow
+# fabs tanh -- and generate both the CUDA source (compiled by NVRTC) and the equivalent numpy
+# callable handed to the oracle in tests, so no CUDA has to be written by hand.
+
+_EXPR_FUNCS = ("sin", "cos", "tan", "exp", "log", "sqrt", "pow", "fabs", "tanh", "sinh", "cosh")
+
+
+def _check_expr(expr):
+    import re
+    expr = str(expr)
+    for name in re.findall(r"[A-Za-z_]\w*", expr):
+        if name not in _EXPR_FUNCS and name not in ("y", "t", "p"):
+            raise ValueError("unknown name %r in expression %r (allowed: y[i], t, p[i], %s)"
+                             % (name, expr, ", ".join(_EXPR_FUNCS)))
+    if ";" in expr or "{" in expr or "}" in expr:
+        raise ValueError("expression %r must be a single arithmetic expression" % expr)
+    return expr
+
+
+def _c_expr(expr):
+    """The expression as C: bare integer literals become doubles (1/3 must not be integer division);
+    subscripts and exponents of floating literals stay as they are."""
+    import re
+    out, depth, pos = [], 0, 0
+    number = re.compile(r"(?:\d+\.?\d*|\.\d+)(?:[eE][+-]?\d+)?")
+    while pos < len(expr):
+        ch = expr[pos]
+        if ch.isalpha() or ch == "_":                 # identifier (may contain digits): copy whole
+            mt = re.match(r"\w+", expr[pos:])
+            out.append(mt.group(0))
+            pos += mt.end()
+            continue
+        mt = number.match(expr, pos)
+        if mt:
+            tok = mt.group(0)
+            out.append(tok + ".0" if depth == 0 and tok.isdigit() else tok)
+            pos = mt.end()
+            continue
+        depth += ch == "["
+        depth -= ch == "]"
+        out.append(ch)
+        pos += 1
+    return "".join(out)
+
+
+def _expr_eval(expr, y, t, p):
+    env = {k: getattr(np, {"fabs": "abs", "pow": "power"}.get(k, k)) for k in _EXPR_FUNCS}
+    env.update(y=y, t=t, p=p)
+    return float(eval(expr, {"__builtins__": {}}, env))      # names were whitelisted by _check_expr
+
+
+class ExprDrift(CudaDrift):
+    """f_i(y, t) = the i-th expression, e.g. ExprDrift(["p[0]*(y[1]-y[0])", "y[0]*(p[1]-y[2])-y[1]",
+    "y[0]*y[1]-p[2]*y[2]"], params=[10, 28, 8/3])."""
+
+    def __init__(self, exprs, params=()):
+        self.exprs = [_check_expr(e) for e in exprs]
+        body = "\n".join("  out[%d] = %s;" % (i, _c_expr(e)) for i, e in enumerate(self.exprs))
+        src = ("__device__ void sde_drift(const double* y, double t, const double* p, double* out) {\n"
+               "%s\n}\n" % body)
+        par = np.asarray(params, dtype=np.float64).reshape(-1)
+        super().__init__(src, len(self.exprs), par,
+                         host=lambda y, t: np.array([_expr_eval(e, np.asarray(y, float), t, par)
+                                                     for e in self.exprs]))
+
+
+class ExprDiffusion(CudaDiffusion):
+    """G_ik(y, t) = exprs[i][k] (d rows of m expressions; "0" for structural zeros).
+    `diagonal=True` promises diagonal noise (see CudaDiffusion)."""
+
+    def __init__(self, exprs, params=(), diagonal=False):
+        rows = [[_check_expr(e) for e in row] for row in exprs]
+        d, m = len(rows), len(rows[0])
+        if any(len(r) != m for r in rows):
+            raise ValueError("ExprDiffusion needs a d x m table of expressions")
+        self.exprs = rows
+        cases = []
+        for k in range(m):
+            lines = "\n".join("      out[%d] = %s;" % (i, _c_expr(rows[i][k])) for i in range(d))
+            cases.append("    case %d:\n%s\n      break;" % (k, lines))
+        src = ("__device__ void sde_diffusion_col(int k, const double* y, double t, const double* p, "
+               "double* out) {\n  switch (k) {\n%s\n  }\n}\n" % "\n".join(cases))
+        par = np.asarray(params, dtype=np.float64).reshape(-1)
+        super().__init__(src, d, m, par, diagonal=diagonal,
+                         host=lambda y, t: np.array([[_expr_eval(rows[i][k], np.asarray(y, float), t, par)
+                                                      for k in range(m)] for i in range(d)]))
+
+
 # ---- named systems of SURVEY.md 8(d) --------------------------------------------------
 
 def sys_lin(d, m):

@@ -739,3 +739,33 @@ def test_fused_euler_heun_linear(sdb, d, m, monkeypatch):
             assert rel_err(y[p], ofn(f, G, y0p[p], tspan, dW[p])) <= TOL
         yd = integ(f, G, y0, tspan, paths=P, seed=seed, path_id0=4, y0_paths=y0p, save_every=7)
         assert np.array_equal(yd, y[:, ::7])
+
+
+def test_expression_operators_all_integrators(sdb):
+    """f and G given as formulas (ops.ExprDrift / ExprDiffusion -> NVRTC): every integrator against the
+    oracle running the SAME formulas as numpy callables; time-dependent, non-commutative noise."""
+    f = sdb.ops.ExprDrift(["p[0]*(y[1]-y[0])", "y[0]*(p[1]-y[2])-y[1]", "y[0]*y[1]-p[2]*y[2]"],
+                          [10.0, 28.0, 8.0 / 3.0])
+    G = sdb.ops.ExprDiffusion([["p[0]*y[0]", "0", "0.1*p[0]*y[1]"],
+                               ["0", "p[0]*(y[1]+y[0]/10)", "0"],
+                               ["0", "0", "p[0]*y[2]*cos(2*t)"]], [0.1])
+    y0 = np.array([1.0, 1.0, 20.0])
+    tspan = np.linspace(0.0, 0.2, 201)
+    h = 0.001
+    rng = np.random.default_rng(31)
+    dW = orc.delta_w(200, 3, h, rng)
+    _, I = orc.iwik(dW, h, generator=rng)
+    _, J = orc.jkpw(dW, h, generator=rng)
+    assert rel_err(sdb.itoEuler(f, G, y0, tspan, dW=dW), orc.euler(f, G, y0, tspan, dW)) <= TOL
+    assert rel_err(sdb.stratHeun(f, G, y0, tspan, dW=dW), orc.heun(f, G, y0, tspan, dW)) <= TOL
+    assert rel_err(sdb.itoSRI2(f, G, y0, tspan, dW=dW, I=I), orc.srk2(f, G, y0, tspan, dW, I)) <= TOL
+    assert rel_err(sdb.itoSRI2(f, G.columns(), y0, tspan, dW=dW, I=I), orc.srk2(f, G, y0, tspan, dW, I)) <= TOL
+    assert rel_err(sdb.stratSRS2(f, G, y0, tspan, dW=dW, J=J), orc.srk2(f, G, y0, tspan, dW, J)) <= TOL
+    yk = sdb.stratKP2iS(f, G, y0, tspan, dW=dW, J=J, rtol=1e-12)
+    assert rel_err(yk, orc.kp2is(f, G, y0, tspan, dW, J, rtol=1e-13, solver="newton")) <= 1e-9
+    # ensemble on device noise
+    P, seed = 33, 8
+    y = sdb.itoSRI2(f, G, y0, tspan, paths=P, seed=seed)
+    dWd = sdb.deltaW(200, 3, h, paths=P, seed=seed)
+    _, Id = sdb.Ikpw(dWd, h, seed=seed, ensemble=True)
+    assert rel_err(y[P - 1], orc.srk2(f, G, y0, tspan, dWd[P - 1], Id[P - 1])) <= TOL

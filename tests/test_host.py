@@ -182,3 +182,24 @@ def test_quantiles_from_histogram_counts():
     ref = np.quantile(x, [0.05, 0.5, 0.95], axis=-1).transpose(1, 2, 0)
     assert q.shape == (2, 3, 3) and np.max(np.abs(q - ref)) < 2 * (hi - lo) / bins
     assert ensemble.quantiles(counts, lo, hi, 0.5).shape == (2, 3, 1)
+
+
+def test_expression_operators_generate_source_and_host_callable():
+    """ops.ExprDrift / ExprDiffusion: formulas as strings -> CUDA source + numpy callable."""
+    from sdeint_b200 import ops
+    f = ops.ExprDrift(["p[0]*(y[1]-y[0])", "y[0]*(p[1]-y[2])-y[1]", "y[0]*y[1]-1/3*p[2]*y[2]"], [10, 28, 8])
+    G = ops.ExprDiffusion([["p[0]*y[0]", "0"], ["0", "p[0]*sqrt(1+y[1]*y[1])"], ["0.5*t", "0"]], [0.1])
+    assert f.d == 3 and (G.d, G.m) == (3, 2) and f.kind == ops.DRIFT_USER and G.kind == ops.DIFF_USER
+    assert "1.0/3.0*p[2]*y[2]" in f.source and "sde_diffusion_col" in G.source and "case 1:" in G.source
+    y = np.array([1.0, 2.0, 3.0])
+    assert np.allclose(f(y, 0.0), [10.0, 23.0, 2.0 - 8.0])
+    assert np.allclose(G(y, 2.0), [[0.1, 0.0], [0.0, 0.1 * np.sqrt(5.0)], [1.0, 0.0]])
+    assert np.allclose(G.column(1, y, 2.0), [0.0, 0.1 * np.sqrt(5.0), 0.0])
+    with pytest.raises(ValueError):
+        ops.ExprDrift(["__import__('os').system('true')"])
+    with pytest.raises(ValueError):
+        ops.ExprDrift(["y[0]; out[1] = 0"])
+    with pytest.raises(ValueError):
+        ops.ExprDiffusion([["y[0]", "1"], ["1"]])
+    Gd = ops.ExprDiffusion([["p[0]*y[0]", "0"], ["0", "p[0]*y[1]"]], [0.2], diagonal=True)
+    assert Gd.kind == ops.DIFF_USER_DIAG
