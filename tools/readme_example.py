@@ -1,0 +1,12 @@
+"""The README example, runnable: python tools/readme_example.py"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, sdeint_b200 as sdb
+f, G, y0 = sdb.ops.sys_lin(10, 10)
+tspan = np.linspace(0.0, 1.0, 1001)
+y = sdb.itoSRI2(f, G, y0, tspan, paths=10**5, seed=1, save_every=100); print(y.shape)
+y1 = sdb.itoint(f, G, y0, tspan); print(y1.shape)
+f = sdb.ops.ExprDrift(["p[0]*(y[1]-y[0])", "y[0]*(p[1]-y[2])-y[1]", "y[0]*y[1]-p[2]*y[2]"], [10, 28, 8/3])
+G = sdb.ops.ExprDiffusion([["p[0]*y[0]", "0", "0"], ["0", "p[0]*y[1]", "0"], ["0", "0", "p[0]*y[2]"]], [0.1],
+                          diagonal=True)
+y = sdb.itoint(f, G, [1.0, 1.0, 20.0], tspan, paths=10**5, seed=2, save_every=100); print(y.shape, y[:, -1].mean(axis=0))
