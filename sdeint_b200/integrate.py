@@ -200,10 +200,11 @@ def _run(scheme, f, G, y0, tspan, dW, IJ, strat, method, generator, kp2is, paths
         else:
             a.noise = NOISE_HOST
             if have_dW:
-                dW_h = np.asarray(dW, dtype=np.float64)
+                # a torch tensor (host or device) is used as it is; anything else goes through numpy
+                dW_h = dW if isinstance(dW, torch.Tensor) else np.asarray(dW, dtype=np.float64)
                 # (N-1, m): one realisation shared by every path -> path stride 0, no replication
                 sW = (m, 1, (N - 1) * m if dW_h.ndim == 3 else 0)
-                d_dW = dev.to_device(dW_h, device)      # (P, N-1, m) or (N-1, m)
+                d_dW = dev.to_device(dW_h, device).contiguous()   # (P, N-1, m) or (N-1, m)
             else:                                        # I/J given, dW drawn (integrate.py:481-483)
                 d_dW = torch.empty((N - 1, m, P), dtype=torch.float64, device=device)
                 _lib.check(lib.sdb_delta_w(N - 1, m, float(h), P, int(path_id0), key,
@@ -214,9 +215,9 @@ def _run(scheme, f, G, y0, tspan, dW, IJ, strat, method, generator, kp2is, paths
             a.dW_stride_step, a.dW_stride_comp, a.dW_stride_path = sW
             if need_ij:
                 if IJ is not None:
-                    IJ_h = np.asarray(IJ, dtype=np.float64)
+                    IJ_h = IJ if isinstance(IJ, torch.Tensor) else np.asarray(IJ, dtype=np.float64)
                     ij_path = (N - 1) * m * m if IJ_h.ndim == 4 else 0
-                    d_IJ = dev.to_device(IJ_h, device)  # (P, N-1, m, m) or (N-1, m, m)
+                    d_IJ = dev.to_device(IJ_h, device).contiguous()  # (P, N-1, m, m) or (N-1, m, m)
                 else:                                    # dW given, I/J drawn from it (:484-487)
                     ij_path = (N - 1) * m * m
                     d_IJ = torch.empty((P, N - 1, m, m), dtype=torch.float64, device=device)

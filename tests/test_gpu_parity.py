@@ -618,6 +618,23 @@ def test_shared_noise_is_broadcast_not_replicated(sdb):
     assert rel_err(spread[5], orc.srk2(f, G, y0p[5], tspan, dW, I)) <= TOL
 
 
+def test_device_resident_noise_tensors(sdb):
+    """dW / I handed over as torch tensors already on the GPU are used in place (no host round
+    trip) and give the same bits as the numpy arrays of the reference's call."""
+    import torch
+    g = load_golden("integrate_r74.npz")
+    f, G, y0 = SYSTEMS["r74"](False)
+    tspan, dW, I = g["tspan"], g["dW"][0], g["I"][0]
+    ref = sdb.itoSRI2(f, G, y0, tspan, dW=dW, I=I)
+    dWd, Id = torch.as_tensor(dW, device="cuda"), torch.as_tensor(I, device="cuda")
+    assert np.array_equal(sdb.itoSRI2(f, G, y0, tspan, dW=dWd, I=Id), ref)
+    assert np.array_equal(sdb.itoEuler(f, G, y0, tspan, dW=dWd), sdb.itoEuler(f, G, y0, tspan, dW=dW))
+    # a strided view (every path's noise, path axis first) is made contiguous, not misread
+    stack = torch.stack([dWd, 2.0 * dWd], dim=1)[:, 0]          # non-contiguous (N-1, m)
+    assert not stack.is_contiguous()
+    assert np.array_equal(sdb.itoEuler(f, G, y0, tspan, dW=stack), sdb.itoEuler(f, G, y0, tspan, dW=dW))
+
+
 @pytest.mark.parametrize("m", [12, 16, 20])
 def test_standalone_repeated_integrals_large_m(sdb, m):
     """Ikpw/Jkpw/Iwik/Jwik with on-device normals at large m go through the TMEM-resident kernel
