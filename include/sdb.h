@@ -54,6 +54,10 @@ extern "C" {
 #define SDB_NOISE_HOST 0 /* dW (and I/J for SRK2, KP2iS) supplied by the caller (dW=, I=/J=) */
 #define SDB_NOISE_KPW 1  /* on-device Philox + Ikpw/Jkpw   wiener.py:77-131 */
 #define SDB_NOISE_WIK 2  /* on-device Philox + Iwik/Jwik   wiener.py:234-305 */
+#define SDB_NOISE_COMM 3 /* on-device Philox dW only; I = (dW dW^T - h 1)/2, J = dW dW^T / 2 with no Levy
+                            areas: COMMUTATIVE noise (L^j g_k = L^k g_j), where the antisymmetric part of
+                            I/J cancels in the order-1.0 term -- exactly so in SRI2/SRS2 for linear g_k = B_k y
+                            with commuting B_k.  The fast path the reference plans at integrate.py:150-151 */
 
 /* ---- flags --------------------------------------------------------------------------- */
 #define SDB_FLAG_Y0_BROADCAST 1 /* d_y0 holds one state (d doubles) used by every path */
@@ -110,13 +114,36 @@ typedef struct sdb_integrate_args {
 /* The per-step loops of integrate.py:235-239, :292-302, :494-522, :613-645 over P paths. */
 int sdb_integrate(sdb_system* sys, const sdb_integrate_args* args);
 
+/* ---- path functionals -------------------------------------------------------------------
+ * Quantities of the full-resolution trajectory that a decimated store (save_every > 1) cannot give
+ * back, evaluated at every grid point t_0..t_{N-1} inside the step loop (the first-passage / `nsim`
+ * role of the reference's to-do list, README.rst:137).  Up to SDB_MAX_OBSERVERS per call. */
+#define SDB_MAX_OBSERVERS 4
+#define SDB_OBS_FIRST_ABOVE 0 /* first grid time with y[comp] >= level (+inf if never) */
+#define SDB_OBS_FIRST_BELOW 1 /* first grid time with y[comp] <= level (+inf if never) */
+#define SDB_OBS_MAX 2         /* max over the grid of y[comp] */
+#define SDB_OBS_MIN 3         /* min over the grid of y[comp] */
+#define SDB_OBS_INTEGRAL 4    /* trapezoidal integral of y[comp] dt over the grid */
+typedef struct sdb_observer {
+  int kind;     /* SDB_OBS_* */
+  int comp;     /* state component, 0 <= comp < d */
+  double level; /* threshold of the FIRST_* kinds */
+} sdb_observer;
+
+/* sdb_integrate plus n_obs observers: d_obs[o * stride_obs + p * stride_path] receives observer o of
+ * path p.  Same kernels and results as sdb_integrate; the observing variants are compiled with NVRTC
+ * on first use per system. */
+int sdb_integrate_observed(sdb_system* sys, const sdb_integrate_args* args, const sdb_observer* h_obs,
+                           int n_obs, double* d_obs, int64_t stride_obs, int64_t stride_path);
+
 /* deltaW (wiener.py:36-52) for P paths: out[step][comp][path] through strides. */
 int sdb_delta_w(int64_t steps, int m, double h, int64_t paths, int64_t path_id0, uint64_t seed,
                 double* d_out, int64_t stride_step, int64_t stride_comp, int64_t stride_path,
                 void* stream);
 
 /* Ikpw/Jkpw/Iwik/Jwik (wiener.py:77-131, :234-305) for P paths x `steps` intervals.
- * method: SDB_NOISE_KPW or SDB_NOISE_WIK; stratonovich: 0 -> I, 1 -> J.
+ * method: SDB_NOISE_KPW, SDB_NOISE_WIK or SDB_NOISE_COMM (A = 0, no normals drawn, n_terms ignored);
+ * stratonovich: 0 -> I, 1 -> J.
  * d_X, d_Y ([n][step][comp][path]) and d_Gt ([step][pair][path]) are OPTIONAL caller-supplied
  * standard normals (construction parity with the reference's draws); when NULL they come
  * from Philox(seed, path_id0 + p, step).  d_A receives A (KPW: m x m) or Atilde (WIK: M). */

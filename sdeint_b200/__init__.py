@@ -6,7 +6,7 @@ work happens in hand-written sm_100a CUDA kernels reached through the C ABI of
 include/sdb.h (libsdb.so, bound with ctypes in `_lib.py`); importing the package does not
 need a GPU, computing does, and there is no CPU fallback."""
 from . import ops  # noqa: F401
-from .wiener import deltaW, Ikpw, Jkpw, Iwik, Jwik  # noqa: F401
+from .wiener import deltaW, Ikpw, Jkpw, Iwik, Jwik, Icomm, Jcomm  # noqa: F401
 from .integrate import (Error, SDEValueError, itoint, stratint, itoEuler, stratHeun,  # noqa: F401
                         itoSRI2, stratSRS2, stratKP2iS, last_status)
 from ._lib import launch_count  # noqa: F401

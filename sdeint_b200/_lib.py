@@ -48,6 +48,11 @@ class RepintArgs(C.Structure):
 
 
 # name -> (restype, argtypes); must list every symbol include/sdb.h declares
+class Observer(C.Structure):
+    """== sdb_observer (include/sdb.h)."""
+    _fields_ = [("kind", C.c_int), ("comp", C.c_int), ("level", C.c_double)]
+
+
 SIGNATURES = {
     "sdb_last_error": (C.c_char_p, []),
     "sdb_version": (C.c_int, []),
@@ -58,6 +63,8 @@ SIGNATURES = {
                                    C.c_int, C.POINTER(C.c_void_p)]),
     "sdb_system_destroy": (C.c_int, [C.c_void_p]),
     "sdb_integrate": (C.c_int, [C.c_void_p, C.POINTER(IntegrateArgs)]),
+    "sdb_integrate_observed": (C.c_int, [C.c_void_p, C.POINTER(IntegrateArgs), C.POINTER(Observer), C.c_int,
+                                         c_dp, c_i64, c_i64]),
     "sdb_delta_w": (C.c_int, [c_i64, C.c_int, C.c_double, c_i64, c_i64, c_u64, c_dp, c_i64, c_i64,
                               c_i64, c_dp]),
     "sdb_repeated_integrals": (C.c_int, [C.POINTER(RepintArgs)]),

@@ -86,8 +86,15 @@ static void keep_pool_memory() {
   }
 }
 
+// Blocks for `total` work items, or 0 when the count does not fit a 1-d grid (2^31 - 1 blocks).
+static unsigned blocks_for(int64_t total, int64_t per_block) {
+  const int64_t b = (total + per_block - 1) / per_block;
+  return b > 0x7fffffffll ? 0u : (unsigned)b;
+}
+
 static int launch(const void* fn, dim3 grid, dim3 block, void** args, cudaStream_t st,
                   size_t smem = 0) {
+  if (grid.x == 0) return fail("launch: too many work items for one grid; split the call");
   SDB_CUDA(cudaLaunchKernel(fn, grid, block, args, smem, st));
   g_launches.fetch_add(1);
   return 0;
@@ -307,17 +314,19 @@ static std::string type_of(const sdb_system* s, bool drift) {
 }
 
 // Find (AOT) or build (NVRTC) the loop kernel for this system / scheme / noise source.
-static int loop_kernel(sdb_system* s, int scheme, int noise, const void** fn) {
-  const std::string key = sdb_loop_key(scheme, s->fk, s->gk, s->d, s->m, noise, s->inline_params);
+static int loop_kernel(sdb_system* s, int scheme, int noise, const void** fn, bool observe = false) {
+  std::string key = sdb_loop_key(scheme, s->fk, s->gk, s->d, s->m, noise, s->inline_params);
   const bool user_g = s->gk == SDB_DIFF_USER || s->gk == SDB_DIFF_USER_DIAG;
   const bool user = s->fk == SDB_DRIFT_USER || user_g;
-  if (!user) {
+  if (!user && !observe) {
     if (const void* f = aot_lookup(key)) { *fn = f; return 0; }
   }
+  if (observe) key += "|obs";  // the observing variant of every kernel is compiled at run time
   std::lock_guard<std::mutex> lk(s->mu);
   auto it = s->jit.find(key);
   if (it == s->jit.end()) {
     std::ostringstream src;
+    if (observe) src << "#define SDB_OBSERVE 1\n";
     if (s->fk == SDB_DRIFT_USER) src << "#define SDB_USER_DRIFT 1\n";
     if (user_g) src << "#define SDB_USER_DIFF 1\n";
     src << "#include \"sdb_kernels.cuh\"\n";
@@ -340,11 +349,43 @@ __global__ void sdb_k_status_init(int64_t* st) {
   st[0] = 0; st[1] = 0x7fffffffffffffffll; st[2] = 0; st[3] = 0x7fffffffffffffffll;
 }
 
+static int integrate_impl(sdb_system* s, const sdb_integrate_args* a, const SdbObsArgs* obs);
+
 extern "C" int sdb_integrate(sdb_system* s, const sdb_integrate_args* a) {
+  return integrate_impl(s, a, nullptr);
+}
+
+extern "C" int sdb_integrate_observed(sdb_system* s, const sdb_integrate_args* a, const sdb_observer* h_obs,
+                                      int n_obs, double* d_obs, int64_t stride_obs, int64_t stride_path) {
+  if (!s || !a) return fail("sdb_integrate_observed: NULL argument");
+  if (n_obs == 0) return integrate_impl(s, a, nullptr);
+  if (n_obs < 0 || n_obs > SDB_MAX_OBSERVERS)
+    return fail("sdb_integrate_observed: need 0 <= n_obs <= SDB_MAX_OBSERVERS");
+  if (!h_obs || !d_obs) return fail("sdb_integrate_observed: NULL observer buffer");
+  static_assert(SDB_MAX_OBSERVERS == SDB_MAX_OBS, "sdb.h and sdb_kernels.cuh disagree");
+  SdbObsArgs o;
+  memset(&o, 0, sizeof o);
+  o.n = n_obs;
+  for (int i = 0; i < n_obs; ++i) {
+    if (h_obs[i].kind < SDB_OBS_FIRST_ABOVE || h_obs[i].kind > SDB_OBS_INTEGRAL)
+      return fail("sdb_integrate_observed: unknown observer kind");
+    if (h_obs[i].comp < 0 || h_obs[i].comp >= s->d)
+      return fail("sdb_integrate_observed: observer component out of range");
+    o.kind[i] = h_obs[i].kind;
+    o.comp[i] = h_obs[i].comp;
+    o.level[i] = h_obs[i].level;
+  }
+  o.out = d_obs;
+  o.sO = stride_obs;
+  o.sP = stride_path;
+  return integrate_impl(s, a, &o);
+}
+
+static int integrate_impl(sdb_system* s, const sdb_integrate_args* a, const SdbObsArgs* obs) {
   if (!s || !a) return fail("sdb_integrate: NULL argument");
   if (a->scheme < SDB_SCHEME_EULER || a->scheme > SDB_SCHEME_KP2IS)
     return fail("sdb_integrate: unknown scheme");
-  if (a->noise < SDB_NOISE_HOST || a->noise > SDB_NOISE_WIK)
+  if (a->noise < SDB_NOISE_HOST || a->noise > SDB_NOISE_COMM)
     return fail("sdb_integrate: unknown noise source");
   if (a->N < 2) return fail("sdb_integrate: need at least two time points");
   if (a->paths < 1) return fail("sdb_integrate: need at least one path");
@@ -358,21 +399,24 @@ extern "C" int sdb_integrate(sdb_system* s, const sdb_integrate_args* a) {
                     a->scheme == SDB_SCHEME_SRK2;  // KP2iS does use the off-diagonal J
   if (a->noise == SDB_NOISE_HOST && (!a->d_dW || (need_ij && !a->d_IJ && !diag)))
     return fail("sdb_integrate: NOISE_HOST needs dW (and I/J for SRK2, KP2iS)");
-  if (a->noise != SDB_NOISE_HOST && a->n_terms < 1)
+  if ((a->noise == SDB_NOISE_KPW || a->noise == SDB_NOISE_WIK) && a->n_terms < 1)
     return fail("sdb_integrate: n_terms must be >= 1");
   if (a->scheme == SDB_SCHEME_KP2IS && !a->h_kp2is)
     return fail("sdb_integrate: KP2iS needs gam, al1, al2");
   cudaStream_t st = (cudaStream_t)a->stream;
 
   int noise = a->noise;
+  int n_terms = a->n_terms;
   if (!need_ij && noise == SDB_NOISE_WIK) noise = SDB_NOISE_KPW;  // only dW is drawn
+  // commutative noise: the Ikpw/Jkpw kernels with an empty series (A = 0, only dW is drawn)
+  if (noise == SDB_NOISE_COMM) { noise = SDB_NOISE_KPW; n_terms = 0; }
   // The production path: linear system, SRI2/SRS2, on-device Philox + Ikpw/Jkpw (or Iwik/Jwik)
   // -> a fused kernel when one is instantiated for this (d, m, method).
   const SdbFusedEntry* fused = nullptr;
   const bool explicit_em = a->scheme == SDB_SCHEME_EULER || a->scheme == SDB_SCHEME_HEUN;
   if ((a->scheme == SDB_SCHEME_SRK2 || explicit_em) && noise != SDB_NOISE_HOST &&
       s->fk == SDB_DRIFT_LINEAR && s->gk == SDB_DIFF_LINEAR_COLS &&
-      a->n_terms <= SDB_FUSED_MAX_TERMS && !getenv("SDB_DISABLE_FUSED")) {
+      n_terms <= SDB_FUSED_MAX_TERMS && !getenv("SDB_DISABLE_FUSED") && !obs) {
     const char* vs = getenv("SDB_FUSED_VARIANT");
     const int want = vs ? atoi(vs) : 0;
     for (const auto& e : sdb_fused_registry())
@@ -394,11 +438,12 @@ extern "C" int sdb_integrate(sdb_system* s, const sdb_integrate_args* a) {
       SdbFusedEhDims(s->d, s->m, a->scheme == SDB_SCHEME_HEUN).supported()) {
     const bool heun = a->scheme == SDB_SCHEME_HEUN;
     const SdbFusedEhDims edims(s->d, s->m, heun);
-    const std::string key = heun ? "fusedehjit|heun" : "fusedehjit|euler";
+    const std::string key = std::string(heun ? "fusedehjit|heun" : "fusedehjit|euler") + (obs ? "|obs" : "");
     std::lock_guard<std::mutex> lk(s->mu);
     auto it = s->jit.find(key);
     if (it == s->jit.end()) {
       std::ostringstream src;
+      if (obs) src << "#define SDB_OBSERVE 1\n";
       src << "#include \"sdb_fusedeh.cuh\"\nSDB_FUSEDEH_KERNEL(sdb_jit_fused, " << s->d << ", " << s->m
           << ", " << (heun ? 1 : 0) << ")\n";
       JitKernel k;
@@ -412,18 +457,21 @@ extern "C" int sdb_integrate(sdb_system* s, const sdb_integrate_args* a) {
   }
   if (!fused && a->scheme == SDB_SCHEME_SRK2 && noise != SDB_NOISE_HOST &&
       s->fk == SDB_DRIFT_LINEAR && s->gk == SDB_DIFF_LINEAR_COLS &&
-      a->n_terms <= SDB_FUSED_MAX_TERMS && !getenv("SDB_DISABLE_FUSED") &&
+      n_terms <= SDB_FUSED_MAX_TERMS && !getenv("SDB_DISABLE_FUSED") &&
       !getenv("SDB_DISABLE_FUSED_JIT") && s->d * s->m >= 16) {  // tiny systems are generator-bound:
     const SdbFusedDims dims(s->d, s->m);                        // the high-occupancy loop kernel wins
     const SdbFusedXDims xdims(s->d, s->m);
     const bool use_v0 = noise == SDB_NOISE_KPW && dims.supported();
     const bool use_x = !use_v0 && xdims.supported();
     if (use_v0 || use_x) {
-      const std::string key = use_v0 ? "fusedjit" : (noise == SDB_NOISE_WIK ? "fusedxjit|wik" : "fusedxjit|kpw");
+      const std::string key =
+          std::string(use_v0 ? "fusedjit" : (noise == SDB_NOISE_WIK ? "fusedxjit|wik" : "fusedxjit|kpw")) +
+          (obs ? "|obs" : "");
       std::lock_guard<std::mutex> lk(s->mu);
       auto it = s->jit.find(key);
       if (it == s->jit.end()) {
         std::ostringstream src;
+        if (obs) src << "#define SDB_OBSERVE 1\n";
         if (use_v0) {
           src << "#include \"sdb_fused.cuh\"\nSDB_FUSED_KERNEL(sdb_jit_fused, " << s->d << ", " << s->m << ")\n";
         } else {
@@ -465,7 +513,7 @@ extern "C" int sdb_integrate(sdb_system* s, const sdb_integrate_args* a) {
       it = s->d_frags.emplace(fn, d).first;
     }
     d_frag = it->second;
-  } else if (loop_kernel(s, a->scheme, noise, &fn)) {
+  } else if (loop_kernel(s, a->scheme, noise, &fn, obs != nullptr)) {
     return 1;
   }
 
@@ -492,7 +540,7 @@ extern "C" int sdb_integrate(sdb_system* s, const sdb_integrate_args* a) {
   SdbLoopArgs k;
   memset(&k, 0, sizeof k);
   k.P = a->paths; k.path_id0 = a->path_id0; k.seed = a->seed;
-  k.N = a->N; k.save_every = a->save_every; k.n_terms = a->n_terms; k.flags = a->flags;
+  k.N = a->N; k.save_every = a->save_every; k.n_terms = n_terms; k.flags = a->flags;
   k.h_global = (a->h_tspan[a->N - 1] - a->h_tspan[0]) / (double)(a->N - 1);
   k.rtol = a->rtol;
   k.tspan = d_aux;
@@ -503,6 +551,7 @@ extern "C" int sdb_integrate(sdb_system* s, const sdb_integrate_args* a) {
   k.IJ_sC = a->IJ_stride_col; k.IJ_sP = a->IJ_stride_path;
   k.kp = nk ? d_aux + nt + 3 * ns : nullptr;
   k.status = a->d_status;
+  if (obs) k.obs = *obs;
   if (a->d_status) {
     sdb_k_status_init<<<1, 1, 0, st>>>(a->d_status);
     g_launches.fetch_add(1);
@@ -523,7 +572,7 @@ extern "C" int sdb_integrate(sdb_system* s, const sdb_integrate_args* a) {
   }
   const unsigned block = fused ? (unsigned)fused->threads : SDB_BLOCK;
   const int64_t per_block = fused ? fused->paths_per_block : SDB_BLOCK;
-  const unsigned grid = (unsigned)((a->paths + per_block - 1) / per_block);
+  const unsigned grid = blocks_for(a->paths, per_block);
   const int rc = launch(fn, dim3(grid), dim3(block), args, st, fused ? fused->smem : 0);
   const cudaError_t fe = cudaFreeAsync(d_aux, st);  // stream-ordered: after the kernel has read it
   if (rc) return 1;
@@ -543,7 +592,7 @@ extern "C" int sdb_delta_w(int64_t steps, int m, double h, int64_t paths, int64_
   SdbDeltaWArgs a{steps, paths, path_id0, seed, m, sqrt(h), d_out, sN, sJ, sP};
   void* args[1] = {&a};
   const int64_t total = steps * paths;
-  return launch((const void*)sdb_k_delta_w, dim3((unsigned)((total + 255) / 256)), dim3(256), args,
+  return launch((const void*)sdb_k_delta_w, dim3(blocks_for(total, 256)), dim3(256), args,
                 (cudaStream_t)stream);
 }
 
@@ -592,23 +641,25 @@ static int repint_kernel(int m, const void** fn) {
 
 extern "C" int sdb_repeated_integrals(const sdb_repint_args* a) {
   if (!a) return fail("sdb_repeated_integrals: NULL argument");
-  if (a->method != SDB_NOISE_KPW && a->method != SDB_NOISE_WIK)
-    return fail("sdb_repeated_integrals: method must be KPW or WIK");
+  if (a->method != SDB_NOISE_KPW && a->method != SDB_NOISE_WIK && a->method != SDB_NOISE_COMM)
+    return fail("sdb_repeated_integrals: method must be KPW, WIK or COMM");
+  const bool comm = a->method == SDB_NOISE_COMM;  // = KPW with an empty series: A = 0, nothing drawn
+  const int method = comm ? SDB_NOISE_KPW : a->method;
   if (a->m < 1 || a->m > 64) return fail("sdb_repeated_integrals: need 1 <= m <= 64");
-  if (a->n_terms < 1) return fail("sdb_repeated_integrals: n_terms must be >= 1");
+  if (!comm && a->n_terms < 1) return fail("sdb_repeated_integrals: n_terms must be >= 1");
   if (a->steps < 0 || a->paths < 1) return fail("sdb_repeated_integrals: bad sizes");
   if (!(a->h > 0.0)) return fail("sdb_repeated_integrals: h must be positive");
   if (!a->d_dW || !a->d_IJ) return fail("sdb_repeated_integrals: NULL buffer");
   if ((a->d_X == nullptr) != (a->d_Y == nullptr))
     return fail("sdb_repeated_integrals: X and Y must be given together");
-  if (a->d_X && a->method == SDB_NOISE_WIK && a->m > 1 && !a->d_Gt)
+  if (a->d_X && method == SDB_NOISE_WIK && a->m > 1 && !a->d_Gt)
     return fail("sdb_repeated_integrals: host normals for WIK also need Gt");
   if (a->steps == 0) return 0;
   // Philox normals and a large even m: the TMEM-resident kernel (ahead of time for m = 20, else NVRTC)
   const void* fn = nullptr;
   size_t smem = 0;
   unsigned block = 128;
-  if (!a->d_X && a->m >= 12 && SdbRepintXDims(a->m).supported() && !getenv("SDB_DISABLE_FUSED")) {
+  if (!comm && !a->d_X && a->m >= 12 && SdbRepintXDims(a->m).supported() && !getenv("SDB_DISABLE_FUSED")) {
     for (const auto& e : sdb_repintx_registry())
       if (e.m == a->m && e.noise == a->method) { fn = e.fn; smem = e.smem; block = (unsigned)e.threads; }
     if (!fn) {
@@ -634,7 +685,7 @@ extern "C" int sdb_repeated_integrals(const sdb_repint_args* a) {
   }
   SdbRepintArgs k;
   memset(&k, 0, sizeof k);
-  k.method = a->method; k.stratonovich = a->stratonovich; k.n_terms = a->n_terms; k.m = a->m;
+  k.method = method; k.stratonovich = a->stratonovich; k.n_terms = comm ? 0 : a->n_terms; k.m = a->m;
   k.steps = a->steps; k.paths = a->paths; k.path_id0 = a->path_id0; k.seed = a->seed; k.h = a->h;
   k.dW = a->d_dW; k.dW_sN = a->dW_stride_step; k.dW_sJ = a->dW_stride_comp; k.dW_sP = a->dW_stride_path;
   k.X = a->d_X; k.Y = a->d_Y;
@@ -646,7 +697,7 @@ extern "C" int sdb_repeated_integrals(const sdb_repint_args* a) {
   k.IJ_sC = a->IJ_stride_col; k.IJ_sP = a->IJ_stride_path;
   void* args[1] = {&k};
   const int64_t total = a->steps * a->paths;
-  return launch(fn, dim3((unsigned)((total + block - 1) / block)), dim3(block), args,
+  return launch(fn, dim3(blocks_for(total, block)), dim3(block), args,
                 (cudaStream_t)a->stream, smem);
 }
 

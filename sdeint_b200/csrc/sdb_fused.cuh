@@ -564,6 +564,10 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
     }
     sdb_store<D>(a, p, 0, Y);
   }
+#if SDB_OBSERVE
+  SdbObs<D> obs;
+  obs.init(a, Y);
+#endif
 
   const double rh_g = sqrt(a.h_global);
   const double cz = sqrt(2.0 / a.h_global);
@@ -755,6 +759,9 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
     for (int q = 0; q < Sh::IL; ++q) Yacc[8 * Sh::IT + q] += wv[q];
 #pragma unroll
     for (int i = 0; i < D; ++i) Y[i] += Yacc[i];  // Y_{n+1} = H20 - f0h/2 + f1h/2 + G dW + sum
+#if SDB_OBSERVE
+    obs.step(a, n, Y);
+#endif
 
     if (n + 1 == next_save) {
       if (active) sdb_store<D>(a, p, slot, Y);
@@ -763,6 +770,9 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
     }
   }
   if (active) sdb_finish<D>(a, p, Y);
+#if SDB_OBSERVE
+  if (active) obs.finish(a, p);
+#endif
 }
 
 }  // namespace SDB_FUSED_NS

@@ -123,6 +123,10 @@ SDB_DEV void sdb_fusedeh_body(const SdbLoopArgs& a, const double* __restrict__ f
     }
     sdb_store<D>(a, p, 0, Y);
   }
+#if SDB_OBSERVE
+  SdbObs<D> obs;
+  obs.init(a, Y);
+#endif
   const double h = a.h_global;  // Euler / Heun use the global mean step (integrate.py:228, :285)
   const double rh = sqrt(h);
   const uint64_t path = (uint64_t)(a.path_id0 + p);
@@ -153,6 +157,9 @@ SDB_DEV void sdb_fusedeh_body(const SdbLoopArgs& a, const double* __restrict__ f
       for (int i = 0; i < D; ++i)  // integrate.py:300-302
         Y[i] = Y[i] + 0.5 * (f0[i] + f1[i]) * h + 0.5 * (GdW[i] + GdW1[i]);
     }
+#if SDB_OBSERVE
+    obs.step(a, n, Y);
+#endif
     if (n + 1 == next_save) {
       if (active) sdb_store<D>(a, p, slot, Y);
       ++slot;
@@ -160,6 +167,9 @@ SDB_DEV void sdb_fusedeh_body(const SdbLoopArgs& a, const double* __restrict__ f
     }
   }
   if (active) sdb_finish<D>(a, p, Y);
+#if SDB_OBSERVE
+  if (active) obs.finish(a, p);
+#endif
 }
 #endif  // __CUDACC__
 

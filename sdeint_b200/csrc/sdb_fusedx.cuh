@@ -224,6 +224,9 @@ SDB_DEV void sdb_srk2_fusedx_body(const SdbLoopArgs& a, const PInline<D * D>& fp
   double* ybuf = gbuf + Xs::R_Y * 32;
   const int64_t p = (int64_t)blockIdx.x * Xs::PATHS + tid;
   const bool active = p < a.P;  // idle lanes of the last warp still take part in the DMMAs
+#if SDB_OBSERVE
+  SdbObs<D> obs;
+#endif
   {
     double Y[D];
 #pragma unroll
@@ -238,6 +241,9 @@ SDB_DEV void sdb_srk2_fusedx_body(const SdbLoopArgs& a, const PInline<D * D>& fp
       }
       sdb_store<D>(a, p, 0, Y);
     }
+#if SDB_OBSERVE
+    obs.init(a, Y);
+#endif
 #pragma unroll
     for (int l = 0; l < D; ++l) ybuf[l * 32 + (lane ^ sdb_swz(l))] = Y[l];
     __syncwarp();
@@ -507,6 +513,9 @@ SDB_DEV void sdb_srk2_fusedx_body(const SdbLoopArgs& a, const PInline<D * D>& fp
     for (int l = 0; l < D; ++l) ybuf[l * 32 + (lane ^ sdb_swz(l))] = Y[l];
     __syncwarp();
 
+#if SDB_OBSERVE
+    obs.step(a, n, Y);
+#endif
     if (n + 1 == next_save) {
       if (active) sdb_store<D>(a, p, slot, Y);
       ++slot;
@@ -514,6 +523,9 @@ SDB_DEV void sdb_srk2_fusedx_body(const SdbLoopArgs& a, const PInline<D * D>& fp
     }
     if (n + 1 == steps && active) sdb_finish<D>(a, p, Y);
   }
+#if SDB_OBSERVE
+  if (active) obs.finish(a, p);
+#endif
   sdb_tm_free512(tm_base);
 }
 #endif  // __CUDACC__

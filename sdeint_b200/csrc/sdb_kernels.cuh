@@ -39,8 +39,32 @@ typedef long long int64_t;
 #define SDB_NOISE_HOST 0
 #define SDB_NOISE_KPW 1
 #define SDB_NOISE_WIK 2
+#define SDB_NOISE_COMM 3  // host-side only: kernels see KPW with n_terms = 0
 #define SDB_FLAG_Y0_BROADCAST 1
 #define SDB_FLAG_STRATONOVICH 2
+
+// ---- path functionals ("observers", include/sdb.h sdb_observer) -----------------------------
+// Quantities of the FULL-resolution trajectory that a decimated store cannot give back: first
+// passage times, running extrema, time integrals -- evaluated at every grid point inside the step
+// loop.  Compiled in only when SDB_OBSERVE is 1 (NVRTC variants; the ahead-of-time kernels are
+// unchanged).
+#ifndef SDB_OBSERVE
+#define SDB_OBSERVE 0
+#endif
+#define SDB_MAX_OBS 4
+#define SDB_OBS_FIRST_ABOVE 0
+#define SDB_OBS_FIRST_BELOW 1
+#define SDB_OBS_MAX 2
+#define SDB_OBS_MIN 3
+#define SDB_OBS_INTEGRAL 4
+struct SdbObsArgs {
+  int n;
+  int kind[SDB_MAX_OBS];
+  int comp[SDB_MAX_OBS];
+  double level[SDB_MAX_OBS];
+  double* out;  // [observer][path] through strides
+  int64_t sO, sP;
+};
 
 // ---- kernel argument block (plain data; mirrored by the host in sdb_capi.cu) ---------------
 struct SdbLoopArgs {
@@ -64,6 +88,7 @@ struct SdbLoopArgs {
   int64_t IJ_sN, IJ_sR, IJ_sC, IJ_sP;
   const double* kp;  // device [3*D]: gam, al1, al2
   int64_t* status;   // [4]
+  SdbObsArgs obs;    // per-path functionals of the trajectory (kernels built with SDB_OBSERVE only)
 };
 
 struct SdbRepintArgs {
@@ -602,6 +627,60 @@ SDB_DEV void sdb_finish(const SdbLoopArgs& a, int64_t p, const double (&Y)[D]) {
   }
 }
 
+// Observer state of one path: registers only, component picked by a select chain (a runtime index
+// into Y would move the whole state to local memory).
+template <int D>
+struct SdbObs {
+  double v[SDB_MAX_OBS], prev[SDB_MAX_OBS];
+  static SDB_DEV double pick(const double (&Y)[D], int c) {
+    double r = Y[0];
+#pragma unroll
+    for (int i = 1; i < D; ++i) r = (i == c) ? Y[i] : r;
+    return r;
+  }
+  SDB_DEV void init(const SdbLoopArgs& a, const double (&Y)[D]) {
+    const double t0 = a.tspan[0];
+#pragma unroll
+    for (int o = 0; o < SDB_MAX_OBS; ++o) {
+      v[o] = 0.0;
+      prev[o] = 0.0;
+      if (o < a.obs.n) {
+        const double y = pick(Y, a.obs.comp[o]);
+        const int kind = a.obs.kind[o];
+        const double inf = __longlong_as_double(0x7ff0000000000000ll);
+        prev[o] = y;
+        if (kind == SDB_OBS_FIRST_ABOVE) v[o] = y >= a.obs.level[o] ? t0 : inf;
+        else if (kind == SDB_OBS_FIRST_BELOW) v[o] = y <= a.obs.level[o] ? t0 : inf;
+        else if (kind == SDB_OBS_INTEGRAL) v[o] = 0.0;
+        else v[o] = y;
+      }
+    }
+  }
+  // after step n: Y = y(t_{n+1})
+  SDB_DEV void step(const SdbLoopArgs& a, int n, const double (&Y)[D]) {
+    if (a.obs.n == 0) return;
+    const double t0 = a.tspan[n], t1 = a.tspan[n + 1];
+#pragma unroll
+    for (int o = 0; o < SDB_MAX_OBS; ++o) {
+      if (o < a.obs.n) {
+        const double y = pick(Y, a.obs.comp[o]);
+        const int kind = a.obs.kind[o];
+        if (kind == SDB_OBS_FIRST_ABOVE) v[o] = (y >= a.obs.level[o] && t1 < v[o]) ? t1 : v[o];
+        else if (kind == SDB_OBS_FIRST_BELOW) v[o] = (y <= a.obs.level[o] && t1 < v[o]) ? t1 : v[o];
+        else if (kind == SDB_OBS_MAX) v[o] = y > v[o] ? y : v[o];
+        else if (kind == SDB_OBS_MIN) v[o] = y < v[o] ? y : v[o];
+        else v[o] = fma(0.5 * (t1 - t0), prev[o] + y, v[o]);  // trapezoid
+        prev[o] = y;
+      }
+    }
+  }
+  SDB_DEV void finish(const SdbLoopArgs& a, int64_t p) const {
+#pragma unroll
+    for (int o = 0; o < SDB_MAX_OBS; ++o)
+      if (o < a.obs.n) a.obs.out[o * a.obs.sO + p * a.obs.sP] = v[o];
+  }
+};
+
 // Small dense solve J x = b with partial pivoting (KP2iS Newton step); J is destroyed.
 template <int D>
 SDB_DEV bool sdb_solve(double (&J)[D][D], double (&b)[D]) {
@@ -661,6 +740,10 @@ SDB_DEV void sdb_loop_body(const SdbLoopArgs& a, const typename F::Params& fp,
     for (int i = 0; i < D; ++i) Y[i] = a.y0[i * a.y0_sI + p * a.y0_sP];
   }
   sdb_store<D>(a, p, 0, Y);
+#if SDB_OBSERVE
+  SdbObs<D> obs;
+  obs.init(a, Y);
+#endif
 
   // KP2iS keeps the previous state, drift and noise term (integrate.py:621,628,635)
   double Ym1[SCHEME == SDB_SCHEME_KP2IS ? D : 1], fm1[SCHEME == SDB_SCHEME_KP2IS ? D : 1],
@@ -871,12 +954,18 @@ SDB_DEV void sdb_loop_body(const SdbLoopArgs& a, const typename F::Params& fp,
       }
     }
 
+#if SDB_OBSERVE
+    obs.step(a, n, Y);
+#endif
     if (n + 1 == next_save) {
       sdb_store<D>(a, p, slot, Y);
       ++slot;
       next_save += a.save_every;
     }
   }
+#if SDB_OBSERVE
+  obs.finish(a, p);
+#endif
   sdb_finish<D>(a, p, Y);
   if (SCHEME == SDB_SCHEME_KP2IS && bad_solve >= 0 && a.status) {
     atomicAdd((unsigned long long*)&a.status[2], 1ull);

@@ -19,14 +19,21 @@ Differences from the reference, all forced by "the loop runs in a CUDA kernel":
     match the reference to <= 1e-12 relative.
 Noise structure is exploited where the result is unchanged: additive noise (ops.ConstDiffusion)
 never builds I/J, diagonal noise (ops.DiagLinearDiffusion, CudaDiffusion(diagonal=True)) builds only
-I_kk = (dW_k^2 - h)/2 for SRI2/SRS2, scalar noise draws nothing beyond dW with Iwik -- the first items
-of the reference's own to-do list (integrate.py:150-151, README.rst:130).
+I_kk = (dW_k^2 - h)/2 for SRI2/SRS2, scalar noise draws nothing beyond dW with Iwik, and commutative
+noise (LinearDiffusion with commuting B_k -- detected --, or `commutative=True` on a user operator or
+on the call, or Imethod=Icomm / Jmethod=Jcomm) runs SRI2/SRS2 on I = (dW dW^T - h 1)/2 without Levy
+areas; `commutative=False` on the call forces the full construction -- the first items of the
+reference's own to-do list (integrate.py:150-151, README.rst:130).
 Keyword-only ENSEMBLE extensions: `paths=P` integrates P independent sample paths in one
 launch (returns (P, n_saved, d)); `seed`, `path_id0` select the Philox streams; `save_every`
 decimates the stored trajectory; `out="torch"` leaves the result on the device in the
 path-minor layout (n_saved, d, P); `host_out=` (a pinned torch tensor (n_saved, d, P)) receives
 large results chunk by chunk while the next chunk of paths is integrated.  `dW` / `I` / `J` may
 then carry a leading path axis (without it, one realisation is shared by all paths).
+`observe=[("first_above", comp, level), ("first_below", comp, level), ("max", comp), ("min", comp),
+("integral", comp)]` (up to 4) evaluates path functionals at EVERY grid point inside the step loop --
+what a decimated store cannot give back -- and makes the call return `(y, obs)`, obs of shape
+(P, n_obs): first-passage times are grid times (inf if never), the integral is trapezoidal.
 """
 from __future__ import annotations
 
@@ -38,10 +45,10 @@ import numpy as np
 from . import _device as dev
 from . import _lib, ops
 from . import wiener
-from .wiener import Ikpw, Iwik, Jkpw, Jwik, deltaW  # noqa: F401  (re-exported like the reference)
+from .wiener import Icomm, Ikpw, Iwik, Jcomm, Jkpw, Jwik, deltaW  # noqa: F401  (re-exported like the reference)
 
 SCHEME_EULER, SCHEME_HEUN, SCHEME_SRK2, SCHEME_KP2IS = 0, 1, 2, 3
-NOISE_HOST, NOISE_KPW, NOISE_WIK = 0, 1, 2
+NOISE_HOST, NOISE_KPW, NOISE_WIK, NOISE_COMM = 0, 1, 2, 3
 FLAG_Y0_BROADCAST, FLAG_STRATONOVICH = 1, 2
 
 
@@ -133,10 +140,11 @@ def _check_args(f, G, y0, tspan, dW=None, IJ=None):
 
 
 def _method_id(method, strat):
-    table = ({Jkpw: NOISE_KPW, Jwik: NOISE_WIK} if strat else {Ikpw: NOISE_KPW, Iwik: NOISE_WIK})
+    table = ({Jkpw: NOISE_KPW, Jwik: NOISE_WIK, Jcomm: NOISE_COMM} if strat
+             else {Ikpw: NOISE_KPW, Iwik: NOISE_WIK, Icomm: NOISE_COMM})
     if method in table:
         return table[method]
-    names = "Jkpw or Jwik" if strat else "Ikpw or Iwik"
+    names = "Jkpw, Jwik or Jcomm" if strat else "Ikpw, Iwik or Icomm"
     raise SDEValueError("the repeated-integral method must be sdeint_b200.%s" % names)
 
 
@@ -163,7 +171,8 @@ def _resolve_paths(paths, dW, IJ):
 
 
 def _run(scheme, f, G, y0, tspan, dW, IJ, strat, method, generator, kp2is, paths, seed,
-         path_id0, save_every, n_terms, device, out, y0_paths=None, host_out=None):
+         path_id0, save_every, n_terms, device, out, y0_paths=None, host_out=None,
+         commutative=None, observe=None):
     global _last_status
     (d, m, f, Gop, y0, tspan, dW, IJ) = _check_args(f, G, y0, tspan, dW, IJ)
     P, ensemble = _resolve_paths(paths, dW, IJ)
@@ -182,6 +191,12 @@ def _run(scheme, f, G, y0, tspan, dW, IJ, strat, method, generator, kp2is, paths
     n_saved = (N - 1) // save_every + 1
     h = (tspan[N - 1] - tspan[0]) / (N - 1)
     method_id = _method_id(method, strat) if need_ij else NOISE_KPW
+    # commutative noise: the antisymmetric part of I/J (the Levy areas) cancels in the order-1.0 term
+    # of SRI2/SRS2 -- exactly for linear g_k = B_k y with commuting B_k, which LinearDiffusion detects --
+    # so unless the caller supplies I/J or says commutative=False the areas are never generated
+    if (need_ij and IJ is None and scheme == SCHEME_SRK2 and commutative is not False
+            and (commutative or Gop.commutative)):
+        method_id = NOISE_COMM
     device = dev.require_cuda(device)
     torch = dev.torch_mod()
     lib = _lib.load()
@@ -256,8 +271,9 @@ def _run(scheme, f, G, y0, tspan, dW, IJ, strat, method, generator, kp2is, paths
             kp = np.ascontiguousarray(np.concatenate(kp2is[:3]), dtype=np.float64)
             a.h_kp2is = dev.host_ptr(kp)
             a.rtol = float(kp2is[3])
+        obs_arr = _observers(observe, d) if observe is not None else None
         if (host_out is not None and out != "torch" and a.noise != NOISE_HOST and y0_paths is None
-                and P >= _PIPELINE_MIN_PATHS):
+                and P >= _PIPELINE_MIN_PATHS and obs_arr is None):
             # Large ensemble, on-device noise, caller-owned host result: integrate the paths in chunks
             # and copy chunk c to the host while chunk c+1 is being integrated (two device buffers).
             if tuple(host_out.shape) != (n_saved, d, P) or host_out.dtype != torch.float64 \
@@ -281,7 +297,13 @@ def _run(scheme, f, G, y0, tspan, dW, IJ, strat, method, generator, kp2is, paths
         a.y_stride_save, a.y_stride_comp, a.y_stride_path = d * P, P, 1
         a.d_status = dev.ptr(d_status)
         a.stream = dev.stream_ptr()
-        _lib.check(lib.sdb_integrate(system.handle, C.byref(a)))
+        d_obs = None
+        if obs_arr is None:
+            _lib.check(lib.sdb_integrate(system.handle, C.byref(a)))
+        else:   # path functionals evaluated at every grid point inside the step loop
+            d_obs = torch.empty((len(obs_arr), P), dtype=torch.float64, device=device)
+            _lib.check(lib.sdb_integrate_observed(system.handle, C.byref(a), obs_arr, len(obs_arr),
+                                                  dev.ptr(d_obs), P, 1))
         status = tuple(int(v) for v in d_status.cpu().tolist())
         _last_status = status
         if scheme == SCHEME_KP2IS and status[2] > 0:
@@ -289,7 +311,7 @@ def _run(scheme, f, G, y0, tspan, dW, IJ, strat, method, generator, kp2is, paths
                 "At time t_n = %g Failed to solve for Y_{n+1}: the implicit equation did not "
                 "converge to rtol=%g on %d path(s)." % (tspan[status[3]], kp2is[3], status[2]))
         if out == "torch":
-            return d_y
+            return d_y if d_obs is None else (d_y, d_obs)
         if host_out is not None:
             # caller-owned (ideally pinned) host tensor in the device layout (n_saved, d, P)
             if tuple(host_out.shape) != tuple(d_y.shape) or host_out.dtype != d_y.dtype:
@@ -300,6 +322,11 @@ def _run(scheme, f, G, y0, tspan, dW, IJ, strat, method, generator, kp2is, paths
             host = host_out.numpy()
         else:
             host = d_y.cpu().numpy()
+    if d_obs is not None:                                # (y, observers): (P, n_obs), or (n_obs,) for one path
+        ob = d_obs.cpu().numpy()
+        if not ensemble:
+            return np.ascontiguousarray(host[:, :, 0]), np.ascontiguousarray(ob[:, 0])
+        return host.transpose(2, 0, 1), np.ascontiguousarray(ob.T)
     if not ensemble:
         return np.ascontiguousarray(host[:, :, 0])      # (N, d), y[0] == y0
     return host.transpose(2, 0, 1)                       # (P, n_saved, d)
@@ -351,7 +378,33 @@ def _run_pipelined(lib, system, a, host_out, P, path_id0, n_saved, d, device):
 
 
 _ENS = dict(paths=None, seed=None, path_id0=0, save_every=1, n_terms=5, device=None, out="numpy",
-            y0_paths=None, host_out=None)
+            y0_paths=None, host_out=None, commutative=None, observe=None)
+
+_OBS_KINDS = {"first_above": 0, "first_below": 1, "max": 2, "min": 3, "integral": 4}
+MAX_OBSERVERS = 4
+
+
+def _observers(observe, d):
+    """`observe=[("first_above", comp, level), ("max", comp), ...]` -> ctypes array of sdb_observer."""
+    specs = [observe] if (isinstance(observe, tuple) and observe and isinstance(observe[0], str)) \
+        else list(observe)
+    if not 1 <= len(specs) <= MAX_OBSERVERS:
+        raise SDEValueError('observe takes 1 to %d observers' % MAX_OBSERVERS)
+    arr = (_lib.Observer * len(specs))()
+    for i, spec in enumerate(specs):
+        kind = spec[0]
+        if kind not in _OBS_KINDS:
+            raise SDEValueError('unknown observer %r (one of %s)' % (kind, ", ".join(sorted(_OBS_KINDS))))
+        need_level = kind.startswith("first_")
+        if len(spec) != (3 if need_level else 2):
+            raise SDEValueError('observer %r takes %s' % (kind, "(kind, comp, level)" if need_level
+                                                          else "(kind, comp)"))
+        comp = int(spec[1])
+        if not 0 <= comp < d:
+            raise SDEValueError('observer component %d out of range for d=%d' % (comp, d))
+        arr[i].kind, arr[i].comp = _OBS_KINDS[kind], comp
+        arr[i].level = float(spec[2]) if need_level else 0.0
+    return arr
 
 
 def itoEuler(f, G, y0, tspan, dW=None, generator=None, **ens):

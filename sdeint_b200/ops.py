@@ -65,6 +65,10 @@ class DiffusionOp:
     m = 0
     params = np.zeros(0)
     source = None
+    # Commutative noise (L^j g_k = L^k g_j for all j, k): the Levy areas cancel in the order-1.0
+    # term, so SRI2/SRS2 can run on I = (dW dW^T - h 1)/2 alone.  LinearDiffusion decides it from
+    # the commutators of its B_k; user operators may promise it (`commutative=True`).
+    commutative = False
 
     @property
     def __name__(self):
@@ -148,6 +152,27 @@ class LinearDiffusion(DiffusionOp):
         self.B = np.ascontiguousarray(B)
         self.m, self.d = B.shape[0], B.shape[1]
         self.params = self.B.reshape(-1).copy()
+        self._commutative = None
+
+    @property
+    def commutative(self):
+        """True when every pair of B_k commutes EXACTLY in floating point (both products are
+        evaluated with the same numpy matmul): then sum_{j,k} B_k B_j y I_jk does not see the
+        antisymmetric part of I, and SRI2/SRS2 are unchanged -- to rounding, pathwise for the same
+        dW -- if the Levy areas are never generated."""
+        if self._commutative is None:
+            ok = True
+            for j in range(self.m):
+                for k in range(j + 1, self.m):
+                    c = self.B[j] @ self.B[k] - self.B[k] @ self.B[j]
+                    scale = np.abs(self.B[j]).max() * np.abs(self.B[k]).max() * self.d
+                    if np.abs(c).max() > 8 * np.finfo(float).eps * scale:
+                        ok = False
+                        break
+                if not ok:
+                    break
+            self._commutative = ok
+        return self._commutative
 
     def __call__(self, y, t):
         if _is_scalar(y) and self.d == 1 and self.m == 1:
@@ -276,11 +301,12 @@ class CudaDiffusion(DiffusionOp):
     integrate.py:516-521)."""
     kind = DIFF_USER
 
-    def __init__(self, source, d, m, params=(), host=None, diagonal=False):
+    def __init__(self, source, d, m, params=(), host=None, diagonal=False, commutative=False):
         self.source = str(source)
         self.d, self.m = int(d), int(m)
         self.params = np.asarray(params, dtype=np.float64).reshape(-1).copy()
         self.host = host
+        self.commutative = bool(commutative)   # promise: L^j g_k = L^k g_j (no Levy areas needed)
         if diagonal:   # promise: column k has only component k and depends only on y_k
             if self.d != self.m:
                 raise ValueError("diagonal noise needs m == d")
@@ -363,9 +389,9 @@ class ExprDrift(CudaDrift):
 
 class ExprDiffusion(CudaDiffusion):
     """G_ik(y, t) = exprs[i][k] (d rows of m expressions; "0" for structural zeros).
-    `diagonal=True` promises diagonal noise (see CudaDiffusion)."""
+    `diagonal=True` promises diagonal noise, `commutative=True` commutative noise (see CudaDiffusion)."""
 
-    def __init__(self, exprs, params=(), diagonal=False):
+    def __init__(self, exprs, params=(), diagonal=False, commutative=False):
         rows = [[_check_expr(e) for e in row] for row in exprs]
         d, m = len(rows), len(rows[0])
         if any(len(r) != m for r in rows):
@@ -378,7 +404,7 @@ class ExprDiffusion(CudaDiffusion):
         src = ("__device__ void sde_diffusion_col(int k, const double* y, double t, const double* p, "
                "double* out) {\n  switch (k) {\n%s\n  }\n}\n" % "\n".join(cases))
         par = np.asarray(params, dtype=np.float64).reshape(-1)
-        super().__init__(src, d, m, par, diagonal=diagonal,
+        super().__init__(src, d, m, par, diagonal=diagonal, commutative=commutative,
                          host=lambda y, t: np.array([[_expr_eval(rows[i][k], np.asarray(y, float), t, par)
                                                       for k in range(m)] for i in range(d)]))
 

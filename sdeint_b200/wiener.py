@@ -23,6 +23,7 @@ from . import _lib
 
 NOISE_KPW = 1
 NOISE_WIK = 2
+NOISE_COMM = 3
 _U63 = (1 << 63) - 1
 
 
@@ -88,15 +89,15 @@ def _repint(method, strat, dW, h, n, generator, seed, path_id0, normals, device,
     arr, kind = _prep_dW(dW, ensemble)
     P, N, m = arr.shape
     n = int(n)
-    if n < 1:
+    if n < 1 and method != NOISE_COMM:
         raise ValueError("need at least one series term")
     M = m * (m - 1) // 2
-    need_rng = normals is None and not (method == NOISE_WIK and m == 1)
+    need_rng = normals is None and method != NOISE_COMM and not (method == NOISE_WIK and m == 1)
     key = _derive_seed(seed, generator) if need_rng else 0
     lib = _lib.load()
     with torch.cuda.device(device):
         d_dW = dev.to_device(arr, device)                      # (P, N, m)
-        nA = m * m if method == NOISE_KPW else max(M, 1)
+        nA = m * m if method != NOISE_WIK else max(M, 1)
         d_A = torch.empty((P, N, nA), dtype=torch.float64, device=device)
         d_IJ = torch.empty((P, N, m, m), dtype=torch.float64, device=device)
         a = _lib.RepintArgs()
@@ -105,7 +106,7 @@ def _repint(method, strat, dW, h, n, generator, seed, path_id0, normals, device,
         a.d_dW = dev.ptr(d_dW)
         a.dW_stride_step, a.dW_stride_comp, a.dW_stride_path = m, 1, N * m
         keep = []
-        if normals is not None and not (method == NOISE_WIK and m == 1):
+        if normals is not None and method != NOISE_COMM and not (method == NOISE_WIK and m == 1):
             X = np.asarray(normals[0], dtype=np.float64)
             Y = np.asarray(normals[1], dtype=np.float64)
             if X.ndim == 3:                                    # (n, N, m) single path
@@ -137,7 +138,7 @@ def _repint(method, strat, dW, h, n, generator, seed, path_id0, normals, device,
         _lib.check(lib.sdb_repeated_integrals(C.byref(a)))
         A = d_A.cpu().numpy()
         IJ = d_IJ.cpu().numpy()
-    if method == NOISE_KPW:
+    if method != NOISE_WIK:
         A = A.reshape(P, N, m, m)
     else:
         A = A.reshape(P, N, max(M, 1), 1)
@@ -171,3 +172,19 @@ def Jwik(dW, h, n=5, generator=None, *, seed=None, path_id0=0, normals=None, dev
          ensemble=None):
     """Stratonovich version of Iwik (sdeint/wiener.py:285-305)."""
     return _repint(NOISE_WIK, True, dW, h, n, generator, seed, path_id0, normals, device, ensemble)
+
+
+def Icomm(dW, h, n=0, generator=None, *, seed=None, path_id0=0, normals=None, device=None,
+          ensemble=None):
+    """Repeated Ito integrals for COMMUTATIVE noise: I = (dW dW^T - h 1)/2, no Levy areas and no
+    random numbers beyond dW (`n`, `generator`, `seed` are accepted and ignored so that it can stand
+    in for Ikpw/Iwik as `Imethod=`).  When L^j g_k = L^k g_j the antisymmetric part of I cancels in
+    the order-1.0 term of the schemes -- the fast path the reference plans at
+    sdeint/integrate.py:150-151.  Returns (A, I) with A == 0, shapes as Ikpw."""
+    return _repint(NOISE_COMM, False, dW, h, 0, None, 0, path_id0, None, device, ensemble)
+
+
+def Jcomm(dW, h, n=0, generator=None, *, seed=None, path_id0=0, normals=None, device=None,
+          ensemble=None):
+    """Stratonovich version of Icomm: J = dW dW^T / 2."""
+    return _repint(NOISE_COMM, True, dW, h, 0, None, 0, path_id0, None, device, ensemble)

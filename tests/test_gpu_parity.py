@@ -618,6 +618,181 @@ def test_shared_noise_is_broadcast_not_replicated(sdb):
     assert rel_err(spread[5], orc.srk2(f, G, y0p[5], tspan, dW, I)) <= TOL
 
 
+# ---- commutative noise: no Levy areas (reference to-do integrate.py:150-151) ----
+
+def _commuting_system(d, m, seed=3):
+    """f = A y, g_k = B_k y with B_k polynomials in one matrix C, so that [B_j, B_k] = 0."""
+    import sdeint_b200 as sdb
+    rng = np.random.default_rng(seed)
+    Cm = rng.standard_normal((d, d)) / np.sqrt(d)
+    B = np.stack([(0.25 / np.sqrt(m)) * ((1.0 + 0.1 * k) * np.eye(d) + 0.5 * Cm + 0.1 * (k - m / 2) * Cm @ Cm)
+                  for k in range(m)])
+    A = np.full((d, d), 0.5 / d)
+    np.fill_diagonal(A, -1.5)
+    return sdb.ops.LinearDrift(A), sdb.ops.LinearDiffusion(B), np.ones(d)
+
+
+def test_icomm_jcomm_standalone(sdb):
+    h, m, N, P = 0.01, 6, 9, 33
+    dW = sdb.deltaW(N, m, h, paths=P, seed=12)
+    A, I = sdb.Icomm(dW, h, ensemble=True)
+    _, J = sdb.Jcomm(dW, h, ensemble=True)
+    sym = 0.5 * dW[..., :, None] * dW[..., None, :]
+    assert A.shape == (P, N, m, m) and not A.any()
+    assert np.allclose(I, sym - 0.5 * h * np.eye(m), rtol=0, atol=1e-16)
+    assert np.allclose(J, sym, rtol=0, atol=1e-16)
+    A1, I1 = sdb.Icomm(dW[0], h)                     # the reference's (N, m) -> (N, m, m) shapes
+    assert A1.shape == (N, m, m) and np.array_equal(I1, I[0])
+
+
+@pytest.mark.parametrize("d,m,strat", [(5, 4, False), (10, 10, False), (10, 10, True), (20, 20, False),
+                                       (3, 2, True)])
+def test_commutative_noise_needs_no_levy_areas(sdb, d, m, strat):
+    """For commuting B_k the SRI2/SRS2 result does not depend on the Levy areas: the automatic
+    area-free path (only dW drawn), the forced full Ikpw construction on the same seed, and the oracle
+    fed the device's dW with I from Icomm and from Ikpw all agree pathwise to rounding."""
+    f, G, y0 = _commuting_system(d, m)
+    assert G.commutative
+    tspan = np.linspace(0.0, 0.25, 51)
+    h = 0.005
+    P, seed = 70, 777
+    integ = sdb.stratSRS2 if strat else sdb.itoSRI2
+    y = integ(f, G, y0, tspan, paths=P, seed=seed)                       # dispatches to COMM
+    full = integ(f, G, y0, tspan, paths=P, seed=seed, commutative=False)  # Levy areas generated
+    assert rel_err(y, full) <= TOL and not np.array_equal(y, full)
+    explicit = integ(f, G, y0, tspan, sdb.Jcomm if strat else sdb.Icomm, paths=P, seed=seed,
+                     commutative=False)
+    assert np.array_equal(explicit, y)
+    dW = sdb.deltaW(50, m, h, paths=P, seed=seed)
+    _, Ic = (sdb.Jcomm if strat else sdb.Icomm)(dW, h, ensemble=True)
+    _, Ik = (sdb.Jkpw if strat else sdb.Ikpw)(dW, h, seed=seed, ensemble=True)
+    for p in (0, 31, P - 1):
+        assert rel_err(y[p], orc.srk2(f, G, y0, tspan, dW[p], Ic[p])) <= TOL
+        assert rel_err(y[p], orc.srk2(f, G, y0, tspan, dW[p], Ik[p])) <= TOL
+    # dW supplied, I omitted: built from dW without random numbers
+    y1 = integ(f, G, y0, tspan, dW=dW[5])
+    assert rel_err(y1, y[5]) <= TOL
+
+
+def test_commutative_flag_on_user_operator(sdb):
+    """A nonlinear system whose columns are multiples of one vector field (g_k = c_k phi(y), so
+    L^j g_k = c_j c_k phi' phi is symmetric): `commutative=True` skips the Levy areas; the result is
+    the scheme applied to I = (dW dW^T - h)/2 and stays within O(h) of the full construction."""
+    import sdeint_b200 as sdb_
+    c = [0.3, 0.2, 0.1]
+    fX = sdb_.ops.ExprDrift(["-y[0] + 0.2*y[1]", "-0.5*y[1] + 0.1*sin(y[0])"], [])
+    rows = [["%g*(1.0+0.5*sin(y[1]))" % ck for ck in c], ["%g*cos(y[0])" % ck for ck in c]]
+    Gc = sdb_.ops.ExprDiffusion(rows, [], commutative=True)
+    Gn = sdb_.ops.ExprDiffusion(rows, [])
+    y0 = np.array([0.5, -0.2])
+    tspan = np.linspace(0.0, 0.5, 101)
+    h = 0.005
+    P, seed = 50, 99
+    y = sdb.itoSRI2(fX, Gc, y0, tspan, paths=P, seed=seed)
+    dW = sdb.deltaW(100, 3, h, paths=P, seed=seed)
+    _, Ic = sdb.Icomm(dW, h, ensemble=True)
+    for p in (0, 17, P - 1):
+        assert rel_err(y[p], orc.srk2(fX, Gn, y0, tspan, dW[p], Ic[p])) <= TOL
+    assert np.array_equal(sdb.itoSRI2(fX, Gn, y0, tspan, paths=P, seed=seed, commutative=True), y)
+    full = sdb.itoSRI2(fX, Gn, y0, tspan, paths=P, seed=seed)             # Ikpw, same dW
+    assert not np.array_equal(full, y)
+    assert np.sqrt(np.mean((full[:, -1] - y[:, -1]) ** 2)) < 5e-3          # both order-1.0 strong
+
+
+# ---- path functionals evaluated inside the step loop (SURVEY 8(f) rank 2: first passage, extrema) ----
+
+def _functionals(y, tspan, specs):
+    """numpy restatement on a full-resolution trajectory y (N, d)."""
+    out = []
+    for spec in specs:
+        c = y[:, spec[1]]
+        if spec[0] in ("first_above", "first_below"):
+            hit = np.nonzero(c >= spec[2] if spec[0] == "first_above" else c <= spec[2])[0]
+            out.append(tspan[hit[0]] if len(hit) else np.inf)
+        elif spec[0] == "max":
+            out.append(c.max())
+        elif spec[0] == "min":
+            out.append(c.min())
+        else:
+            out.append(np.sum(0.5 * np.diff(tspan) * (c[:-1] + c[1:])))
+    return np.array(out)
+
+
+def _check_functionals(obs, y, tspan, specs):
+    """obs (P, n_obs) against the trajectories y (P, N, d) the same launch stored."""
+    for p in range(y.shape[0]):
+        ref = _functionals(y[p], tspan, specs)
+        for o, spec in enumerate(specs):
+            if spec[0] == "integral":
+                assert abs(obs[p, o] - ref[o]) <= 1e-13 * max(1.0, abs(ref[o]))
+            else:   # grid times and extrema are exact
+                assert obs[p, o] == ref[o], (p, spec, obs[p, o], ref[o])
+
+
+@pytest.mark.parametrize("name,scheme,method", [
+    ("lin10", "sri2", "kpw"), ("lin10", "sri2", "wik"), ("lin10", "heun", None), ("lin10", "euler", None),
+    ("r74", "sri2", "kpw"), ("kp4446", "sri2", "kpw"), ("lin2", "euler", None), ("lin20", "srs2", "wik"),
+    ("r74", "kp2is", "kpw"),
+])
+def test_observers_match_full_trajectory(sdb, name, scheme, method):
+    """first passage / max / min / integral from inside the step loop == the same functionals of the
+    full-resolution trajectory of the same launch; a decimated store changes nothing; the states are
+    those of the non-observing kernels."""
+    strat = scheme in ("heun", "srs2", "kp2is")
+    f, G, y0 = (sdb.ops.sys_lin(20, 20) if name == "lin20" else SYSTEMS[name](strat))
+    y0v = np.atleast_1d(np.asarray(y0, dtype=float))
+    d = len(y0v)
+    tspan = np.linspace(0.0, 0.3, 61)
+    P, seed = 45, 2024
+    c1 = d - 1
+    up, dn = float(y0v[0]) * 1.02 + 0.01, float(y0v[c1]) * 0.9 - 0.01
+    specs = [("first_above", 0, up), ("first_below", c1, dn), ("max", 0), ("integral", c1)]
+    kw = dict(paths=P, seed=seed)
+    if scheme == "sri2":
+        call = lambda **k: sdb.itoSRI2(f, G, y0, tspan, sdb.Ikpw if method == "kpw" else sdb.Iwik, **kw, **k)
+    elif scheme == "srs2":
+        call = lambda **k: sdb.stratSRS2(f, G, y0, tspan, sdb.Jkpw if method == "kpw" else sdb.Jwik, **kw, **k)
+    elif scheme == "kp2is":
+        call = lambda **k: sdb.stratKP2iS(f, G, y0, tspan, rtol=1e-10, **kw, **k)
+    elif scheme == "heun":
+        call = lambda **k: sdb.stratHeun(f, G, y0, tspan, **kw, **k)
+    else:
+        call = lambda **k: sdb.itoEuler(f, G, y0, tspan, **kw, **k)
+    y, obs = call(observe=specs)
+    assert y.shape == (P, 61, d) and obs.shape == (P, 4)
+    _check_functionals(obs, y, tspan, specs)
+    assert np.isfinite(obs[:, 0]).any() or np.isfinite(obs[:, 1]).any()    # thresholds are reachable
+    yd, obsd = call(observe=specs, save_every=20)
+    assert np.array_equal(obsd, obs) and np.array_equal(yd, y[:, ::20])
+    assert rel_err(y, call()) <= (1e-9 if scheme == "kp2is" else TOL)   # Newton to rtol=1e-10
+    # "min" and a single observer given as one tuple
+    _, mn = call(observe=("min", c1))
+    assert mn.shape == (P, 1) and np.array_equal(mn[:, 0], y[:, :, c1].min(axis=1))
+
+
+def test_observers_user_system_single_path_and_validation(sdb):
+    fX = sdb.ops.ExprDrift(["-y[0] + 0.2*y[1]", "-0.5*y[1] + 0.1*sin(y[0])"], [])
+    GX = sdb.ops.ExprDiffusion([["0.3*(1.0+0.5*sin(y[1]))", "0.1"], ["0.05", "0.2*cos(y[0])"]], [])
+    y0 = np.array([0.5, -0.2])
+    tspan = np.linspace(0.0, 1.0, 201)
+    specs = [("max", 1), ("first_above", 0, 0.55)]
+    y, obs = sdb.itoint(fX, GX, y0, tspan, paths=30, seed=4, observe=specs)
+    _check_functionals(obs, y, tspan, specs)
+    dW = sdb.deltaW(200, 2, 0.005, paths=30, seed=4)
+    _, I = sdb.Ikpw(dW, 0.005, seed=4, ensemble=True)
+    for p in (0, 29):                                      # and against the oracle's trajectory
+        ref = orc.srk2(fX, GX, y0, tspan, dW[p], I[p])
+        assert abs(obs[p, 0] - ref[:, 1].max()) <= 1e-12 * max(1.0, abs(ref[:, 1].max()))
+    y1, o1 = sdb.itoint(fX, GX, y0, tspan, generator=np.random.default_rng(3), observe=specs)
+    assert y1.shape == (201, 2) and o1.shape == (2,) and o1[0] == y1[:, 1].max()
+    # host-supplied noise goes through the same observers
+    y2, o2 = sdb.itoSRI2(fX, GX, y0, tspan, dW=dW[3], I=I[3], observe=specs)
+    assert np.array_equal(o2, _functionals(y2, tspan, specs))
+    for bad in ([("median", 0)], [("max", 2)], [("first_above", 0)], [("max", 0)] * 5, []):
+        with pytest.raises(sdb.SDEValueError):
+            sdb.itoint(fX, GX, y0, tspan, observe=bad)
+
+
 def test_device_resident_noise_tensors(sdb):
     """dW / I handed over as torch tensors already on the GPU are used in place (no host round
     trip) and give the same bits as the numpy arrays of the reference's call."""

@@ -203,3 +203,20 @@ def test_expression_operators_generate_source_and_host_callable():
         ops.ExprDiffusion([["y[0]", "1"], ["1"]])
     Gd = ops.ExprDiffusion([["p[0]*y[0]", "0"], ["0", "p[0]*y[1]"]], [0.2], diagonal=True)
     assert Gd.kind == ops.DIFF_USER_DIAG
+
+
+def test_commutative_noise_detection():
+    """LinearDiffusion decides commutativity from the commutators of its B_k (host logic of the
+    Levy-area-free dispatch); user operators carry the caller's promise."""
+    from sdeint_b200 import ops
+    assert ops.sys_r74(False)[1].commutative            # identical B_k (Roessler 7.4)
+    assert not ops.sys_lin(10, 10)[1].commutative       # SYS_LIN is non-commutative by construction
+    Cm = np.random.default_rng(0).standard_normal((6, 6))
+    B = np.stack([np.eye(6) * (k + 1) + 0.3 * Cm + 0.1 * k * Cm @ Cm for k in range(4)])
+    assert ops.LinearDiffusion(B).commutative
+    B[2, 0, 1] += 1e-9
+    assert not ops.LinearDiffusion(B).commutative
+    assert not ops.ExprDiffusion([["y[0]", "0"], ["0", "y[1]"]]).commutative
+    assert ops.ExprDiffusion([["y[0]", "2*y[0]"], ["y[1]", "2*y[1]"]], commutative=True).commutative
+    import sdeint_b200 as sdb
+    assert callable(sdb.Icomm) and callable(sdb.Jcomm)
