@@ -10,3 +10,6 @@ f = sdb.ops.ExprDrift(["p[0]*(y[1]-y[0])", "y[0]*(p[1]-y[2])-y[1]", "y[0]*y[1]-p
 G = sdb.ops.ExprDiffusion([["p[0]*y[0]", "0", "0"], ["0", "p[0]*y[1]", "0"], ["0", "0", "p[0]*y[2]"]], [0.1],
                           diagonal=True)
 y = sdb.itoint(f, G, [1.0, 1.0, 20.0], tspan, paths=10**5, seed=2, save_every=100); print(y.shape, y[:, -1].mean(axis=0))
+y, obs = sdb.itoint(f, G, [1.0, 1.0, 20.0], tspan, paths=10**5, seed=2, save_every=100,
+                    observe=[("first_above", 0, 15.0), ("max", 2)])
+print(obs.shape, np.isfinite(obs[:, 0]).mean(), obs[:, 1].mean())
