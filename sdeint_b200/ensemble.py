@@ -85,6 +85,26 @@ def quantiles(counts, lo, hi, q):
     return out
 
 
+def first_passage_cdf(times_dev, bins, t0, t1, paths, group=None):
+    """Distribution of first-passage times from the in-loop observers (`observe=("first_above", ...)`
+    with out="torch": a device tensor (n_obs, P), +inf where the level was never reached): the
+    fraction of ALL paths that have hit by each of `bins` equal sub-intervals of [t0, t1), histogrammed
+    on the device (sdb_moments) and summed over the ranks of `group`.  `paths` is the global ensemble
+    size.  Returns (right bin edges (bins,), cdf (n_obs, bins)) as numpy arrays; 1 - cdf is the
+    survival function."""
+    torch = dev.torch_mod()
+    if times_dev.dim() != 2 or times_dev.dtype != torch.float64:
+        raise ValueError("first_passage_cdf: need a float64 device tensor (n_obs, P)")
+    n_obs, P = times_dev.shape
+    _, counts = moments(times_dev.contiguous().view(n_obs, 1, P), hist=(int(bins), float(t0), float(t1)))
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+    c = counts[:, 0, :].cpu().numpy().astype(np.float64)
+    edges = t0 + (t1 - t0) * np.arange(1, int(bins) + 1) / int(bins)
+    return edges, np.cumsum(c, axis=1) / float(paths)
+
+
 def allreduce_moments(sums, counts=None, group=None, deterministic=False):
     """Sum the per-rank partials over all ranks (torch.distributed; NCCL on GPUs), in place.
 

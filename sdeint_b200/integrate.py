@@ -273,20 +273,25 @@ def _run(scheme, f, G, y0, tspan, dW, IJ, strat, method, generator, kp2is, paths
             a.rtol = float(kp2is[3])
         obs_arr = _observers(observe, d) if observe is not None else None
         if (host_out is not None and out != "torch" and a.noise != NOISE_HOST and y0_paths is None
-                and P >= _PIPELINE_MIN_PATHS and obs_arr is None):
+                and P >= _PIPELINE_MIN_PATHS):
             # Large ensemble, on-device noise, caller-owned host result: integrate the paths in chunks
             # and copy chunk c to the host while chunk c+1 is being integrated (two device buffers).
             if tuple(host_out.shape) != (n_saved, d, P) or host_out.dtype != torch.float64 \
                     or not host_out.is_contiguous():
                 raise SDEValueError('host_out must be a contiguous float64 tensor of shape %s'
                                     % ((n_saved, d, P),))
-            status = _run_pipelined(lib, system, a, host_out, P, int(path_id0), n_saved, d, device)
+            d_obs = None if obs_arr is None else \
+                torch.empty((len(obs_arr), P), dtype=torch.float64, device=device)
+            status = _run_pipelined(lib, system, a, host_out, P, int(path_id0), n_saved, d, device,
+                                    obs_arr, d_obs)
             _last_status = status
             if scheme == SCHEME_KP2IS and status[2] > 0:
                 raise RuntimeError(
                     "At time t_n = %g Failed to solve for Y_{n+1}: the implicit equation did not "
                     "converge to rtol=%g on %d path(s)." % (tspan[status[3]], kp2is[3], status[2]))
             host = host_out.numpy()
+            if d_obs is not None:
+                return host.transpose(2, 0, 1), np.ascontiguousarray(d_obs.cpu().numpy().T)
             if not ensemble:
                 return np.ascontiguousarray(host[:, :, 0])
             return host.transpose(2, 0, 1)
@@ -336,7 +341,7 @@ _PIPELINE_MIN_PATHS = 1 << 19
 _PIPELINE_CHUNKS = 8
 
 
-def _run_pipelined(lib, system, a, host_out, P, path_id0, n_saved, d, device):
+def _run_pipelined(lib, system, a, host_out, P, path_id0, n_saved, d, device, obs_arr=None, d_obs=None):
     """Chunked integration with overlapped device -> host copies; returns the merged status."""
     torch = dev.torch_mod()
     # chunk = a whole number of waves of the fused kernels (one 256-path block per SM), so that only
@@ -362,7 +367,11 @@ def _run_pipelined(lib, system, a, host_out, P, path_id0, n_saved, d, device):
         a.y_stride_save, a.y_stride_comp, a.y_stride_path = d * Pc, Pc, 1
         a.d_status = C.c_void_p(stats[c].data_ptr())
         a.stream = C.c_void_p(compute.cuda_stream)
-        _lib.check(lib.sdb_integrate(system.handle, C.byref(a)))
+        if obs_arr is None:
+            _lib.check(lib.sdb_integrate(system.handle, C.byref(a)))
+        else:   # observers of chunk c land at their global path offset
+            _lib.check(lib.sdb_integrate_observed(system.handle, C.byref(a), obs_arr, len(obs_arr),
+                                                  C.c_void_p(d_obs.data_ptr() + 8 * p0), P, 1))
         done = torch.cuda.Event()
         done.record(compute)
         copier.wait_event(done)

@@ -793,6 +793,32 @@ def test_observers_user_system_single_path_and_validation(sdb):
             sdb.itoint(fX, GX, y0, tspan, observe=bad)
 
 
+def test_first_passage_distribution_ou(sdb):
+    """First-passage statistics of an Ornstein-Uhlenbeck process through the in-loop observer and the
+    on-device histogram: the CDF equals the empirical one of the returned times, and the probability of
+    having hit by T agrees with a fine-step numpy simulation of the same SDE within sampling error."""
+    f, G, y0 = sdb.ops.sys_ou(1.0, 0.5)
+    tspan = np.linspace(0.0, 2.0, 401)
+    P = 200000
+    y, t = sdb.itoEuler(f, G, y0, tspan, paths=P, seed=8, save_every=400, out="torch",
+                        observe=[("first_above", 0, 0.4)])
+    assert t.shape == (1, P)
+    edges, cdf = sdb.ensemble.first_passage_cdf(t, 20, 0.0, 2.0 + 1e-9, P)
+    th = t.cpu().numpy()[0]
+    emp = np.array([(th < e).mean() for e in edges])
+    assert np.allclose(cdf[0], emp, atol=1e-12) and 0.2 < cdf[0, -1] < 0.9
+    rng = np.random.default_rng(1)                       # independent reference simulation, same grid
+    Q = 100000
+    x = np.zeros(Q)
+    hit = np.zeros(Q, dtype=bool)
+    h = tspan[1] - tspan[0]
+    for _ in range(400):
+        x = x - x * h + 0.5 * np.sqrt(h) * rng.standard_normal(Q)
+        hit |= x >= 0.4
+    se = np.sqrt(cdf[0, -1] * (1 - cdf[0, -1]) * (1.0 / P + 1.0 / Q))
+    assert abs(cdf[0, -1] - hit.mean()) < 5 * se
+
+
 def test_device_resident_noise_tensors(sdb):
     """dW / I handed over as torch tensors already on the GPU are used in place (no host round
     trip) and give the same bits as the numpy arrays of the reference's call."""
@@ -859,6 +885,11 @@ def test_pipelined_host_output_matches_single_launch(sdb):
     y2 = sdb.itoEuler(f2, G2, y02, tspan, paths=P, seed=4, save_every=10, host_out=host2)
     ref2 = sdb.itoEuler(f2, G2, y02, tspan, paths=P, seed=4, save_every=10, out="torch").cpu().numpy()
     assert np.array_equal(y2, ref2.transpose(2, 0, 1))
+    # observers ride along chunk by chunk, each chunk at its global path offset
+    specs = [("max", 0), ("first_below", 1, 2.99)]
+    _, oref = sdb.itoEuler(f2, G2, y02, tspan, paths=P, seed=4, save_every=10, observe=specs)
+    y3, o3 = sdb.itoEuler(f2, G2, y02, tspan, paths=P, seed=4, save_every=10, host_out=host2, observe=specs)
+    assert o3.shape == (P, 2) and np.array_equal(o3, oref) and np.array_equal(y3, y2)
 
 
 def test_second_moments_covariance_quantiles(sdb):
