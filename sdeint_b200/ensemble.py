@@ -105,6 +105,48 @@ def first_passage_cdf(times_dev, bins, t0, t1, paths, group=None):
     return edges, np.cumsum(c, axis=1) / float(paths)
 
 
+def autocovariance(y_dev, comp, paths=None, group=None):
+    """Ensemble autocovariance of one component across the saved times of a device trajectory tensor
+    (n_saved, d, P):  C[s, t] = E[(y_s - E y_s)(y_t - E y_t)], the expectation over paths.
+    A plain fp64 library GEMM (X X^T through torch/cuBLAS -- analysis plumbing, not the integration
+    path) on the raw sums, so that ranks can be combined exactly like the moments: the (n_saved,
+    n_saved) Gram matrix and the (n_saved,) sums are all-reduced over `group` before centring.
+    `paths` is the global ensemble size (default: this tensor's P).  Returns a numpy array."""
+    torch = dev.torch_mod()
+    if y_dev.dim() != 3 or y_dev.dtype != torch.float64:
+        raise ValueError("autocovariance: need a float64 device tensor (n_saved, d, P)")
+    X = y_dev[:, int(comp), :]
+    gram = X @ X.T
+    tot = X.sum(dim=1)
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(gram, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
+    n = float(paths if paths is not None else y_dev.shape[2])
+    mean = tot / n
+    return (gram / n - mean[:, None] * mean[None, :]).cpu().numpy()
+
+
+def periodogram(y_dev, comp, dt, first=0, paths=None, group=None):
+    """Ensemble-averaged periodogram of one component over the saved times `first:` (uniform spacing
+    `dt`), an estimate of the two-sided power spectral density at the non-negative frequencies:
+        S(f_k) = dt / n * E |sum_j (y_j - mean) exp(-2 pi i j k / n)|^2,   f_k = k / (n dt).
+    The spectral check the reference leaves as a to-do (sdeint/tests/test_integrate.py:455-456,
+    :479-480).  torch.fft along the time axis of the path-minor tensor (library plumbing); the sum
+    over paths is all-reduced over `group`.  Returns (freqs (n//2+1,), S (n//2+1,)) numpy arrays."""
+    torch = dev.torch_mod()
+    X = y_dev[int(first):, int(comp), :]
+    n = X.shape[0]
+    X = X - X.mean(dim=0, keepdim=True)                 # per-path mean removed (stationary segment)
+    power = (torch.fft.rfft(X, dim=0).abs() ** 2).sum(dim=1)
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(power, op=dist.ReduceOp.SUM, group=group)
+    total = float(paths if paths is not None else y_dev.shape[2])
+    S = (power * (float(dt) / n / total)).cpu().numpy()
+    return np.arange(n // 2 + 1) / (n * float(dt)), S
+
+
 def allreduce_moments(sums, counts=None, group=None, deterministic=False):
     """Sum the per-rank partials over all ranks (torch.distributed; NCCL on GPUs), in place.
 

@@ -190,3 +190,36 @@ def test_device_normals_chi_square_1e9(sdb):
     assert abs(tail - want) < 6.0 * np.sqrt(want), (tail, want)
     m4 = float((z.reshape(-1)[: 10 ** 8] ** 4).mean().item())
     assert abs(m4 - 3.0) < 6.0 * np.sqrt(96.0 / 1e8)
+
+
+def test_ou_autocovariance_and_spectrum(sdb):
+    """Stationary statistics of an Ornstein-Uhlenbeck ensemble against the exact values of the
+    discrete (Euler-Maruyama = AR(1)) process: variance sigma^2 / (2 theta - theta^2 h), autocorrelation
+    (1 - theta h)^k, spectral density of AR(1) -- the spectral test the reference leaves as a to-do
+    (sdeint/tests/test_integrate.py:455-456)."""
+    theta, sigma, h = 2.0, 0.6, 0.01
+    f, G, y0 = sdb.ops.sys_ou(theta, sigma)
+    N = 1101
+    tspan = np.arange(N) * h
+    P = 100000
+    y = sdb.itoEuler(f, G, y0, tspan, paths=P, seed=77, out="torch")          # (N, 1, P)
+    first = 500                                                                  # 10 relaxation times
+    a = 1.0 - theta * h
+    var = sigma ** 2 * h / (1.0 - a * a)
+    C = sdb.ensemble.autocovariance(y[first:], 0)
+    lag = np.abs(np.arange(N - first)[:, None] - np.arange(N - first)[None, :])
+    se = 4.0 * var * np.sqrt(2.0 / P)
+    assert np.abs(C - var * a ** lag).max() < 1.5 * se
+    freqs, S = sdb.ensemble.periodogram(y, 0, h, first=first)
+    n = N - first
+    # expectation of the mean-removed periodogram of a stationary AR(1) segment, from its covariance
+    cov = var * a ** lag
+    Q = np.eye(n) - 1.0 / n                                                      # removes the segment mean
+    covq = Q @ cov @ Q
+    k = np.arange(n // 2 + 1)
+    Fm = np.exp(-2j * np.pi * np.outer(k, np.arange(n)) / n)
+    expect = h / n * np.real(np.einsum("ki,ij,kj->k", Fm, covq, Fm.conj()))
+    assert freqs.shape == S.shape == (n // 2 + 1,)
+    rel = np.abs(S[1:] - expect[1:]) / expect[1:]
+    assert rel.max() < 6.0 / np.sqrt(P)                                          # chi^2_2 / P scatter
+    assert abs(S[0]) < 1e-20
