@@ -155,10 +155,11 @@ static int jit_compile(const std::string& source, const char* kernel_name, JitKe
   if (nvrtc_load(&rt)) return 1;
   nvrtcProgram prog;
   const char* hdr_src[] = {kKernelHeader, kTablesHeader, kFusedHeader, kTmemHeader, kFusedWsHeader,
-                           kFusedXHeader, kRepintXHeader, kFusedEhHeader};
+                           kFusedXHeader, kRepintXHeader, kFusedEhHeader, kFusedCHeader};
   const char* hdr_name[] = {"sdb_kernels.cuh", "sdb_tables.cuh", "sdb_fused.cuh", "sdb_tmem.cuh",
-                            "sdb_fusedws.cuh", "sdb_fusedx.cuh", "sdb_repintx.cuh", "sdb_fusedeh.cuh"};
-  int rc = rt->CreateProgram(&prog, source.c_str(), "sdb_jit.cu", 8, hdr_src, hdr_name);
+                            "sdb_fusedws.cuh", "sdb_fusedx.cuh", "sdb_repintx.cuh", "sdb_fusedeh.cuh",
+                            "sdb_fusedc.cuh"};
+  int rc = rt->CreateProgram(&prog, source.c_str(), "sdb_jit.cu", 9, hdr_src, hdr_name);
   if (rc) return fail(std::string("nvrtcCreateProgram: ") + rt->GetErrorString(rc));
   // -default-device: un-annotated functions (the generic lambdas of the compile-time loops) are
   // device functions in JIT mode
@@ -409,12 +410,44 @@ static int integrate_impl(sdb_system* s, const sdb_integrate_args* a, const SdbO
   int n_terms = a->n_terms;
   if (!need_ij && noise == SDB_NOISE_WIK) noise = SDB_NOISE_KPW;  // only dW is drawn
   // commutative noise: the Ikpw/Jkpw kernels with an empty series (A = 0, only dW is drawn)
-  if (noise == SDB_NOISE_COMM) { noise = SDB_NOISE_KPW; n_terms = 0; }
+  const bool comm = noise == SDB_NOISE_COMM;
+  if (comm) { noise = SDB_NOISE_KPW; n_terms = 0; }
   // The production path: linear system, SRI2/SRS2, on-device Philox + Ikpw/Jkpw (or Iwik/Jwik)
   // -> a fused kernel when one is instantiated for this (d, m, method).
   const SdbFusedEntry* fused = nullptr;
+  SdbFusedEntry jit_entry{};
+  int jit_rb = 4;
+  bool jit_comm = false;
   const bool explicit_em = a->scheme == SDB_SCHEME_EULER || a->scheme == SDB_SCHEME_HEUN;
-  if ((a->scheme == SDB_SCHEME_SRK2 || explicit_em) && noise != SDB_NOISE_HOST &&
+  // Commutative-noise integrals on a linear system: the dedicated kernel (sdb_fusedc.cuh) -- stage-2 sum
+  // as W (W y) / 2 - (h/2) S y, no per-path products with I at all; (10,10) ahead of time, else NVRTC.
+  if (comm && need_ij && a->scheme == SDB_SCHEME_SRK2 && s->fk == SDB_DRIFT_LINEAR &&
+      s->gk == SDB_DIFF_LINEAR_COLS && !getenv("SDB_DISABLE_FUSED") && !getenv("SDB_DISABLE_FUSEDC") &&
+      SdbFusedCDims(s->d, s->m).supported()) {
+    if (!obs)
+      for (const auto& e : sdb_fused_registry())
+        if (e.d == s->d && e.m == s->m && e.noise == SDB_NOISE_COMM && e.scheme == SDB_SCHEME_SRK2) fused = &e;
+    if (!fused && !getenv("SDB_DISABLE_FUSED_JIT") && s->d * s->m >= 16) {
+      const SdbFusedCDims cd(s->d, s->m);
+      const std::string key = std::string("fusedcjit") + (obs ? "|obs" : "");
+      std::lock_guard<std::mutex> lk(s->mu);
+      auto it = s->jit.find(key);
+      if (it == s->jit.end()) {
+        std::ostringstream src;
+        if (obs) src << "#define SDB_OBSERVE 1\n";
+        src << "#include \"sdb_fusedc.cuh\"\nSDB_FUSEDC_KERNEL(sdb_jit_fused, " << s->d << ", " << s->m << ")\n";
+        JitKernel k;
+        if (jit_compile(src.str(), "sdb_jit_fused", &k)) return 1;
+        it = s->jit.emplace(key, k).first;
+      }
+      jit_entry = SdbFusedEntry{s->d, s->m, 0, (const void*)it->second.kern, cd.smem_bytes(),
+                                cd.table_doubles(), nullptr, cd.threads(), cd.threads(),
+                                SDB_NOISE_COMM, SDB_SCHEME_SRK2};
+      jit_comm = true;
+      fused = &jit_entry;
+    }
+  }
+  if (!fused && (a->scheme == SDB_SCHEME_SRK2 || explicit_em) && noise != SDB_NOISE_HOST &&
       s->fk == SDB_DRIFT_LINEAR && s->gk == SDB_DIFF_LINEAR_COLS &&
       n_terms <= SDB_FUSED_MAX_TERMS && !getenv("SDB_DISABLE_FUSED") && !obs) {
     const char* vs = getenv("SDB_FUSED_VARIANT");
@@ -427,8 +460,6 @@ static int integrate_impl(sdb_system* s, const sdb_integrate_args* a, const SdbO
   // No ahead-of-time instantiation for this (d, m, method): compile a fused kernel with NVRTC when
   // the shape is one it supports -- sdb_fused.cuh (8 warps per SM; Ikpw/Jkpw, even m <= 10, d < 16) or
   // sdb_fusedx.cuh (Levy areas in tensor memory; Iwik/Jwik and larger shapes) -- else the generic loop.
-  SdbFusedEntry jit_entry{};
-  int jit_rb = 4;
   if (!fused && explicit_em && noise != SDB_NOISE_HOST && s->fk == SDB_DRIFT_LINEAR &&
       s->gk == SDB_DIFF_LINEAR_COLS && !getenv("SDB_DISABLE_FUSED") &&
       !getenv("SDB_DISABLE_FUSED_JIT") &&
@@ -506,6 +537,7 @@ static int integrate_impl(sdb_system* s, const sdb_integrate_args* a, const SdbO
       SDB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused->smem));
       std::vector<double> tab(fused->table_doubles);
       if (fused->build) fused->build(s->fp.data(), s->gp.data(), tab.data());
+      else if (jit_comm) SdbFusedCDims(s->d, s->m).build_tables(s->fp.data(), s->gp.data(), tab.data());
       else SdbFusedDims(s->d, s->m, jit_rb).build_tables(s->fp.data(), s->gp.data(), tab.data());
       double* d = nullptr;
       SDB_CUDA(cudaMalloc(&d, tab.size() * sizeof(double)));
@@ -563,10 +595,10 @@ static int integrate_impl(sdb_system* s, const sdb_integrate_args* a, const SdbO
   args[1] = s->inline_params ? (void*)s->fp.data() : (void*)&gf;
   args[2] = s->inline_params ? (void*)s->gp.data() : (void*)&gg;
   if (fused) {
-    if (fused->scheme == SDB_SCHEME_SRK2) {
+    if (fused->scheme == SDB_SCHEME_SRK2 && fused->noise != SDB_NOISE_COMM) {
       args[1] = (void*)s->fp.data();
       args[2] = (void*)&d_frag;
-    } else {  // fused Euler / Heun: (a, frag)
+    } else {  // fused Euler / Heun and the commutative-noise kernel: (a, frag)
       args[1] = (void*)&d_frag;
     }
   }

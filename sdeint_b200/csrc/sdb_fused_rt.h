@@ -131,3 +131,42 @@ struct SdbFusedEhDims {
     return sh.M >= 2 && sh.M % 2 == 0 && sh.D >= 1 && sh.D <= 16 && smem_bytes() <= 227u * 1024u;
   }
 };
+
+// Run-time mirror of SdbFcShape / sdb_fusedc_build_tables (sdb_fusedc.cuh): SRI2/SRS2 on the
+// commutative-noise integrals, two P1 products per step.
+struct SdbFusedCDims {
+  SdbFusedDims s1, s2;  // pseudo-system [B_1 .. B_m, A^2, S ; A] and the plain [B_1 .. B_m ; A]
+  constexpr SdbFusedCDims(int d, int m) : s1(d, m + 2, 4), s2(d, m, 4) {}
+  static constexpr int threads() { return 256; }
+  constexpr int grows() const {
+    int g = SdbFusedDims::max2(8, s1.D);
+    for (int b = 0; b < s1.NB(); ++b) g = SdbFusedDims::max2(g, 8 * s1.t1(b));
+    for (int b = 0; b < s2.NB(); ++b) g = SdbFusedDims::max2(g, 8 * s2.t1(b));
+    return g;
+  }
+  constexpr size_t table1_doubles() const { return s1.table_doubles(); }
+  constexpr size_t table_doubles() const { return s1.table_doubles() + s2.table_doubles(); }
+  constexpr size_t smem_bytes() const { return (size_t)grows() * 32 * 8 * (threads() / 32) + 128 * 16; }
+  constexpr bool supported() const {
+    return s2.M >= 2 && s2.M % 2 == 0 && s2.D >= 1 && s2.D <= 12 && smem_bytes() <= 227u * 1024u;
+  }
+  void build_tables(const double* A, const double* B, double* out) const {
+    const int D = s2.D, M = s2.M;
+    double* Bx = new double[(size_t)(M + 2) * D * D];
+    for (int i = 0; i < M * D * D; ++i) Bx[i] = B[i];
+    double* A2 = Bx + (size_t)M * D * D;
+    double* S = A2 + D * D;
+    for (int i = 0; i < D; ++i)
+      for (int j = 0; j < D; ++j) {
+        double a2 = 0.0, s = 0.0;
+        for (int l = 0; l < D; ++l) a2 += A[i * D + l] * A[l * D + j];
+        for (int k = 0; k < M; ++k)
+          for (int l = 0; l < D; ++l) s += B[(k * D + i) * D + l] * B[(k * D + l) * D + j];
+        A2[i * D + j] = a2;
+        S[i * D + j] = s;
+      }
+    s1.build_tables(A, Bx, out);
+    s2.build_tables(A, B, out + table1_doubles());
+    delete[] Bx;
+  }
+};

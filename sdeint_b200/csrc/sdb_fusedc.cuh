@@ -1,0 +1,231 @@
+// sdb_fusedc.cuh -- fused itoSRI2 / stratSRS2 (sdeint/integrate.py:494-522) for LINEAR systems
+// f = A y, g_k = B_k y driven by the COMMUTATIVE-noise repeated integrals (SDB_NOISE_COMM):
+//     I = (dW dW^T - h 1) / 2   (Ito),      J = dW dW^T / 2   (Stratonovich),
+// only dW drawn (on-device Philox), the whole time loop in one launch.
+//
+// With a symmetric I of that form the stage-2 sum of the scheme collapses algebraically.  For linear
+// g_k the sum over k of (sqrt h / 2)(g_k(H2_k) - g_k(H3_k)) (integrate.py:516-521) is
+//     sum_{j,k} B_k B_j y I_jk  =  W (W y) / 2  -  (h / 2) S y,      W = sum_k dW_k B_k,  S = sum_k B_k^2
+// (the S term is absent for J), and W y = G_n dW is the diffusion term the step needs anyway.  The
+// second drift evaluation is f(y + f h) h = (A y) h + (A^2 y) h^2.  One step is therefore
+//     P1   rows [B_1 .. B_m ; A^2 ; S ; A] y      (DMMA, (m + 3) d rows)
+//          v = G_n dW   per lane                  (d m DFMA)
+//     P2   rows [B_1 .. B_m] v                    (DMMA)
+//          w = (rows) dW per lane                 (d m DFMA)
+//     Y += h A y + (h^2 / 2) A^2 y + v + w / 2 - (h / 2) S y
+// instead of the d m^2 per-lane products with I of the general kernel: no repeated integrals exist at
+// all.  Same values as the reference's arithmetic up to reassociation (parity <= 1e-12 in
+// tests/test_gpu_parity.py::test_commutative_noise_needs_no_levy_areas).  The formula needs I to have
+// the commutative form, NOT the B_k to commute -- whether skipping the Levy areas is legitimate is
+// the caller's decision (ops.LinearDiffusion.commutative).
+#pragma once
+#include "sdb_fusedeh.cuh"
+
+#define SDB_FC_THREADS 256
+
+namespace SDB_FUSED_NS {
+
+template <int D, int M>
+struct SdbFcShape {
+  typedef SdbFusedShape<D, M + 2> S1;  // pseudo-system [B_1 .. B_m, A^2, S ; A]
+  typedef SdbFusedShape<D, M> S2;      // [B_1 .. B_m ; A]
+  static SDB_CX int grows() {
+    int g = S1::max2(8, D);
+    for (int b = 0; b < S1::NB; ++b) g = S1::max2(g, 8 * S1::t1(b));
+    for (int b = 0; b < S2::NB; ++b) g = S1::max2(g, 8 * S2::t1(b));
+    return g;
+  }
+  static SDB_CX size_t table1_doubles() { return (size_t)S1::n_frags() * 32 + S1::n_left(); }
+  static SDB_CX size_t table_doubles() { return table1_doubles() + (size_t)S2::n_frags() * 32 + S2::n_left(); }
+  static SDB_CX size_t smem_bytes() { return (size_t)grows() * 32 * 8 * (SDB_FC_THREADS / 32) + 128 * 16; }
+};
+
+#ifndef __CUDACC_RTC__
+// Fragment tables of both products: the P1 tables of the pseudo-system (B_1 .. B_m, A^2, S; A), then
+// those of (B_1 .. B_m; A).
+template <int D, int M>
+inline void sdb_fusedc_build_tables(const double* A, const double* B, double* out) {
+  double* Bx = new double[(size_t)(M + 2) * D * D];
+  for (int i = 0; i < M * D * D; ++i) Bx[i] = B[i];
+  double* A2 = Bx + (size_t)M * D * D;
+  double* S = A2 + D * D;
+  for (int i = 0; i < D; ++i)
+    for (int j = 0; j < D; ++j) {
+      double a2 = 0.0, s = 0.0;
+      for (int l = 0; l < D; ++l) a2 += A[i * D + l] * A[l * D + j];
+      for (int k = 0; k < M; ++k)
+        for (int l = 0; l < D; ++l) s += B[(k * D + i) * D + l] * B[(k * D + l) * D + j];
+      A2[i * D + j] = a2;
+      S[i * D + j] = s;
+    }
+  sdb_fused_build_tables<D, M + 2>(A, Bx, out);
+  sdb_fused_build_tables<D, M>(A, B, out + SdbFcShape<D, M>::table1_doubles());
+  delete[] Bx;
+}
+#endif
+
+#ifdef __CUDACC__
+// Rows [B'_j[R,:] ; A[R,:]] Yin for every row block R (DMMA into the staging rows), then per lane:
+//   v[i]     = sum_{j < MV} row(j, i) dW_j
+//   ex[x][i] = row(MV + x, i)            x < MT - MV
+//   f[i]     = (A Yin)_i                 (when WANT_F)
+template <int D, int MT, int MV, bool WANT_F>
+SDB_DEV void sdb_fc_eval(const double* __restrict__ frag, double* gbuf, const double (&Yin)[D],
+                         const double (&dW)[MV], int lane, double (&v)[D],
+                         double (&ex)[MT - MV > 0 ? MT - MV : 1][D], double (&f)[D]) {
+  typedef SdbFusedShape<D, MT> Sh;
+  constexpr int LT = Sh::LT;
+  const int fr = lane >> 2, fc = lane & 3;
+  double Yf[LT][4];
+#pragma unroll
+  for (int l = 0; l < D; ++l) gbuf[l * 32 + (lane ^ sdb_swz(l))] = Yin[l];
+  __syncwarp();
+#pragma unroll
+  for (int lt = 0; lt < LT; ++lt) {
+    const int l = 4 * lt + fc;
+    const bool ok = (4 * lt + 3 < D) || (l < D);
+    const int lc = ok ? l : 0;
+#pragma unroll
+    for (int pt = 0; pt < 4; ++pt) {
+      const double q = gbuf[lc * 32 + ((8 * pt + fr) ^ sdb_swz(lc))];
+      Yf[lt][pt] = ok ? q : 0.0;
+    }
+  }
+  __syncwarp();
+  sdb_static_for<0, Sh::NB>([&](auto bb) {
+    constexpr int b = decltype(bb)::value;
+    constexpr int RN = Sh::rn(b), R0 = Sh::r0(b);
+    // row tiles actually needed: without the drift rows when they are not wanted
+    constexpr int T1 = WANT_F ? Sh::t1(b) : (MT * RN + 7) / 8;
+    const double* f1 = frag + (size_t)Sh::p1_off(b) * 32 + lane;
+#pragma unroll
+    for (int t = 0; t < T1; ++t) {
+      double af[LT];
+#pragma unroll
+      for (int lt = 0; lt < LT; ++lt) af[lt] = __ldg(f1 + (t * LT + lt) * 32);
+      double c[4][2];
+#pragma unroll
+      for (int pt = 0; pt < 4; ++pt) {
+        c[pt][0] = 0.0;
+        c[pt][1] = 0.0;
+      }
+#pragma unroll
+      for (int lt = 0; lt < LT; ++lt)
+#pragma unroll
+        for (int pt = 0; pt < 4; ++pt) sdb_dmma(c[pt][0], c[pt][1], af[lt], Yf[lt][pt]);
+      double* row = gbuf + (8 * t + fr) * 32;
+      const int sw = sdb_swz(fr);
+#pragma unroll
+      for (int pt = 0; pt < 4; ++pt) {
+        row[(8 * pt + 2 * fc) ^ sw] = c[pt][0];
+        row[(8 * pt + 2 * fc + 1) ^ sw] = c[pt][1];
+      }
+    }
+    __syncwarp();
+    const volatile double* gv = gbuf;
+#pragma unroll
+    for (int r = 0; r < RN; ++r) {
+      double acc = 0.0;
+#pragma unroll
+      for (int j = 0; j < MV; ++j) {
+        const int n = j * RN + r;
+        acc = fma(gv[n * 32 + (lane ^ sdb_swz(n))], dW[j], acc);
+      }
+      v[R0 + r] = acc;
+#pragma unroll
+      for (int x = 0; x < MT - MV; ++x) {
+        const int n = (MV + x) * RN + r;
+        ex[x][R0 + r] = gv[n * 32 + (lane ^ sdb_swz(n))];
+      }
+      if (WANT_F) {
+        const int n = MT * RN + r;
+        f[R0 + r] = gv[n * 32 + (lane ^ sdb_swz(n))];
+      }
+    }
+    __syncwarp();
+  });
+}
+
+template <int D, int M>
+SDB_DEV void sdb_fusedc_body(const SdbLoopArgs& a, const double* __restrict__ frag, double* smem) {
+  typedef SdbFcShape<D, M> Cs;
+  static_assert(M % 2 == 0, "fused kernel needs an even number of Wiener processes");
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double2* tab = reinterpret_cast<double2*>(smem + (size_t)Cs::grows() * 32 * (SDB_FC_THREADS / 32));
+  if (tid < 128) tab[tid] = reinterpret_cast<const double2*>(sdb_logtab)[tid];
+  __syncthreads();
+  double* gbuf = smem + (size_t)warp * Cs::grows() * 32;
+  const double* __restrict__ frag2 = frag + Cs::table1_doubles();
+  const int64_t p = (int64_t)blockIdx.x * SDB_FC_THREADS + tid;
+  const bool active = p < a.P;  // idle lanes of the last warp still take part in the DMMAs
+  double Y[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) Y[i] = 0.0;
+  if (active) {
+    if (a.flags & SDB_FLAG_Y0_BROADCAST) {
+#pragma unroll
+      for (int i = 0; i < D; ++i) Y[i] = a.y0[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < D; ++i) Y[i] = a.y0[i * a.y0_sI + p * a.y0_sP];
+    }
+    sdb_store<D>(a, p, 0, Y);
+  }
+#if SDB_OBSERVE
+  SdbObs<D> obs;
+  obs.init(a, Y);
+#endif
+  const double rh_g = sqrt(a.h_global);  // dW ~ N(0, h_global) (integrate.py:480); the step uses t[n+1]-t[n]
+  const double cs = (a.flags & SDB_FLAG_STRATONOVICH) ? 0.0 : -0.5;  // J has no -h/2 on the diagonal
+  const uint64_t path = (uint64_t)(a.path_id0 + p);
+  const uint32_t p_lo = (uint32_t)path, p_hi = (uint32_t)(path >> 32);
+  const SdbPhiloxKey pkey(a.seed);
+  const int steps = a.N - 1;
+  const double* __restrict__ hs = a.tspan + a.N;  // per-step h (host-built)
+  int next_save = a.save_every;
+  int64_t slot = 1;
+#pragma unroll 1
+  for (int n = 0; n < steps; ++n) {
+    const double h = hs[n];
+    double dW[M];
+    {
+      uint32_t w[M / 2][4];
+      sdb_philox_batch<M / 2>(pkey, p_lo, p_hi, (uint32_t)n, 0u, w);
+      sdb_normal_batch<M / 2, true>(w, tab, rh_g, dW);
+    }
+    double v[D], ex[2][D], f0[D];
+    sdb_fc_eval<D, M + 2, M, true>(frag, gbuf, Y, dW, lane, v, ex, f0);
+    // everything but the W v term: y + h A y + (h^2/2) A^2 y + G dW - (h/2) S y
+    const double hh = 0.5 * h * h, ch = cs * h;
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+      Y[i] = fma(ch, ex[1][i], fma(hh, ex[0][i], fma(h, f0[i], Y[i]))) + v[i];
+    double wv[D], none[1][D], fnone[D];
+    sdb_fc_eval<D, M, M, false>(frag2, gbuf, v, dW, lane, wv, none, fnone);
+#pragma unroll
+    for (int i = 0; i < D; ++i) Y[i] = fma(0.5, wv[i], Y[i]);
+#if SDB_OBSERVE
+    obs.step(a, n, Y);
+#endif
+    if (n + 1 == next_save) {
+      if (active) sdb_store<D>(a, p, slot, Y);
+      ++slot;
+      next_save += a.save_every;
+    }
+  }
+  if (active) sdb_finish<D>(a, p, Y);
+#if SDB_OBSERVE
+  if (active) obs.finish(a, p);
+#endif
+}
+#endif  // __CUDACC__
+
+}  // namespace SDB_FUSED_NS
+using namespace SDB_FUSED_NS;
+
+#define SDB_FUSEDC_KERNEL(NAME, D, M)                                                         \
+  extern "C" __global__ void __launch_bounds__(SDB_FC_THREADS, 1)                             \
+      NAME(const __grid_constant__ SdbLoopArgs a, const double* __restrict__ frag) {          \
+    extern __shared__ __align__(16) double sdb_fused_smem[];                                  \
+    sdb_fusedc_body<D, M>(a, frag, sdb_fused_smem);                                           \
+  }
