@@ -674,6 +674,19 @@ def test_commutative_noise_needs_no_levy_areas(sdb, d, m, strat):
     assert rel_err(y1, y[5]) <= TOL
 
 
+def test_commutative_kernels_agree(sdb, monkeypatch):
+    """The dedicated commutative-noise kernel (sdb_fusedc.cuh) against the Ikpw kernel run with an empty
+    series (SDB_DISABLE_FUSEDC) and against the generic loop (SDB_DISABLE_FUSED): same paths."""
+    f, G, y0 = _commuting_system(10, 10)
+    tspan = np.linspace(0.0, 0.25, 51)
+    kw = dict(paths=300, seed=5, path_id0=11, save_every=5)
+    y = sdb.stratSRS2(f, G, y0, tspan, **kw)
+    monkeypatch.setenv("SDB_DISABLE_FUSEDC", "1")
+    assert rel_err(sdb.stratSRS2(f, G, y0, tspan, **kw), y) <= TOL
+    monkeypatch.setenv("SDB_DISABLE_FUSED", "1")
+    assert rel_err(sdb.stratSRS2(f, G, y0, tspan, **kw), y) <= TOL
+
+
 def test_commutative_flag_on_user_operator(sdb):
     """A nonlinear system whose columns are multiples of one vector field (g_k = c_k phi(y), so
     L^j g_k = c_j c_k phi' phi is symmetric): `commutative=True` skips the Levy areas; the result is
