@@ -155,11 +155,11 @@ static int jit_compile(const std::string& source, const char* kernel_name, JitKe
   if (nvrtc_load(&rt)) return 1;
   nvrtcProgram prog;
   const char* hdr_src[] = {kKernelHeader, kTablesHeader, kFusedHeader, kTmemHeader, kFusedWsHeader,
-                           kFusedXHeader, kRepintXHeader, kFusedEhHeader, kFusedCHeader};
+                           kFusedXHeader, kRepintXHeader, kFusedEhHeader, kFusedCHeader, kFusedX2Header};
   const char* hdr_name[] = {"sdb_kernels.cuh", "sdb_tables.cuh", "sdb_fused.cuh", "sdb_tmem.cuh",
                             "sdb_fusedws.cuh", "sdb_fusedx.cuh", "sdb_repintx.cuh", "sdb_fusedeh.cuh",
-                            "sdb_fusedc.cuh"};
-  int rc = rt->CreateProgram(&prog, source.c_str(), "sdb_jit.cu", 9, hdr_src, hdr_name);
+                            "sdb_fusedc.cuh", "sdb_fusedx2.cuh"};
+  int rc = rt->CreateProgram(&prog, source.c_str(), "sdb_jit.cu", 10, hdr_src, hdr_name);
   if (rc) return fail(std::string("nvrtcCreateProgram: ") + rt->GetErrorString(rc));
   // -default-device: un-annotated functions (the generic lambdas of the compile-time loops) are
   // device functions in JIT mode
@@ -494,10 +494,13 @@ static int integrate_impl(sdb_system* s, const sdb_integrate_args* a, const SdbO
     const SdbFusedXDims xdims(s->d, s->m);
     const bool use_v0 = noise == SDB_NOISE_KPW && dims.supported();
     const bool use_x = !use_v0 && xdims.supported();
+    // one warp per sub-partition in sdb_fusedx.cuh (m >= 16): the two-lanes-per-path kernel instead
+    const SdbFusedX2Dims x2dims(s->d, s->m);
+    const bool use_x2 = use_x && x2dims.supported() && !getenv("SDB_DISABLE_FUSEDX2");
     if (use_v0 || use_x) {
       const std::string key =
           std::string(use_v0 ? "fusedjit" : (noise == SDB_NOISE_WIK ? "fusedxjit|wik" : "fusedxjit|kpw")) +
-          (obs ? "|obs" : "");
+          (use_x2 ? "|x2" : "") + (obs ? "|obs" : "");
       std::lock_guard<std::mutex> lk(s->mu);
       auto it = s->jit.find(key);
       if (it == s->jit.end()) {
@@ -506,9 +509,10 @@ static int integrate_impl(sdb_system* s, const sdb_integrate_args* a, const SdbO
         if (use_v0) {
           src << "#include \"sdb_fused.cuh\"\nSDB_FUSED_KERNEL(sdb_jit_fused, " << s->d << ", " << s->m << ")\n";
         } else {
-          src << "#define SDB_FUSED_RB 2\n#define SDB_FUSED_VOL_MMA 0\n#include \"sdb_fusedx.cuh\"\n"
-              << "SDB_FUSEDX_KERNEL(sdb_jit_fused, " << s->d << ", " << s->m << ", "
-              << (noise == SDB_NOISE_WIK ? 1 : 0) << ")\n";
+          src << "#define SDB_FUSED_RB 2\n#define SDB_FUSED_VOL_MMA 0\n#include \""
+              << (use_x2 ? "sdb_fusedx2.cuh" : "sdb_fusedx.cuh") << "\"\n"
+              << (use_x2 ? "SDB_FUSEDX2_KERNEL" : "SDB_FUSEDX_KERNEL") << "(sdb_jit_fused, " << s->d << ", "
+              << s->m << ", " << (noise == SDB_NOISE_WIK ? 1 : 0) << ")\n";
         }
         JitKernel k;
         if (jit_compile(src.str(), "sdb_jit_fused", &k)) return 1;
@@ -520,9 +524,11 @@ static int integrate_impl(sdb_system* s, const sdb_integrate_args* a, const SdbO
                                   SdbFusedDims::THREADS, SDB_NOISE_KPW, SDB_SCHEME_SRK2};
       } else {
         jit_rb = 2;
-        jit_entry = SdbFusedEntry{s->d, s->m, 0, (const void*)it->second.kern, xdims.smem_bytes(),
-                                  xdims.sh.table_doubles(), nullptr, xdims.threads(),
-                                  xdims.threads(), noise, SDB_SCHEME_SRK2};
+        jit_entry = SdbFusedEntry{s->d, s->m, 0, (const void*)it->second.kern,
+                                  use_x2 ? x2dims.smem_bytes() : xdims.smem_bytes(),
+                                  xdims.sh.table_doubles(), nullptr,
+                                  use_x2 ? x2dims.threads() : xdims.threads(),
+                                  use_x2 ? x2dims.paths_per_block() : xdims.threads(), noise, SDB_SCHEME_SRK2};
       }
       fused = &jit_entry;
     }

@@ -105,6 +105,26 @@ struct SdbFusedXDims {
   }
 };
 
+// Run-time mirror of SdbX2Shape (sdb_fusedx2.cuh): the TMEM kernel with two lanes per path, for
+// shapes whose areas leave room for only one warp per sub-partition in SdbFusedXDims.
+struct SdbFusedX2Dims {
+  SdbFusedXDims x;
+  constexpr SdbFusedX2Dims(int d, int m) : x(d, m) {}
+  static constexpr int threads() { return 256; }
+  static constexpr int paths_per_block() { return 128; }
+  constexpr int GR() const { return x.sh.grows() >= 2 * x.sh.M ? x.sh.grows() : 2 * x.sh.M; }
+  constexpr size_t smem_bytes() const {
+    const size_t b = ((size_t)GR() * 32 * 8 + (size_t)x.sh.D * 32 * 4) * 8 + 128 * 16 +
+                     (SdbFusedDims::MAX_TERMS + 1 + x.sh.n_left() + 1) * sizeof(double) + 16;
+    return b < 120u * 1024u ? 120u * 1024u : b;
+  }
+  // an even number of row blocks and at least two area chunks to split
+  constexpr bool supported() const {
+    return x.supported() && x.WPQ() == 1 && x.sh.NB() % 2 == 0 && x.MMP() >= 32 &&
+           smem_bytes() <= 227u * 1024u;
+  }
+};
+
 // Run-time mirror of SdbRxShape (sdb_repintx.cuh).
 struct SdbRepintXDims {
   int M;

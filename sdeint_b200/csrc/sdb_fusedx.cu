@@ -8,18 +8,19 @@
 
 #include <cuda_runtime.h>
 
-#define SDB_FUSEDX_AOT(D, M, WIK, TAG)                                                         \
+#define SDB_FUSEDX_AOT(D, M, WIK, TAG, VARIANT)                                                       \
   SDB_FUSEDX_KERNEL(sdbk_fusedx_srk2_d##D##_m##M##_##TAG, D, M, WIK)                           \
   static SdbFusedRegistrar sdbreg_fusedx_d##D##_m##M##_##TAG(                                  \
-      SdbFusedEntry{D, M, 0, (const void*)sdbk_fusedx_srk2_d##D##_m##M##_##TAG,                \
+      SdbFusedEntry{D, M, VARIANT, (const void*)sdbk_fusedx_srk2_d##D##_m##M##_##TAG,          \
                     SdbXShape<D, M>::smem_bytes(), sdb_fused_table_doubles<D, M>(),            \
                     &sdb_fused_build_tables<D, M>, SdbXShape<D, M>::THREADS,                   \
                     SdbXShape<D, M>::PATHS,                                                    \
                     WIK ? SDB_NOISE_WIK : SDB_NOISE_KPW, SDB_SCHEME_SRK2});
 
-SDB_FUSEDX_AOT(20, 20, 0, kpw)
-SDB_FUSEDX_AOT(20, 20, 1, wik)
-SDB_FUSEDX_AOT(10, 10, 1, wik)
+// d = m = 20: the default is the two-lanes-per-path kernel (sdb_fusedx2.cu); this one is variant 20
+SDB_FUSEDX_AOT(20, 20, 0, kpw, 20)
+SDB_FUSEDX_AOT(20, 20, 1, wik, 20)
+SDB_FUSEDX_AOT(10, 10, 1, wik, 0)
 
 // The run-time mirror used for NVRTC-compiled shapes (sdb_fused_rt.h) must agree with the templates.
 #include "sdb_fused_rt.h"

@@ -17,5 +17,13 @@
                     SdbX2Shape<D, M>::PATHS,                                                   \
                     WIK ? SDB_NOISE_WIK : SDB_NOISE_KPW, SDB_SCHEME_SRK2});
 
-SDB_FUSEDX2_AOT(20, 20, 0, kpw, 21)
-SDB_FUSEDX2_AOT(20, 20, 1, wik, 21)
+SDB_FUSEDX2_AOT(20, 20, 0, kpw, 0)
+SDB_FUSEDX2_AOT(20, 20, 1, wik, 0)
+
+// The run-time mirror used for NVRTC-compiled shapes (sdb_fused_rt.h) must agree with the templates.
+#include "sdb_fused_rt.h"
+#define SDB_CHECK_X2DIMS(D, M)                                                                  \
+  static_assert(SdbFusedX2Dims(D, M).smem_bytes() == SdbX2Shape<D, M>::smem_bytes() &&          \
+                    SdbFusedX2Dims(D, M).supported(),                                           \
+                "sdb_fused_rt.h disagrees with SdbX2Shape");
+SDB_CHECK_X2DIMS(20, 20) SDB_CHECK_X2DIMS(8, 16) SDB_CHECK_X2DIMS(12, 18) SDB_CHECK_X2DIMS(16, 16)

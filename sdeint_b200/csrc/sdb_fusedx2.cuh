@@ -35,8 +35,9 @@ struct SdbX2Shape {
   static constexpr int GR = Xs::GR >= 2 * M ? Xs::GR : 2 * M;  // staging rows of one warp (>= the X/Z swap)
   static constexpr int WARPS = 8, THREADS = 256, PATHS = 128;
   static SDB_CX size_t smem_bytes() {
-    return ((size_t)GR * 32 * WARPS + (size_t)D * 32 * 4) * 8 + 128 * 16 +
-           (SDB_FUSED_MAX_TERMS + 1 + Sh::n_left() + 1) * sizeof(double) + 16;
+    size_t b = ((size_t)GR * 32 * WARPS + (size_t)D * 32 * 4) * 8 + 128 * 16 +
+               (SDB_FUSED_MAX_TERMS + 1 + Sh::n_left() + 1) * sizeof(double) + 16;
+    return b < 120 * 1024 ? 120 * 1024 : b;  // > half an SM: one block (one TMEM allocation) per SM
   }
 };
 

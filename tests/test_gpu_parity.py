@@ -446,6 +446,20 @@ def test_fused_tmem_kernel_d20(sdb, strat, method, monkeypatch):
     assert np.array_equal(yd, y[:, ::4])
 
 
+def test_fused_tmem_kernel_d20_one_and_two_lanes_per_path(sdb, monkeypatch):
+    """d = m = 20 runs two lanes per path by default (sdb_fusedx2.cuh: warp pairs sharing a TMEM lane
+    quadrant); the one-lane kernel (SDB_FUSED_VARIANT=20) draws the same noise and agrees to rounding,
+    also for a block with idle pairs and for more than one block."""
+    f, G, y0 = sdb.ops.sys_lin(20, 20)
+    tspan = np.linspace(0.0, 0.05, 11)
+    for P in (33, 128 * 3 + 5):
+        y2 = sdb.stratSRS2(f, G, y0, tspan, sdb.Jwik, paths=P, seed=11, path_id0=P)
+        monkeypatch.setenv("SDB_FUSED_VARIANT", "20")
+        y1 = sdb.stratSRS2(f, G, y0, tspan, sdb.Jwik, paths=P, seed=11, path_id0=P)
+        monkeypatch.delenv("SDB_FUSED_VARIANT")
+        assert rel_err(y2, y1) <= 1e-14 and not np.array_equal(y2, y1)
+
+
 def test_additive_noise_never_builds_repeated_integrals(sdb):
     """Noise-structure dispatch, first case (integrate.py:150-151): for additive noise the stage-2
     differences of SRI2/SRS2 and the G(Ybar) - G_n of KP2iS vanish identically, so I / J are neither
@@ -574,10 +588,12 @@ def test_diagonal_noise_needs_no_levy_areas(sdb):
 
 
 @pytest.mark.parametrize("d,m,method,strat", [(6, 4, "wik", False), (12, 8, "wik", True),
-                                              (16, 12, "kpw", False), (14, 14, "wik", False)])
+                                              (16, 12, "kpw", False), (14, 14, "wik", False),
+                                              (8, 16, "wik", False), (12, 18, "kpw", True)])
 def test_fused_tmem_kernel_jit_shapes(sdb, d, m, method, strat, monkeypatch):
-    """Shapes / methods without an ahead-of-time kernel: sdb_fusedx.cuh compiled by NVRTC (run-time
-    shape mirror in sdb_fused_rt.h) against the generic loop kernel and the oracle."""
+    """Shapes / methods without an ahead-of-time kernel: sdb_fusedx.cuh -- or, from m = 16, where only
+    one warp per sub-partition fits, the two-lanes-per-path sdb_fusedx2.cuh -- compiled by NVRTC
+    (run-time shape mirror in sdb_fused_rt.h) against the generic loop kernel and the oracle."""
     rng = np.random.default_rng(1000 * d + m)
     A = -1.1 * np.eye(d) + 0.3 * rng.standard_normal((d, d)) / np.sqrt(d)
     B = 0.4 * rng.standard_normal((m, d, d)) / np.sqrt(d * m)
