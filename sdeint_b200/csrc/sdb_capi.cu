@@ -697,7 +697,8 @@ extern "C" int sdb_repeated_integrals(const sdb_repint_args* a) {
   const void* fn = nullptr;
   size_t smem = 0;
   unsigned block = 128;
-  if (!comm && !a->d_X && a->m >= 12 && SdbRepintXDims(a->m).supported() && !getenv("SDB_DISABLE_FUSED")) {
+  if (!comm && !a->d_X && a->m >= 12 && a->n_terms <= SDB_FUSED_MAX_TERMS &&
+      SdbRepintXDims(a->m).supported() && !getenv("SDB_DISABLE_FUSED")) {
     for (const auto& e : sdb_repintx_registry())
       if (e.m == a->m && e.noise == a->method) { fn = e.fn; smem = e.smem; block = (unsigned)e.threads; }
     if (!fn) {

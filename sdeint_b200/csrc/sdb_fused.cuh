@@ -39,7 +39,7 @@
 
 #define SDB_FUSED_THREADS 256
 #define SDB_FUSED_WARPS (SDB_FUSED_THREADS / 32)
-#define SDB_FUSED_MAX_TERMS 64
+#define SDB_FUSED_MAX_TERMS 256
 #ifndef SDB_FUSED_KUNROLL
 #define SDB_FUSED_KUNROLL 1  // unroll factor of the Levy-series loop over k
 #endif
@@ -541,8 +541,8 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
   double* s_hk = reinterpret_cast<double*>(tab + 128);
   double* s_left = s_hk + SDB_FUSED_MAX_TERMS + 1;
   if (tid < 128) tab[tid] = reinterpret_cast<const double2*>(sdb_logtab)[tid];
-  if (tid <= SDB_FUSED_MAX_TERMS)
-    s_hk[tid] = tid == 0 ? 0.0 : a.h_global * SDB_INV_2PI / (double)tid;
+  for (int i = tid; i <= SDB_FUSED_MAX_TERMS; i += NT)
+    s_hk[i] = i == 0 ? 0.0 : a.h_global * SDB_INV_2PI / (double)i;
   for (int i = tid; i < Sh::n_left(); i += NT) s_left[i] = frag[(size_t)Sh::n_frags() * 32 + i];
   __syncthreads();
 

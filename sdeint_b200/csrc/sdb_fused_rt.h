@@ -8,7 +8,7 @@
 struct SdbFusedDims {
   int D, M, RB;  // RB: state rows per block (4: sdb_fused.cuh default; 2: sdb_fusedx.cuh)
   constexpr SdbFusedDims(int d, int m, int rb = 4) : D(d), M(m), RB(d > rb ? rb : 4) {}
-  static constexpr int THREADS = 256, WARPS = 8, MAX_TERMS = 64;
+  static constexpr int THREADS = 256, WARPS = 8, MAX_TERMS = 256;
   constexpr int MM() const { return M * (M - 1) / 2; }
   constexpr int NB() const { return (D + RB - 1) / RB; }
   constexpr int LT() const { return (D + 3) / 4; }

@@ -514,8 +514,8 @@ SDB_DEV void sdb_srk2_fusedws_body(const SdbLoopArgs& a, const PInline<D * D>& f
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_left + Sh::n_left() + 1);  // [main][full 8 | empty 8]
   uint32_t* tm_slot = reinterpret_cast<uint32_t*>(bars + SDB_WS_MAIN * 16);
   if (tid < 128) tab[tid] = reinterpret_cast<const double2*>(sdb_logtab)[tid];
-  if (tid <= SDB_FUSED_MAX_TERMS)
-    s_hk[tid] = tid == 0 ? 0.0 : a.h_global * SDB_INV_2PI / (double)tid;
+  for (int i = tid; i <= SDB_FUSED_MAX_TERMS; i += (int)blockDim.x)
+    s_hk[i] = i == 0 ? 0.0 : a.h_global * SDB_INV_2PI / (double)i;
   for (int i = tid; i < Sh::n_left(); i += SDB_WS_THREADS) s_left[i] = frag[(size_t)Sh::n_frags() * 32 + i];
   if (tid < SDB_WS_MAIN * 16) sdb_mbar_init(&bars[tid], 1u);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");

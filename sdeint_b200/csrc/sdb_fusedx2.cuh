@@ -141,8 +141,8 @@ SDB_DEV void sdb_srk2_fusedx2_body(const SdbLoopArgs& a, const PInline<D * D>& f
   double* s_left = s_hk + SDB_FUSED_MAX_TERMS + 1;
   uint32_t* tm_slot = reinterpret_cast<uint32_t*>(s_left + Sh::n_left() + 1);
   if (tid < 128) tab[tid] = reinterpret_cast<const double2*>(sdb_logtab)[tid];
-  if (tid <= SDB_FUSED_MAX_TERMS)
-    s_hk[tid] = tid == 0 ? 0.0 : a.h_global * SDB_INV_2PI / (double)tid;
+  for (int i = tid; i <= SDB_FUSED_MAX_TERMS; i += (int)blockDim.x)
+    s_hk[i] = i == 0 ? 0.0 : a.h_global * SDB_INV_2PI / (double)i;
   for (int i = tid; i < Sh::n_left(); i += X2::THREADS) s_left[i] = frag[(size_t)Sh::n_frags() * 32 + i];
   const uint32_t tm_base = sdb_tm_alloc512(tm_slot);  // contains a __syncthreads()
   const uint32_t tm = tm_base + (((uint32_t)pair * 32u) << 16);  // the pair's 32 lanes, all columns

@@ -34,7 +34,8 @@ SDB_DEV void sdb_repintx_body(const SdbRepintArgs& a, double* smem) {
   double* s_hk = reinterpret_cast<double*>(tab + 128);
   uint32_t* tm_slot = reinterpret_cast<uint32_t*>(s_hk + SDB_FUSED_MAX_TERMS + 1);
   if (tid < 128) tab[tid] = reinterpret_cast<const double2*>(sdb_logtab)[tid];
-  if (tid <= SDB_FUSED_MAX_TERMS) s_hk[tid] = tid == 0 ? 0.0 : a.h * SDB_INV_2PI / (double)tid;
+  for (int i = tid; i <= SDB_FUSED_MAX_TERMS; i += (int)blockDim.x)
+    s_hk[i] = i == 0 ? 0.0 : a.h * SDB_INV_2PI / (double)i;
   const uint32_t tm_base = sdb_tm_alloc512(tm_slot);  // contains a __syncthreads()
   const uint32_t tm = tm_base + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)((warp >> 2) * Rs::C_STRIDE);
 

@@ -30,6 +30,8 @@ decimates the stored trajectory; `out="torch"` leaves the result on the device i
 path-minor layout (n_saved, d, P); `host_out=` (a pinned torch tensor (n_saved, d, P)) receives
 large results chunk by chunk while the next chunk of paths is integrated.  `dW` / `I` / `J` may
 then carry a leading path axis (without it, one realisation is shared by all paths).
+`n_terms=` sets the number of series terms of Ikpw/Iwik (the reference's n = 5 by default);
+`n_terms="auto"` picks the number that keeps strong order 1.0 at this h (wiener.series_terms).
 `observe=[("first_above", comp, level), ("first_below", comp, level), ("max", comp), ("min", comp),
 ("integral", comp)]` (up to 4) evaluates path functionals at EVERY grid point inside the step loop --
 what a decimated store cannot give back -- and makes the call return `(y, obs)`, obs of shape
@@ -191,6 +193,11 @@ def _run(scheme, f, G, y0, tspan, dW, IJ, strat, method, generator, kp2is, paths
     n_saved = (N - 1) // save_every + 1
     h = (tspan[N - 1] - tspan[0]) / (N - 1)
     method_id = _method_id(method, strat) if need_ij else NOISE_KPW
+    if isinstance(n_terms, str):
+        if n_terms != "auto":
+            raise SDEValueError('n_terms must be an integer or "auto"')
+        # enough series terms for strong order 1.0 at this step size (wiener.series_terms)
+        n_terms = wiener.series_terms(h, m, "wik" if method_id == NOISE_WIK else "kpw") if need_ij else 1
     # commutative noise: the antisymmetric part of I/J (the Levy areas) cancels in the order-1.0 term
     # of SRI2/SRS2 -- exactly for linear g_k = B_k y with commuting B_k, which LinearDiffusion detects --
     # so unless the caller supplies I/J or says commutative=False the areas are never generated

@@ -188,3 +188,41 @@ def Jcomm(dW, h, n=0, generator=None, *, seed=None, path_id0=0, normals=None, de
           ensemble=None):
     """Stratonovich version of Icomm: J = dW dW^T / 2."""
     return _repint(NOISE_COMM, True, dW, h, 0, None, 0, path_id0, None, device, ensemble)
+
+
+def _a_tail(n):
+    """pi^2/6 - sum_{k<=n} 1/k^2 (sdeint/wiener.py:229-231)."""
+    return np.pi ** 2 / 6.0 - sum(1.0 / (k * k) for k in range(1, int(n) + 1))
+
+
+def series_terms(h, m, method="kpw", C=1.0, n_max=100000):
+    """Number of series terms n for which the repeated integrals keep the schemes at strong order 1.0
+    as h -> 0: the mean-square error of the approximation must not exceed C h^3 per step
+    (Kloeden & Platen 1992, sec. 10.3).  The reference fixes n = 5 (wiener.py:77, :234), which is a
+    constant relative accuracy of the Levy areas and degrades non-commutative problems to order 1/2
+    for small h.
+
+    "kpw"  the truncated series of Ikpw/Jkpw as the reference sums it (no tail correction): each
+           Levy area has E|A_ij - A_ij^(n)|^2 = 3 h^2 a(n) / (2 pi^2), a(n) = pi^2/6 - sum_{k<=n} 1/k^2
+           ~ 1/n (derived from wiener.py:67-74; checked numerically in tests/test_host.py), so
+           n ~ 3 / (2 pi^2 C h).
+    "wik"  Wiktorsson's tail-corrected approximation (Iwik/Jwik): the published bound
+           sum_{i<j} E|A_ij - A_ij^(n)|^2 <= 5 m^2 (m - 1) h^2 / (24 pi^2 n^2) (Wiktorsson 2001, Thm 4.1),
+           so n = ceil(sqrt(5 m^2 (m - 1) / (24 pi^2 C h))) -- O(h^-1/2) instead of O(h^-1).
+    Scalar noise (m = 1) has no Levy areas: 1 term."""
+    h, m = float(h), int(m)
+    if not h > 0.0 or m < 1 or not C > 0.0:
+        raise ValueError("series_terms: need h > 0, m >= 1, C > 0")
+    if m == 1:
+        return 1
+    if method in ("kpw", Ikpw, Jkpw):
+        target = 2.0 * np.pi ** 2 * C * h / 3.0
+        n = max(1, int(3.0 / (2.0 * np.pi ** 2 * C * h)) - 2)
+        a = _a_tail(n)
+        while a > target and n < n_max:
+            n += 1
+            a -= 1.0 / (n * n)
+        return n
+    if method in ("wik", Iwik, Jwik):
+        return max(1, int(np.ceil(np.sqrt(5.0 * m * m * (m - 1) / (24.0 * np.pi ** 2 * C * h)))))
+    raise ValueError("series_terms: method must be 'kpw' or 'wik'")

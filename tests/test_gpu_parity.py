@@ -848,6 +848,30 @@ def test_first_passage_distribution_ou(sdb):
     assert abs(cdf[0, -1] - hit.mean()) < 5 * se
 
 
+def test_auto_series_length_and_long_series(sdb):
+    """n_terms="auto" picks wiener.series_terms(h, m, method) and the fused kernels take long series
+    (up to 256 terms): same result as the explicit n, checked against the oracle on replayed normals."""
+    f, G, y0 = SYSTEMS["lin10"](False)
+    tspan = np.linspace(0.0, 0.02, 11)
+    h = 0.002
+    n = sdb.wiener.series_terms(h, 10, "kpw")
+    assert 70 <= n <= 80
+    kw = dict(paths=40, seed=123, path_id0=4)
+    y_auto = sdb.itoSRI2(f, G, y0, tspan, n_terms="auto", **kw)
+    assert np.array_equal(y_auto, sdb.itoSRI2(f, G, y0, tspan, n_terms=n, **kw))
+    assert not np.array_equal(y_auto, sdb.itoSRI2(f, G, y0, tspan, **kw))
+    dW = sdb.deltaW(10, 10, h, paths=40, seed=123, path_id0=4)
+    _, I = sdb.Ikpw(dW, h, n=n, seed=123, path_id0=4, ensemble=True)
+    for p in (0, 39):
+        assert rel_err(y_auto[p], orc.srk2(f, G, y0, tspan, dW[p], I[p])) <= TOL
+    nw = sdb.wiener.series_terms(h, 10, "wik")
+    yw = sdb.itoSRI2(f, G, y0, tspan, sdb.Iwik, n_terms="auto", **kw)
+    _, Iw = sdb.Iwik(dW, h, n=nw, seed=123, path_id0=4, ensemble=True)
+    assert rel_err(yw[7], orc.srk2(f, G, y0, tspan, dW[7], Iw[7])) <= TOL
+    with pytest.raises(sdb.SDEValueError):
+        sdb.itoSRI2(f, G, y0, tspan, n_terms="many")
+
+
 def test_device_resident_noise_tensors(sdb):
     """dW / I handed over as torch tensors already on the GPU are used in place (no host round
     trip) and give the same bits as the numpy arrays of the reference's call."""

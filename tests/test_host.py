@@ -220,3 +220,34 @@ def test_commutative_noise_detection():
     assert ops.ExprDiffusion([["y[0]", "2*y[0]"], ["y[1]", "2*y[1]"]], commutative=True).commutative
     import sdeint_b200 as sdb
     assert callable(sdb.Icomm) and callable(sdb.Jcomm)
+
+
+def test_series_terms_for_strong_order_one():
+    """wiener.series_terms: the truncation error of the KPW series as the reference sums it is
+    3 h^2 a(n) / (2 pi^2) per Levy area (checked here by direct simulation of wiener.py:67-74), so
+    order 1.0 needs n ~ 3 / (2 pi^2 C h); Wiktorsson's tail correction brings that down to O(h^-1/2)."""
+    from sdeint_b200 import wiener
+    rng = np.random.default_rng(0)
+    h, N, nbig = 0.01, 60000, 200
+    dW = rng.normal(0.0, np.sqrt(h), (N, 2))
+    c = np.sqrt(2.0 / h)
+    acc = np.zeros(N)
+    part = {}
+    for k in range(1, nbig + 1):
+        X, Y = rng.standard_normal((N, 2)), rng.standard_normal((N, 2))
+        Z = Y + c * dW
+        acc += (X[:, 0] * Z[:, 1] - Z[:, 0] * X[:, 1]) / k
+        if k in (2, 5, 20):
+            part[k] = acc.copy()
+    for n, v in part.items():
+        err = (acc - v) * h / (2.0 * np.pi)
+        pred = 3.0 * h * h / (2.0 * np.pi ** 2) * (wiener._a_tail(n) - wiener._a_tail(nbig))
+        assert abs(err.var() / pred - 1.0) < 0.03
+    assert abs(wiener._a_tail(5) - 0.181322955737115) < 1e-15         # sdeint/tests/test_wiener.py:91
+    n = wiener.series_terms(1e-3, 10, "kpw")
+    assert 148 <= n <= 156 and wiener._a_tail(n) <= 2 * np.pi ** 2 * 1e-3 / 3 < wiener._a_tail(n - 1)
+    assert wiener.series_terms(1e-3, 10, "wik") == 138
+    assert wiener.series_terms(1e-1, 10, "kpw") <= 2 and wiener.series_terms(1e-3, 1, "wik") == 1
+    assert wiener.series_terms(1e-4, 10, "wik") < wiener.series_terms(1e-4, 10, "kpw") / 3
+    with pytest.raises(ValueError):
+        wiener.series_terms(-1.0, 3)
