@@ -1,4 +1,5 @@
-"""A/B of the two-lanes-per-path TMEM kernel (SDB_FUSED_VARIANT=21) against sdb_fusedx.cuh at d=m=20."""
+"""A/B at d=m=20: the two-lanes-per-path TMEM kernel (sdb_fusedx2.cuh, default) against the one-lane
+kernel (sdb_fusedx.cuh, SDB_FUSED_VARIANT=20): agreement and throughput.  python tools/check_x2.py [paths]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -15,12 +16,12 @@ def rel(a, b):
 for meth, name in ((sdb.Jkpw, "Jkpw"), (sdb.Jwik, "Jwik")):
     os.environ.pop("SDB_FUSED_VARIANT", None)
     ref = sdb.stratSRS2(f, G, y0, ts, meth, paths=333, seed=5, path_id0=7, save_every=10)
-    os.environ["SDB_FUSED_VARIANT"] = "21"
+    os.environ["SDB_FUSED_VARIANT"] = "20"
     new = sdb.stratSRS2(f, G, y0, ts, meth, paths=333, seed=5, path_id0=7, save_every=10)
-    print(name, "rel err variant 21 vs default:", rel(new, ref), "finite:", np.isfinite(new).all(), flush=True)
+    print(name, "rel err one-lane (variant 20) vs default:", rel(new, ref), "finite:", np.isfinite(new).all(), flush=True)
 tspan = np.linspace(0.0, 1.0, 1001)
 P = int(float(sys.argv[1])) if len(sys.argv) > 1 else 500000
-for var in (None, "21"):
+for var in (None, "20"):
     if var is None:
         os.environ.pop("SDB_FUSED_VARIANT", None)
     else:
