@@ -76,6 +76,9 @@ if __name__ == "__main__":
     assert y_stub.shape == y_shim.shape == (21, 5) and np.array_equal(y_stub, y_shim)
     # on-device noise, ensemble
     y2 = srk2(system, y0, tspan, paths=100, seed=5)
-    y3 = sdb.itoSRI2(f, G, y0, tspan, paths=100, seed=5)
+    # (Roessler 7.4 has commuting B_k: the shim would skip the Levy areas; the stub asks for Ikpw)
+    y3 = sdb.itoSRI2(f, G, y0, tspan, paths=100, seed=5, commutative=False)
     assert np.array_equal(y2, y3)
+    y4 = sdb.itoSRI2(f, G, y0, tspan, paths=100, seed=5)          # area-free dispatch: same paths
+    assert np.max(np.abs(y4 - y3)) <= 1e-12 * np.max(np.abs(y3))
     print("INTEGRATION.md stub ok")
