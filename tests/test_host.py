@@ -251,3 +251,15 @@ def test_series_terms_for_strong_order_one():
     assert wiener.series_terms(1e-4, 10, "wik") < wiener.series_terms(1e-4, 10, "kpw") / 3
     with pytest.raises(ValueError):
         wiener.series_terms(-1.0, 3)
+
+
+def test_observer_specs_host_logic():
+    """observe= is translated to sdb_observer records on the host; bad specs are rejected with the
+    reference's exception type before anything touches the GPU."""
+    from sdeint_b200 import integrate
+    arr = integrate._observers([("first_above", 1, 0.5), ("max", 0), ("integral", 2)], 3)
+    assert [(o.kind, o.comp, o.level) for o in arr] == [(0, 1, 0.5), (2, 0, 0.0), (4, 2, 0.0)]
+    assert len(integrate._observers(("min", 0), 1)) == 1
+    for bad in ([("median", 0)], [("max", 3)], [("first_below", 0)], [("max", 0, 1.0)], [("max", 0)] * 5, []):
+        with pytest.raises(integrate.SDEValueError):
+            integrate._observers(bad, 3)
