@@ -136,6 +136,25 @@ typedef struct sdb_observer {
 int sdb_integrate_observed(sdb_system* sys, const sdb_integrate_args* args, const sdb_observer* h_obs,
                            int n_obs, double* d_obs, int64_t stride_obs, int64_t stride_path);
 
+/* ---- resumed / segmented runs --------------------------------------------------------------
+ * The on-device noise of interval n of path p is a pure function of (seed, path id, step counter), so a
+ * run can be cut anywhere in time and continued later -- checkpoint / resume, or full-resolution output
+ * produced segment by segment -- with bit-identical results: integrate the second segment with the
+ * states the first one reached (d_y0 per path) and step0 = number of intervals already done.
+ * h_noise > 0 fixes the variance of the increments to that of the whole run (the h of integrate.py:228,
+ * :480; a segment's own (t[N-1]-t[0])/(N-1) may differ from it in the last bits).  Not for
+ * SDB_SCHEME_KP2IS, a two-step scheme whose first step is special (integrate.py:632).  Observers as in
+ * sdb_integrate_observed (n_obs = 0: none); they restart in every segment. */
+typedef struct sdb_integrate_ext {
+  int64_t step0;
+  double h_noise;
+  int n_obs;
+  const sdb_observer* h_obs;
+  double* d_obs;
+  int64_t obs_stride_obs, obs_stride_path;
+} sdb_integrate_ext;
+int sdb_integrate_segment(sdb_system* sys, const sdb_integrate_args* args, const sdb_integrate_ext* ext);
+
 /* deltaW (wiener.py:36-52) for P paths: out[step][comp][path] through strides. */
 int sdb_delta_w(int64_t steps, int m, double h, int64_t paths, int64_t path_id0, uint64_t seed,
                 double* d_out, int64_t stride_step, int64_t stride_comp, int64_t stride_path,

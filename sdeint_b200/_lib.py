@@ -53,6 +53,13 @@ class Observer(C.Structure):
     _fields_ = [("kind", C.c_int), ("comp", C.c_int), ("level", C.c_double)]
 
 
+class IntegrateExt(C.Structure):
+    """== sdb_integrate_ext (include/sdb.h)."""
+    _fields_ = [("step0", c_i64), ("h_noise", C.c_double), ("n_obs", C.c_int),
+                ("h_obs", C.POINTER(Observer)), ("d_obs", C.c_void_p),
+                ("obs_stride_obs", c_i64), ("obs_stride_path", c_i64)]
+
+
 SIGNATURES = {
     "sdb_last_error": (C.c_char_p, []),
     "sdb_version": (C.c_int, []),
@@ -65,6 +72,7 @@ SIGNATURES = {
     "sdb_integrate": (C.c_int, [C.c_void_p, C.POINTER(IntegrateArgs)]),
     "sdb_integrate_observed": (C.c_int, [C.c_void_p, C.POINTER(IntegrateArgs), C.POINTER(Observer), C.c_int,
                                          c_dp, c_i64, c_i64]),
+    "sdb_integrate_segment": (C.c_int, [C.c_void_p, C.POINTER(IntegrateArgs), C.POINTER(IntegrateExt)]),
     "sdb_delta_w": (C.c_int, [c_i64, C.c_int, C.c_double, c_i64, c_i64, c_u64, c_dp, c_i64, c_i64,
                               c_i64, c_dp]),
     "sdb_repeated_integrals": (C.c_int, [C.POINTER(RepintArgs)]),

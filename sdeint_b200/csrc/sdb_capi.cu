@@ -315,19 +315,25 @@ static std::string type_of(const sdb_system* s, bool drift) {
 }
 
 // Find (AOT) or build (NVRTC) the loop kernel for this system / scheme / noise source.
-static int loop_kernel(sdb_system* s, int scheme, int noise, const void** fn, bool observe = false) {
+// ext: 0 = plain (ahead-of-time kernels allowed), 1 = resumable (SDB_RESUME), 2 = observing + resumable
+static const char* ext_suffix(int ext) { return ext == 2 ? "|obs" : ext == 1 ? "|res" : ""; }
+static const char* ext_defines(int ext) {
+  return ext == 2 ? "#define SDB_OBSERVE 1\n#define SDB_RESUME 1\n" : ext == 1 ? "#define SDB_RESUME 1\n" : "";
+}
+
+static int loop_kernel(sdb_system* s, int scheme, int noise, const void** fn, int ext = 0) {
   std::string key = sdb_loop_key(scheme, s->fk, s->gk, s->d, s->m, noise, s->inline_params);
   const bool user_g = s->gk == SDB_DIFF_USER || s->gk == SDB_DIFF_USER_DIAG;
   const bool user = s->fk == SDB_DRIFT_USER || user_g;
-  if (!user && !observe) {
+  if (!user && !ext) {
     if (const void* f = aot_lookup(key)) { *fn = f; return 0; }
   }
-  if (observe) key += "|obs";  // the observing variant of every kernel is compiled at run time
+  key += ext_suffix(ext);  // the observing / resumable variant of every kernel is compiled at run time
   std::lock_guard<std::mutex> lk(s->mu);
   auto it = s->jit.find(key);
   if (it == s->jit.end()) {
     std::ostringstream src;
-    if (observe) src << "#define SDB_OBSERVE 1\n";
+    src << ext_defines(ext);
     if (s->fk == SDB_DRIFT_USER) src << "#define SDB_USER_DRIFT 1\n";
     if (user_g) src << "#define SDB_USER_DIFF 1\n";
     src << "#include \"sdb_kernels.cuh\"\n";
@@ -350,7 +356,8 @@ __global__ void sdb_k_status_init(int64_t* st) {
   st[0] = 0; st[1] = 0x7fffffffffffffffll; st[2] = 0; st[3] = 0x7fffffffffffffffll;
 }
 
-static int integrate_impl(sdb_system* s, const sdb_integrate_args* a, const SdbObsArgs* obs);
+static int integrate_impl(sdb_system* s, const sdb_integrate_args* a, const SdbObsArgs* obs,
+                          int64_t step0 = 0, double h_noise = 0.0);
 
 extern "C" int sdb_integrate(sdb_system* s, const sdb_integrate_args* a) {
   return integrate_impl(s, a, nullptr);
@@ -358,31 +365,48 @@ extern "C" int sdb_integrate(sdb_system* s, const sdb_integrate_args* a) {
 
 extern "C" int sdb_integrate_observed(sdb_system* s, const sdb_integrate_args* a, const sdb_observer* h_obs,
                                       int n_obs, double* d_obs, int64_t stride_obs, int64_t stride_path) {
-  if (!s || !a) return fail("sdb_integrate_observed: NULL argument");
-  if (n_obs == 0) return integrate_impl(s, a, nullptr);
-  if (n_obs < 0 || n_obs > SDB_MAX_OBSERVERS)
-    return fail("sdb_integrate_observed: need 0 <= n_obs <= SDB_MAX_OBSERVERS");
-  if (!h_obs || !d_obs) return fail("sdb_integrate_observed: NULL observer buffer");
-  static_assert(SDB_MAX_OBSERVERS == SDB_MAX_OBS, "sdb.h and sdb_kernels.cuh disagree");
-  SdbObsArgs o;
-  memset(&o, 0, sizeof o);
-  o.n = n_obs;
-  for (int i = 0; i < n_obs; ++i) {
-    if (h_obs[i].kind < SDB_OBS_FIRST_ABOVE || h_obs[i].kind > SDB_OBS_INTEGRAL)
-      return fail("sdb_integrate_observed: unknown observer kind");
-    if (h_obs[i].comp < 0 || h_obs[i].comp >= s->d)
-      return fail("sdb_integrate_observed: observer component out of range");
-    o.kind[i] = h_obs[i].kind;
-    o.comp[i] = h_obs[i].comp;
-    o.level[i] = h_obs[i].level;
-  }
-  o.out = d_obs;
-  o.sO = stride_obs;
-  o.sP = stride_path;
-  return integrate_impl(s, a, &o);
+  const sdb_integrate_ext x{0, 0.0, n_obs, h_obs, d_obs, stride_obs, stride_path};
+  return sdb_integrate_segment(s, a, &x);
 }
 
-static int integrate_impl(sdb_system* s, const sdb_integrate_args* a, const SdbObsArgs* obs) {
+static int make_observers(sdb_system* s, const sdb_observer* h_obs, int n_obs, double* d_obs,
+                          int64_t stride_obs, int64_t stride_path, SdbObsArgs* o) {
+  if (n_obs < 0 || n_obs > SDB_MAX_OBSERVERS)
+    return fail("observers: need 0 <= n_obs <= SDB_MAX_OBSERVERS");
+  if (!h_obs || !d_obs) return fail("observers: NULL observer buffer");
+  static_assert(SDB_MAX_OBSERVERS == SDB_MAX_OBS, "sdb.h and sdb_kernels.cuh disagree");
+  memset(o, 0, sizeof *o);
+  o->n = n_obs;
+  for (int i = 0; i < n_obs; ++i) {
+    if (h_obs[i].kind < SDB_OBS_FIRST_ABOVE || h_obs[i].kind > SDB_OBS_INTEGRAL)
+      return fail("observers: unknown observer kind");
+    if (h_obs[i].comp < 0 || h_obs[i].comp >= s->d)
+      return fail("observers: observer component out of range");
+    o->kind[i] = h_obs[i].kind;
+    o->comp[i] = h_obs[i].comp;
+    o->level[i] = h_obs[i].level;
+  }
+  o->out = d_obs;
+  o->sO = stride_obs;
+  o->sP = stride_path;
+  return 0;
+}
+
+extern "C" int sdb_integrate_segment(sdb_system* s, const sdb_integrate_args* a, const sdb_integrate_ext* x) {
+  if (!s || !a || !x) return fail("sdb_integrate_segment: NULL argument");
+  if (x->step0 < 0 || x->step0 + (int64_t)a->N - 1 > 0xffffffffll)
+    return fail("sdb_integrate_segment: step counter out of range");
+  if (x->h_noise < 0.0) return fail("sdb_integrate_segment: h_noise must be >= 0");
+  if (x->step0 != 0 && a->scheme == SDB_SCHEME_KP2IS)
+    return fail("sdb_integrate_segment: the two-step scheme KP2iS cannot be resumed");
+  if (x->n_obs == 0) return integrate_impl(s, a, nullptr, x->step0, x->h_noise);
+  SdbObsArgs o;
+  if (make_observers(s, x->h_obs, x->n_obs, x->d_obs, x->obs_stride_obs, x->obs_stride_path, &o)) return 1;
+  return integrate_impl(s, a, &o, x->step0, x->h_noise);
+}
+
+static int integrate_impl(sdb_system* s, const sdb_integrate_args* a, const SdbObsArgs* obs, int64_t step0,
+                          double h_noise) {
   if (!s || !a) return fail("sdb_integrate: NULL argument");
   if (a->scheme < SDB_SCHEME_EULER || a->scheme > SDB_SCHEME_KP2IS)
     return fail("sdb_integrate: unknown scheme");
@@ -412,6 +436,7 @@ static int integrate_impl(sdb_system* s, const sdb_integrate_args* a, const SdbO
   // commutative noise: the Ikpw/Jkpw kernels with an empty series (A = 0, only dW is drawn)
   const bool comm = noise == SDB_NOISE_COMM;
   if (comm) { noise = SDB_NOISE_KPW; n_terms = 0; }
+  const int ext = obs ? 2 : (step0 != 0 ? 1 : 0);  // which build of the kernel (see ext_defines)
   // The production path: linear system, SRI2/SRS2, on-device Philox + Ikpw/Jkpw (or Iwik/Jwik)
   // -> a fused kernel when one is instantiated for this (d, m, method).
   const SdbFusedEntry* fused = nullptr;
@@ -424,17 +449,17 @@ static int integrate_impl(sdb_system* s, const sdb_integrate_args* a, const SdbO
   if (comm && need_ij && a->scheme == SDB_SCHEME_SRK2 && s->fk == SDB_DRIFT_LINEAR &&
       s->gk == SDB_DIFF_LINEAR_COLS && !getenv("SDB_DISABLE_FUSED") && !getenv("SDB_DISABLE_FUSEDC") &&
       SdbFusedCDims(s->d, s->m).supported()) {
-    if (!obs)
+    if (!ext)
       for (const auto& e : sdb_fused_registry())
         if (e.d == s->d && e.m == s->m && e.noise == SDB_NOISE_COMM && e.scheme == SDB_SCHEME_SRK2) fused = &e;
     if (!fused && !getenv("SDB_DISABLE_FUSED_JIT") && s->d * s->m >= 16) {
       const SdbFusedCDims cd(s->d, s->m);
-      const std::string key = std::string("fusedcjit") + (obs ? "|obs" : "");
+      const std::string key = std::string("fusedcjit") + ext_suffix(ext);
       std::lock_guard<std::mutex> lk(s->mu);
       auto it = s->jit.find(key);
       if (it == s->jit.end()) {
         std::ostringstream src;
-        if (obs) src << "#define SDB_OBSERVE 1\n";
+        src << ext_defines(ext);
         src << "#include \"sdb_fusedc.cuh\"\nSDB_FUSEDC_KERNEL(sdb_jit_fused, " << s->d << ", " << s->m << ")\n";
         JitKernel k;
         if (jit_compile(src.str(), "sdb_jit_fused", &k)) return 1;
@@ -449,7 +474,7 @@ static int integrate_impl(sdb_system* s, const sdb_integrate_args* a, const SdbO
   }
   if (!fused && (a->scheme == SDB_SCHEME_SRK2 || explicit_em) && noise != SDB_NOISE_HOST &&
       s->fk == SDB_DRIFT_LINEAR && s->gk == SDB_DIFF_LINEAR_COLS &&
-      n_terms <= SDB_FUSED_MAX_TERMS && !getenv("SDB_DISABLE_FUSED") && !obs) {
+      n_terms <= SDB_FUSED_MAX_TERMS && !getenv("SDB_DISABLE_FUSED") && !ext) {
     const char* vs = getenv("SDB_FUSED_VARIANT");
     const int want = vs ? atoi(vs) : 0;
     for (const auto& e : sdb_fused_registry())
@@ -469,12 +494,12 @@ static int integrate_impl(sdb_system* s, const sdb_integrate_args* a, const SdbO
       SdbFusedEhDims(s->d, s->m, a->scheme == SDB_SCHEME_HEUN).supported()) {
     const bool heun = a->scheme == SDB_SCHEME_HEUN;
     const SdbFusedEhDims edims(s->d, s->m, heun);
-    const std::string key = std::string(heun ? "fusedehjit|heun" : "fusedehjit|euler") + (obs ? "|obs" : "");
+    const std::string key = std::string(heun ? "fusedehjit|heun" : "fusedehjit|euler") + ext_suffix(ext);
     std::lock_guard<std::mutex> lk(s->mu);
     auto it = s->jit.find(key);
     if (it == s->jit.end()) {
       std::ostringstream src;
-      if (obs) src << "#define SDB_OBSERVE 1\n";
+      src << ext_defines(ext);
       src << "#include \"sdb_fusedeh.cuh\"\nSDB_FUSEDEH_KERNEL(sdb_jit_fused, " << s->d << ", " << s->m
           << ", " << (heun ? 1 : 0) << ")\n";
       JitKernel k;
@@ -500,12 +525,12 @@ static int integrate_impl(sdb_system* s, const sdb_integrate_args* a, const SdbO
     if (use_v0 || use_x) {
       const std::string key =
           std::string(use_v0 ? "fusedjit" : (noise == SDB_NOISE_WIK ? "fusedxjit|wik" : "fusedxjit|kpw")) +
-          (use_x2 ? "|x2" : "") + (obs ? "|obs" : "");
+          (use_x2 ? "|x2" : "") + ext_suffix(ext);
       std::lock_guard<std::mutex> lk(s->mu);
       auto it = s->jit.find(key);
       if (it == s->jit.end()) {
         std::ostringstream src;
-        if (obs) src << "#define SDB_OBSERVE 1\n";
+        src << ext_defines(ext);
         if (use_v0) {
           src << "#include \"sdb_fused.cuh\"\nSDB_FUSED_KERNEL(sdb_jit_fused, " << s->d << ", " << s->m << ")\n";
         } else {
@@ -551,7 +576,7 @@ static int integrate_impl(sdb_system* s, const sdb_integrate_args* a, const SdbO
       it = s->d_frags.emplace(fn, d).first;
     }
     d_frag = it->second;
-  } else if (loop_kernel(s, a->scheme, noise, &fn, obs != nullptr)) {
+  } else if (loop_kernel(s, a->scheme, noise, &fn, ext)) {
     return 1;
   }
 
@@ -579,7 +604,8 @@ static int integrate_impl(sdb_system* s, const sdb_integrate_args* a, const SdbO
   memset(&k, 0, sizeof k);
   k.P = a->paths; k.path_id0 = a->path_id0; k.seed = a->seed;
   k.N = a->N; k.save_every = a->save_every; k.n_terms = n_terms; k.flags = a->flags;
-  k.h_global = (a->h_tspan[a->N - 1] - a->h_tspan[0]) / (double)(a->N - 1);
+  k.h_global = h_noise > 0.0 ? h_noise : (a->h_tspan[a->N - 1] - a->h_tspan[0]) / (double)(a->N - 1);
+
   k.rtol = a->rtol;
   k.tspan = d_aux;
   k.y0 = a->d_y0; k.y0_sI = a->y0_stride_comp; k.y0_sP = a->y0_stride_path;
@@ -590,6 +616,7 @@ static int integrate_impl(sdb_system* s, const sdb_integrate_args* a, const SdbO
   k.kp = nk ? d_aux + nt + 3 * ns : nullptr;
   k.status = a->d_status;
   if (obs) k.obs = *obs;
+  k.obs.step0 = (uint32_t)step0;
   if (a->d_status) {
     sdb_k_status_init<<<1, 1, 0, st>>>(a->d_status);
     g_launches.fetch_add(1);

@@ -594,12 +594,12 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
 #endif
     // ---- noise: dW (wiener.py:52), Levy areas (wiener.py:67-74, :102-105), one lane per path ------
     {
-      const SdbStream st(pkey, path, (uint32_t)n, tab);
+      const SdbStream st(pkey, path, SDB_STEP(n), tab);
       double dW[M];
 #if SDB_FUSED_BATCH
       {
         uint32_t w[M / 2][4];
-        sdb_philox_batch<M / 2>(pkey, st.p_lo, st.p_hi, (uint32_t)n, 0u, w);
+        sdb_philox_batch<M / 2>(pkey, st.p_lo, st.p_hi, SDB_STEP(n), 0u, w);
         sdb_normal_batch<M / 2, true>(w, tab, rh_g, dW);
       }
 #else
@@ -629,7 +629,7 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
         {
           uint32_t w[M][4];
           double xz[2 * M];
-          sdb_philox_batch<M>(pkey, st.p_lo, st.p_hi, (uint32_t)n, sx, w);
+          sdb_philox_batch<M>(pkey, st.p_lo, st.p_hi, SDB_STEP(n), sx, w);
           sdb_normal_batch<M, false>(w, tab, 1.0, xz);
 #pragma unroll
           for (int j = 0; j < M; ++j) {
@@ -640,9 +640,9 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
 #else
         {
           uint32_t w[M / 2][4];
-          sdb_philox_batch<M / 2>(pkey, st.p_lo, st.p_hi, (uint32_t)n, sx, w);
+          sdb_philox_batch<M / 2>(pkey, st.p_lo, st.p_hi, SDB_STEP(n), sx, w);
           sdb_normal_batch<M / 2, true>(w, tab, hk, X);
-          sdb_philox_batch<M / 2>(pkey, st.p_lo, st.p_hi, (uint32_t)n, sx + M / 2, w);
+          sdb_philox_batch<M / 2>(pkey, st.p_lo, st.p_hi, SDB_STEP(n), sx + M / 2, w);
           sdb_normal_batch<M / 2, false>(w, tab, 1.0, Z);
         }
 #endif

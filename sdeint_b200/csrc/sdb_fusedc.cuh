@@ -190,7 +190,7 @@ SDB_DEV void sdb_fusedc_body(const SdbLoopArgs& a, const double* __restrict__ fr
     double dW[M];
     {
       uint32_t w[M / 2][4];
-      sdb_philox_batch<M / 2>(pkey, p_lo, p_hi, (uint32_t)n, 0u, w);
+      sdb_philox_batch<M / 2>(pkey, p_lo, p_hi, SDB_STEP(n), 0u, w);
       sdb_normal_batch<M / 2, true>(w, tab, rh_g, dW);
     }
     double v[D], ex[2][D], f0[D];

@@ -140,7 +140,7 @@ SDB_DEV void sdb_fusedeh_body(const SdbLoopArgs& a, const double* __restrict__ f
     double dW[M];
     {
       uint32_t w[M / 2][4];
-      sdb_philox_batch<M / 2>(pkey, p_lo, p_hi, (uint32_t)n, 0u, w);
+      sdb_philox_batch<M / 2>(pkey, p_lo, p_hi, SDB_STEP(n), 0u, w);
       sdb_normal_batch<M / 2, true>(w, tab, rh, dW);
     }
     double GdW[D], f0[D];

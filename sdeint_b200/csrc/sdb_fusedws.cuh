@@ -120,7 +120,7 @@ SDB_DEV void sdb_ws_helper(const SdbLoopArgs& a, const double2* __restrict__ tab
     {  // batch 0: dW (wiener.py:52)
       double dW[M];
       uint32_t w[M / 2][4];
-      sdb_philox_batch<M / 2>(pkey, p_lo, p_hi, (uint32_t)n, 0u, w);
+      sdb_philox_batch<M / 2>(pkey, p_lo, p_hi, SDB_STEP(n), 0u, w);
       sdb_normal_batch<M / 2, true>(w, tab, rh_g, dW);
 #pragma unroll
       for (int j = 0; j < M; ++j) czdW[j] = cz * dW[j];
@@ -139,12 +139,12 @@ SDB_DEV void sdb_ws_helper(const SdbLoopArgs& a, const double2* __restrict__ tab
       double X[M], Z[M];
       {
         uint32_t w[M / 2][4];
-        sdb_philox_batch<M / 2>(pkey, p_lo, p_hi, (uint32_t)n, sx, w);
+        sdb_philox_batch<M / 2>(pkey, p_lo, p_hi, SDB_STEP(n), sx, w);
         sdb_normal_batch<M / 2, true>(w, tab, hk, X);
       }
       {
         uint32_t w[M / 2][4];
-        sdb_philox_batch<M / 2>(pkey, p_lo, p_hi, (uint32_t)n, sx + M / 2, w);
+        sdb_philox_batch<M / 2>(pkey, p_lo, p_hi, SDB_STEP(n), sx + M / 2, w);
         sdb_normal_batch<M / 2, false>(w, tab, 1.0, Z);
       }
 #pragma unroll
@@ -406,7 +406,7 @@ SDB_DEV void sdb_ws_main(const SdbLoopArgs& a, const PInline<D * D>& fp,
         double dW[M];
         {
           uint32_t w[M / 2][4];
-          sdb_philox_batch<M / 2>(pkey, p_lo, p_hi, (uint32_t)n, 0u, w);
+          sdb_philox_batch<M / 2>(pkey, p_lo, p_hi, SDB_STEP(n), 0u, w);
           sdb_normal_batch<M / 2, true>(w, tab, rh_g, dW);
         }
         sdb_tm_st<M>(tm + Ws::C_DW, dW);
@@ -417,9 +417,9 @@ SDB_DEV void sdb_ws_main(const SdbLoopArgs& a, const PInline<D * D>& fp,
           const double hk = s_hk[k];
           {
             uint32_t w[M / 2][4];
-            sdb_philox_batch<M / 2>(pkey, p_lo, p_hi, (uint32_t)n, sx, w);
+            sdb_philox_batch<M / 2>(pkey, p_lo, p_hi, SDB_STEP(n), sx, w);
             sdb_normal_batch<M / 2, true>(w, tab, hk, X);
-            sdb_philox_batch<M / 2>(pkey, p_lo, p_hi, (uint32_t)n, sx + M / 2, w);
+            sdb_philox_batch<M / 2>(pkey, p_lo, p_hi, SDB_STEP(n), sx + M / 2, w);
             sdb_normal_batch<M / 2, false>(w, tab, 1.0, Z);
           }
 #pragma unroll

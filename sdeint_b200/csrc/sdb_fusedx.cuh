@@ -269,7 +269,7 @@ SDB_DEV void sdb_srk2_fusedx_body(const SdbLoopArgs& a, const PInline<D * D>& fp
     // ---- dW (wiener.py:52) ---------------------------------------------------------------------------
     {
       double dW[M];
-      sdb_gen_pairs<M / 2, 0, M, true>(pkey, p_lo, p_hi, (uint32_t)n, 0u, tab, rh_g, dW);
+      sdb_gen_pairs<M / 2, 0, M, true>(pkey, p_lo, p_hi, SDB_STEP(n), 0u, tab, rh_g, dW);
       sdb_tm_st<M>(tm + Xs::C_DW, dW);
       double zero[CH];
 #pragma unroll
@@ -279,7 +279,7 @@ SDB_DEV void sdb_srk2_fusedx_body(const SdbLoopArgs& a, const PInline<D * D>& fp
       sdb_tm_wait_st();
     }
     // ---- Levy areas (series + Wiktorsson tail) into tensor memory ------------------------------------
-    sdb_x_levy_areas<M, WIK>(pkey, p_lo, p_hi, (uint32_t)n, tab, s_hk, hg, cz, tail_scale, n_terms,
+    sdb_x_levy_areas<M, WIK>(pkey, p_lo, p_hi, SDB_STEP(n), tab, s_hk, hg, cz, tail_scale, n_terms,
                              tm + Xs::C_AT, tm + Xs::C_DW);
 
     // ---- row blocks (runtime loop: every block has RN rows) ------------------------------------------

@@ -51,6 +51,17 @@ typedef long long int64_t;
 #ifndef SDB_OBSERVE
 #define SDB_OBSERVE 0
 #endif
+// Philox step counter of interval n.  Resumed segments (sdb_integrate_segment, step0 != 0) offset it;
+// like the observers this is compiled in only on request (NVRTC variants), so the ahead-of-time
+// kernels do not pay for it (the extra add cost the headline kernel 1.2 %).
+#ifndef SDB_RESUME
+#define SDB_RESUME 0
+#endif
+#if SDB_RESUME
+#define SDB_STEP(n) ((uint32_t)(n) + a.obs.step0)
+#else
+#define SDB_STEP(n) ((uint32_t)(n))
+#endif
 #define SDB_MAX_OBS 4
 #define SDB_OBS_FIRST_ABOVE 0
 #define SDB_OBS_FIRST_BELOW 1
@@ -61,6 +72,10 @@ struct SdbObsArgs {
   int n;
   int kind[SDB_MAX_OBS];
   int comp[SDB_MAX_OBS];
+  // Philox step counter of the first interval (resumed segments, SDB_RESUME builds).  It sits in the
+  // alignment hole of this block on purpose: the size and layout of the kernel parameters -- and with
+  // them the register allocation of the ahead-of-time kernels -- stay what they were.
+  uint32_t step0;
   double level[SDB_MAX_OBS];
   double* out;  // [observer][path] through strides
   int64_t sO, sP;
@@ -88,7 +103,7 @@ struct SdbLoopArgs {
   int64_t IJ_sN, IJ_sR, IJ_sC, IJ_sP;
   const double* kp;  // device [3*D]: gam, al1, al2
   int64_t* status;   // [4]
-  SdbObsArgs obs;    // per-path functionals of the trajectory (kernels built with SDB_OBSERVE only)
+  SdbObsArgs obs;    // per-path functionals of the trajectory (SDB_OBSERVE builds) and the step offset
 };
 
 struct SdbRepintArgs {
@@ -593,7 +608,7 @@ SDB_DEV void sdb_step_noise(const SdbLoopArgs& a, int64_t p, int n, double (&dW)
     }
   } else {
     const SdbPhiloxKey key(a.seed);
-    const SdbStream st(key, (uint64_t)(a.path_id0 + p), (uint32_t)n);
+    const SdbStream st(key, (uint64_t)(a.path_id0 + p), SDB_STEP(n));
     const double rh = sqrt(a.h_global);  // deltaW(N-1, m, h_global): integrate.py:483
     SdbNormalSeq s(st, 0u);
 #pragma unroll

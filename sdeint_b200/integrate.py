@@ -30,6 +30,10 @@ decimates the stored trajectory; `out="torch"` leaves the result on the device i
 path-minor layout (n_saved, d, P); `host_out=` (a pinned torch tensor (n_saved, d, P)) receives
 large results chunk by chunk while the next chunk of paths is integrated.  `dW` / `I` / `J` may
 then carry a leading path axis (without it, one realisation is shared by all paths).
+`step0=k` (with `y0_paths=` the states reached and, for bit-identical noise, `h_noise=` the h of the
+whole run) continues a run after k intervals: the on-device noise depends only on (seed, path id, step
+counter), so a run cut into segments -- checkpoint / resume, full-resolution output produced piecewise --
+gives the same bits as one call.
 `n_terms=` sets the number of series terms of Ikpw/Iwik (the reference's n = 5 by default);
 `n_terms="auto"` picks the number that keeps strong order 1.0 at this h (wiener.series_terms).
 `observe=[("first_above", comp, level), ("first_below", comp, level), ("max", comp), ("min", comp),
@@ -174,7 +178,7 @@ def _resolve_paths(paths, dW, IJ):
 
 def _run(scheme, f, G, y0, tspan, dW, IJ, strat, method, generator, kp2is, paths, seed,
          path_id0, save_every, n_terms, device, out, y0_paths=None, host_out=None,
-         commutative=None, observe=None):
+         commutative=None, observe=None, step0=0, h_noise=None):
     global _last_status
     (d, m, f, Gop, y0, tspan, dW, IJ) = _check_args(f, G, y0, tspan, dW, IJ)
     P, ensemble = _resolve_paths(paths, dW, IJ)
@@ -187,6 +191,11 @@ def _run(scheme, f, G, y0, tspan, dW, IJ, strat, method, generator, kp2is, paths
     if diag and IJ is None and scheme == SCHEME_SRK2:   # (KP2iS does use off-diagonal J)
         need_ij = False
     N = len(tspan)
+    step0 = int(step0)
+    if step0 < 0 or (h_noise is not None and not h_noise > 0.0):
+        raise SDEValueError('step0 must be >= 0 and h_noise > 0')
+    if step0 and scheme == SCHEME_KP2IS:
+        raise SDEValueError('stratKP2iS is a two-step scheme and cannot be resumed (step0 != 0)')
     save_every = int(save_every)
     if save_every < 1:
         raise SDEValueError('save_every must be >= 1')
@@ -211,6 +220,8 @@ def _run(scheme, f, G, y0, tspan, dW, IJ, strat, method, generator, kp2is, paths
     key = 0
     if not (have_dW and have_IJ):
         key = wiener._derive_seed(seed, generator)
+        if step0 and (have_dW or (need_ij and IJ is not None)):
+            raise SDEValueError('a resumed segment (step0 != 0) needs dW and I/J both supplied or both drawn')
 
     with torch.cuda.device(device):
         system = dev.get_system(f, Gop, device)
@@ -290,7 +301,7 @@ def _run(scheme, f, G, y0, tspan, dW, IJ, strat, method, generator, kp2is, paths
             d_obs = None if obs_arr is None else \
                 torch.empty((len(obs_arr), P), dtype=torch.float64, device=device)
             status = _run_pipelined(lib, system, a, host_out, P, int(path_id0), n_saved, d, device,
-                                    obs_arr, d_obs)
+                                    obs_arr, d_obs, step0, h_noise)
             _last_status = status
             if scheme == SCHEME_KP2IS and status[2] > 0:
                 raise RuntimeError(
@@ -310,12 +321,9 @@ def _run(scheme, f, G, y0, tspan, dW, IJ, strat, method, generator, kp2is, paths
         a.d_status = dev.ptr(d_status)
         a.stream = dev.stream_ptr()
         d_obs = None
-        if obs_arr is None:
-            _lib.check(lib.sdb_integrate(system.handle, C.byref(a)))
-        else:   # path functionals evaluated at every grid point inside the step loop
+        if obs_arr is not None:   # path functionals evaluated at every grid point inside the step loop
             d_obs = torch.empty((len(obs_arr), P), dtype=torch.float64, device=device)
-            _lib.check(lib.sdb_integrate_observed(system.handle, C.byref(a), obs_arr, len(obs_arr),
-                                                  dev.ptr(d_obs), P, 1))
+        _launch(lib, system, a, obs_arr, dev.ptr(d_obs) if d_obs is not None else None, P, step0, h_noise)
         status = tuple(int(v) for v in d_status.cpu().tolist())
         _last_status = status
         if scheme == SCHEME_KP2IS and status[2] > 0:
@@ -348,7 +356,21 @@ _PIPELINE_MIN_PATHS = 1 << 19
 _PIPELINE_CHUNKS = 8
 
 
-def _run_pipelined(lib, system, a, host_out, P, path_id0, n_saved, d, device, obs_arr=None, d_obs=None):
+def _launch(lib, system, a, obs_arr, d_obs_ptr, obs_stride, step0, h_noise):
+    """sdb_integrate, or sdb_integrate_segment when observers / a resumed segment are asked for."""
+    if obs_arr is None and not step0 and not h_noise:
+        _lib.check(lib.sdb_integrate(system.handle, C.byref(a)))
+        return
+    x = _lib.IntegrateExt()
+    x.step0, x.h_noise = int(step0), float(h_noise or 0.0)
+    if obs_arr is not None:
+        x.n_obs, x.h_obs, x.d_obs = len(obs_arr), obs_arr, d_obs_ptr
+        x.obs_stride_obs, x.obs_stride_path = obs_stride, 1
+    _lib.check(lib.sdb_integrate_segment(system.handle, C.byref(a), C.byref(x)))
+
+
+def _run_pipelined(lib, system, a, host_out, P, path_id0, n_saved, d, device, obs_arr=None, d_obs=None,
+                   step0=0, h_noise=None):
     """Chunked integration with overlapped device -> host copies; returns the merged status."""
     torch = dev.torch_mod()
     # chunk = a whole number of waves of the fused kernels (one 256-path block per SM), so that only
@@ -374,11 +396,9 @@ def _run_pipelined(lib, system, a, host_out, P, path_id0, n_saved, d, device, ob
         a.y_stride_save, a.y_stride_comp, a.y_stride_path = d * Pc, Pc, 1
         a.d_status = C.c_void_p(stats[c].data_ptr())
         a.stream = C.c_void_p(compute.cuda_stream)
-        if obs_arr is None:
-            _lib.check(lib.sdb_integrate(system.handle, C.byref(a)))
-        else:   # observers of chunk c land at their global path offset
-            _lib.check(lib.sdb_integrate_observed(system.handle, C.byref(a), obs_arr, len(obs_arr),
-                                                  C.c_void_p(d_obs.data_ptr() + 8 * p0), P, 1))
+        # observers of chunk c land at their global path offset
+        _launch(lib, system, a, obs_arr, C.c_void_p(d_obs.data_ptr() + 8 * p0) if d_obs is not None else None,
+                P, step0, h_noise)
         done = torch.cuda.Event()
         done.record(compute)
         copier.wait_event(done)
@@ -394,7 +414,7 @@ def _run_pipelined(lib, system, a, host_out, P, path_id0, n_saved, d, device, ob
 
 
 _ENS = dict(paths=None, seed=None, path_id0=0, save_every=1, n_terms=5, device=None, out="numpy",
-            y0_paths=None, host_out=None, commutative=None, observe=None)
+            y0_paths=None, host_out=None, commutative=None, observe=None, step0=0, h_noise=None)
 
 _OBS_KINDS = {"first_above": 0, "first_below": 1, "max": 2, "min": 3, "integral": 4}
 MAX_OBSERVERS = 4

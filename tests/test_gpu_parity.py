@@ -872,6 +872,48 @@ def test_auto_series_length_and_long_series(sdb):
         sdb.itoSRI2(f, G, y0, tspan, n_terms="many")
 
 
+@pytest.mark.parametrize("name,scheme", [("lin10", "sri2"), ("lin10", "sri2wik"), ("lin10", "heun"),
+                                         ("lin20", "srs2"), ("kp4446", "sri2"), ("lin2", "euler"),
+                                         ("r74", "sri2")])
+def test_resumed_segments_are_bit_identical(sdb, name, scheme):
+    """Checkpoint / resume: the on-device noise depends only on (seed, path id, step counter), so a run
+    cut after k intervals and continued with `step0=k` from the states it had reached reproduces the
+    single call bit for bit (every fused and generic kernel; sdb_integrate_segment)."""
+    strat = scheme in ("heun", "srs2")
+    f, G, y0 = (sdb.ops.sys_lin(20, 20) if name == "lin20" else SYSTEMS[name](strat))
+    tspan = np.linspace(0.0, 0.2, 41)
+    h = (tspan[-1] - tspan[0]) / 40
+    kw = dict(paths=70, seed=99, path_id0=6)
+    if scheme == "sri2":
+        call = lambda ts, **k: sdb.itoSRI2(f, G, y0, ts, **kw, **k)
+    elif scheme == "sri2wik":
+        call = lambda ts, **k: sdb.itoSRI2(f, G, y0, ts, sdb.Iwik, **kw, **k)
+    elif scheme == "srs2":
+        call = lambda ts, **k: sdb.stratSRS2(f, G, y0, ts, sdb.Jwik, **kw, **k)
+    elif scheme == "heun":
+        call = lambda ts, **k: sdb.stratHeun(f, G, y0, ts, **kw, **k)
+    else:
+        call = lambda ts, **k: sdb.itoEuler(f, G, y0, ts, **kw, **k)
+    whole = call(tspan)
+    cut = 17
+    first = call(tspan[:cut + 1], h_noise=h)
+    assert np.array_equal(first, whole[:, :cut + 1])
+    second = call(tspan[cut:], y0_paths=first[:, -1], step0=cut, h_noise=h)
+    assert np.array_equal(second, whole[:, cut:])
+    assert not np.array_equal(call(tspan[cut:], y0_paths=first[:, -1], h_noise=h), whole[:, cut:])
+
+
+def test_resume_argument_checks(sdb):
+    f, G, y0 = SYSTEMS["r74"](True)
+    tspan = np.linspace(0.0, 0.1, 21)
+    with pytest.raises(sdb.SDEValueError):
+        sdb.stratKP2iS(f, G, y0, tspan, step0=3)
+    with pytest.raises(sdb.SDEValueError):
+        sdb.stratSRS2(f, G, y0, tspan, step0=-1)
+    with pytest.raises(sdb.SDEValueError):
+        sdb.stratSRS2(f, G, y0, tspan, dW=np.zeros((20, 4)), step0=2)      # J would be drawn from step 0
+
+
 def test_device_resident_noise_tensors(sdb):
     """dW / I handed over as torch tensors already on the GPU are used in place (no host round
     trip) and give the same bits as the numpy arrays of the reference's call."""
