@@ -147,6 +147,51 @@ def periodogram(y_dev, comp, dt, first=0, paths=None, group=None):
     return np.arange(n // 2 + 1) / (n * float(dt)), S
 
 
+def checkpointed(integrator, f, G, y0, tspan, *, paths, seed, segment, checkpoint, on_segment=None,
+                 **kw):
+    """Integrate a long run in time segments of `segment` intervals with a checkpoint after each, and
+    resume from the checkpoint file if there is one -- same final states, bit for bit, as one call
+    (the noise depends only on (seed, path id, step counter); see `step0=` in sdeint_b200.integrate).
+
+    integrator   itoEuler / stratHeun / itoSRI2 / stratSRS2 / itoint / stratint (not the two-step KP2iS)
+    checkpoint   path of an .npz file holding (step, states, seed, paths, grid fingerprint); written
+                 atomically after every segment, read on entry when it exists and matches
+    on_segment   optional callback(step_done, states_dev (paths, d) device view) after each segment,
+                 e.g. to accumulate statistics (`moments`) without storing trajectories
+    Returns the final states as a numpy array (paths, d)."""
+    import os
+    torch = dev.torch_mod()
+    tspan = np.asarray(tspan, dtype=np.float64)
+    n_int = len(tspan) - 1
+    segment = int(segment)
+    if segment < 1:
+        raise ValueError("checkpointed: segment must be >= 1")
+    h = (tspan[-1] - tspan[0]) / n_int
+    finger = np.array([tspan[0], tspan[-1], float(n_int)])
+    step, states = 0, None
+    if os.path.exists(checkpoint):
+        with np.load(checkpoint) as ck:
+            if (int(ck["seed"]) == int(seed) and int(ck["paths"]) == int(paths)
+                    and np.array_equal(ck["grid"], finger)):
+                step, states = int(ck["step"]), ck["states"]
+    opts = dict(kw)
+    opts.update(paths=paths, seed=seed, out="torch", h_noise=h)
+    cur = None if states is None else dev.to_device(np.ascontiguousarray(states), dev.require_cuda(kw.get("device")))
+    while step < n_int:
+        stop = min(step + segment, n_int)
+        y = integrator(f, G, y0, tspan[step:stop + 1], save_every=stop - step, step0=step,
+                       y0_paths=cur, **opts)                     # (2, d, P) on the device
+        cur = y[-1].T                                            # (P, d) view, no copy
+        step = stop
+        if on_segment is not None:
+            on_segment(step, cur)
+        tmp = checkpoint + ".tmp.npz"
+        np.savez(tmp, step=step, states=cur.contiguous().cpu().numpy(), seed=int(seed), paths=int(paths),
+                 grid=finger)
+        os.replace(tmp, checkpoint)
+    return cur.contiguous().cpu().numpy() if cur is not None else np.asarray(states)
+
+
 def allreduce_moments(sums, counts=None, group=None, deterministic=False):
     """Sum the per-rank partials over all ranks (torch.distributed; NCCL on GPUs), in place.
 

@@ -269,7 +269,15 @@ def _run(scheme, f, G, y0, tspan, dW, IJ, strat, method, generator, kp2is, paths
                 a.IJ_stride_path, a.IJ_stride_step = ij_path, m * m
                 a.IJ_stride_row, a.IJ_stride_col = m, 1
         # --- state --------------------------------------------------------------------
-        if y0_paths is not None:
+        if isinstance(y0_paths, torch.Tensor):
+            # a device tensor is used in place through its strides: `y[-1].T` of an out="torch" result
+            # (path-minor storage) continues a run without a copy
+            if tuple(y0_paths.shape) != (P, d) or y0_paths.dtype != torch.float64:
+                raise SDEValueError('y0_paths must be float64 of shape (paths, d)')
+            d_y0 = y0_paths.to(device)
+            a.flags = 0
+            a.y0_stride_path, a.y0_stride_comp = d_y0.stride(0), d_y0.stride(1)
+        elif y0_paths is not None:
             y0p = np.asarray(y0_paths, dtype=np.float64)
             if y0p.shape != (P, d):
                 raise SDEValueError('y0_paths must have shape (paths, d)')

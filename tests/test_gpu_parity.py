@@ -903,6 +903,41 @@ def test_resumed_segments_are_bit_identical(sdb, name, scheme):
     assert not np.array_equal(call(tspan[cut:], y0_paths=first[:, -1], h_noise=h), whole[:, cut:])
 
 
+def test_checkpointed_run_resumes_bit_for_bit(sdb, tmp_path):
+    """ensemble.checkpointed: a run in segments with a checkpoint file after each; killing it and
+    calling it again continues from the file -- final states identical to one uninterrupted call."""
+    f, G, y0 = SYSTEMS["lin10"](False)
+    tspan = np.linspace(0.0, 0.3, 61)
+    P, seed = 500, 4321
+    whole = sdb.itoSRI2(f, G, y0, tspan, paths=P, seed=seed, save_every=60)[:, -1]
+    ck = str(tmp_path / "run.npz")
+    seen = []
+
+    class Stop(Exception):
+        pass
+
+    def crash_after_two(step, states):
+        seen.append(step)
+        if len(seen) == 2:
+            raise Stop()                      # the checkpoint of segment 2 is NOT written
+
+    with pytest.raises(Stop):
+        sdb.ensemble.checkpointed(sdb.itoSRI2, f, G, y0, tspan, paths=P, seed=seed, segment=16,
+                                  checkpoint=ck, on_segment=crash_after_two)
+    assert seen == [16, 32] and int(np.load(ck)["step"]) == 16
+    seen.clear()
+    final = sdb.ensemble.checkpointed(sdb.itoSRI2, f, G, y0, tspan, paths=P, seed=seed, segment=16,
+                                      checkpoint=ck, on_segment=lambda s_, y_: seen.append(s_))
+    assert seen == [32, 48, 60] and np.array_equal(final, whole)
+    # a finished run returns its states without integrating again; another seed ignores the file
+    n0 = sdb.launch_count()
+    again = sdb.ensemble.checkpointed(sdb.itoSRI2, f, G, y0, tspan, paths=P, seed=seed, segment=16, checkpoint=ck)
+    assert sdb.launch_count() == n0 and np.array_equal(again, whole)
+    other = sdb.ensemble.checkpointed(sdb.itoSRI2, f, G, y0, tspan, paths=P, seed=seed + 1, segment=30,
+                                      checkpoint=ck)
+    assert not np.array_equal(other, whole)
+
+
 def test_resume_argument_checks(sdb):
     f, G, y0 = SYSTEMS["r74"](True)
     tspan = np.linspace(0.0, 0.1, 21)
