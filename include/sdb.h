@@ -155,6 +155,11 @@ typedef struct sdb_integrate_ext {
 } sdb_integrate_ext;
 int sdb_integrate_segment(sdb_system* sys, const sdb_integrate_args* args, const sdb_integrate_ext* ext);
 
+/* Name of the kernel the last sdb_integrate* call of this thread launched: an ahead-of-time kernel's
+ * symbol (e.g. "sdbk_fused_srk2_d10_m10_v0") or "jit:<cache key>" for an NVRTC-built one.  With the
+ * environment variable SDB_TRACE set, every dispatch is also logged to stderr. */
+const char* sdb_last_kernel(void);
+
 /* deltaW (wiener.py:36-52) for P paths: out[step][comp][path] through strides. */
 int sdb_delta_w(int64_t steps, int m, double h, int64_t paths, int64_t path_id0, uint64_t seed,
                 double* d_out, int64_t stride_step, int64_t stride_comp, int64_t stride_path,

@@ -63,6 +63,7 @@ class IntegrateExt(C.Structure):
 SIGNATURES = {
     "sdb_last_error": (C.c_char_p, []),
     "sdb_version": (C.c_int, []),
+    "sdb_last_kernel": (C.c_char_p, []),
     "sdb_launch_count": (c_u64, []),
     "sdb_system_builtin": (C.c_int, [C.c_int, c_dp, c_i64, C.c_int, c_dp, c_i64, C.c_int, C.c_int,
                                      C.POINTER(C.c_void_p)]),
@@ -119,3 +120,9 @@ def check(rc):
 
 def launch_count():
     return int(load().sdb_launch_count())
+
+
+def last_kernel():
+    """Name of the kernel the last integrator call of this thread launched (include/sdb.h:
+    sdb_last_kernel): an ahead-of-time kernel's symbol or "jit:<key>"."""
+    return load().sdb_last_kernel().decode()

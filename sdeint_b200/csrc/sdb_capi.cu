@@ -27,6 +27,7 @@
 // errors, counters
 // ---------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
+static thread_local std::string g_last_kernel;  // which kernel the last sdb_integrate of this thread launched
 static std::atomic<uint64_t> g_launches{0};
 
 static int fail(const std::string& msg) {
@@ -321,12 +322,23 @@ static const char* ext_defines(int ext) {
   return ext == 2 ? "#define SDB_OBSERVE 1\n#define SDB_RESUME 1\n" : ext == 1 ? "#define SDB_RESUME 1\n" : "";
 }
 
-static int loop_kernel(sdb_system* s, int scheme, int noise, const void** fn, int ext = 0) {
+static std::string aot_name(const void* fn) {
+  const char* name = nullptr;
+  if (cudaFuncGetName(&name, fn) != cudaSuccess || !name) { cudaGetLastError(); return "aot:?"; }
+  return name;
+}
+
+static int loop_kernel(sdb_system* s, int scheme, int noise, const void** fn, int ext = 0,
+                       std::string* label = nullptr) {
   std::string key = sdb_loop_key(scheme, s->fk, s->gk, s->d, s->m, noise, s->inline_params);
   const bool user_g = s->gk == SDB_DIFF_USER || s->gk == SDB_DIFF_USER_DIAG;
   const bool user = s->fk == SDB_DRIFT_USER || user_g;
   if (!user && !ext) {
-    if (const void* f = aot_lookup(key)) { *fn = f; return 0; }
+    if (const void* f = aot_lookup(key)) {
+      *fn = f;
+      if (label) *label = aot_name(f);
+      return 0;
+    }
   }
   key += ext_suffix(ext);  // the observing / resumable variant of every kernel is compiled at run time
   std::lock_guard<std::mutex> lk(s->mu);
@@ -346,8 +358,11 @@ static int loop_kernel(sdb_system* s, int scheme, int noise, const void** fn, in
     it = s->jit.emplace(key, k).first;
   }
   *fn = (const void*)it->second.kern;
+  if (label) *label = "jit:" + key;
   return 0;
 }
+
+extern "C" const char* sdb_last_kernel(void) { return g_last_kernel.c_str(); }
 
 // ---------------------------------------------------------------------------------------------
 // sdb_integrate
@@ -443,6 +458,7 @@ static int integrate_impl(sdb_system* s, const sdb_integrate_args* a, const SdbO
   SdbFusedEntry jit_entry{};
   int jit_rb = 4;
   bool jit_comm = false;
+  std::string label;  // what gets launched (sdb_last_kernel): an ahead-of-time kernel's name or "jit:<key>"
   const bool explicit_em = a->scheme == SDB_SCHEME_EULER || a->scheme == SDB_SCHEME_HEUN;
   // Commutative-noise integrals on a linear system: the dedicated kernel (sdb_fusedc.cuh) -- stage-2 sum
   // as W (W y) / 2 - (h/2) S y, no per-path products with I at all; (10,10) ahead of time, else NVRTC.
@@ -470,6 +486,7 @@ static int integrate_impl(sdb_system* s, const sdb_integrate_args* a, const SdbO
                                 SDB_NOISE_COMM, SDB_SCHEME_SRK2};
       jit_comm = true;
       fused = &jit_entry;
+      label = "jit:" + key;
     }
   }
   if (!fused && (a->scheme == SDB_SCHEME_SRK2 || explicit_em) && noise != SDB_NOISE_HOST &&
@@ -510,6 +527,7 @@ static int integrate_impl(sdb_system* s, const sdb_integrate_args* a, const SdbO
                               edims.sh.table_doubles(), nullptr, edims.threads(), edims.threads(),
                               SDB_NOISE_KPW, a->scheme};
     fused = &jit_entry;
+    label = "jit:" + key;
   }
   if (!fused && a->scheme == SDB_SCHEME_SRK2 && noise != SDB_NOISE_HOST &&
       s->fk == SDB_DRIFT_LINEAR && s->gk == SDB_DIFF_LINEAR_COLS &&
@@ -556,6 +574,7 @@ static int integrate_impl(sdb_system* s, const sdb_integrate_args* a, const SdbO
                                   use_x2 ? x2dims.paths_per_block() : xdims.threads(), noise, SDB_SCHEME_SRK2};
       }
       fused = &jit_entry;
+      label = "jit:" + key;
     }
   }
   const void* fn = nullptr;
@@ -576,9 +595,14 @@ static int integrate_impl(sdb_system* s, const sdb_integrate_args* a, const SdbO
       it = s->d_frags.emplace(fn, d).first;
     }
     d_frag = it->second;
-  } else if (loop_kernel(s, a->scheme, noise, &fn, ext)) {
+  } else if (loop_kernel(s, a->scheme, noise, &fn, ext, &label)) {
     return 1;
   }
+  if (fused && label.empty()) label = aot_name(fn);
+  g_last_kernel = label;
+  if (getenv("SDB_TRACE"))
+    fprintf(stderr, "sdb_integrate: scheme=%d d=%d m=%d noise=%d n_terms=%d paths=%lld steps=%d -> %s\n",
+            a->scheme, s->d, s->m, a->noise, n_terms, (long long)a->paths, a->N - 1, label.c_str());
 
   // tspan, the per-step h = t[n+1]-t[n] with its square root and reciprocal root (uniform over
   // paths, so computed once here with IEEE sqrt / division) and the KP2iS coefficients go to

@@ -949,6 +949,48 @@ def test_resume_argument_checks(sdb):
         sdb.stratSRS2(f, G, y0, tspan, dW=np.zeros((20, 4)), step0=2)      # J would be drawn from step 0
 
 
+def test_dispatch_launches_the_documented_kernels(sdb, monkeypatch):
+    """sdb_last_kernel(): every route of DESIGN.md section 4 ends in the kernel it names -- no silent
+    fall-back to the generic loop (ahead-of-time kernels by symbol, NVRTC-built ones by cache key)."""
+    ts = np.linspace(0.0, 0.01, 11)
+    kw = dict(paths=64, seed=1)
+
+    def ran(fn, *a, **k):
+        fn(*a, **k)
+        return sdb.last_kernel()
+
+    f, G, y0 = sdb.ops.sys_lin(10, 10)
+    assert ran(sdb.itoSRI2, f, G, y0, ts, **kw) == "sdbk_fused_srk2_d10_m10_v0"
+    assert ran(sdb.itoSRI2, f, G, y0, ts, sdb.Iwik, **kw) == "sdbk_fusedx_srk2_d10_m10_wik"
+    assert ran(sdb.stratHeun, f, G, y0, ts, **kw) == "sdbk_fusedeh_heun_d10_m10"
+    assert ran(sdb.itoEuler, f, G, y0, ts, **kw) == "sdbk_fusedeh_euler_d10_m10"
+    assert ran(sdb.itoSRI2, f, G, y0, ts, observe=[("max", 0)], **kw) == "jit:fusedjit|obs"
+    assert ran(sdb.itoSRI2, f, G, y0, ts, step0=3, **kw) == "jit:fusedjit|res"
+    assert ran(sdb.itoSRI2, f, G, y0, ts, dW=np.zeros((10, 10)), I=np.zeros((10, 10, 10))) == "sdbk_lin10_s2_n0"
+    monkeypatch.setenv("SDB_DISABLE_FUSED", "1")
+    assert ran(sdb.itoSRI2, f, G, y0, ts, **kw) == "sdbk_lin10_s2_n1"
+    monkeypatch.delenv("SDB_DISABLE_FUSED")
+    f, G, y0 = sdb.ops.sys_lin(20, 20)
+    assert ran(sdb.stratSRS2, f, G, y0, ts, sdb.Jwik, **kw) == "sdbk_fusedx2_srk2_d20_m20_wik"
+    assert ran(sdb.stratSRS2, f, G, y0, ts, **kw) == "sdbk_fusedx2_srk2_d20_m20_kpw"
+    monkeypatch.setenv("SDB_FUSED_VARIANT", "20")
+    assert ran(sdb.stratSRS2, f, G, y0, ts, sdb.Jwik, **kw) == "sdbk_fusedx_srk2_d20_m20_wik"
+    monkeypatch.delenv("SDB_FUSED_VARIANT")
+    f, G, y0 = SYSTEMS["r74"](False)
+    assert ran(sdb.itoSRI2, f, G, y0, ts, **kw) == "jit:fusedcjit"                       # commuting B_k
+    assert ran(sdb.itoSRI2, f, G, y0, ts, commutative=False, **kw) == "sdbk_fused_srk2_d5_m4_v0"
+    f, G, y0 = _commuting_system(10, 10)
+    assert ran(sdb.itoSRI2, f, G, y0, ts, **kw) == "sdbk_fusedc_srk2_d10_m10"
+    f, G, y0 = sdb.ops.sys_lin(8, 16)
+    assert ran(sdb.itoSRI2, f, G, y0, ts, sdb.Iwik, **kw) == "jit:fusedxjit|wik|x2"      # two lanes per path
+    f, G, y0 = sdb.ops.sys_lin(6, 4)
+    assert ran(sdb.itoSRI2, f, G, y0, ts, **kw) == "jit:fusedjit"
+    f, G, y0 = SYSTEMS["lin2"](False)
+    assert ran(sdb.itoEuler, f, G, y0, ts, **kw) == "sdbk_lin2_s0_n1"
+    fX, GX = sdb.ops.ExprDrift(["-y[0]"], []), sdb.ops.ExprDiffusion([["0.1*y[0]"]], [])
+    assert ran(sdb.itoint, fX, GX, [1.0], ts, **kw).startswith("jit:loop|s2|f9|g9|d1|m1")
+
+
 def test_device_resident_noise_tensors(sdb):
     """dW / I handed over as torch tensors already on the GPU are used in place (no host round
     trip) and give the same bits as the numpy arrays of the reference's call."""
