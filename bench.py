@@ -226,6 +226,7 @@ def run_gpu(args):
         y = sdb.itoSRI2(f, G, y0, tspan, paths=P, seed=SEED, path_id0=path_id0,
                         save_every=SAVE_EVERY, out="torch")
         k1[i].record()                       # brackets the integrator launch (dominant kernel)
+        kernel_symbol = sdb.last_kernel()    # what sdb_integrate dispatched to (include/sdb.h)
         sums, counts = sdb.ensemble.moments(y, hist=HIST)
         sdb.ensemble.allreduce_moments(sums, counts)
     e1.record()
@@ -299,6 +300,7 @@ def run_gpu(args):
                            "nominal 37.2",
             "peak_sustained": float(peak_sus.value),
             "kernel": "sdb fused SRI2 step loop (one launch per step)",
+            "kernel_symbol": kernel_symbol,
             "kernel_ms": ms_kernel,
             "flops_per_path_step": FLOPS_PER_PATH_STEP,
             "flops_note": "executed flop: SURVEY 8d count 10280 minus 2md^2+2dm=2200 for the "
