@@ -160,6 +160,15 @@ for r in range(world):
     part = y[:, :, s0:s0 + c0]
     parts.append(np.stack([part.sum(-1), (part * part).sum(-1)], axis=-1))
 assert np.array_equal(mine2.numpy(), parts[0] + parts[1]), rank
+# autocovariance across saved times and the ensemble periodogram combine ranks through their raw sums
+yt = torch.from_numpy(np.ascontiguousarray(mine))
+C = sdb.ensemble.autocovariance(yt, 1, paths=P)
+full = y[:, 1, :] - y[:, 1, :].mean(-1, keepdims=True)
+assert np.allclose(C, full @ full.T / P, rtol=1e-12, atol=1e-14), rank
+freqs, S_ = sdb.ensemble.periodogram(yt, 0, 0.1, paths=P)
+x0 = y[:, 0, :] - y[:, 0, :].mean(0, keepdims=True)
+want_S = (np.abs(np.fft.rfft(x0, axis=0)) ** 2).sum(-1) * 0.1 / S / P
+assert np.allclose(S_, want_S, rtol=1e-12, atol=1e-15) and freqs.shape == (S // 2 + 1,), rank
 dist.destroy_process_group()
 print("rank", rank, "ok")
 ''' % ROOT)
