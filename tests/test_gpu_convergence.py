@@ -125,6 +125,42 @@ def test_weak_mean_of_headline_system(sdb):
     assert np.all(var > 0)
 
 
+@pytest.mark.parametrize("which", ["lin20_strat_wik", "lin20_ito_kpw", "commuting10_ito", "commuting10_strat"])
+def test_weak_mean_of_large_and_commutative_kernels(sdb, which):
+    """The ensemble mean of the kernels beside the headline one -- two lanes per path at d = m = 20
+    (sdb_fusedx2.cuh), the commutative-noise kernel (sdb_fusedc.cuh) -- against the exact mean of the
+    linear SDE: E y(T) = expm(A T) y0 (Ito), expm((A + sum B_k^2 / 2) T) y0 (Stratonovich)."""
+    from scipy.linalg import expm
+    if which.startswith("lin20"):
+        f, G, y0 = sdb.ops.sys_lin(20, 20)
+        want_kernel = "sdbk_fusedx2_srk2_d20_m20_" + ("wik" if which.endswith("wik") else "kpw")
+    else:
+        rng = np.random.default_rng(3)
+        Cm = rng.standard_normal((10, 10)) / np.sqrt(10)
+        B = np.stack([(0.6 / np.sqrt(10)) * ((1.0 + 0.1 * k) * np.eye(10) + 0.5 * Cm) for k in range(10)])
+        A = np.full((10, 10), 0.05)
+        np.fill_diagonal(A, -1.5)
+        f, G, y0 = sdb.ops.LinearDrift(A), sdb.ops.LinearDiffusion(B), np.ones(10)
+        want_kernel = "sdbk_fusedc_srk2_d10_m10"
+    strat = "strat" in which
+    T, n, P = 0.5, 100, 100000
+    tspan = np.linspace(0.0, T, n + 1)
+    if strat:
+        y = sdb.stratSRS2(f, G, y0, tspan, sdb.Jwik if which.endswith("wik") else sdb.Jkpw,
+                          paths=P, seed=21, save_every=n, out="torch")
+    else:
+        y = sdb.itoSRI2(f, G, y0, tspan, paths=P, seed=21, save_every=n, out="torch")
+    assert sdb.last_kernel() == want_kernel
+    sums, _ = sdb.ensemble.moments(y)
+    mean, var = sdb.ensemble.mean_var(sums, float(P))
+    mean, var = mean[-1].cpu().numpy(), var[-1].cpu().numpy()
+    Aeff = f.A + (0.5 * sum(Bk @ Bk for Bk in G.B) if strat else 0.0)
+    want = expm(Aeff * T).dot(y0)
+    tol = 5.0 * np.sqrt(var / P) + 3e-4
+    assert np.all(np.abs(mean - want) <= tol), (np.abs(mean - want).max(), tol.min())
+    assert np.all(var > 0)
+
+
 def test_second_moments_of_headline_system(sdb):
     """E[y y^T](T) of the linear Ito system solves dP/dt = A P + P A^T + sum_k B_k P B_k^T; the
     ensemble second moments (sum y^2 from the moments kernel) of 2e5 fused-kernel paths must agree
