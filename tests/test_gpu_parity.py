@@ -1136,6 +1136,42 @@ def test_fused_euler_heun_linear(sdb, d, m, monkeypatch):
         assert np.array_equal(yd, y[:, ::7])
 
 
+def test_mid_size_nonlinear_user_system(sdb):
+    """A d = 7, m = 5 nonlinear, non-commutative, time-dependent system from formulas (the generic
+    thread-per-path kernels built by NVRTC, G_n and I beyond the register file): every scheme against the
+    oracle on the same noise, host-supplied and device-drawn."""
+    d, m = 7, 5
+    drift = ["-1.2*y[%d] + 0.3*sin(y[%d]) + 0.1*y[%d]*y[%d]/(1.0+y[%d]*y[%d]) + 0.05*cos(t)"
+             % (i, (i + 1) % d, (i + 2) % d, (i + 3) % d, (i + 2) % d, (i + 2) % d) for i in range(d)]
+    rows = [["%g*(%s)" % (0.08 + 0.01 * ((3 * i + k) % 5),
+                          ["y[%d]" % ((i + k) % d), "sin(y[%d])+0.5" % ((i + 2 * k) % d),
+                           "1.0+0.2*y[%d]*y[%d]" % (i, (k + 1) % d), "cos(y[%d]+t)" % ((i + k + 3) % d),
+                           "0.3+tanh(y[%d])" % ((2 * i + k) % d)][(i + k) % 5])
+             for k in range(m)] for i in range(d)]
+    f, G = sdb.ops.ExprDrift(drift, []), sdb.ops.ExprDiffusion(rows, [])
+    y0 = 0.5 + 0.1 * np.arange(d)
+    tspan = np.linspace(0.0, 0.25, 101)
+    h = 0.0025
+    rng = np.random.default_rng(77)
+    dW = orc.delta_w(100, m, h, rng)
+    _, I = orc.ikpw(dW, h, generator=rng)
+    _, J = orc.jwik(dW, h, generator=rng)
+    assert rel_err(sdb.itoEuler(f, G, y0, tspan, dW=dW), orc.euler(f, G, y0, tspan, dW)) <= TOL
+    assert rel_err(sdb.stratHeun(f, G, y0, tspan, dW=dW), orc.heun(f, G, y0, tspan, dW)) <= TOL
+    assert rel_err(sdb.itoSRI2(f, G, y0, tspan, dW=dW, I=I), orc.srk2(f, G, y0, tspan, dW, I)) <= TOL
+    assert rel_err(sdb.stratSRS2(f, G, y0, tspan, dW=dW, J=J), orc.srk2(f, G, y0, tspan, dW, J)) <= TOL
+    yk = sdb.stratKP2iS(f, G, y0, tspan, dW=dW, J=J, rtol=1e-12)
+    assert rel_err(yk, orc.kp2is(f, G, y0, tspan, dW, J, rtol=1e-13, solver="newton")) <= 1e-9
+    P, seed = 40, 15
+    for meth, integ, strat in ((sdb.Iwik, sdb.itoSRI2, False), (sdb.Jkpw, sdb.stratSRS2, True)):
+        y = integ(f, G, y0, tspan, meth, paths=P, seed=seed)
+        assert sdb.last_kernel().startswith("jit:loop|s2|f9|g9|d7|m5")
+        dWd = sdb.deltaW(100, m, h, paths=P, seed=seed)
+        _, IJd = meth(dWd, h, seed=seed, ensemble=True)
+        for p in (0, P - 1):
+            assert rel_err(y[p], orc.srk2(f, G, y0, tspan, dWd[p], IJd[p])) <= TOL
+
+
 def test_expression_operators_all_integrators(sdb):
     """f and G given as formulas (ops.ExprDrift / ExprDiffusion -> NVRTC): every integrator against the
     oracle running the SAME formulas as numpy callables; time-dependent, non-commutative noise."""
