@@ -151,7 +151,34 @@ struct JitKernel {
   cudaKernel_t kern = nullptr;
 };
 
-static int jit_compile(const std::string& source, const char* kernel_name, JitKernel* out) {
+// Bytes of machine code in a cubin: the sum of its .text.* sections (ELF64; -lineinfo makes the file
+// size useless as a measure).
+static size_t cubin_text_bytes(const std::vector<char>& elf) {
+  struct Ehdr { unsigned char ident[16]; uint16_t type, machine; uint32_t version; uint64_t entry, phoff, shoff;
+                uint32_t flags; uint16_t ehsize, phentsize, phnum, shentsize, shnum, shstrndx; };
+  struct Shdr { uint32_t name, type; uint64_t flags, addr, offset, size; uint32_t link, info;
+                uint64_t addralign, entsize; };
+  if (elf.size() < sizeof(Ehdr)) return 0;
+  Ehdr eh;
+  memcpy(&eh, elf.data(), sizeof eh);
+  if (memcmp(eh.ident, "\177ELF", 4) != 0 || eh.shentsize != sizeof(Shdr) ||
+      eh.shoff + (uint64_t)eh.shnum * sizeof(Shdr) > elf.size() || eh.shstrndx >= eh.shnum)
+    return 0;
+  std::vector<Shdr> sh(eh.shnum);
+  memcpy(sh.data(), elf.data() + eh.shoff, sh.size() * sizeof(Shdr));
+  const Shdr& str = sh[eh.shstrndx];
+  if (str.offset + str.size > elf.size()) return 0;
+  size_t total = 0;
+  for (const Shdr& x : sh) {
+    if (x.name >= str.size) continue;
+    const char* nm = elf.data() + str.offset + x.name;
+    if (strncmp(nm, ".text.", 6) == 0) total += (size_t)x.size;
+  }
+  return total;
+}
+
+static int jit_compile(const std::string& source, const char* kernel_name, JitKernel* out,
+                       size_t* text_bytes = nullptr) {
   Nvrtc* rt;
   if (nvrtc_load(&rt)) return 1;
   nvrtcProgram prog;
@@ -180,6 +207,7 @@ static int jit_compile(const std::string& source, const char* kernel_name, JitKe
   std::vector<char> cubin(sz);
   rt->GetCUBIN(prog, cubin.data());
   rt->DestroyProgram(&prog);
+  if (text_bytes) *text_bytes = cubin_text_bytes(cubin);
   SDB_CUDA(cudaLibraryLoadData(&out->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
   SDB_CUDA(cudaLibraryGetKernel(&out->kern, out->lib, kernel_name));
   return 0;
@@ -344,17 +372,33 @@ static int loop_kernel(sdb_system* s, int scheme, int noise, const void** fn, in
   std::lock_guard<std::mutex> lk(s->mu);
   auto it = s->jit.find(key);
   if (it == s->jit.end()) {
-    std::ostringstream src;
-    src << ext_defines(ext);
-    if (s->fk == SDB_DRIFT_USER) src << "#define SDB_USER_DRIFT 1\n";
-    if (user_g) src << "#define SDB_USER_DIFF 1\n";
-    src << "#include \"sdb_kernels.cuh\"\n";
-    if (user) src << "#line 1 \"user_source.cu\"\n" << s->src << "\n";
-    src << "typedef " << type_of(s, true) << " F_jit;\n";
-    src << "typedef " << type_of(s, false) << " G_jit;\n";
-    src << "SDB_LOOP_KERNEL(sdb_jit_loop, " << scheme << ", F_jit, G_jit, " << noise << ")\n";
+    // Small systems get their column loops unrolled (sdb_loop_body: SMALL).  When the user's code is
+    // heavy that multiplies it: a kernel of 150 KB at 8 warps per SM is instruction-fetch bound (ncu:
+    // no_instruction the top stall; +20 % from rolling the loops at d=7, m=5 with libm calls, -4 % for a
+    // cheap d=m=3 system, -25 % for Euler).  So: build unrolled, and rebuild rolled only if the machine
+    // code comes out larger than 100 KB.
+    const char* lim = getenv("SDB_SMALL_LIMIT");
     JitKernel k;
-    if (jit_compile(src.str(), "sdb_jit_loop", &k)) return 1;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      std::ostringstream src;
+      src << ext_defines(ext);
+      if (lim) src << "#define SDB_SMALL_LIMIT " << atoi(lim) << "\n";
+      else if (attempt == 1) src << "#define SDB_SMALL_LIMIT 0\n";
+      if (s->fk == SDB_DRIFT_USER) src << "#define SDB_USER_DRIFT 1\n";
+      if (user_g) src << "#define SDB_USER_DIFF 1\n";
+      src << "#include \"sdb_kernels.cuh\"\n";
+      if (user) src << "#line 1 \"user_source.cu\"\n" << s->src << "\n";
+      src << "typedef " << type_of(s, true) << " F_jit;\n";
+      src << "typedef " << type_of(s, false) << " G_jit;\n";
+      src << "SDB_LOOP_KERNEL(sdb_jit_loop, " << scheme << ", F_jit, G_jit, " << noise << ")\n";
+      size_t bytes = 0;
+      JitKernel cand;
+      if (jit_compile(src.str(), "sdb_jit_loop", &cand, &bytes)) return 1;
+      if (attempt == 1) cudaLibraryUnload(k.lib);  // the unrolled build is dropped
+      k = cand;
+      // (Euler / Heun evaluate G once or twice per step and stay faster unrolled: 3.6e9 vs 3.1e9)
+      if (lim || !user || s->d * s->m > 36 || scheme < SDB_SCHEME_SRK2 || bytes <= 100u * 1024u) break;
+    }
     it = s->jit.emplace(key, k).first;
   }
   *fn = (const void*)it->second.kern;

@@ -736,7 +736,13 @@ SDB_DEV void sdb_loop_body(const SdbLoopArgs& a, const typename F::Params& fp,
   constexpr int D = G::D;
   constexpr int M = G::M;
   static_assert(F::D == G::D, "drift and diffusion disagree on d");
-  constexpr bool SMALL = (D * M <= 36);
+  // Column loops are unrolled for small systems (column index known at compile time: structural zeros
+  // of G vanish).  SDB_SMALL_LIMIT lets the NVRTC path switch that off for user systems whose G is
+  // expensive (every unrolled copy inlines the user's code again).
+#ifndef SDB_SMALL_LIMIT
+#define SDB_SMALL_LIMIT 36
+#endif
+  constexpr bool SMALL = (D * M <= SDB_SMALL_LIMIT);
   // Additive noise (G independent of y): the stage-2 differences g_k(H2) - g_k(H3) of SRK2 and the
   // G(Ybar) - G_n of KP2iS are exactly zero, so the repeated integrals are never used and are neither
   // generated nor read (bit-identical results; the first step of the reference's planned
