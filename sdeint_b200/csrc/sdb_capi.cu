@@ -382,8 +382,15 @@ static int loop_kernel(sdb_system* s, int scheme, int noise, const void** fn, in
     for (int attempt = 0; attempt < 2; ++attempt) {
       std::ostringstream src;
       src << ext_defines(ext);
+      const char* mb = getenv("SDB_LOOP_MINBLOCKS");
+      if (mb) src << "#define SDB_LOOP_MINBLOCKS " << atoi(mb) << "\n";
       if (lim) src << "#define SDB_SMALL_LIMIT " << atoi(lim) << "\n";
-      else if (attempt == 1) src << "#define SDB_SMALL_LIMIT 0\n";
+      else if (attempt == 1) {
+        // rolled loops need fewer registers: cap them at 168 for 12 warps per SM instead of 8
+        // (d=7, m=5 with libm calls: Ikpw +5 %, Iwik +36 %)
+        src << "#define SDB_SMALL_LIMIT 0\n";
+        if (!mb) src << "#define SDB_LOOP_MINBLOCKS 3\n";
+      }
       if (s->fk == SDB_DRIFT_USER) src << "#define SDB_USER_DRIFT 1\n";
       if (user_g) src << "#define SDB_USER_DIFF 1\n";
       src << "#include \"sdb_kernels.cuh\"\n";

@@ -994,8 +994,12 @@ SDB_DEV void sdb_loop_body(const SdbLoopArgs& a, const typename F::Params& fp,
   }
 }
 
+// SDB_LOOP_MINBLOCKS (NVRTC builds): minimum resident blocks per SM, i.e. a register cap.
+#ifndef SDB_LOOP_MINBLOCKS
+#define SDB_LOOP_MINBLOCKS 1
+#endif
 #define SDB_LOOP_KERNEL(NAME, SCHEME, F, G, NOISE)                                              \
-  extern "C" __global__ void __launch_bounds__(SDB_BLOCK)                                       \
+  extern "C" __global__ void __launch_bounds__(SDB_BLOCK, SDB_LOOP_MINBLOCKS)                   \
       NAME(const __grid_constant__ SdbLoopArgs a, const __grid_constant__ F::Params fp,         \
            const __grid_constant__ G::Params gp) {                                              \
     sdb_loop_body<SCHEME, F, G, NOISE>(a, fp, gp);                                              \
