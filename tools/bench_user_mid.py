@@ -1,7 +1,7 @@
 """Throughput of the generic (thread-per-path, NVRTC-built) kernels on a mid-size NONLINEAR system
 given as formulas: d = 7, m = 5, non-commutative, time-dependent (the system of
 tests/test_gpu_parity.py::test_mid_size_nonlinear_user_system).
-    python tools/bench_user_mid.py [paths] [steps]"""
+    python tools/bench_user_mid.py [paths] [steps] [d] [m]"""
 import os
 import sys
 
@@ -13,7 +13,8 @@ import sdeint_b200 as sdb
 
 P = int(float(sys.argv[1])) if len(sys.argv) > 1 else 1000000
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 500
-d, m = 7, 5
+d = int(sys.argv[3]) if len(sys.argv) > 3 else 7
+m = int(sys.argv[4]) if len(sys.argv) > 4 else 5
 drift = ["-1.2*y[%d] + 0.3*sin(y[%d]) + 0.1*y[%d]*y[%d]/(1.0+y[%d]*y[%d]) + 0.05*cos(t)"
          % (i, (i + 1) % d, (i + 2) % d, (i + 3) % d, (i + 2) % d, (i + 2) % d) for i in range(d)]
 rows = [["%g*(%s)" % (0.08 + 0.01 * ((3 * i + k) % 5),
@@ -36,5 +37,5 @@ for name, fn, kw in (("itoSRI2+Ikpw", sdb.itoSRI2, {}), ("itoSRI2+Iwik", sdb.ito
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
         best = ms if best is None else min(best, ms)
-    print("user d=7 m=5 %-13s %d paths x %d steps in %.1f ms -> %.3e path-steps/s  [%s]"
-          % (name, P, T, best, P * T / best * 1e3, sdb.last_kernel()), flush=True)
+    print("user d=%d m=%d %-13s %d paths x %d steps in %.1f ms -> %.3e path-steps/s  [%s]"
+          % (d, m, name, P, T, best, P * T / best * 1e3, sdb.last_kernel()), flush=True)
