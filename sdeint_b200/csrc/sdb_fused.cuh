@@ -523,7 +523,7 @@ struct SdbFusedBlocks<D, M, -1> {
   static SDB_DEV void run(Args&...) {}
 };
 
-template <int D, int M>
+template <int D, int M, int WIK = 0>
 SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * D>& fp,
                                         const double* __restrict__ frag, double* smem) {
   typedef SdbFusedShape<D, M> Sh;
@@ -684,6 +684,51 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
             At[r] = fma(-Z[i], X[j], At[r]);
           }
       }
+      if constexpr (WIK != 0) {
+        // Wiktorsson's tail (wiener.py:269-277) in its O(m^2) form (the arithmetic of
+        // sdb_x_levy_areas in sdb_fusedx.cuh), the areas staying in registers:
+        //   1. A_ij += c1 g_ij,  u_i += g_ij dW_j,  u_j -= g_ij dW_i   (u = G^ dW; g in batches of 5 pairs)
+        //   2. A_ij += c2 (dW_j u_i - dW_i u_j)
+        double u[M];
+        double nrm = 0.0;
+#pragma unroll
+        for (int j = 0; j < M; ++j) {
+          nrm = fma(dW[j], dW[j], nrm);
+          u[j] = 0.0;
+        }
+        const double hgl = a.h_global;
+        const double rad = sqrt(1.0 + nrm / hgl);
+        const double den = hgl * SDB_INV_2PI * sqrt(sdb_a_tail(n_terms)) / (1.4142135623730951 * (1.0 + rad));
+        const double c1 = den * (2.0 + 2.0 * rad);
+        const double c2 = den * (2.0 / hgl);
+        const uint32_t st0 = (uint32_t)((M + 2 * n_terms * M) >> 1);
+        constexpr int NPAIR = (MM + 1) / 2;  // Box-Muller pairs holding the MM tail normals
+        sdb_static_for<0, (NPAIR + 4) / 5>([&](auto bb) {
+          constexpr int b = decltype(bb)::value;
+          constexpr int NBP = NPAIR - 5 * b >= 5 ? 5 : NPAIR - 5 * b;
+          uint32_t w[NBP][4];
+          double g[2 * NBP];
+          sdb_philox_batch<NBP>(pkey, st.p_lo, st.p_hi, SDB_STEP(n), st0 + (uint32_t)(5 * b), w);
+          sdb_normal_batch<NBP, false>(w, tab, 1.0, g);
+          sdb_static_for<0, 2 * NBP>([&](auto ee) {
+            constexpr int e = decltype(ee)::value;
+            constexpr int r = 10 * b + e;
+            if constexpr (r < MM) {
+              constexpr int i = sdb_pair_j<M>(r), j = sdb_pair_k<M>(r);
+              At[r] = fma(c1, g[e], At[r]);
+              u[i] = fma(g[e], dW[j], u[i]);
+              u[j] = fma(-g[e], dW[i], u[j]);
+            }
+          });
+        });
+        sdb_static_for<0, MM>([&](auto rr) {
+          constexpr int r = decltype(rr)::value;
+          constexpr int i = sdb_pair_j<M>(r), j = sdb_pair_k<M>(r);
+          // column-major unvec puts +Atilde BELOW the diagonal (wiener.py:278-280): the stage-2 code
+          // places +A above it (Ikpw, wiener.py:106), hence the sign
+          At[r] = -fma(c2, fma(dW[j], u[i], -dW[i] * u[j]), At[r]);
+        });
+      }
 #pragma unroll
       for (int r = 0; r < MM; ++r) sA[r * NT] = At[r];
 #if !SDB_FUSED_PARK_DW
@@ -778,13 +823,14 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
 }  // namespace SDB_FUSED_NS
 using namespace SDB_FUSED_NS;
 
-#define SDB_FUSED_KERNEL(NAME, D, M)                                                          \
+#define SDB_FUSED_KERNEL_W(NAME, D, M, WIK)                                                   \
   extern "C" __global__ void __launch_bounds__(SDB_FUSED_THREADS, 1)                          \
       NAME(const __grid_constant__ SdbLoopArgs a, const __grid_constant__ PInline<D * D> fp,  \
            const double* __restrict__ frag) {                                                 \
     extern __shared__ __align__(16) double sdb_fused_smem[];                                  \
-    sdb_srk2_fused_linear_body<D, M>(a, fp, frag, sdb_fused_smem);                            \
+    sdb_srk2_fused_linear_body<D, M, WIK>(a, fp, frag, sdb_fused_smem);                       \
   }
+#define SDB_FUSED_KERNEL(NAME, D, M) SDB_FUSED_KERNEL_W(NAME, D, M, 0)
 #endif  // __CUDACC__
 #ifndef __CUDACC__
 }  // namespace SDB_FUSED_NS

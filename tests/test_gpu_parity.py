@@ -419,6 +419,28 @@ def test_fused_tuning_variants_agree(sdb, variant, monkeypatch):
         assert rel_err(alt[p], ref[::5]) <= TOL
 
 
+def test_register_resident_wiktorsson_variant(sdb, monkeypatch):
+    """Iwik/Jwik at d = m = 10 runs the TMEM-resident kernel; the register-resident kernel with
+    Wiktorsson's tail (sdb_fused.cuh WIK, SDB_FUSED_VARIANT=30, kept for A/B: 3 % slower) draws the same
+    noise and agrees with it to rounding and with the oracle to 1e-12."""
+    f, G, y0 = SYSTEMS["lin10"](False)
+    tspan = np.linspace(0.0, 0.1, 21)
+    P, seed = 300, 31
+    base = sdb.itoSRI2(f, G, y0, tspan, sdb.Iwik, paths=P, seed=seed)
+    assert sdb.last_kernel() == "sdbk_fusedx_srk2_d10_m10_wik"
+    monkeypatch.setenv("SDB_FUSED_VARIANT", "30")
+    alt = sdb.itoSRI2(f, G, y0, tspan, sdb.Iwik, paths=P, seed=seed)
+    assert sdb.last_kernel() == "sdbk_fused_srk2_d10_m10_wik"
+    alt_s = sdb.stratSRS2(f, G, y0, tspan, sdb.Jwik, paths=P, seed=seed)
+    monkeypatch.delenv("SDB_FUSED_VARIANT")
+    assert rel_err(alt, base) <= 1e-14
+    assert rel_err(alt_s, sdb.stratSRS2(f, G, y0, tspan, sdb.Jwik, paths=P, seed=seed)) <= 1e-14
+    dW = sdb.deltaW(20, 10, 0.005, paths=P, seed=seed)
+    _, I = sdb.Iwik(dW, 0.005, seed=seed, ensemble=True)
+    for p in (0, 256, P - 1):
+        assert rel_err(alt[p], orc.srk2(f, G, y0, tspan, dW[p], I[p])) <= TOL
+
+
 @pytest.mark.parametrize("strat,method", [(False, "kpw"), (True, "kpw"), (False, "wik"), (True, "wik")])
 def test_fused_tmem_kernel_d20(sdb, strat, method, monkeypatch):
     """d = m = 20 (BASELINE configs[3]): the TMEM-resident fused kernel (sdb_fusedx.cuh: Levy areas
