@@ -174,6 +174,9 @@ def checkpointed(integrator, f, G, y0, tspan, *, paths, seed, segment, checkpoin
             if (int(ck["seed"]) == int(seed) and int(ck["paths"]) == int(paths)
                     and np.array_equal(ck["grid"], finger)):
                 step, states = int(ck["step"]), ck["states"]
+    managed = {"save_every", "step0", "y0_paths", "out", "h_noise", "host_out", "observe", "dW", "I", "J"}
+    if managed & set(kw):
+        raise ValueError("checkpointed manages %s itself" % ", ".join(sorted(managed & set(kw))))
     opts = dict(kw)
     opts.update(paths=paths, seed=seed, out="torch", h_noise=h)
     cur = None if states is None else dev.to_device(np.ascontiguousarray(states), dev.require_cuda(kw.get("device")))
