@@ -201,6 +201,8 @@ def _run(scheme, f, G, y0, tspan, dW, IJ, strat, method, generator, kp2is, paths
         raise SDEValueError('save_every must be >= 1')
     n_saved = (N - 1) // save_every + 1
     h = (tspan[N - 1] - tspan[0]) / (N - 1)
+    if h_noise:
+        h = float(h_noise)      # the h of the whole run when this call is one segment of it
     method_id = _method_id(method, strat) if need_ij else NOISE_KPW
     if isinstance(n_terms, str):
         if n_terms != "auto":
