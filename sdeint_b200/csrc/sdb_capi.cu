@@ -516,9 +516,14 @@ static int integrate_impl(sdb_system* s, const sdb_integrate_args* a, const SdbO
   if (comm && need_ij && a->scheme == SDB_SCHEME_SRK2 && s->fk == SDB_DRIFT_LINEAR &&
       s->gk == SDB_DIFF_LINEAR_COLS && !getenv("SDB_DISABLE_FUSED") && !getenv("SDB_DISABLE_FUSEDC") &&
       SdbFusedCDims(s->d, s->m).supported()) {
-    if (!ext)
+    if (!ext) {
+      const char* vs = getenv("SDB_FUSED_VARIANT");
+      const int want = vs ? atoi(vs) : 0;
       for (const auto& e : sdb_fused_registry())
-        if (e.d == s->d && e.m == s->m && e.noise == SDB_NOISE_COMM && e.scheme == SDB_SCHEME_SRK2) fused = &e;
+        if (e.d == s->d && e.m == s->m && e.noise == SDB_NOISE_COMM && e.scheme == SDB_SCHEME_SRK2 &&
+            (e.variant == want || (!fused && e.variant == 0)))
+          fused = &e;
+    }
     if (!fused && !getenv("SDB_DISABLE_FUSED_JIT") && s->d * s->m >= 16) {
       const SdbFusedCDims cd(s->d, s->m);
       const std::string key = std::string("fusedcjit") + ext_suffix(ext);
