@@ -259,3 +259,27 @@ def test_ou_autocovariance_and_spectrum(sdb):
     rel = np.abs(S[1:] - expect[1:]) / expect[1:]
     assert rel.max() < 6.0 / np.sqrt(P)                                          # chi^2_2 / P scatter
     assert abs(S[0]) < 1e-20
+
+
+def test_levy_area_variances(sdb):
+    """Distribution of the generated Levy areas A_ij = I_ij - dW_i dW_j / 2 over 4e5 intervals: the exact
+    area has variance h^2/4; the truncated KPW series reaches (3 h^2 / 2 pi^2) sum_{k<=n} 1/k^2 of it (the
+    formula behind wiener.series_terms), Wiktorsson's tail correction restores h^2/4 for any n; both
+    are centred, uncorrelated with dW and between pairs."""
+    h, m, P, N = 0.01, 4, 20000, 20
+    dW = sdb.deltaW(N, m, h, paths=P, seed=5)                       # (P, N, m)
+    sym = 0.5 * dW[..., :, None] * dW[..., None, :]
+    total = float(P * N)
+    for n in (1, 5):
+        _, Ik = sdb.Ikpw(dW, h, n=n, seed=5, ensemble=True)
+        _, Iw = sdb.Iwik(dW, h, n=n, seed=5, ensemble=True)
+        want_kpw = 3.0 * h * h / (2.0 * np.pi ** 2) * sum(1.0 / k ** 2 for k in range(1, n + 1))
+        for I, want in ((Ik, want_kpw), (Iw, h * h / 4.0)):
+            A = I - sym + 0.5 * h * np.eye(m)                         # antisymmetric part
+            assert np.abs(A + A.transpose(0, 1, 3, 2)).max() < 1e-15
+            a01, a23, a02 = A[..., 0, 1].ravel(), A[..., 2, 3].ravel(), A[..., 0, 2].ravel()
+            for a in (a01, a23, a02):
+                assert abs(a.mean()) < 5.0 * np.sqrt(want / total)
+                assert abs(a.var() / want - 1.0) < 0.03, (n, a.var(), want)     # kurtosis ~ 6: sd ~ 0.35 %
+            assert abs(np.corrcoef(a01, a23)[0, 1]) < 0.01 and abs(np.corrcoef(a01, a02)[0, 1]) < 0.01
+            assert abs(np.corrcoef(a01, dW[..., 0].ravel())[0, 1]) < 0.01
