@@ -283,3 +283,12 @@ def test_levy_area_variances(sdb):
                 assert abs(a.var() / want - 1.0) < 0.03, (n, a.var(), want)     # kurtosis ~ 6: sd ~ 0.35 %
             assert abs(np.corrcoef(a01, a23)[0, 1]) < 0.01 and abs(np.corrcoef(a01, a02)[0, 1]) < 0.01
             assert abs(np.corrcoef(a01, dW[..., 0].ravel())[0, 1]) < 0.01
+        # conditional variance given dW: E[A_01^2 | dW] = c0 + c1 (dW_0^2 + dW_1^2) with, for the exact area,
+        # c0 = h^2/12, c1 = h/12 (Wiktorsson keeps both for any n); the series has c1 = (h / 2 pi^2) sum 1/k^2
+        s2 = (dW[..., 0] ** 2 + dW[..., 1] ** 2).ravel()
+        zeta = sum(1.0 / k ** 2 for k in range(1, n + 1))
+        for I, c0, c1 in ((Ik, h * h * zeta / (2 * np.pi ** 2), h * zeta / (2 * np.pi ** 2)),
+                          (Iw, h * h / 12.0, h / 12.0)):
+            a2 = ((I - sym)[..., 0, 1].ravel()) ** 2
+            slope, icpt = np.polyfit(s2, a2, 1)
+            assert abs(slope / c1 - 1.0) < 0.05 and abs(icpt / c0 - 1.0) < 0.08, (n, slope, c1, icpt, c0)
