@@ -556,7 +556,7 @@ static int integrate_impl(sdb_system* s, const sdb_integrate_args* a, const SdbO
         fused = &e;
   }
   // No ahead-of-time instantiation for this (d, m, method): compile a fused kernel with NVRTC when
-  // the shape is one it supports -- sdb_fused.cuh (8 warps per SM; Ikpw/Jkpw, even m <= 10, d < 16) or
+  // the shape is one it supports -- sdb_fused.cuh (8 warps per SM; Ikpw/Jkpw, m <= 10, d < 16) or
   // sdb_fusedx.cuh (Levy areas in tensor memory; Iwik/Jwik and larger shapes) -- else the generic loop.
   if (!fused && explicit_em && noise != SDB_NOISE_HOST && s->fk == SDB_DRIFT_LINEAR &&
       s->gk == SDB_DIFF_LINEAR_COLS && !getenv("SDB_DISABLE_FUSED") &&

@@ -359,6 +359,22 @@ SDB_DEV void sdb_normal_batch(const uint32_t (&w)[NB][4], const double2* __restr
 // Compile-time loop and the inverse of sdb_pair_index.
 template <int I>
 struct SdbInt { static constexpr int value = I; };
+// M normals of one (path, step) from normal index 2 slot0 + ODD on: Box-Muller pairs are addressed by
+// slot = normal index >> 1 (element = index & 1), so a block of normals that starts at an odd index
+// skips the first element of its first pair.  Used for an ODD number of Wiener processes, where the
+// blocks dW | X_1 | Y_1 | X_2 | ... of the reference's draw order alternate between even and odd starts.
+template <int M, int ODD, bool SCALED>
+SDB_DEV void sdb_normals_m(const SdbPhiloxKey& key, uint32_t p_lo, uint32_t p_hi, uint32_t step,
+                           uint32_t slot0, const double2* __restrict__ tab, double scale, double (&out)[M]) {
+  constexpr int NP = (M + ODD + 1) / 2;
+  uint32_t w[NP][4];
+  double z[2 * NP];
+  sdb_philox_batch<NP>(key, p_lo, p_hi, step, slot0, w);
+  sdb_normal_batch<NP, SCALED>(w, tab, scale, z);
+#pragma unroll
+  for (int j = 0; j < M; ++j) out[j] = z[j + ODD];
+}
+
 template <int I, int N, class F>
 SDB_DEV void sdb_static_for(F&& f) {
   if constexpr (I < N) {
@@ -529,7 +545,8 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
   typedef SdbFusedShape<D, M> Sh;
   constexpr int NT = SDB_FUSED_THREADS;
   constexpr int MM = Sh::MM, LT = Sh::LT, GR = Sh::grows();
-  static_assert(M % 2 == 0, "fused kernel needs an even number of Wiener processes");
+  static_assert(M % 2 == 0 || (SDB_FUSED_BATCH && !SDB_FUSED_BATCH_XZ && WIK == 0),
+                "an odd number of Wiener processes needs the batched generator (and Ikpw/Jkpw)");
   static_assert(Sh::IT <= 1, "stage-2 DMMA tiles: d < 16 supported");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -597,10 +614,12 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
       const SdbStream st(pkey, path, SDB_STEP(n), tab);
       double dW[M];
 #if SDB_FUSED_BATCH
-      {
+      if constexpr (M % 2 == 0) {
         uint32_t w[M / 2][4];
         sdb_philox_batch<M / 2>(pkey, st.p_lo, st.p_hi, SDB_STEP(n), 0u, w);
         sdb_normal_batch<M / 2, true>(w, tab, rh_g, dW);
+      } else {
+        sdb_normals_m<M, 0, true>(pkey, st.p_lo, st.p_hi, SDB_STEP(n), 0u, tab, rh_g, dW);
       }
 #else
 #pragma unroll
@@ -638,12 +657,15 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
           }
         }
 #else
-        {
+        if constexpr (M % 2 == 0) {
           uint32_t w[M / 2][4];
           sdb_philox_batch<M / 2>(pkey, st.p_lo, st.p_hi, SDB_STEP(n), sx, w);
           sdb_normal_batch<M / 2, true>(w, tab, hk, X);
           sdb_philox_batch<M / 2>(pkey, st.p_lo, st.p_hi, SDB_STEP(n), sx + M / 2, w);
           sdb_normal_batch<M / 2, false>(w, tab, 1.0, Z);
+        } else {  // X_k starts at the odd normal index M (2k - 1), Y_k at the even one 2 k M
+          sdb_normals_m<M, 1, true>(pkey, st.p_lo, st.p_hi, SDB_STEP(n), sx, tab, hk, X);
+          sdb_normals_m<M, 0, false>(pkey, st.p_lo, st.p_hi, SDB_STEP(n), sx + (M + 1) / 2, tab, 1.0, Z);
         }
 #endif
 #pragma unroll

@@ -47,9 +47,9 @@ struct SdbFusedDims {
     return ((size_t)MM() * THREADS + (size_t)(grows() + M) * 32 * WARPS) * sizeof(double) + 128 * 16 +
            (MAX_TERMS + 1 + n_left() + 1) * sizeof(double);
   }
-  // the kernel needs an even m, d < 16 (one DMMA tile of the stage-2 sum) and must fit an SM
+  // the kernel needs d < 16 (one DMMA tile of the stage-2 sum) and must fit an SM
   constexpr bool supported() const {
-    return D >= 1 && M >= 2 && M % 2 == 0 && D < 16 && smem_bytes() <= 227u * 1024u;
+    return D >= 1 && M >= 2 && D < 16 && smem_bytes() <= 227u * 1024u;
   }
   // lane-major fragment tables: out[frag * 32 + lane], then the leftover rows (as sdb_fused_build_tables)
   void build_tables(const double* A, const double* B, double* out) const {
@@ -148,7 +148,7 @@ struct SdbFusedEhDims {
   }
   constexpr size_t smem_bytes() const { return (size_t)grows() * 32 * 8 * (threads() / 32) + 128 * 16; }
   constexpr bool supported() const {
-    return sh.M >= 2 && sh.M % 2 == 0 && sh.D >= 1 && sh.D <= 16 && smem_bytes() <= 227u * 1024u;
+    return sh.M >= 2 && sh.D >= 1 && sh.D <= 16 && smem_bytes() <= 227u * 1024u;
   }
 };
 
@@ -168,7 +168,7 @@ struct SdbFusedCDims {
   constexpr size_t table_doubles() const { return s1.table_doubles() + s2.table_doubles(); }
   constexpr size_t smem_bytes() const { return (size_t)grows() * 32 * 8 * (threads() / 32) + 128 * 16; }
   constexpr bool supported() const {
-    return s2.M >= 2 && s2.M % 2 == 0 && s2.D >= 1 && s2.D <= 12 && smem_bytes() <= 227u * 1024u;
+    return s2.M >= 2 && s2.D >= 1 && s2.D <= 12 && smem_bytes() <= 227u * 1024u;
   }
   void build_tables(const double* A, const double* B, double* out) const {
     const int D = s2.D, M = s2.M;

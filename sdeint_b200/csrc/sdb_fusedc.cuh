@@ -149,7 +149,6 @@ SDB_DEV void sdb_fc_eval(const double* __restrict__ frag, double* gbuf, const do
 template <int D, int M>
 SDB_DEV void sdb_fusedc_body(const SdbLoopArgs& a, const double* __restrict__ frag, double* smem) {
   typedef SdbFcShape<D, M> Cs;
-  static_assert(M % 2 == 0, "fused kernel needs an even number of Wiener processes");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double2* tab = reinterpret_cast<double2*>(smem + (size_t)Cs::grows() * 32 * (SDB_FC_THREADS / 32));
   if (tid < 128) tab[tid] = reinterpret_cast<const double2*>(sdb_logtab)[tid];
@@ -188,10 +187,12 @@ SDB_DEV void sdb_fusedc_body(const SdbLoopArgs& a, const double* __restrict__ fr
   for (int n = 0; n < steps; ++n) {
     const double h = hs[n];
     double dW[M];
-    {
+    if constexpr (M % 2 == 0) {
       uint32_t w[M / 2][4];
       sdb_philox_batch<M / 2>(pkey, p_lo, p_hi, SDB_STEP(n), 0u, w);
       sdb_normal_batch<M / 2, true>(w, tab, rh_g, dW);
+    } else {
+      sdb_normals_m<M, 0, true>(pkey, p_lo, p_hi, SDB_STEP(n), 0u, tab, rh_g, dW);
     }
     double v[D], ex[2][D], f0[D];
     sdb_fc_eval<D, M + 2, M, true>(frag, gbuf, Y, dW, lane, v, ex, f0);

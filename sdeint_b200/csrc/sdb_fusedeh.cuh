@@ -102,7 +102,6 @@ SDB_DEV void sdb_eh_eval(const double* __restrict__ frag, double* gbuf, const do
 template <int D, int M, int HEUN>
 SDB_DEV void sdb_fusedeh_body(const SdbLoopArgs& a, const double* __restrict__ frag, double* smem) {
   typedef SdbEhShape<D, M> Es;
-  static_assert(M % 2 == 0, "fused kernel needs an even number of Wiener processes");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double2* tab = reinterpret_cast<double2*>(smem + (size_t)Es::grows() * 32 * (SDB_EH_THREADS(HEUN) / 32));
   if (tid < 128) tab[tid] = reinterpret_cast<const double2*>(sdb_logtab)[tid];
@@ -138,10 +137,12 @@ SDB_DEV void sdb_fusedeh_body(const SdbLoopArgs& a, const double* __restrict__ f
 #pragma unroll 1
   for (int n = 0; n < steps; ++n) {
     double dW[M];
-    {
+    if constexpr (M % 2 == 0) {
       uint32_t w[M / 2][4];
       sdb_philox_batch<M / 2>(pkey, p_lo, p_hi, SDB_STEP(n), 0u, w);
       sdb_normal_batch<M / 2, true>(w, tab, rh, dW);
+    } else {
+      sdb_normals_m<M, 0, true>(pkey, p_lo, p_hi, SDB_STEP(n), 0u, tab, rh, dW);
     }
     double GdW[D], f0[D];
     sdb_eh_eval<D, M>(frag, gbuf, Y, dW, lane, GdW, f0);

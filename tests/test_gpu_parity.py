@@ -365,7 +365,8 @@ def test_jit_builtin_dimensions(sdb):
 
 
 @pytest.mark.parametrize("d,m", [(10, 10), (4, 4), (8, 2), (5, 4),          # ahead-of-time kernels
-                                 (6, 4), (4, 6), (12, 6), (9, 10), (15, 8)])  # NVRTC-compiled fused kernel
+                                 (6, 4), (4, 6), (12, 6), (9, 10), (15, 8),   # NVRTC-compiled fused kernel
+                                 (7, 5), (10, 3), (5, 9)])                     # ... odd numbers of Wiener processes
 @pytest.mark.parametrize("strat", [False, True])
 def test_fused_dmma_kernel_shapes(sdb, d, m, strat, monkeypatch):
     """The fused linear SRI2/SRS2 kernel (DMMA products, exact linear collapse of the two
@@ -684,7 +685,7 @@ def test_icomm_jcomm_standalone(sdb):
 
 
 @pytest.mark.parametrize("d,m,strat", [(5, 4, False), (10, 10, False), (10, 10, True), (20, 20, False),
-                                       (3, 2, True)])
+                                       (3, 2, True), (7, 5, False), (9, 3, True)])
 def test_commutative_noise_needs_no_levy_areas(sdb, d, m, strat):
     """For commuting B_k the SRI2/SRS2 result does not depend on the Levy areas: the automatic
     area-free path (only dW drawn), the forced full Ikpw construction on the same seed, and the oracle
@@ -1007,6 +1008,9 @@ def test_dispatch_launches_the_documented_kernels(sdb, monkeypatch):
     assert ran(sdb.itoSRI2, f, G, y0, ts, sdb.Iwik, **kw) == "jit:fusedxjit|wik|x2"      # two lanes per path
     f, G, y0 = sdb.ops.sys_lin(6, 4)
     assert ran(sdb.itoSRI2, f, G, y0, ts, **kw) == "jit:fusedjit"
+    f, G, y0 = sdb.ops.sys_lin(7, 5)                                                     # odd m
+    assert ran(sdb.itoSRI2, f, G, y0, ts, **kw) == "jit:fusedjit"
+    assert ran(sdb.itoSRI2, f, G, y0, ts, sdb.Iwik, **kw).startswith("jit:loop|s2|f0|g1|d7|m5|n2")   # TMEM kernels: even m
     f, G, y0 = SYSTEMS["lin2"](False)
     assert ran(sdb.itoEuler, f, G, y0, ts, **kw) == "sdbk_lin2_s0_n1"
     fX, GX = sdb.ops.ExprDrift(["-y[0]"], []), sdb.ops.ExprDiffusion([["0.1*y[0]"]], [])
@@ -1131,7 +1135,7 @@ def test_series_length_in_integrators(sdb, name, n):
     assert rel_err(yw[0], orc.srk2(f, G, np.atleast_1d(y0), tspan, dW[0], Iw)) <= TOL
 
 
-@pytest.mark.parametrize("d,m", [(10, 10), (8, 6), (12, 8)])
+@pytest.mark.parametrize("d,m", [(10, 10), (8, 6), (12, 8), (12, 9)])
 def test_fused_euler_heun_linear(sdb, d, m, monkeypatch):
     """itoEuler / stratHeun for linear multiplicative systems on device noise: the DMMA kernel of
     sdb_fusedeh.cuh ((10,10) ahead of time, other shapes NVRTC) against the generic loop kernel and
