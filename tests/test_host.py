@@ -272,3 +272,25 @@ def test_observer_specs_host_logic():
     for bad in ([("median", 0)], [("max", 3)], [("first_below", 0)], [("max", 0, 1.0)], [("max", 0)] * 5, []):
         with pytest.raises(integrate.SDEValueError):
             integrate._observers(bad, 3)
+
+
+def test_python_constants_match_the_header():
+    """Every SDB_* enumerator of include/sdb.h that the shim mirrors has the same value on the Python
+    side (schemes, noise sources, flags, operator kinds, observer kinds, limits)."""
+    import re
+    from sdeint_b200 import integrate, ops, wiener
+    hdr = open(os.path.join(ROOT, "include", "sdb.h")).read()
+    defs = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+SDB_(\w+)\s+(\d+)\b", hdr)}
+    for mod, prefix in ((integrate, "SCHEME_"), (integrate, "NOISE_"), (integrate, "FLAG_"),
+                        (ops, "DRIFT_"), (ops, "DIFF_"), (wiener, "NOISE_")):
+        names = [n for n in dir(mod) if n.startswith(prefix)]
+        assert names
+        for n in names:
+            assert defs[n] == getattr(mod, n), n
+    for kind, value in integrate._OBS_KINDS.items():
+        assert defs["OBS_" + kind.upper()] == value
+    assert defs["MAX_OBSERVERS"] == integrate.MAX_OBSERVERS
+    # and the kernel-side copies of the same enumerators (sdb_kernels.cuh) agree with the header
+    kern = open(os.path.join(ROOT, "sdeint_b200", "csrc", "sdb_kernels.cuh")).read()
+    for m in re.finditer(r"#define\s+SDB_((?:SCHEME|NOISE|FLAG|DRIFT|DIFF|OBS)_\w+)\s+(\d+)\b", kern):
+        assert defs[m.group(1)] == int(m.group(2)), m.group(1)
