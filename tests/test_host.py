@@ -294,3 +294,31 @@ def test_python_constants_match_the_header():
     kern = open(os.path.join(ROOT, "sdeint_b200", "csrc", "sdb_kernels.cuh")).read()
     for m in re.finditer(r"#define\s+SDB_((?:SCHEME|NOISE|FLAG|DRIFT|DIFF|OBS)_\w+)\s+(\d+)\b", kern):
         assert defs[m.group(1)] == int(m.group(2)), m.group(1)
+
+
+def test_ctypes_structures_match_the_header_layout(tmp_path):
+    """The ctypes mirrors in _lib.py have the size and field offsets a C compiler gives the structs of
+    include/sdb.h (gcc on the header itself): ABI drift between header and binding fails here."""
+    import ctypes as C
+    import shutil
+    from sdeint_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("no C compiler")
+    pairs = (("sdb_integrate_args", _lib.IntegrateArgs), ("sdb_repint_args", _lib.RepintArgs),
+             ("sdb_observer", _lib.Observer), ("sdb_integrate_ext", _lib.IntegrateExt))
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "sdb.h"', "int main(void) {"]
+    for cname, cls in pairs:
+        lines.append('  printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('  printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(line.split() for line in subprocess.run([str(exe)], capture_output=True, text=True,
+                                                       check=True).stdout.splitlines())
+    for cname, cls in pairs:
+        assert int(out[cname]) == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(out["%s.%s" % (cname, fname)]) == getattr(cls, fname).offset, (cname, fname)
