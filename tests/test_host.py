@@ -322,3 +322,21 @@ def test_ctypes_structures_match_the_header_layout(tmp_path):
         assert int(out[cname]) == C.sizeof(cls), cname
         for fname, _ in cls._fields_:
             assert int(out["%s.%s" % (cname, fname)]) == getattr(cls, fname).offset, (cname, fname)
+
+
+def test_integration_md_stub_structure_matches_binding():
+    """The IntegrateArgs structure printed in INTEGRATION.md (the binding a maintainer of the reference
+    would write) is field for field the one the shipping binding uses."""
+    import ctypes as C
+    import re
+    from sdeint_b200 import _lib
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    m = re.search(r"(class IntegrateArgs\(C\.Structure\):.*?\n)\ndef _check", text, re.S)
+    assert m, "INTEGRATION.md no longer shows the IntegrateArgs stub"
+    ns = {"C": C}
+    exec(m.group(1), ns)
+    doc = ns["IntegrateArgs"]
+    assert [n for n, _ in doc._fields_] == [n for n, _ in _lib.IntegrateArgs._fields_]
+    assert C.sizeof(doc) == C.sizeof(_lib.IntegrateArgs)
+    for name, _ in doc._fields_:
+        assert getattr(doc, name).offset == getattr(_lib.IntegrateArgs, name).offset, name
