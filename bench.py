@@ -360,6 +360,12 @@ def main():
     ap.add_argument("--paths", type=int, default=10 ** 7, help="paths per GPU")
     ap.add_argument("--impl", default="sdb", choices=["sdb", "reference"])
     args = ap.parse_args()
+    if args.impl != "reference" and args.warmup < 3:
+        # timing rule: at least three untimed steps before the timed region (clocks, caches, module load)
+        print("bench.py: --warmup %d raised to 3" % args.warmup, file=sys.stderr)
+        args.warmup = 3
+    if args.steps < 1:
+        ap.error("--steps must be >= 1")
     if args.impl == "reference":
         run_reference(args)
     else:
