@@ -210,8 +210,14 @@ int sdb_copy2d_d2h_async(void* h_dst, int64_t dst_pitch_bytes, const void* d_src
  * returns TFLOP/s (roofline denominator of bench.py). */
 int sdb_fp64_peak(int iters, double* tflops_out, void* stream);
 
-/* Raw generator access (tests): Philox4x32-10 block for (seed, path, step, slot). */
+/* Raw generator access (tests): the Philox4x32-10 block with counter (path lo, path hi, step, slot)
+ * and key seed (Random123 known-answer vectors), and the 128-bit block the kernels turn into the
+ * Box-Muller pair `slot` of (seed, path, step): slot 0 is that Philox block at counter word 3 = 0,
+ * slot s >= 1 is the MX2 expansion MX2(K, s) of the key block K = Philox at counter word
+ * 3 = 0xFFFFFFFF (csrc/sdb_kernels.cuh; restated in oracle/philox_oracle.py).  Replaces numpy's
+ * Generator.normal / standard_normal streams of sdeint/wiener.py:52,70-71,275. */
 int sdb_philox_block(uint64_t seed, uint64_t path, uint32_t step, uint32_t slot, uint32_t out[4]);
+int sdb_random_block(uint64_t seed, uint64_t path, uint32_t step, uint32_t slot, uint32_t out[4]);
 
 #ifdef __cplusplus
 }

@@ -10,8 +10,16 @@ Normal transform (sdeint_b200/csrc/sdb_kernels.cuh, sdb_normal_pair): one 128-bi
 t = ((lo >> 9) mod 2^52) 2^-52 in [0,1);  (c, s) = (cos, sin)(pi t / 4);  o = lo >> 61;
 z0 = (o&2 ? -1 : 1) rad (o&1 ? s : c),  z1 = (o&4 ? -1 : 1) rad (o&1 ? c : s)
 (Box-Muller with the angle folded into one octant and unfolded by three random bits).
-Normal number q of (path, step) is element q&1 of the block with counter
-(path_lo, path_hi, step, q>>1) and key (seed_lo, seed_hi).
+Normal number q of (path, step) is element q&1 of random block q>>1 of (seed, path, step).
+
+Random block `slot` of (seed, path, step) (sdb_random_block in csrc/sdb_kernels.cuh):
+  slot 0      the Philox4x32-10 block with counter (path_lo, path_hi, step, 0), key (seed_lo, seed_hi);
+  slot s >= 1 MX2(K, s), K = the Philox4x32-10 block with counter (path_lo, path_hi, step, 0xFFFFFFFF):
+              x_i = K_i + s G_i;  x_i ^= x_i >> 15;  y_i = x_i C_i + x_{i+1};  y_i ^= y_i >> 13;
+              x_i = y_i C_{i+1} + y_{i+1};  out_i = x_i ^ (x_i >> 16)      (indices mod 4, 32-bit wrap)
+(the 64-bit products of Philox share the FP64 pipe's issue resource on sm_100a, so only two Philox
+blocks are computed per (path, step); the other slots are a 32-bit multiply-xorshift expansion of a
+key block that is never output itself).
 """
 import numpy as np
 
@@ -40,11 +48,40 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
     return c0, c1, c2, c3
 
 
+KEYSLOT = 0xFFFFFFFF
+MX_G = (0x9E3779B1, 0x85EBCA77, 0xC2B2AE3D, 0x27D4EB2F)
+MX_C = (0xED5AD4BB, 0xAC4C1B51, 0x31848BAB, 0x7FEB352D)
+
+
+def mx2_block(K, s):
+    """MX2 expansion (module doc); K = 4 arrays of uint32-valued uint64, s = slot array."""
+    s = np.asarray(s, dtype=np.uint64) & MASK
+    x = [(K[i] + s * np.uint64(MX_G[i])) & MASK for i in range(4)]
+    x = [v ^ (v >> np.uint64(15)) for v in x]
+    y = [(x[i] * np.uint64(MX_C[i]) + x[(i + 1) & 3]) & MASK for i in range(4)]
+    y = [v ^ (v >> np.uint64(13)) for v in y]
+    x = [(y[i] * np.uint64(MX_C[(i + 1) & 3]) + y[(i + 1) & 3]) & MASK for i in range(4)]
+    return tuple(v ^ (v >> np.uint64(16)) for v in x)
+
+
+def random_block(seed, path, step, slot):
+    """The 128-bit block of (seed, path, step, slot) as four uint32-valued arrays."""
+    path = np.asarray(path, dtype=np.uint64)
+    step = np.asarray(step, dtype=np.uint64)
+    slot = np.asarray(slot, dtype=np.uint64)
+    path, step, slot = np.broadcast_arrays(path, step, slot)
+    k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+    first = philox4x32_10(path & MASK, path >> np.uint64(32), step, np.zeros_like(slot), k0, k1)
+    if not np.any(slot != 0):
+        return first
+    K = philox4x32_10(path & MASK, path >> np.uint64(32), step, np.full_like(slot, KEYSLOT), k0, k1)
+    rest = mx2_block(K, slot)
+    return tuple(np.where(slot == 0, a, b) for a, b in zip(first, rest))
+
+
 def normal_pairs(seed, path, step, slot):
     """(z0, z1) for broadcastable integer arrays path, step, slot (spec in the module doc)."""
-    path = np.asarray(path, dtype=np.uint64)
-    r0, r1, r2, r3 = philox4x32_10(path & MASK, path >> np.uint64(32), step, slot,
-                                   seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    r0, r1, r2, r3 = random_block(seed, path, step, slot)
     hi = (r0 << np.uint64(32)) | r1
     lo = (r2 << np.uint64(32)) | r3
     x = (hi >> np.uint64(11)) | np.uint64(1)                      # 53-bit odd integer

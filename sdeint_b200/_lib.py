@@ -84,6 +84,8 @@ SIGNATURES = {
     "sdb_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), c_dp]),
     "sdb_philox_block": (C.c_int, [c_u64, c_u64, C.c_uint32, C.c_uint32,
                                    C.POINTER(C.c_uint32 * 4)]),
+    "sdb_random_block": (C.c_int, [c_u64, c_u64, C.c_uint32, C.c_uint32,
+                                   C.POINTER(C.c_uint32 * 4)]),
 }
 
 _lib = None

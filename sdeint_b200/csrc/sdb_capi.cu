@@ -1067,6 +1067,14 @@ extern "C" int sdb_fp64_peak(int iters, double* tflops_out, void* stream) {
   return 0;
 }
 
+extern "C" int sdb_random_block(uint64_t seed, uint64_t path, uint32_t step, uint32_t slot,
+                                uint32_t out[4]) {
+  uint32_t r[4];
+  sdb_random_block(SdbPhiloxKey(seed), path, step, slot, r);
+  for (int i = 0; i < 4; ++i) out[i] = r[i];
+  return 0;
+}
+
 extern "C" int sdb_philox_block(uint64_t seed, uint64_t path, uint32_t step, uint32_t slot,
                                 uint32_t out[4]) {
   uint32_t r[4];

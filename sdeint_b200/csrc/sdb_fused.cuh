@@ -213,6 +213,64 @@ SDB_DEV void sdb_philox_batch(const SdbPhiloxKey& key, uint32_t p_lo, uint32_t p
   for (int b = 0; b < NB; ++b) { w[b][0] = c0[b]; w[b][1] = c1[b]; w[b][2] = c2[b]; w[b][3] = c3[b]; }
 }
 
+#ifndef SDB_FUSED_RNG
+#define SDB_FUSED_RNG 1  // 1: slots >= 1 by the MX2 expansion of the step's key block; 0: Philox per slot
+#endif
+// The random blocks of one (path, step): slot 0 and the expansion key are the two Philox blocks.
+struct SdbGen {
+  const SdbPhiloxKey& key;
+  uint32_t p_lo, p_hi, step;
+#if SDB_FUSED_RNG
+  uint32_t B0[4], K[4];
+#endif
+  // expand = false: only slot 0 will be read (m <= 2 Wiener processes, dW only)
+  SDB_DEV SdbGen(const SdbPhiloxKey& key_, uint32_t p_lo_, uint32_t p_hi_, uint32_t step_,
+                 bool expand = true)
+      : key(key_), p_lo(p_lo_), p_hi(p_hi_), step(step_) {
+#if SDB_FUSED_RNG
+    if (!expand) {
+      sdb_philox4x32_10(p_lo, p_hi, step, 0u, key, B0);
+      K[0] = K[1] = K[2] = K[3] = 0u;
+      return;
+    }
+    uint32_t c0[2], c1[2], c2[2], c3[2];
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      c0[b] = p_lo; c1[b] = p_hi; c2[b] = step; c3[b] = b == 0 ? 0u : SDB_RNG_KEYSLOT;
+    }
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const uint64_t p0 = (uint64_t)SDB_PHILOX_M0 * c0[b];
+        const uint64_t p1 = (uint64_t)SDB_PHILOX_M1 * c2[b];
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1[b] ^ key.a[r];
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3[b] ^ key.b[r];
+        c1[b] = (uint32_t)p1; c3[b] = (uint32_t)p0; c0[b] = n0; c2[b] = n2;
+      }
+    }
+    B0[0] = c0[0]; B0[1] = c1[0]; B0[2] = c2[0]; B0[3] = c3[0];
+    K[0] = c0[1]; K[1] = c1[1]; K[2] = c2[1]; K[3] = c3[1];
+#endif
+  }
+  // blocks of slots slot0 .. slot0 + NB - 1; FIRST: slot0 == 0 (compile-time knowledge)
+  template <int NB, bool FIRST>
+  SDB_DEV void blocks(uint32_t slot0, uint32_t (&w)[NB][4]) const {
+#if SDB_FUSED_RNG
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      if (FIRST && b == 0) {
+        w[0][0] = B0[0]; w[0][1] = B0[1]; w[0][2] = B0[2]; w[0][3] = B0[3];
+      } else {
+        sdb_mx2_block(K, slot0 + (uint32_t)b, w[b]);
+      }
+    }
+#else
+    sdb_philox_batch<NB>(key, p_lo, p_hi, step, slot0, w);
+#endif
+  }
+};
+
 // z[2b], z[2b+1] = scale * (normal pair b); SCALED = false skips the multiplication.
 template <int NB, bool SCALED>
 SDB_DEV void sdb_normal_batch(const uint32_t (&w)[NB][4], const double2* __restrict__ tab,
@@ -363,13 +421,13 @@ struct SdbInt { static constexpr int value = I; };
 // slot = normal index >> 1 (element = index & 1), so a block of normals that starts at an odd index
 // skips the first element of its first pair.  Used for an ODD number of Wiener processes, where the
 // blocks dW | X_1 | Y_1 | X_2 | ... of the reference's draw order alternate between even and odd starts.
-template <int M, int ODD, bool SCALED>
-SDB_DEV void sdb_normals_m(const SdbPhiloxKey& key, uint32_t p_lo, uint32_t p_hi, uint32_t step,
-                           uint32_t slot0, const double2* __restrict__ tab, double scale, double (&out)[M]) {
+template <int M, int ODD, bool SCALED, bool FIRST = false>
+SDB_DEV void sdb_normals_m(const SdbGen& gen, uint32_t slot0, const double2* __restrict__ tab, double scale,
+                           double (&out)[M]) {
   constexpr int NP = (M + ODD + 1) / 2;
   uint32_t w[NP][4];
   double z[2 * NP];
-  sdb_philox_batch<NP>(key, p_lo, p_hi, step, slot0, w);
+  gen.template blocks<NP, FIRST>(slot0, w);
   sdb_normal_batch<NP, SCALED>(w, tab, scale, z);
 #pragma unroll
   for (int j = 0; j < M; ++j) out[j] = z[j + ODD];
@@ -612,14 +670,15 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
     // ---- noise: dW (wiener.py:52), Levy areas (wiener.py:67-74, :102-105), one lane per path ------
     {
       const SdbStream st(pkey, path, SDB_STEP(n), tab);
+      const SdbGen gen(pkey, st.p_lo, st.p_hi, SDB_STEP(n));
       double dW[M];
 #if SDB_FUSED_BATCH
       if constexpr (M % 2 == 0) {
         uint32_t w[M / 2][4];
-        sdb_philox_batch<M / 2>(pkey, st.p_lo, st.p_hi, SDB_STEP(n), 0u, w);
+        gen.template blocks<M / 2, true>(0u, w);
         sdb_normal_batch<M / 2, true>(w, tab, rh_g, dW);
       } else {
-        sdb_normals_m<M, 0, true>(pkey, st.p_lo, st.p_hi, SDB_STEP(n), 0u, tab, rh_g, dW);
+        sdb_normals_m<M, 0, true, true>(gen, 0u, tab, rh_g, dW);
       }
 #else
 #pragma unroll
@@ -648,7 +707,7 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
         {
           uint32_t w[M][4];
           double xz[2 * M];
-          sdb_philox_batch<M>(pkey, st.p_lo, st.p_hi, SDB_STEP(n), sx, w);
+          gen.template blocks<M, false>(sx, w);
           sdb_normal_batch<M, false>(w, tab, 1.0, xz);
 #pragma unroll
           for (int j = 0; j < M; ++j) {
@@ -659,13 +718,13 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
 #else
         if constexpr (M % 2 == 0) {
           uint32_t w[M / 2][4];
-          sdb_philox_batch<M / 2>(pkey, st.p_lo, st.p_hi, SDB_STEP(n), sx, w);
+          gen.template blocks<M / 2, false>(sx, w);
           sdb_normal_batch<M / 2, true>(w, tab, hk, X);
-          sdb_philox_batch<M / 2>(pkey, st.p_lo, st.p_hi, SDB_STEP(n), sx + M / 2, w);
+          gen.template blocks<M / 2, false>(sx + M / 2, w);
           sdb_normal_batch<M / 2, false>(w, tab, 1.0, Z);
         } else {  // X_k starts at the odd normal index M (2k - 1), Y_k at the even one 2 k M
-          sdb_normals_m<M, 1, true>(pkey, st.p_lo, st.p_hi, SDB_STEP(n), sx, tab, hk, X);
-          sdb_normals_m<M, 0, false>(pkey, st.p_lo, st.p_hi, SDB_STEP(n), sx + (M + 1) / 2, tab, 1.0, Z);
+          sdb_normals_m<M, 1, true>(gen, sx, tab, hk, X);
+          sdb_normals_m<M, 0, false>(gen, sx + (M + 1) / 2, tab, 1.0, Z);
         }
 #endif
 #pragma unroll
@@ -730,7 +789,7 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
           constexpr int NBP = NPAIR - 5 * b >= 5 ? 5 : NPAIR - 5 * b;
           uint32_t w[NBP][4];
           double g[2 * NBP];
-          sdb_philox_batch<NBP>(pkey, st.p_lo, st.p_hi, SDB_STEP(n), st0 + (uint32_t)(5 * b), w);
+          gen.template blocks<NBP, false>(st0 + (uint32_t)(5 * b), w);
           sdb_normal_batch<NBP, false>(w, tab, 1.0, g);
           sdb_static_for<0, 2 * NBP>([&](auto ee) {
             constexpr int e = decltype(ee)::value;

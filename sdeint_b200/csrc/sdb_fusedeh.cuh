@@ -137,12 +137,13 @@ SDB_DEV void sdb_fusedeh_body(const SdbLoopArgs& a, const double* __restrict__ f
 #pragma unroll 1
   for (int n = 0; n < steps; ++n) {
     double dW[M];
+    const SdbGen gen(pkey, p_lo, p_hi, SDB_STEP(n), M > 2);
     if constexpr (M % 2 == 0) {
       uint32_t w[M / 2][4];
-      sdb_philox_batch<M / 2>(pkey, p_lo, p_hi, SDB_STEP(n), 0u, w);
+      gen.template blocks<M / 2, true>(0u, w);
       sdb_normal_batch<M / 2, true>(w, tab, rh, dW);
     } else {
-      sdb_normals_m<M, 0, true>(pkey, p_lo, p_hi, SDB_STEP(n), 0u, tab, rh, dW);
+      sdb_normals_m<M, 0, true, true>(gen, 0u, tab, rh, dW);
     }
     double GdW[D], f0[D];
     sdb_eh_eval<D, M>(frag, gbuf, Y, dW, lane, GdW, f0);

@@ -116,11 +116,12 @@ SDB_DEV void sdb_ws_helper(const SdbLoopArgs& a, const double2* __restrict__ tab
   SdbRing ring;
 #pragma unroll 1
   for (int n = 0; n < steps; ++n) {
+    const SdbGen gen(pkey, p_lo, p_hi, SDB_STEP(n));
     double czdW[M];
     {  // batch 0: dW (wiener.py:52)
       double dW[M];
       uint32_t w[M / 2][4];
-      sdb_philox_batch<M / 2>(pkey, p_lo, p_hi, SDB_STEP(n), 0u, w);
+      gen.template blocks<M / 2, true>(0u, w);
       sdb_normal_batch<M / 2, true>(w, tab, rh_g, dW);
 #pragma unroll
       for (int j = 0; j < M; ++j) czdW[j] = cz * dW[j];
@@ -139,12 +140,12 @@ SDB_DEV void sdb_ws_helper(const SdbLoopArgs& a, const double2* __restrict__ tab
       double X[M], Z[M];
       {
         uint32_t w[M / 2][4];
-        sdb_philox_batch<M / 2>(pkey, p_lo, p_hi, SDB_STEP(n), sx, w);
+        gen.template blocks<M / 2, false>(sx, w);
         sdb_normal_batch<M / 2, true>(w, tab, hk, X);
       }
       {
         uint32_t w[M / 2][4];
-        sdb_philox_batch<M / 2>(pkey, p_lo, p_hi, SDB_STEP(n), sx + M / 2, w);
+        gen.template blocks<M / 2, false>(sx + M / 2, w);
         sdb_normal_batch<M / 2, false>(w, tab, 1.0, Z);
       }
 #pragma unroll
@@ -403,10 +404,11 @@ SDB_DEV void sdb_ws_main(const SdbLoopArgs& a, const PInline<D * D>& fp,
       }
 #else
       {
+        const SdbGen gen(pkey, p_lo, p_hi, SDB_STEP(n));
         double dW[M];
         {
           uint32_t w[M / 2][4];
-          sdb_philox_batch<M / 2>(pkey, p_lo, p_hi, SDB_STEP(n), 0u, w);
+          gen.template blocks<M / 2, true>(0u, w);
           sdb_normal_batch<M / 2, true>(w, tab, rh_g, dW);
         }
         sdb_tm_st<M>(tm + Ws::C_DW, dW);
@@ -417,9 +419,9 @@ SDB_DEV void sdb_ws_main(const SdbLoopArgs& a, const PInline<D * D>& fp,
           const double hk = s_hk[k];
           {
             uint32_t w[M / 2][4];
-            sdb_philox_batch<M / 2>(pkey, p_lo, p_hi, SDB_STEP(n), sx, w);
+            gen.template blocks<M / 2, false>(sx, w);
             sdb_normal_batch<M / 2, true>(w, tab, hk, X);
-            sdb_philox_batch<M / 2>(pkey, p_lo, p_hi, SDB_STEP(n), sx + M / 2, w);
+            gen.template blocks<M / 2, false>(sx + M / 2, w);
             sdb_normal_batch<M / 2, false>(w, tab, 1.0, Z);
           }
 #pragma unroll

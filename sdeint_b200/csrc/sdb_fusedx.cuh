@@ -70,19 +70,19 @@ struct SdbXShape {
 
 #ifdef __CUDACC__
 // NP Box-Muller pairs (slots slot0 ..) in lock-step batches of at most 5: out[0 .. 2 NP)
-template <int NP, int OFF, int TOT, bool SCALED>
-SDB_DEV void sdb_gen_pairs(const SdbPhiloxKey& key, uint32_t p_lo, uint32_t p_hi, uint32_t step,
-                           uint32_t slot0, const double2* __restrict__ tab, double scale,
+// FIRST: slot0 == 0 (slot 0 is the step's plain Philox block, the others its keyed expansion)
+template <int NP, int OFF, int TOT, bool SCALED, bool FIRST = false>
+SDB_DEV void sdb_gen_pairs(const SdbGen& gen, uint32_t slot0, const double2* __restrict__ tab, double scale,
                            double (&out)[TOT]) {
   if constexpr (NP > 0) {
     constexpr int B = NP >= 5 ? 5 : NP;
     uint32_t w[B][4];
     double z[2 * B];
-    sdb_philox_batch<B>(key, p_lo, p_hi, step, slot0 + (uint32_t)OFF, w);
+    gen.template blocks<B, FIRST && OFF == 0>(slot0 + (uint32_t)OFF, w);
     sdb_normal_batch<B, SCALED>(w, tab, scale, z);
 #pragma unroll
     for (int i = 0; i < 2 * B; ++i) out[2 * OFF + i] = z[i];
-    sdb_gen_pairs<NP - B, OFF + B, TOT, SCALED>(key, p_lo, p_hi, step, slot0, tab, scale, out);
+    sdb_gen_pairs<NP - B, OFF + B, TOT, SCALED, FIRST>(gen, slot0, tab, scale, out);
   }
 }
 
@@ -92,7 +92,7 @@ SDB_DEV void sdb_gen_pairs(const SdbPhiloxKey& key, uint32_t p_lo, uint32_t p_hi
 // s_hk[k] = h / (2 pi k).  Used by the fused step kernel below and by the standalone
 // Ikpw/Jkpw/Iwik/Jwik kernel (sdb_repintx.cuh).
 template <int M, int WIK>
-SDB_DEV void sdb_x_levy_areas(const SdbPhiloxKey& pkey, uint32_t p_lo, uint32_t p_hi, uint32_t step,
+SDB_DEV void sdb_x_levy_areas(const SdbGen& gen,
                               const double2* __restrict__ tab, const double* __restrict__ s_hk,
                               double hg, double cz, double tail_scale, int n_terms, uint32_t tm_at,
                               uint32_t tm_dw) {
@@ -102,8 +102,8 @@ SDB_DEV void sdb_x_levy_areas(const SdbPhiloxKey& pkey, uint32_t p_lo, uint32_t 
   for (int k = 1; k <= n_terms; ++k) {
     double X[M], Z[M];
     const uint32_t sx = (uint32_t)((M + 2 * (k - 1) * M) >> 1);
-    sdb_gen_pairs<M / 2, 0, M, true>(pkey, p_lo, p_hi, step, sx, tab, s_hk[k], X);
-    sdb_gen_pairs<M / 2, 0, M, false>(pkey, p_lo, p_hi, step, sx + M / 2, tab, 1.0, Z);
+    sdb_gen_pairs<M / 2, 0, M, true>(gen, sx, tab, s_hk[k], X);
+    sdb_gen_pairs<M / 2, 0, M, false>(gen, sx + M / 2, tab, 1.0, Z);
     {
       double dW[M];
       sdb_tm_ld<M>(tm_dw, dW);
@@ -159,7 +159,7 @@ SDB_DEV void sdb_x_levy_areas(const SdbPhiloxKey& pkey, uint32_t p_lo, uint32_t 
 #pragma unroll 1
     for (int c = 0; c < NCH; ++c) {
       double g[CH], At[CH];
-      sdb_gen_pairs<CH / 2, 0, CH, false>(pkey, p_lo, p_hi, step, st0 + (uint32_t)(c * CH / 2),
+      sdb_gen_pairs<CH / 2, 0, CH, false>(gen, st0 + (uint32_t)(c * CH / 2),
                                           tab, 1.0, g);
       sdb_tm_ld<CH>(tm_at + 2 * CH * c, At);
       sdb_static_for<0, NCH>([&](auto cc) {
@@ -266,10 +266,11 @@ SDB_DEV void sdb_srk2_fusedx_body(const SdbLoopArgs& a, const PInline<D * D>& fp
 #pragma unroll 1
   for (int n = 0; n < steps; ++n) {
     const double h = hs[n];
+    const SdbGen gen(pkey, p_lo, p_hi, SDB_STEP(n));
     // ---- dW (wiener.py:52) ---------------------------------------------------------------------------
     {
       double dW[M];
-      sdb_gen_pairs<M / 2, 0, M, true>(pkey, p_lo, p_hi, SDB_STEP(n), 0u, tab, rh_g, dW);
+      sdb_gen_pairs<M / 2, 0, M, true, true>(gen, 0u, tab, rh_g, dW);
       sdb_tm_st<M>(tm + Xs::C_DW, dW);
       double zero[CH];
 #pragma unroll
@@ -279,7 +280,7 @@ SDB_DEV void sdb_srk2_fusedx_body(const SdbLoopArgs& a, const PInline<D * D>& fp
       sdb_tm_wait_st();
     }
     // ---- Levy areas (series + Wiktorsson tail) into tensor memory ------------------------------------
-    sdb_x_levy_areas<M, WIK>(pkey, p_lo, p_hi, SDB_STEP(n), tab, s_hk, hg, cz, tail_scale, n_terms,
+    sdb_x_levy_areas<M, WIK>(gen, tab, s_hk, hg, cz, tail_scale, n_terms,
                              tm + Xs::C_AT, tm + Xs::C_DW);
 
     // ---- row blocks (runtime loop: every block has RN rows) ------------------------------------------

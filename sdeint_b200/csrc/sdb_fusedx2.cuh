@@ -201,11 +201,12 @@ SDB_DEV void sdb_srk2_fusedx2_body(const SdbLoopArgs& a, const PInline<D * D>& f
 #pragma unroll 1
   for (int n = 0; n < steps; ++n) {
     const double h = hs[n];
+    const SdbGen gen(pkey, p_lo, p_hi, SDB_STEP(n));
     // ---- dW (wiener.py:52) by role 0; both roles clear their area chunks -----------------------------
     {
       if (lead) {
         double dW[M];
-        sdb_gen_pairs<M / 2, 0, M, true>(pkey, p_lo, p_hi, SDB_STEP(n), 0u, tab, rh_g, dW);
+        sdb_gen_pairs<M / 2, 0, M, true, true>(gen, 0u, tab, rh_g, dW);
         sdb_tm_st<M>(tm + Xs::C_DW, dW);
       }
       double zero[CH];
@@ -224,7 +225,7 @@ SDB_DEV void sdb_srk2_fusedx2_body(const SdbLoopArgs& a, const PInline<D * D>& f
         const int buf = (k & 1) * M;
         {
           double V[M];
-          sdb_gen_pairs<M / 2, 0, M, true>(pkey, p_lo, p_hi, SDB_STEP(n), sx, tab, lead ? s_hk[k] : 1.0, V);
+          sdb_gen_pairs<M / 2, 0, M, true>(gen, sx, tab, lead ? s_hk[k] : 1.0, V);
           if (!lead) {
             double dW[M];
             sdb_tm_ld<M>(tm + Xs::C_DW, dW);
@@ -262,7 +263,7 @@ SDB_DEV void sdb_srk2_fusedx2_body(const SdbLoopArgs& a, const PInline<D * D>& f
 #pragma unroll 1
         for (int c = c_lo; c < c_hi; ++c) {
           double g[CH], At[CH];
-          sdb_gen_pairs<CH / 2, 0, CH, false>(pkey, p_lo, p_hi, SDB_STEP(n), st0 + (uint32_t)(c * CH / 2),
+          sdb_gen_pairs<CH / 2, 0, CH, false>(gen, st0 + (uint32_t)(c * CH / 2),
                                               tab, 1.0, g);
           sdb_tm_ld<CH>(tm + Xs::C_AT + 2 * CH * c, At);
           sdb_static_for<0, NCH>([&](auto cc) {

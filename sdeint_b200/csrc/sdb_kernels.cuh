@@ -165,6 +165,34 @@ SDB_HD void sdb_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+// ---- keyed expansion of the per-(path, step) Philox block ("MX2") -----------------------------
+// IMAD.WIDE, the 64-bit product of Philox, occupies the FP64 pipe's issue resource on sm_100a
+// (profiles/r01_microbench.md), so only TWO Philox4x32-10 blocks are computed per (path, step):
+//   slot 0                 -> the block itself (counter word 3 = 0), as before;
+//   slot s >= 1            -> MX2(K, s) with K = Philox4x32-10 at counter word 3 = SDB_RNG_KEYSLOT.
+// MX2 is two rounds of 32-bit multiply-xorshift over four coupled words (12 IMAD + 24 ALU
+// instructions, none on the FP64 pipe); K is never output.  Spec restated in oracle/philox_oracle.py;
+// avalanche / correlation / normal-distribution tests in tests/test_philox.py.
+#define SDB_RNG_KEYSLOT 0xFFFFFFFFu
+#define SDB_MX_G0 0x9E3779B1u
+#define SDB_MX_G1 0x85EBCA77u
+#define SDB_MX_G2 0xC2B2AE3Du
+#define SDB_MX_G3 0x27D4EB2Fu
+#define SDB_MX_C0 0xED5AD4BBu
+#define SDB_MX_C1 0xAC4C1B51u
+#define SDB_MX_C2 0x31848BABu
+#define SDB_MX_C3 0x7FEB352Du
+SDB_HD void sdb_mx2_block(const uint32_t (&K)[4], uint32_t s, uint32_t (&o)[4]) {
+  uint32_t x0 = K[0] + s * SDB_MX_G0, x1 = K[1] + s * SDB_MX_G1, x2 = K[2] + s * SDB_MX_G2,
+           x3 = K[3] + s * SDB_MX_G3;
+  x0 ^= x0 >> 15; x1 ^= x1 >> 15; x2 ^= x2 >> 15; x3 ^= x3 >> 15;
+  uint32_t y0 = x0 * SDB_MX_C0 + x1, y1 = x1 * SDB_MX_C1 + x2, y2 = x2 * SDB_MX_C2 + x3,
+           y3 = x3 * SDB_MX_C3 + x0;
+  y0 ^= y0 >> 13; y1 ^= y1 >> 13; y2 ^= y2 >> 13; y3 ^= y3 >> 13;
+  x0 = y0 * SDB_MX_C1 + y1; x1 = y1 * SDB_MX_C2 + y2; x2 = y2 * SDB_MX_C3 + y3; x3 = y3 * SDB_MX_C0 + y0;
+  o[0] = x0 ^ (x0 >> 16); o[1] = x1 ^ (x1 >> 16); o[2] = x2 ^ (x2 >> 16); o[3] = x3 ^ (x3 >> 16);
+}
+
 // Counter layout: (path low, path high, step, slot); key = seed.  One 128-bit block yields one
 // Box-Muller pair (spec restated in oracle/philox_oracle.py):
 //   hi = w0:w1, lo = w2:w3;  x = (hi >> 11) | 1 (53-bit odd integer), u1 = x 2^-53 in (0,1)
@@ -239,16 +267,44 @@ SDB_DEV void sdb_normal_pair(const uint32_t (&w)[4], const double2* __restrict__
   z1 = __hiloint2double(__double2hiint(p1) ^ (int)s1, __double2loint(p1));
 }
 
+// The 128-bit random block of (seed, path, step, slot): host and device (sdb_random_block in
+// include/sdb.h exposes it to the tests).
+SDB_HD void sdb_random_block(const SdbPhiloxKey& key, uint64_t path, uint32_t step, uint32_t slot,
+                             uint32_t (&out)[4]) {
+  if (slot == 0u) {
+    sdb_philox4x32_10((uint32_t)path, (uint32_t)(path >> 32), step, 0u, key, out);
+  } else {
+    uint32_t K[4];
+    sdb_philox4x32_10((uint32_t)path, (uint32_t)(path >> 32), step, SDB_RNG_KEYSLOT, key, K);
+    sdb_mx2_block(K, slot, out);
+  }
+}
+
 struct SdbStream {
   const SdbPhiloxKey& key;
   uint32_t p_lo, p_hi, step;
   const double2* tab;  // log table: global (sdb_logtab) or a shared-memory copy
+  uint32_t K[4];       // expansion key of this (path, step); only built when slots >= 1 are read
   SDB_DEV SdbStream(const SdbPhiloxKey& key_, uint64_t path, uint32_t step_,
-                    const double2* tab_ = reinterpret_cast<const double2*>(sdb_logtab))
-      : key(key_), p_lo((uint32_t)path), p_hi((uint32_t)(path >> 32)), step(step_), tab(tab_) {}
+                    const double2* tab_ = reinterpret_cast<const double2*>(sdb_logtab),
+                    bool expand = true)
+      : key(key_), p_lo((uint32_t)path), p_hi((uint32_t)(path >> 32)), step(step_), tab(tab_) {
+    if (expand) {
+      sdb_philox4x32_10(p_lo, p_hi, step, SDB_RNG_KEYSLOT, key, K);
+    } else {
+      K[0] = K[1] = K[2] = K[3] = 0u;
+    }
+  }
+  SDB_DEV void block(uint32_t slot, uint32_t (&r)[4]) const {
+    if (slot == 0u) {
+      sdb_philox4x32_10(p_lo, p_hi, step, 0u, key, r);
+    } else {
+      sdb_mx2_block(K, slot, r);
+    }
+  }
   SDB_DEV void pair(uint32_t slot, double& z0, double& z1) const {
     uint32_t r[4];
-    sdb_philox4x32_10(p_lo, p_hi, step, slot, key, r);
+    block(slot, r);
     sdb_normal_pair(r, tab, z0, z1);
   }
 };
@@ -608,7 +664,9 @@ SDB_DEV void sdb_step_noise(const SdbLoopArgs& a, int64_t p, int n, double (&dW)
     }
   } else {
     const SdbPhiloxKey key(a.seed);
-    const SdbStream st(key, (uint64_t)(a.path_id0 + p), SDB_STEP(n));
+    // slots >= 1 (the keyed expansion) are read for m > 2 and for the Levy-series normals
+    const SdbStream st(key, (uint64_t)(a.path_id0 + p), SDB_STEP(n),
+                       reinterpret_cast<const double2*>(sdb_logtab), M > 2 || (NEED_IJ && !DIAG));
     const double rh = sqrt(a.h_global);  // deltaW(N-1, m, h_global): integrate.py:483
     SdbNormalSeq s(st, 0u);
 #pragma unroll
@@ -1022,7 +1080,8 @@ extern "C" __global__ void __launch_bounds__(256) sdb_k_delta_w(const SdbDeltaWA
   const int64_t n = idx / a.paths;
   const int64_t p = idx - n * a.paths;
   const SdbPhiloxKey key(a.seed);
-  const SdbStream st(key, (uint64_t)(a.path_id0 + p), (uint32_t)n);
+  const SdbStream st(key, (uint64_t)(a.path_id0 + p), (uint32_t)n,
+                     reinterpret_cast<const double2*>(sdb_logtab), a.m > 2);
   SdbNormalSeq s(st, 0u);
   double* o = a.out + n * a.sN + p * a.sP;
   for (int j = 0; j < a.m; ++j) o[j * a.sJ] = a.sqrt_h * s.next();

@@ -61,8 +61,9 @@ SDB_DEV void sdb_repintx_body(const SdbRepintArgs& a, double* smem) {
   {
     const uint64_t path = (uint64_t)(a.path_id0 + p);
     const SdbPhiloxKey pkey(a.seed);
+    const SdbGen gen(pkey, (uint32_t)path, (uint32_t)(path >> 32), (uint32_t)n);
     const double tail_scale = WIK ? a.h * SDB_INV_2PI * sqrt(sdb_a_tail(a.n_terms)) : 0.0;
-    sdb_x_levy_areas<M, WIK>(pkey, (uint32_t)path, (uint32_t)(path >> 32), (uint32_t)n, tab, s_hk, a.h,
+    sdb_x_levy_areas<M, WIK>(gen, tab, s_hk, a.h,
                              sqrt(2.0 / a.h), tail_scale, a.n_terms, tm + Rs::C_AT, tm + Rs::C_DW);
   }
   // ---- assemble and store: KPW places +A above the diagonal (wiener.py:106), Wiktorsson's

@@ -81,7 +81,8 @@ def _check_args(f, G, y0, tspan, dW=None, IJ=None):
     sdeint/integrate.py:47-121 (equal spacing, scalar promotion, int -> float64, shape of
     f(y0), G as one (d, m) operator or a list of m columns, shapes of dW and I/J), with an
     optional leading path axis on dW / IJ.  Returns (d, m, f, Gop, y0, tspan, dW, IJ)."""
-    tspan = np.asarray(tspan, dtype=np.float64)
+    # C-contiguous: the C ABI reads h_tspan[i] with unit stride (a view such as t[::2] is copied)
+    tspan = np.ascontiguousarray(tspan, dtype=np.float64)
     if tspan.ndim != 1 or tspan.shape[0] < 2:
         raise SDEValueError('tspan must be a 1-d sequence of at least two time points.')
     steps = np.diff(tspan)
@@ -379,22 +380,54 @@ def _launch(lib, system, a, obs_arr, d_obs_ptr, obs_stride, step0, h_noise):
     _lib.check(lib.sdb_integrate_segment(system.handle, C.byref(a), C.byref(x)))
 
 
+_RING_SLOT_BYTES = 512 << 20
+_ring = {}
+
+
+def _pinned_ring(device, nbytes):
+    """Two pinned staging slots of `nbytes` each, kept for the life of the process (pinning is slow)."""
+    torch = dev.torch_mod()
+    key = str(device)
+    ring = _ring.get(key)
+    if ring is None or ring[0].numel() * 8 < nbytes:
+        ring = [torch.empty((nbytes + 7) // 8, dtype=torch.float64).pin_memory() for _ in range(2)]
+        _ring[key] = ring
+    return ring
+
+
 def _run_pipelined(lib, system, a, host_out, P, path_id0, n_saved, d, device, obs_arr=None, d_obs=None,
                    step0=0, h_noise=None):
-    """Chunked integration with overlapped device -> host copies; returns the merged status."""
+    """Chunked integration with overlapped device -> host copies; returns the merged status.
+
+    A pinned `host_out` receives the chunks directly.  A pageable one is filled through a fixed ring
+    of two pinned slots (<= 512 MB each): chunk c is integrated while chunk c-1 is copied into its
+    slot and the host drains that slot into the caller's array, so the pinned footprint does not grow
+    with the ensemble (8 ranks x 8.8 GB results on one host)."""
     torch = dev.torch_mod()
     # chunk = a whole number of waves of the fused kernels (one 256-path block per SM), so that only
     # the last chunk has a partial wave -- exactly like the single launch it replaces
     wave = 256 * torch.cuda.get_device_properties(device).multi_processor_count
+    direct = host_out.is_pinned()
     chunks = min(_PIPELINE_CHUNKS, max(2, P >> 18))
+    if not direct:
+        chunks = max(chunks, -(-(8 * n_saved * d * P) // _RING_SLOT_BYTES))
     Pc = max(wave, (P // chunks) // wave * wave)
     chunks = -(-P // Pc)
     compute = torch.cuda.current_stream()
     copier = torch.cuda.Stream(device=device)
     bufs = [torch.empty((n_saved, d, Pc), dtype=torch.float64, device=device) for _ in range(2)]
+    ring = None if direct else _pinned_ring(device, 8 * n_saved * d * Pc)
+    host_np = None if direct else host_out.numpy()
     stats = torch.empty((chunks, 4), dtype=torch.int64, device=device)
     copied = [None, None]
     base = host_out.data_ptr()
+
+    def drain(c):   # pinned slot of chunk c -> the caller's pageable array (host memcpy)
+        p0 = c * Pc
+        n = min(Pc, P - p0)
+        copied[c & 1].synchronize()
+        host_np[:, :, p0:p0 + n] = ring[c & 1].numpy()[:n_saved * d * n].reshape(n_saved, d, n)
+
     for c in range(chunks):
         p0 = c * Pc
         n = min(Pc, P - p0)
@@ -411,12 +444,21 @@ def _run_pipelined(lib, system, a, host_out, P, path_id0, n_saved, d, device, ob
                 P, step0, h_noise)
         done = torch.cuda.Event()
         done.record(compute)
+        if not direct and c >= 1:
+            drain(c - 1)                          # host copy overlaps the kernel of chunk c
         copier.wait_event(done)
-        _lib.check(lib.sdb_copy2d_d2h_async(C.c_void_p(base + 8 * p0), 8 * P, dev.ptr(buf), 8 * Pc,
-                                            8 * n, n_saved * d, C.c_void_p(copier.cuda_stream)))
+        if direct:
+            _lib.check(lib.sdb_copy2d_d2h_async(C.c_void_p(base + 8 * p0), 8 * P, dev.ptr(buf), 8 * Pc,
+                                                8 * n, n_saved * d, C.c_void_p(copier.cuda_stream)))
+        else:   # rows of n doubles, packed, into slot c & 1 (drained of chunk c-2 one iteration ago)
+            _lib.check(lib.sdb_copy2d_d2h_async(C.c_void_p(ring[c & 1].data_ptr()), 8 * n, dev.ptr(buf),
+                                                8 * Pc, 8 * n, n_saved * d,
+                                                C.c_void_p(copier.cuda_stream)))
         ev = torch.cuda.Event()
         ev.record(copier)
         copied[c & 1] = ev
+    if not direct:
+        drain(chunks - 1)
     copier.synchronize()
     compute.wait_stream(copier)
     st = stats.cpu().numpy()

@@ -1078,6 +1078,18 @@ def test_pipelined_host_output_matches_single_launch(sdb):
     assert sdb.launch_count() - n0 >= 4                       # more than one chunk
     assert y.shape == (P, 3, 10) and np.array_equal(y, ref.transpose(2, 0, 1))
     assert sdb.last_status()[0] == 0
+    # a pageable result array is filled through the fixed ring of two pinned staging slots
+    import sdeint_b200.integrate as integ
+    pageable = torch.zeros((3, 10, P), dtype=torch.float64)
+    old_slot = integ._RING_SLOT_BYTES
+    integ._RING_SLOT_BYTES = 3 * 10 * 8 * (1 << 16)        # force > 8 chunks of 2^16.. paths
+    try:
+        n0 = sdb.launch_count()
+        yp = sdb.itoSRI2(f, G, y0, tspan, paths=P, seed=3, path_id0=10, save_every=5, host_out=pageable)
+        assert sdb.launch_count() - n0 >= 8
+    finally:
+        integ._RING_SLOT_BYTES = old_slot
+    assert not pageable.is_pinned() and np.array_equal(yp, ref.transpose(2, 0, 1))
     f2, G2, y02 = SYSTEMS["lin2"](False)
     host2 = torch.empty((2, 2, P), dtype=torch.float64).pin_memory()
     y2 = sdb.itoEuler(f2, G2, y02, tspan, paths=P, seed=4, save_every=10, host_out=host2)

@@ -79,6 +79,12 @@ def test_check_args_host_logic():
     assert integrate._resolve_paths(None, np.zeros((20, 4)), None) == (1, False)
     with pytest.raises(sdb.SDEValueError):
         integrate._resolve_paths(3, np.zeros((7, 20, 4)), None)
+    # a strided view of a finer grid reaches the C ABI as a contiguous copy with the same values
+    # (h_tspan is read with unit stride)
+    fine = np.linspace(0.0, 0.1, 41)
+    t2 = integrate._check_args(f, G, y0, fine[::2])[5]
+    assert t2.flags["C_CONTIGUOUS"] and np.array_equal(t2, tspan) or np.allclose(t2, tspan, rtol=0, atol=1e-17)
+    assert t2.ctypes.data != fine.ctypes.data or t2.strides == (8,)
 
 
 def test_ops_host_callables_follow_reference_conventions():
