@@ -192,6 +192,14 @@ int sdb_repeated_integrals(const sdb_repint_args* args);
 int sdb_moments(const double* d_y, int64_t n_saved, int d, int64_t paths, double* d_sums,
                 unsigned long long* d_hist, int bins, double lo, double hi, void* stream);
 
+/* Ensemble (count, mean, M2 = sum (y - mean)^2) per (saved point, component), the numerically safe
+ * form of the variance: every chunk of 4096 paths is centred on its own mean and the
+ * chunks are merged in chunk order with Chan's update; d_out[save][comp][3] is UPDATED by the same
+ * merge (zero it for a fresh result), so successive calls -- or the per-rank results gathered by
+ * the caller, merged in rank order -- accumulate deterministically. */
+int sdb_moments_welford(const double* d_y, int64_t n_saved, int d, int64_t paths, double* d_out,
+                        void* stream);
+
 /* Ensemble second moments of saved states y[save][comp][path] (path stride 1):
  * d_out[save][i][j] += sum_p y_i y_j (full symmetric d x d matrix, d <= 16), summed per chunk of
  * 4096 paths and then over chunks in a fixed order (deterministic, partition-independent per chunk).

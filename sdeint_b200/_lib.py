@@ -79,6 +79,7 @@ SIGNATURES = {
     "sdb_repeated_integrals": (C.c_int, [C.POINTER(RepintArgs)]),
     "sdb_moments": (C.c_int, [c_dp, c_i64, C.c_int, c_i64, c_dp, c_dp, C.c_int, C.c_double,
                               C.c_double, c_dp]),
+    "sdb_moments_welford": (C.c_int, [c_dp, c_i64, C.c_int, c_i64, c_dp, c_dp]),
     "sdb_cross_moments": (C.c_int, [c_dp, c_i64, C.c_int, c_i64, c_dp, c_dp]),
     "sdb_copy2d_d2h_async": (C.c_int, [c_dp, c_i64, c_dp, c_i64, c_i64, c_i64, c_dp]),
     "sdb_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), c_dp]),

@@ -938,6 +938,99 @@ extern "C" int sdb_moments(const double* d_y, int64_t n_saved, int d, int64_t pa
   return 0;
 }
 
+
+// ---- (count, mean, M2) partials with a fixed-order Chan merge -------------------------
+// E[y^2] - E[y]^2 cancels catastrophically when |mean| >> std; here every chunk of 4096 paths is
+// centred on its OWN mean (two passes over data that is L1/L2 resident after the first), and chunks
+// are merged in chunk order with Chan's update  M2 = M2_a + M2_b + delta^2 n_a n_b / (n_a + n_b).
+__global__ void __launch_bounds__(SDB_MOM_BLOCK)
+sdb_k_welford_partial(const double* __restrict__ y, int64_t paths, int64_t nchunks,
+                      double2* __restrict__ partial) {
+  __shared__ double sh[SDB_MOM_BLOCK / 32];
+  __shared__ double sh_mean;
+  const int64_t row = blockIdx.y, chunk = blockIdx.x;
+  const double* src = y + row * paths;
+  const int64_t base = chunk * SDB_MOM_CHUNK;
+  const int64_t cnt = paths - base < SDB_MOM_CHUNK ? paths - base : SDB_MOM_CHUNK;
+  double v[SDB_MOM_CHUNK / SDB_MOM_BLOCK];
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < SDB_MOM_CHUNK / SDB_MOM_BLOCK; ++i) {
+    const int64_t p = base + (int64_t)i * SDB_MOM_BLOCK + threadIdx.x;
+    v[i] = p < paths ? src[p] : 0.0;
+    s += v[i];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ts = 0.0;
+#pragma unroll
+    for (int w = 0; w < SDB_MOM_BLOCK / 32; ++w) ts += sh[w];
+    sh_mean = ts / (double)cnt;
+  }
+  __syncthreads();
+  const double mean = sh_mean;
+  double q = 0.0;
+#pragma unroll
+  for (int i = 0; i < SDB_MOM_CHUNK / SDB_MOM_BLOCK; ++i) {
+    const int64_t p = base + (int64_t)i * SDB_MOM_BLOCK + threadIdx.x;
+    const double dlt = v[i] - mean;
+    if (p < paths) q = fma(dlt, dlt, q);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_down_sync(0xffffffffu, q, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = q;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tq = 0.0;
+#pragma unroll
+    for (int w = 0; w < SDB_MOM_BLOCK / 32; ++w) tq += sh[w];
+    partial[row * nchunks + chunk] = make_double2(mean, tq);
+  }
+}
+
+// out[row] = (count, mean, M2): Chan merge of the chunk partials in chunk order, then of the value
+// already in out[row] (count 0 = empty), one thread per row: deterministic.
+__global__ void sdb_k_welford_final(const double2* __restrict__ partial, int64_t rows, int64_t paths,
+                                    int64_t nchunks, double* __restrict__ out) {
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  double n = out[3 * row], mean = out[3 * row + 1], m2 = out[3 * row + 2];
+  for (int64_t c = 0; c < nchunks; ++c) {
+    const double2 v = partial[row * nchunks + c];
+    const int64_t left = paths - c * SDB_MOM_CHUNK;
+    const double nb = (double)(left < SDB_MOM_CHUNK ? left : SDB_MOM_CHUNK);
+    const double tot = n + nb, dlt = v.x - mean;
+    mean += dlt * (nb / tot);
+    m2 += v.y + dlt * dlt * (n * nb / tot);
+    n = tot;
+  }
+  out[3 * row] = n; out[3 * row + 1] = mean; out[3 * row + 2] = m2;
+}
+
+extern "C" int sdb_moments_welford(const double* d_y, int64_t n_saved, int d, int64_t paths,
+                                   double* d_out, void* stream) {
+  if (!d_y || !d_out || n_saved < 1 || d < 1 || paths < 1) return fail("sdb_moments_welford: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t rows = n_saved * d;
+  const int64_t nchunks = (paths + SDB_MOM_CHUNK - 1) / SDB_MOM_CHUNK;
+  if (rows > 65535) return fail("sdb_moments_welford: too many (saved point, component) rows");
+  double2* partial = nullptr;
+  keep_pool_memory();
+  SDB_CUDA(cudaMallocAsync(&partial, rows * nchunks * sizeof(double2), st));
+  sdb_k_welford_partial<<<dim3((unsigned)nchunks, (unsigned)rows), SDB_MOM_BLOCK, 0, st>>>(
+      d_y, paths, nchunks, partial);
+  SDB_CUDA(cudaGetLastError());
+  sdb_k_welford_final<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(partial, rows, paths, nchunks, d_out);
+  SDB_CUDA(cudaGetLastError());
+  g_launches.fetch_add(2);
+  SDB_CUDA(cudaFreeAsync(partial, st));
+  return 0;
+}
+
 // cross[save][chunk][i*d+j] = sum over the 4096 paths of the chunk of y_i y_j: the chunk is staged
 // through shared memory 256 paths at a time, thread t < d*d owns the pair (t / d, t % d).
 __global__ void __launch_bounds__(256)

@@ -46,6 +46,59 @@ def moments(y_dev, hist=None):
     return sums, counts
 
 
+def welford(y_dev, into=None):
+    """(count, mean, M2 = sum (y - mean)^2) per (saved point, component) of a device trajectory tensor
+    (n_saved, d, P): float64 device tensor (n_saved, d, 3).  Unlike E[y^2] - E[y]^2 this does not
+    cancel when |mean| >> std: every chunk of 4096 paths is centred on its own mean and chunks are
+    merged in a fixed order with Chan's update (sdb_moments_welford).  `into` = a previous result to
+    merge this tensor's paths into (successive batches of one ensemble)."""
+    torch = dev.torch_mod()
+    if y_dev.dim() != 3 or y_dev.dtype != torch.float64 or not y_dev.is_contiguous():
+        raise ValueError("welford: need a contiguous float64 tensor (n_saved, d, P)")
+    S, d, P = y_dev.shape
+    with torch.cuda.device(y_dev.device):
+        out = into if into is not None else torch.zeros((S, d, 3), dtype=torch.float64, device=y_dev.device)
+        _lib.check(_lib.load().sdb_moments_welford(dev.ptr(y_dev), S, d, P, dev.ptr(out), dev.stream_ptr()))
+    return out
+
+
+def chan_merge(parts):
+    """Fixed-order Chan merge of (count, mean, M2) partials (arrays or tensors (..., 3), e.g. one per
+    rank in rank order): the bit-reproducible combination SURVEY 8e asks for."""
+    acc = None
+    for part in parts:
+        if acc is None:
+            acc = part.clone() if hasattr(part, "clone") else np.array(part, dtype=np.float64)
+            continue
+        n, mean, m2 = acc[..., 0], acc[..., 1], acc[..., 2]
+        nb, mb, qb = part[..., 0], part[..., 1], part[..., 2]
+        tot = n + nb
+        safe = tot + (tot == 0)
+        dlt = mb - mean
+        new_mean = mean + dlt * (nb / safe)
+        new_m2 = m2 + qb + dlt * dlt * (n * nb / safe)
+        acc = acc.clone() if hasattr(acc, "clone") else acc.copy()
+        acc[..., 0], acc[..., 1], acc[..., 2] = tot, new_mean, new_m2
+    return acc
+
+
+def allgather_welford(w, group=None):
+    """All ranks' (count, mean, M2) partials gathered (torch.distributed; NCCL on GPUs) and merged in
+    rank order: every rank gets the same bits."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        torch = dev.torch_mod()
+        parts = [torch.empty_like(w) for _ in range(dist.get_world_size(group))]
+        dist.all_gather(parts, w.contiguous(), group=group)
+        return chan_merge(parts)
+    return w
+
+
+def welford_mean_var(w, ddof=0):
+    """Ensemble mean and variance from (count, mean, M2)."""
+    return w[..., 1], w[..., 2] / (w[..., 0] - ddof)
+
+
 def second_moments(y_dev):
     """sum_p y_i y_j at every saved point of a device trajectory tensor (n_saved, d, P), d <= 16:
     returns a float64 device tensor (n_saved, d, d) (deterministic; all-reduce it like the sums)."""

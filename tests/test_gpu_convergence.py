@@ -228,6 +228,33 @@ def test_device_normals_chi_square_1e9(sdb):
     assert abs(m4 - 3.0) < 6.0 * np.sqrt(96.0 / 1e8)
 
 
+def test_device_normals_independent_across_slots(sdb):
+    """The 110 normals of one (path, step) of the headline shape come from slot 0 (the Philox block)
+    and 54 slots of its keyed MX2 expansion: pairwise sample correlations of z and of z^2 over 4 10^6
+    path-steps within 6 sigma (110 x 109 pairs each), first four moments of every slot position."""
+    import torch
+    N, m, P = 40, 110, 100000
+    z = sdb.deltaW(N, m, 1.0, paths=P, seed=424242, out="torch")            # (N, m, P)
+    v = z.permute(1, 0, 2).reshape(m, N * P)
+    n = N * P
+    mean, var = v.mean(dim=1), v.var(dim=1)
+    assert mean.abs().max().item() < 6.0 / np.sqrt(n)
+    assert (var - 1.0).abs().max().item() < 6.0 * np.sqrt(2.0 / n)
+    assert ((v ** 4).mean(dim=1) - 3.0).abs().max().item() < 6.0 * np.sqrt(96.0 / n)
+    for w in (v, v * v - 1.0):
+        w = (w - w.mean(dim=1, keepdim=True)) / w.std(dim=1, keepdim=True)
+        c = (w @ w.T) / n
+        c.fill_diagonal_(0.0)
+        assert c.abs().max().item() < 6.0 / np.sqrt(n)
+    # the same slot in consecutive steps and in neighbouring paths (fresh Philox key blocks)
+    a = z[:-1].reshape(-1)
+    b = z[1:].reshape(-1)
+    assert abs((a * b).mean().item()) < 6.0 / np.sqrt(a.numel())
+    a = z[:, :, :-1].reshape(-1)
+    b = z[:, :, 1:].reshape(-1)
+    assert abs((a * b).mean().item()) < 6.0 / np.sqrt(a.numel())
+
+
 def test_ou_autocovariance_and_spectrum(sdb):
     """Stationary statistics of an Ornstein-Uhlenbeck ensemble against the exact values of the
     discrete (Euler-Maruyama = AR(1)) process: variance sigma^2 / (2 theta - theta^2 h), autocorrelation

@@ -1102,6 +1102,35 @@ def test_pipelined_host_output_matches_single_launch(sdb):
     assert o3.shape == (P, 2) and np.array_equal(o3, oref) and np.array_equal(y3, y2)
 
 
+def test_welford_moments_chan_merge(sdb):
+    """(count, mean, M2) partials with a fixed-order Chan merge: exact where
+    E[y^2] - E[y]^2 has lost every digit (|mean| = 1e8 std), identical bits for any split of the
+    ensemble into successive batches of whole 4096-path chunks, and the rank-order merge."""
+    import torch
+    rng = np.random.default_rng(12)
+    S, d, P = 2, 3, 5 * 4096 + 123
+    y = rng.standard_normal((S, d, P)) * 0.5 + 5e7
+    yd = torch.from_numpy(y).cuda()
+    w = sdb.ensemble.welford(yd)
+    mean, var = sdb.ensemble.welford_mean_var(w)
+    assert np.all(w[..., 0].cpu().numpy() == P)
+    assert np.max(np.abs(mean.cpu().numpy() - y.mean(axis=-1))) <= 1e-7
+    assert np.max(np.abs(var.cpu().numpy() / y.var(axis=-1) - 1.0)) <= 1e-9
+    sums, _ = sdb.ensemble.moments(yd)
+    _, naive = sdb.ensemble.mean_var(sums, float(P))
+    assert np.max(np.abs(naive.cpu().numpy() / y.var(axis=-1) - 1.0)) > 1e-3     # what it replaces
+    # successive batches merged on the device == one call, bit for bit (chunk-aligned split)
+    cut = 2 * 4096
+    w2 = sdb.ensemble.welford(yd[:, :, :cut].contiguous())
+    w2 = sdb.ensemble.welford(yd[:, :, cut:].contiguous(), into=w2)
+    assert torch.equal(w2, w)
+    # per-"rank" partials merged in rank order on the host side of the collective
+    parts = [sdb.ensemble.welford(yd[:, :, a:b].contiguous()) for a, b in ((0, cut), (cut, P))]
+    merged = sdb.ensemble.chan_merge(parts)
+    assert torch.equal(merged[..., 0], w[..., 0])
+    assert np.max(np.abs((merged[..., 2] / w[..., 2]).cpu().numpy() - 1.0)) <= 1e-12
+
+
 def test_second_moments_covariance_quantiles(sdb):
     """Ensemble analysis beyond mean/variance: sum_p y_i y_j per saved point on the
     device (deterministic), covariance, and quantiles from the on-device histograms."""

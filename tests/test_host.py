@@ -166,6 +166,18 @@ for r in range(world):
     part = y[:, :, s0:s0 + c0]
     parts.append(np.stack([part.sum(-1), (part * part).sum(-1)], axis=-1))
 assert np.array_equal(mine2.numpy(), parts[0] + parts[1]), rank
+# (count, mean, M2) partials all-gathered and Chan-merged in rank order: same bits on every rank,
+# and the variance survives a mean 1e8 standard deviations away from zero
+big = mine + 1e8
+wpart = torch.from_numpy(np.stack([np.full(big.shape[:2], float(count)), big.mean(-1),
+                                   ((big - big.mean(-1, keepdims=True)) ** 2).sum(-1)], axis=-1))
+w = sdb.ensemble.allgather_welford(wpart)
+wm, wv = sdb.ensemble.welford_mean_var(w)
+assert np.all(w[..., 0].numpy() == P), rank
+assert np.allclose(wv.numpy(), y.var(-1), rtol=1e-7) and np.allclose(wm.numpy(), y.mean(-1) + 1e8), rank
+gathered = [torch.empty_like(w) for _ in range(world)]
+dist.all_gather(gathered, w)
+assert all(torch.equal(g, w) for g in gathered), rank
 # autocovariance across saved times and the ensemble periodogram combine ranks through their raw sums
 yt = torch.from_numpy(np.ascontiguousarray(mine))
 C = sdb.ensemble.autocovariance(yt, 1, paths=P)
