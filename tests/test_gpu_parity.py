@@ -2,7 +2,9 @@
 the public shim -> ctypes -> C ABI (include/sdb.h) -> CUDA kernels, and is compared with
 (a) the committed outputs of the unmodified reference (tests/golden) and (b) the pinned
 oracle on seeded inputs.  Tolerance: 1e-12 relative (fp64), the north-star bound; the
-KP2iS scheme, whose implicit solve the reference delegates to MINPACK, gets 1e-10."""
+KP2iS scheme, whose implicit solve the reference delegates to MINPACK hybrd (fixtures generated at
+the tightest xtol it completes with, 1e-12 / 1e-11; its termination leaves a few 1e-12 relative
+against an exact solve), gets 5e-12 against the reference and 1e-11 against the oracle's Newton solve."""
 import numpy as np
 import pytest
 
@@ -43,7 +45,7 @@ def test_integrators_vs_reference_golden(sdb, name):
         assert rel_err(y, g["y_itoSRI2_listG"]) <= TOL
     if "y_stratKP2iS" in g:
         y = sdb.stratKP2iS(f_str, G, y0, tspan, dW=dW, J=J, rtol=1e-12)
-        assert rel_err(y, g["y_stratKP2iS"]) <= 1e-10
+        assert rel_err(y, g["y_stratKP2iS"]) <= 5e-12
     assert sdb.launch_count() > before          # kernels really launched
     # single-path form: the reference's exact call and return layout (N, d)
     y1 = sdb.itoSRI2(f_ito, G, y0, tspan, dW=dW[0], I=I[0])
@@ -222,6 +224,46 @@ def test_euler_heun_device_noise(sdb):
     assert g1.integers(1 << 30) != np.random.default_rng(8).integers(1 << 30)
 
 
+@pytest.mark.parametrize("d,wik", [(10, False), (20, True)])
+def test_long_run_parity_every_integrator(sdb, d, wik):
+    """SURVEY 8(d) parity run: P = 64 paths, N - 1 = 1000 steps, EVERY integrator, at the cfg3 shape
+    (SYS_LIN(10,10), Ikpw/Jkpw) and the cfg4 shape (SYS_LIN(20,20), Iwik/Jwik), on the noise the
+    production kernels generate on the device (replayed through the standalone deltaW / Ikpw.. kernels,
+    which share the generator), every saved state against the oracle: max_n |y - y_ref| / |y_ref|
+    <= 1e-12 (1e-11 for KP2iS: Newton to 1e-12 on the device, to 1e-13 in the oracle; first 16 paths).
+    Error growth over 1000 steps through the DMMA / TMEM kernels is what this pins."""
+    m = d
+    f, G, y0 = sdb.ops.sys_lin(d, m)
+    N = 1001
+    tspan = np.linspace(0.0, 1.0, N)
+    h = (tspan[-1] - tspan[0]) / (N - 1)
+    P, seed = 64, 8675309
+    Im, Jm = (sdb.Iwik, sdb.Jwik) if wik else (sdb.Ikpw, sdb.Jkpw)
+    dW = sdb.deltaW(N - 1, m, h, paths=P, seed=seed)
+    _, I = Im(dW, h, seed=seed, ensemble=True)
+    J = I + 0.5 * h * np.eye(m)
+    runs = {
+        "itoEuler": (sdb.itoEuler(f, G, y0, tspan, paths=P, seed=seed),
+                     lambda p: orc.euler(f, G, y0, tspan, dW[p]), 1e-12, P),
+        "stratHeun": (sdb.stratHeun(f, G, y0, tspan, paths=P, seed=seed),
+                      lambda p: orc.heun(f, G, y0, tspan, dW[p]), 1e-12, P),
+        "itoSRI2": (sdb.itoSRI2(f, G, y0, tspan, Im, paths=P, seed=seed),
+                    lambda p: orc.srk2(f, G.columns(), y0, tspan, dW[p], I[p]), 1e-12, P),
+        "stratSRS2": (sdb.stratSRS2(f, G, y0, tspan, Jm, paths=P, seed=seed),
+                      lambda p: orc.srk2(f, G.columns(), y0, tspan, dW[p], J[p]), 1e-12, P),
+        "stratKP2iS": (sdb.stratKP2iS(f, G, y0, tspan, Jm, rtol=1e-12, paths=16, seed=seed),
+                       lambda p: orc.kp2is(f, G, y0, tspan, dW[p], J[p], rtol=1e-13, solver="newton"),
+                       1e-11, 16),
+    }
+    worst = {}
+    for name, (y, ref, tol, count) in runs.items():
+        assert y.shape == (count, N, d), name
+        worst[name] = max(rel_err(y[p], ref(p)) for p in range(count))
+        assert worst[name] <= tol, (name, worst)
+    print("long-run parity d=m=%d %s: %s" % (d, "wik" if wik else "kpw",
+                                             ", ".join("%s %.1e" % kv for kv in worst.items())))
+
+
 def test_mixed_noise_inputs(sdb):
     """Only one of dW / I supplied: the other is drawn on the device (integrate.py:481-489)."""
     f, G, y0 = SYSTEMS["r74"](False)
@@ -248,7 +290,7 @@ def test_kp2is_device_noise_and_params(sdb):
     _, J = sdb.Jwik(dW, h, seed=seed, ensemble=True)
     for p in range(P):
         ref = orc.kp2is(f, G, y0, tspan, dW[p], J[p], gam, al1, al2, rtol=1e-13, solver="newton")
-        assert rel_err(y[p], ref) <= 1e-10
+        assert rel_err(y[p], ref) <= 1e-11
 
 
 # ---- argument validation (integrate.py:47-121 semantics) ---------------------------------------
@@ -340,7 +382,7 @@ def test_nvrtc_user_system(sdb):
     assert rel_err(sdb.itoSRI2(f, G, y0, tspan, dW=dW, I=I), orc.srk2(f_host, g_host, y0, tspan, dW, I)) <= TOL
     assert rel_err(sdb.stratSRS2(f, G, y0, tspan, dW=dW, J=J), orc.srk2(f_host, g_host, y0, tspan, dW, J)) <= TOL
     yk = sdb.stratKP2iS(f, G, y0, tspan, dW=dW, J=J, rtol=1e-12)
-    assert rel_err(yk, orc.kp2is(f_host, g_host, y0, tspan, dW, J, rtol=1e-13, solver="newton")) <= 1e-10
+    assert rel_err(yk, orc.kp2is(f_host, g_host, y0, tspan, dW, J, rtol=1e-13, solver="newton")) <= 1e-11
 
 
 def test_jit_builtin_dimensions(sdb):
@@ -498,7 +540,7 @@ def test_additive_noise_never_builds_repeated_integrals(sdb):
     assert rel_err(without_I, g["y_itoSRI2"]) <= TOL
     assert rel_err(sdb.stratSRS2(f, G, y0, tspan, dW=dW), g["y_stratSRS2"]) <= TOL
     if "y_stratKP2iS" in g:
-        assert rel_err(sdb.stratKP2iS(f, G, y0, tspan, dW=dW, rtol=1e-12), g["y_stratKP2iS"]) <= 1e-10
+        assert rel_err(sdb.stratKP2iS(f, G, y0, tspan, dW=dW, rtol=1e-12), g["y_stratKP2iS"]) <= 5e-12
     # on-device noise: only dW is drawn; any I gives the same oracle result
     P, seed = 50, 606
     y = sdb.itoSRI2(f, G, y0, tspan, paths=P, seed=seed)
@@ -591,7 +633,7 @@ def test_diagonal_noise_needs_no_levy_areas(sdb):
     # KP2iS does use off-diagonal J: it still gets the full construction
     yk = sdb.stratKP2iS(f, G, y0, tspan, dW=dW, J=J_full, rtol=1e-12)
     ref = orc.kp2is(f, G, y0, tspan, dW, J_full, rtol=1e-13, solver="newton")
-    assert rel_err(yk, ref) <= 1e-10
+    assert rel_err(yk, ref) <= 1e-11
     # user CUDA source with the diagonal promise
     kf, kg = np.array([1.2, 0.3]), np.array([0.25, 0.1])
 
@@ -1228,7 +1270,7 @@ def test_mid_size_nonlinear_user_system(sdb):
     assert rel_err(sdb.itoSRI2(f, G, y0, tspan, dW=dW, I=I), orc.srk2(f, G, y0, tspan, dW, I)) <= TOL
     assert rel_err(sdb.stratSRS2(f, G, y0, tspan, dW=dW, J=J), orc.srk2(f, G, y0, tspan, dW, J)) <= TOL
     yk = sdb.stratKP2iS(f, G, y0, tspan, dW=dW, J=J, rtol=1e-12)
-    assert rel_err(yk, orc.kp2is(f, G, y0, tspan, dW, J, rtol=1e-13, solver="newton")) <= 1e-9
+    assert rel_err(yk, orc.kp2is(f, G, y0, tspan, dW, J, rtol=1e-13, solver="newton")) <= 1e-11
     P, seed = 40, 15
     for meth, integ, strat in ((sdb.Iwik, sdb.itoSRI2, False), (sdb.Jkpw, sdb.stratSRS2, True)):
         y = integ(f, G, y0, tspan, meth, paths=P, seed=seed)
@@ -1260,7 +1302,7 @@ def test_expression_operators_all_integrators(sdb):
     assert rel_err(sdb.itoSRI2(f, G.columns(), y0, tspan, dW=dW, I=I), orc.srk2(f, G, y0, tspan, dW, I)) <= TOL
     assert rel_err(sdb.stratSRS2(f, G, y0, tspan, dW=dW, J=J), orc.srk2(f, G, y0, tspan, dW, J)) <= TOL
     yk = sdb.stratKP2iS(f, G, y0, tspan, dW=dW, J=J, rtol=1e-12)
-    assert rel_err(yk, orc.kp2is(f, G, y0, tspan, dW, J, rtol=1e-13, solver="newton")) <= 1e-9
+    assert rel_err(yk, orc.kp2is(f, G, y0, tspan, dW, J, rtol=1e-13, solver="newton")) <= 1e-11
     # ensemble on device noise
     P, seed = 33, 8
     y = sdb.itoSRI2(f, G, y0, tspan, paths=P, seed=seed)

@@ -27,9 +27,12 @@ def test_integrators_match_reference_golden(name):
             assert rel_err(y, g["y_itoSRI2_listG"][p]) <= TOL
         if "y_stratKP2iS" in g:
             for solver in ("fsolve", "newton"):
-                y = orc.kp2is(f_str, G, y0, tspan, dW[p], J[p], rtol=1e-9 if
+                # fsolve at the fixture's own xtol reproduces the reference exactly in structure
+                # (same MINPACK calls); the Newton solve is exact to 1e-13 and sits within hybrd's
+                # termination noise of it (a few 1e-12)
+                y = orc.kp2is(f_str, G, y0, tspan, dW[p], J[p], rtol=float(g["kp2is_rtol"]) if
                               solver == "fsolve" else 1e-13, solver=solver)
-                assert rel_err(y, g["y_stratKP2iS"][p]) <= 1e-11, solver
+                assert rel_err(y, g["y_stratKP2iS"][p]) <= 5e-12, solver
 
 
 def test_wiener_constants():
