@@ -507,7 +507,7 @@ static int integrate_impl(sdb_system* s, const sdb_integrate_args* a, const SdbO
   // -> a fused kernel when one is instantiated for this (d, m, method).
   const SdbFusedEntry* fused = nullptr;
   SdbFusedEntry jit_entry{};
-  int jit_rb = 4;
+  int jit_rb = 4, jit_xr = 0;
   bool jit_comm = false;
   std::string label;  // what gets launched (sdb_last_kernel): an ahead-of-time kernel's name or "jit:<key>"
   const bool explicit_em = a->scheme == SDB_SCHEME_EULER || a->scheme == SDB_SCHEME_HEUN;
@@ -589,7 +589,7 @@ static int integrate_impl(sdb_system* s, const sdb_integrate_args* a, const SdbO
       s->fk == SDB_DRIFT_LINEAR && s->gk == SDB_DIFF_LINEAR_COLS &&
       n_terms <= SDB_FUSED_MAX_TERMS && !getenv("SDB_DISABLE_FUSED") &&
       !getenv("SDB_DISABLE_FUSED_JIT") && s->d * s->m >= 16) {  // tiny systems are generator-bound:
-    const SdbFusedDims dims(s->d, s->m);                        // the high-occupancy loop kernel wins
+    const SdbFusedDims dims(s->d, s->m, 4, SDB_FUSED_A2);       // the high-occupancy loop kernel wins
     const SdbFusedXDims xdims(s->d, s->m);
     const bool use_v0 = noise == SDB_NOISE_KPW && dims.supported();
     const bool use_x = !use_v0 && xdims.supported();
@@ -618,6 +618,7 @@ static int integrate_impl(sdb_system* s, const sdb_integrate_args* a, const SdbO
         it = s->jit.emplace(key, k).first;
       }
       if (use_v0) {
+        jit_xr = SDB_FUSED_A2;
         jit_entry = SdbFusedEntry{s->d, s->m, 0, (const void*)it->second.kern, dims.smem_bytes(),
                                   dims.table_doubles(), nullptr, SdbFusedDims::THREADS,
                                   SdbFusedDims::THREADS, SDB_NOISE_KPW, SDB_SCHEME_SRK2};
@@ -644,7 +645,7 @@ static int integrate_impl(sdb_system* s, const sdb_integrate_args* a, const SdbO
       std::vector<double> tab(fused->table_doubles);
       if (fused->build) fused->build(s->fp.data(), s->gp.data(), tab.data());
       else if (jit_comm) SdbFusedCDims(s->d, s->m).build_tables(s->fp.data(), s->gp.data(), tab.data());
-      else SdbFusedDims(s->d, s->m, jit_rb).build_tables(s->fp.data(), s->gp.data(), tab.data());
+      else SdbFusedDims(s->d, s->m, jit_rb, jit_xr).build_tables(s->fp.data(), s->gp.data(), tab.data());
       double* d = nullptr;
       SDB_CUDA(cudaMalloc(&d, tab.size() * sizeof(double)));
       SDB_CUDA(cudaMemcpy(d, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));

@@ -83,7 +83,11 @@
 #define SDB_FUSED_NS SDB_FUSED_NS1(SDB_FUSED_VARIANT)
 namespace SDB_FUSED_NS {
 
-template <int D, int M>
+#ifndef SDB_FUSED_A2
+#define SDB_FUSED_A2 1  // 1: rows of A^2 ride in the P1 product (its padding rows at d = m = 10): the second
+#endif                  //    drift evaluation f(Y + f h) h = f h + h^2 A^2 Y needs no DFMA loop of its own
+// XR: extra row groups of the P1 product after the drift rows (1: the rows of A^2)
+template <int D, int M, int XR = 0>
 struct SdbFusedShape {
   static constexpr int MM = M * (M - 1) / 2;
   static constexpr int RB = (SDB_FUSED_RB > 0 && D > SDB_FUSED_RB) ? SDB_FUSED_RB : 4;  // rows per block
@@ -93,7 +97,7 @@ struct SdbFusedShape {
   static constexpr int IL = D - 8 * IT;               // leftover rows done by DFMA
   static SDB_CX int rn(int b) { return b < NB - 1 ? RB : D - RB * (NB - 1); }
   static SDB_CX int r0(int b) { return RB * b; }
-  static SDB_CX int nr(int b) { return (M + 1) * rn(b); }       // P1 rows: m columns + drift
+  static SDB_CX int nr(int b) { return (M + 1 + XR) * rn(b); }  // P1 rows: m columns + drift (+ A^2)
   static SDB_CX int t1(int b) { return (nr(b) + 7) / 8; }       // P1 row tiles
   static SDB_CX int kt3(int b) { return (rn(b) * M + 3) / 4; }  // P3 k tiles
   static SDB_CX int max2(int a, int b) { return a > b ? a : b; }
@@ -120,17 +124,27 @@ struct SdbFusedShape {
   }
   static SDB_CX int n_left() { return left_off(NB); }
   static SDB_CX int warp_doubles() { return (grows() + M) * 32; }
-  static SDB_CX size_t smem_bytes() {
+  static SDB_CX size_t smem_base() {
     return ((size_t)MM * SDB_FUSED_THREADS + (size_t)warp_doubles() * SDB_FUSED_WARPS) * sizeof(double) +
-           128 * 16 + (SDB_FUSED_MAX_TERMS + 1 + n_left() + 1) * sizeof(double);
+           (SDB_FUSED_MAX_TERMS + 1 + n_left() + 1) * sizeof(double);
   }
+  // copies of the log table: 8 (conflict-free, see sdb_normal_batch) when an SM's shared memory has room
+  static SDB_CX int tab_copies() { return smem_base() + 8 * 128 * 16 <= 227u * 1024u ? 8 : 1; }
+  static SDB_CX size_t smem_bytes() { return smem_base() + (size_t)tab_copies() * 128 * 16; }
 };
 
 #ifndef __CUDACC_RTC__  // host functions are not allowed in NVRTC; sdb_fused_rt.h serves JIT shapes
 // Host: lane-major fragment tables.  out[frag * 32 + lane]; then the leftover rows.
-template <int D, int M>
+template <int D, int M, int XR = 0>
 inline void sdb_fused_build_tables(const double* A, const double* B, double* out) {
-  typedef SdbFusedShape<D, M> Sh;
+  typedef SdbFusedShape<D, M, XR> Sh;
+  double A2[D * D];
+  for (int i = 0; i < D; ++i)
+    for (int j = 0; j < D; ++j) {
+      double acc = 0.0;
+      for (int l = 0; l < D; ++l) acc += A[i * D + l] * A[l * D + j];
+      A2[i * D + j] = acc;
+    }
   for (int b = 0; b < Sh::NB; ++b) {
     const int rn = Sh::rn(b), r0 = Sh::r0(b);
     for (int t = 0; t < Sh::t1(b); ++t)
@@ -140,7 +154,8 @@ inline void sdb_fused_build_tables(const double* A, const double* B, double* out
           double v = 0.0;
           if (l < D) {
             if (n < M * rn) v = B[((n / rn) * D + r0 + n % rn) * D + l];       // B_j[r0+r][l]
-            else if (n < Sh::nr(b)) v = A[(r0 + n - M * rn) * D + l];          // drift rows
+            else if (n < (M + 1) * rn) v = A[(r0 + n - M * rn) * D + l];       // drift rows
+            else if (n < Sh::nr(b)) v = A2[(r0 + n - (M + 1) * rn) * D + l];   // rows of A^2 (XR)
           }
           out[(size_t)(Sh::p1_off(b) + t * Sh::LT + lt) * 32 + lane] = v;
         }
@@ -160,9 +175,9 @@ inline void sdb_fused_build_tables(const double* A, const double* B, double* out
         left[Sh::left_off(b) + q * Sh::rn(b) * M + K] =
             B[((K % M) * D + 8 * Sh::IT + q) * D + Sh::r0(b) + K / M];
 }
-template <int D, int M>
+template <int D, int M, int XR = 0>
 inline size_t sdb_fused_table_doubles() {
-  typedef SdbFusedShape<D, M> Sh;
+  typedef SdbFusedShape<D, M, XR> Sh;
   return (size_t)Sh::n_frags() * 32 + Sh::n_left();
 }
 #endif  // !__CUDACC_RTC__
@@ -181,6 +196,11 @@ SDB_DEV void sdb_dmma(double& c0, double& c1, double a, double b) {
 
 // column swizzle of the staging buffer: keeps every access pattern used below conflict-free
 SDB_DEV constexpr int sdb_swz(int row) { return (row & 1) | (((row >> 1) & 1) << 3); }
+// Rows that are written one lane per path and read back as DMMA B-fragments (P0: the state, P3: the
+// stage-2 columns): lane (fr, fc) reads row 4 q + fc, column 8 pt + fr, so the four rows of one load
+// must land in four different 4-column groups -- sdb_swz maps two of them onto the same banks (2-way
+// conflict on every P3 / P0 load; profiles/r02_fused_v0_mx2_ncu_summary.txt).
+SDB_DEV constexpr int sdb_swz3(int row) { return (row & 3) << 2; }
 
 template <int M>
 SDB_DEV constexpr int sdb_pair_index(int i, int j) {  // (i < j) in K_m row order
@@ -272,7 +292,10 @@ struct SdbGen {
 };
 
 // z[2b], z[2b+1] = scale * (normal pair b); SCALED = false skips the multiplication.
-template <int NB, bool SCALED>
+// TS: stride (in entries) of the log table -- 1 for the plain 128-entry table, 8 when every lane
+// position of a quarter-warp has its own copy in its own four banks (tab then points at this lane's
+// copy): the random index makes the plain table a 2.5-way bank conflict per LDS.128.
+template <int NB, bool SCALED, int TS = 1>
 SDB_DEV void sdb_normal_batch(const uint32_t (&w)[NB][4], const double2* __restrict__ tab,
                               double scale, double (&z)[2 * NB]) {
   double x[NB], zz[NB], r[NB], r2[NB], q[NB], L[NB], t[NB], t2[NB], sn[NB], cs[NB], rad[NB];
@@ -291,7 +314,7 @@ SDB_DEV void sdb_normal_batch(const uint32_t (&w)[NB][4], const double2* __restr
     const int tmp = xh - 0x3FE60000;
     kk[b] = (tmp >> 20) - 53;
     zz[b] = __hiloint2double(xh - (tmp & (int)0xFFF00000), __double2loint(x[b]));
-    tc[b] = tab[(tmp >> 13) & 127];
+    tc[b] = tab[((tmp >> 13) & 127) * TS];
   }
 #if SDB_FUSED_BATCH_ORDER == 0
 #pragma unroll
@@ -421,14 +444,14 @@ struct SdbInt { static constexpr int value = I; };
 // slot = normal index >> 1 (element = index & 1), so a block of normals that starts at an odd index
 // skips the first element of its first pair.  Used for an ODD number of Wiener processes, where the
 // blocks dW | X_1 | Y_1 | X_2 | ... of the reference's draw order alternate between even and odd starts.
-template <int M, int ODD, bool SCALED, bool FIRST = false>
+template <int M, int ODD, bool SCALED, bool FIRST = false, int TS = 1>
 SDB_DEV void sdb_normals_m(const SdbGen& gen, uint32_t slot0, const double2* __restrict__ tab, double scale,
                            double (&out)[M]) {
   constexpr int NP = (M + ODD + 1) / 2;
   uint32_t w[NP][4];
   double z[2 * NP];
   gen.template blocks<NP, FIRST>(slot0, w);
-  sdb_normal_batch<NP, SCALED>(w, tab, scale, z);
+  sdb_normal_batch<NP, SCALED, TS>(w, tab, scale, z);
 #pragma unroll
   for (int j = 0; j < M; ++j) out[j] = z[j + ODD];
 }
@@ -457,7 +480,7 @@ SDB_CX int sdb_pair_k(int idx) {
 
 template <int D, int M, int B_>
 struct SdbFusedBlock {
-  typedef SdbFusedShape<D, M> Sh;
+  typedef SdbFusedShape<D, M, SDB_FUSED_A2> Sh;
   static constexpr int RN = Sh::rn(B_), R0 = Sh::r0(B_), T1 = Sh::t1(B_), KT3 = Sh::kt3(B_);
 
   // P1 + P2 + P3 for row block B_.
@@ -540,7 +563,13 @@ struct SdbFusedBlock {
       for (int r = 0; r < RN; ++r) {
         const int n = M * RN + r;
         const double f0h = g[n * 32 + (lane ^ sdb_swz(n))] * h;
+#if SDB_FUSED_A2
+        // f(H20) h = f0 h + h^2 A^2 Y (linear drift): Y_{n+1} - H20 = h^2 A^2 Y / 2 + G dW + stage-2 sum
+        const int n2 = (M + 1) * RN + r;
+        Yacc[R0 + r] = fma(0.5 * h * h, g[n2 * 32 + (lane ^ sdb_swz(n2))], GdW[r]);
+#else
         Yacc[R0 + r] = fma(-0.5, f0h, GdW[r]);
+#endif
         H20[R0 + r] += f0h;  // H20 held Y
       }
       // rows 8.. of the stage-2 sum on the FMA pipe (uniform operands from shared memory)
@@ -562,7 +591,7 @@ struct SdbFusedBlock {
 #pragma unroll
         for (int k = 0; k < M; ++k) {
           const int K = r * M + k;
-          gbuf[K * 32 + (lane ^ sdb_swz(K))] = s[r][k];
+          gbuf[K * 32 + (lane ^ sdb_swz3(K))] = s[r][k];
         }
     }
     __syncwarp();
@@ -574,7 +603,7 @@ struct SdbFusedBlock {
         const double a = __ldg(f3 + kt * Sh::IT * 32);
         const int K = 4 * kt + fc;
         const double* row = gbuf + K * 32;
-        const int sw = sdb_swz(K);
+        const int sw = sdb_swz3(K);
 #pragma unroll
         for (int pt = 0; pt < 4; ++pt) sdb_dmma(w[pt][0], w[pt][1], a, row[(8 * pt + fr) ^ sw]);
       }
@@ -600,7 +629,7 @@ struct SdbFusedBlocks<D, M, -1> {
 template <int D, int M, int WIK = 0>
 SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * D>& fp,
                                         const double* __restrict__ frag, double* smem) {
-  typedef SdbFusedShape<D, M> Sh;
+  typedef SdbFusedShape<D, M, SDB_FUSED_A2> Sh;
   constexpr int NT = SDB_FUSED_THREADS;
   constexpr int MM = Sh::MM, LT = Sh::LT, GR = Sh::grows();
   static_assert(M % 2 == 0 || (SDB_FUSED_BATCH && !SDB_FUSED_BATCH_XZ && WIK == 0),
@@ -613,9 +642,11 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
   double* gbuf = warp_base;
   double2* tab =
       reinterpret_cast<double2*>(smem + (size_t)MM * NT + (size_t)Sh::warp_doubles() * SDB_FUSED_WARPS);
-  double* s_hk = reinterpret_cast<double*>(tab + 128);
+  constexpr int TS = SDB_FUSED_BATCH ? Sh::tab_copies() : 1;  // (the pair-at-a-time variant reads a plain table)
+  double* s_hk = reinterpret_cast<double*>(tab + 128 * TS);
   double* s_left = s_hk + SDB_FUSED_MAX_TERMS + 1;
-  if (tid < 128) tab[tid] = reinterpret_cast<const double2*>(sdb_logtab)[tid];
+  for (int i = tid; i < 128 * TS; i += NT) tab[i] = reinterpret_cast<const double2*>(sdb_logtab)[i / TS];
+  tab += lane & (TS - 1);  // this lane's copy: entry i at tab[i * TS]
   for (int i = tid; i <= SDB_FUSED_MAX_TERMS; i += NT)
     s_hk[i] = i == 0 ? 0.0 : a.h_global * SDB_INV_2PI / (double)i;
   for (int i = tid; i < Sh::n_left(); i += NT) s_left[i] = frag[(size_t)Sh::n_frags() * 32 + i];
@@ -664,7 +695,7 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
     // The state waits in the staging buffer (where P0 needs it anyway) while the noise is generated:
     // 20 registers less across the register-hungry Levy loop.
 #pragma unroll
-    for (int l = 0; l < D; ++l) gbuf[l * 32 + (lane ^ sdb_swz(l))] = Y[l];
+    for (int l = 0; l < D; ++l) gbuf[l * 32 + (lane ^ sdb_swz3(l))] = Y[l];
     __syncwarp();
 #endif
     // ---- noise: dW (wiener.py:52), Levy areas (wiener.py:67-74, :102-105), one lane per path ------
@@ -676,9 +707,9 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
       if constexpr (M % 2 == 0) {
         uint32_t w[M / 2][4];
         gen.template blocks<M / 2, true>(0u, w);
-        sdb_normal_batch<M / 2, true>(w, tab, rh_g, dW);
+        sdb_normal_batch<M / 2, true, TS>(w, tab, rh_g, dW);
       } else {
-        sdb_normals_m<M, 0, true, true>(gen, 0u, tab, rh_g, dW);
+        sdb_normals_m<M, 0, true, true, TS>(gen, 0u, tab, rh_g, dW);
       }
 #else
 #pragma unroll
@@ -708,7 +739,7 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
           uint32_t w[M][4];
           double xz[2 * M];
           gen.template blocks<M, false>(sx, w);
-          sdb_normal_batch<M, false>(w, tab, 1.0, xz);
+          sdb_normal_batch<M, false, TS>(w, tab, 1.0, xz);
 #pragma unroll
           for (int j = 0; j < M; ++j) {
             X[j] = hk * xz[j];
@@ -719,12 +750,12 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
         if constexpr (M % 2 == 0) {
           uint32_t w[M / 2][4];
           gen.template blocks<M / 2, false>(sx, w);
-          sdb_normal_batch<M / 2, true>(w, tab, hk, X);
+          sdb_normal_batch<M / 2, true, TS>(w, tab, hk, X);
           gen.template blocks<M / 2, false>(sx + M / 2, w);
-          sdb_normal_batch<M / 2, false>(w, tab, 1.0, Z);
+          sdb_normal_batch<M / 2, false, TS>(w, tab, 1.0, Z);
         } else {  // X_k starts at the odd normal index M (2k - 1), Y_k at the even one 2 k M
-          sdb_normals_m<M, 1, true>(gen, sx, tab, hk, X);
-          sdb_normals_m<M, 0, false>(gen, sx + (M + 1) / 2, tab, 1.0, Z);
+          sdb_normals_m<M, 1, true, false, TS>(gen, sx, tab, hk, X);
+          sdb_normals_m<M, 0, false, false, TS>(gen, sx + (M + 1) / 2, tab, 1.0, Z);
         }
 #endif
 #pragma unroll
@@ -790,7 +821,7 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
           uint32_t w[NBP][4];
           double g[2 * NBP];
           gen.template blocks<NBP, false>(st0 + (uint32_t)(5 * b), w);
-          sdb_normal_batch<NBP, false>(w, tab, 1.0, g);
+          sdb_normal_batch<NBP, false, TS>(w, tab, 1.0, g);
           sdb_static_for<0, 2 * NBP>([&](auto ee) {
             constexpr int e = decltype(ee)::value;
             constexpr int r = 10 * b + e;
@@ -822,10 +853,10 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
     double Yf[LT][4];
 #if SDB_FUSED_PARK_Y
 #pragma unroll
-    for (int l = 0; l < D; ++l) Y[l] = gbuf[l * 32 + (lane ^ sdb_swz(l))];
+    for (int l = 0; l < D; ++l) Y[l] = gbuf[l * 32 + (lane ^ sdb_swz3(l))];
 #else
 #pragma unroll
-    for (int l = 0; l < D; ++l) gbuf[l * 32 + (lane ^ sdb_swz(l))] = Y[l];
+    for (int l = 0; l < D; ++l) gbuf[l * 32 + (lane ^ sdb_swz3(l))] = Y[l];
     __syncwarp();
 #endif
 #pragma unroll
@@ -835,7 +866,7 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
       const int lc = ok ? l : 0;
 #pragma unroll
       for (int pt = 0; pt < 4; ++pt) {
-        const double v = gbuf[lc * 32 + ((8 * pt + fr) ^ sdb_swz(lc))];
+        const double v = gbuf[lc * 32 + ((8 * pt + fr) ^ sdb_swz3(lc))];
         Yf[lt][pt] = ok ? v : 0.0;
       }
     }
@@ -860,6 +891,7 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
     // Y now holds H20 = Y + f(Y) h
 
     // ---- second drift evaluation f(H20, t_{n+1}) h (integrate.py:514) ----------------------------
+#if !SDB_FUSED_A2
 #pragma unroll
     for (int i = 0; i < D; ++i) {
       double acc = fp.v[i * D] * Y[0];
@@ -867,6 +899,7 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
       for (int l = 1; l < D; ++l) acc = fma(fp.v[i * D + l], Y[l], acc);
       Yacc[i] = fma(0.5 * h, acc, Yacc[i]);
     }
+#endif
     // ---- stage-2 sum back to one lane per path ---------------------------------------------------
     if (Sh::IT > 0) {
       double* row = gbuf + fr * 32;

@@ -7,7 +7,8 @@
 
 struct SdbFusedDims {
   int D, M, RB;  // RB: state rows per block (4: sdb_fused.cuh default; 2: sdb_fusedx.cuh)
-  constexpr SdbFusedDims(int d, int m, int rb = 4) : D(d), M(m), RB(d > rb ? rb : 4) {}
+  int XR;        // extra P1 row groups after the drift rows (1: the rows of A^2, sdb_fused.cuh)
+  constexpr SdbFusedDims(int d, int m, int rb = 4, int xr = 0) : D(d), M(m), RB(d > rb ? rb : 4), XR(xr) {}
   static constexpr int THREADS = 256, WARPS = 8, MAX_TERMS = 256;
   constexpr int MM() const { return M * (M - 1) / 2; }
   constexpr int NB() const { return (D + RB - 1) / RB; }
@@ -16,7 +17,7 @@ struct SdbFusedDims {
   constexpr int IL() const { return D - 8 * IT(); }
   constexpr int rn(int b) const { return b < NB() - 1 ? RB : D - RB * (NB() - 1); }
   constexpr int r0(int b) const { return RB * b; }
-  constexpr int nr(int b) const { return (M + 1) * rn(b); }
+  constexpr int nr(int b) const { return (M + 1 + XR) * rn(b); }
   constexpr int t1(int b) const { return (nr(b) + 7) / 8; }
   constexpr int kt3(int b) const { return (rn(b) * M + 3) / 4; }
   static constexpr int max2(int a, int b) { return a > b ? a : b; }
@@ -43,16 +44,25 @@ struct SdbFusedDims {
   }
   constexpr int n_left() const { return left_off(NB()); }
   constexpr size_t table_doubles() const { return (size_t)n_frags() * 32 + n_left(); }
-  constexpr size_t smem_bytes() const {
-    return ((size_t)MM() * THREADS + (size_t)(grows() + M) * 32 * WARPS) * sizeof(double) + 128 * 16 +
+  constexpr size_t smem_base() const {
+    return ((size_t)MM() * THREADS + (size_t)(grows() + M) * 32 * WARPS) * sizeof(double) +
            (MAX_TERMS + 1 + n_left() + 1) * sizeof(double);
   }
+  constexpr int tab_copies() const { return smem_base() + 8 * 128 * 16 <= 227u * 1024u ? 8 : 1; }
+  constexpr size_t smem_bytes() const { return smem_base() + (size_t)tab_copies() * 128 * 16; }
   // the kernel needs d < 16 (one DMMA tile of the stage-2 sum) and must fit an SM
   constexpr bool supported() const {
     return D >= 1 && M >= 2 && D < 16 && smem_bytes() <= 227u * 1024u;
   }
   // lane-major fragment tables: out[frag * 32 + lane], then the leftover rows (as sdb_fused_build_tables)
   void build_tables(const double* A, const double* B, double* out) const {
+    double* A2 = new double[(size_t)D * D];
+    for (int i = 0; i < D; ++i)
+      for (int j = 0; j < D; ++j) {
+        double acc = 0.0;
+        for (int l = 0; l < D; ++l) acc += A[i * D + l] * A[l * D + j];
+        A2[i * D + j] = acc;
+      }
     for (int b = 0; b < NB(); ++b) {
       const int rnb = rn(b), r0b = r0(b);
       for (int t = 0; t < t1(b); ++t)
@@ -62,7 +72,8 @@ struct SdbFusedDims {
             double v = 0.0;
             if (l < D) {
               if (n < M * rnb) v = B[((n / rnb) * D + r0b + n % rnb) * D + l];
-              else if (n < nr(b)) v = A[(r0b + n - M * rnb) * D + l];
+              else if (n < (M + 1) * rnb) v = A[(r0b + n - M * rnb) * D + l];
+              else if (n < nr(b)) v = A2[(r0b + n - (M + 1) * rnb) * D + l];
             }
             out[(size_t)(p1_off(b) + t * LT() + lt) * 32 + lane] = v;
           }
@@ -80,6 +91,7 @@ struct SdbFusedDims {
       for (int q = 0; q < IL(); ++q)
         for (int K = 0; K < rn(b) * M; ++K)
           left[left_off(b) + q * rn(b) * M + K] = B[((K % M) * D + 8 * IT() + q) * D + r0(b) + K / M];
+    delete[] A2;
   }
 };
 

@@ -12,8 +12,9 @@
   SDB_FUSED_KERNEL_W(sdbk_fused_srk2_d##D##_m##M##_wik, D, M, 1)                                \
   static SdbFusedRegistrar sdbreg_fused_wik_d##D##_m##M(                                        \
       SdbFusedEntry{D, M, VARIANT, (const void*)sdbk_fused_srk2_d##D##_m##M##_wik,              \
-                    SdbFusedShape<D, M>::smem_bytes(), sdb_fused_table_doubles<D, M>(),         \
-                    &sdb_fused_build_tables<D, M>, SDB_FUSED_THREADS, SDB_FUSED_THREADS,         \
+                    SdbFusedShape<D, M, SDB_FUSED_A2>::smem_bytes(),                            \
+                    sdb_fused_table_doubles<D, M, SDB_FUSED_A2>(),                              \
+                    &sdb_fused_build_tables<D, M, SDB_FUSED_A2>, SDB_FUSED_THREADS, SDB_FUSED_THREADS, \
                     SDB_NOISE_WIK, SDB_SCHEME_SRK2});
 
 SDB_FUSED_WIK_AOT(10, 10, 30)

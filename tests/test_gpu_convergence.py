@@ -70,6 +70,112 @@ def test_exact_solution_kp4459_ensemble(sdb):
     _assert_close(sdb.stratHeun(f_str, G, y0, tspan, dW=dW)[:, :, 0], exact, 1e-1, 1e-1)
 
 
+def test_exact_solution_kps445_ensemble(sdb):
+    """test_integrate.py:255-326 (Kloeden, Platen & Schurz (4.5): dy = -(sin 2y + sin(4y)/4) dt +
+    sqrt2 cos^2(y) dW) batched over 32 paths at the reference's h = 4e-4, 10^4 steps: the exact path
+    y_n = arctan(exp(-t_n) (tan(1) + sqrt2 sum exp(t_k) (dW (1+h) + dZ + dQ))) needs the correlated
+    triples (dW, dZ, dQ) of :269-278, drawn on the host and the dW column handed to every integrator."""
+    h, P, steps = 0.0004, 32, 10000
+    tspan = np.arange(steps + 1) * h
+    sqrt2 = np.sqrt(2.0)
+    eq2 = (np.exp(2.0 * h) - 1) / 2.0 - 2.0 * h * np.exp(h) + h + h ** 2 + h ** 3 / 3.0
+    ewq = np.exp(h) - (1 + h + h ** 2 / 2.0)
+    ezq = np.exp(h) - (1 + h + h ** 2 / 2.0 + h ** 3 / 6.0)
+    covar = np.array([[h, h ** 2 / 2.0, ewq], [h ** 2 / 2.0, h ** 3 / 3.0, ezq], [ewq, ezq, eq2]])
+    from scipy import stats
+    WZQ = stats.multivariate_normal(mean=np.zeros(3), cov=covar, allow_singular=True).rvs(
+        size=(P, steps), random_state=np.random.default_rng(445))              # (P, steps, 3)
+    dW = np.ascontiguousarray(WZQ[:, :, 0:1])
+    _, I = sdb.Iwik(dW, h, seed=1, ensemble=True)                               # m = 1: (dW^2 - h)/2
+    J = I + 0.5 * h
+    n = np.arange(steps)
+    incr = sqrt2 * np.exp(n * h)[None, :] * (WZQ[:, :, 0] * (1 + h) + WZQ[:, :, 1] + WZQ[:, :, 2])
+    etv = np.tan(1.0) + np.concatenate([np.zeros((P, 1)), np.cumsum(incr, axis=1)], axis=1)
+    exact = np.arctan(np.exp(-tspan)[None, :] * etv)
+    f_ito, G, y0 = SYSTEMS["kps445"](False)
+    f_str, _, _ = SYSTEMS["kps445"](True)
+    _assert_close(sdb.itoEuler(f_ito, G, y0, tspan, dW=dW)[:, :, 0], exact, 1e-1, 1e-1)
+    _assert_close(sdb.itoSRI2(f_ito, G, y0, tspan, dW=dW, I=I)[:, :, 0], exact, 1e-2, 1e-2)
+    _assert_close(sdb.stratHeun(f_str, G, y0, tspan, dW=dW)[:, :, 0], exact, 1e-2, 1e-2)
+    _assert_close(sdb.stratSRS2(f_str, G, y0, tspan, dW=dW, J=J)[:, :, 0], exact, 1e-2, 1e-2)
+    _assert_close(sdb.stratKP2iS(f_str, G, y0, tspan, dW=dW, J=J)[:, :, 0], exact, 1e-1, 1e-1)
+
+
+def test_exact_solution_r74_ensemble(sdb):
+    """test_integrate.py:350-422 (Roessler (7.4): d = 5, m = 4 linear system with identical B_k):
+    y_n = expm((A - sum B_k^2 / 2) t_n + sum_k B_k W_k(t_n)) y0, 32 device-noise paths at h = 4e-4,
+    5000 steps; SRI2 / SRS2 take the list-of-columns G like the reference's G_separate (:369)."""
+    from scipy.linalg import expm
+    h, P, steps = 0.0004, 32, 5000
+    tspan = np.arange(steps + 1) * h
+    f_ito, G, y0 = SYSTEMS["r74"](False)
+    f_str, _, _ = SYSTEMS["r74"](True)
+    d, m = 5, 4
+    dW = sdb.deltaW(steps, m, h, paths=P, seed=74)
+    _, I = sdb.Iwik(dW, h, seed=74, ensemble=True)
+    J = I + 0.5 * h * np.eye(m)[None, None]
+    A, B0 = np.array(f_ito.A), np.array(G.B[0])
+    term1 = A - 0.5 * m * B0 @ B0
+    W = np.concatenate([np.zeros((P, 1, m)), np.cumsum(dW, axis=1)], axis=1).sum(axis=2)  # sum_k W_k
+    # A and B0 are both alpha 1 + beta ones(d,d): expm of such a matrix is
+    # e^alpha (1 + (e^(d beta) - 1)/d ones); checked against scipy's expm at a few points below
+    al = term1[0, 0] - term1[0, 1], B0[0, 0] - B0[0, 1]
+    be = term1[0, 1], B0[0, 1]
+    alpha = al[0] * tspan[None, :] + al[1] * W
+    beta = be[0] * tspan[None, :] + be[1] * W
+    exact = (np.exp(alpha) * (1.0 + (np.exp(d * beta) - 1.0) / d * y0.sum()))[:, :, None] * np.ones(d)
+    exact = exact - (np.exp(alpha) * (np.exp(d * beta) - 1.0) / d * y0.sum())[:, :, None] \
+        + (np.exp(alpha) * (np.exp(d * beta) - 1.0) / d)[:, :, None] * y0.sum()
+    for p, nn in ((0, 17), (5, steps), (P - 1, 2500)):
+        want = expm(term1 * tspan[nn] + B0 * W[p, nn]).dot(y0)
+        assert np.allclose(exact[p, nn], want, rtol=1e-12)
+    _assert_close(sdb.itoEuler(f_ito, G, y0, tspan, dW=dW), exact, 1e-1, 1e-1)
+    _assert_close(sdb.itoSRI2(f_ito, G.columns(), y0, tspan, dW=dW, I=I), exact, 1e-2, 1e-2)
+    _assert_close(sdb.stratHeun(f_str, G, y0, tspan, dW=dW), exact, 1e-2, 1e-2)
+    _assert_close(sdb.stratSRS2(f_str, G.columns(), y0, tspan, dW=dW, J=J), exact, 1e-2, 1e-2)
+    _assert_close(sdb.stratKP2iS(f_str, G, y0, tspan, dW=dW, J=J), exact, 1e-1, 1e-1)
+
+
+def test_series_length_restores_strong_order_noncommutative(sdb):
+    """with the reference's fixed n = 5 series terms (wiener.py:77) the Levy areas
+    carry a relative error that does not shrink with h, so on NON-commutative noise the strong error
+    of SRI2 falls only like h^(1/2); n_terms="auto" (wiener.series_terms, n ~ 3 / (2 pi^2 h)) keeps
+    it at order 1.  Measured on a 2-d linear system with [B_1, B_2] != 0 and on-device noise: the
+    normals of series term k sit at fixed generator slots whatever n is, so runs with n = 5, n = auto
+    and n = 64 x auto share dW and the leading terms, and the pathwise difference to the long series
+    isolates the truncation error:  E|y_T(n=5) - y_T(long)| ~ h^0.5,  E|y_T(auto) - y_T(long)| ~ h^1."""
+    A = np.array([[-0.5, 0.3], [-0.2, -0.4]])
+    B = np.array([[[0.0, 0.9], [0.0, 0.0]], [[0.0, 0.0], [0.8, 0.0]]])           # [B1, B2] != 0
+    assert np.abs(B[0] @ B[1] - B[1] @ B[0]).max() > 0.5
+    f, G, y0 = sdb.ops.LinearDrift(A), sdb.ops.LinearDiffusion(B), np.array([1.0, 0.8])
+    T, P = 1.0, 4000
+    levels = [4, 5, 6, 7, 8]
+    e5, ea, terms = [], [], []
+    for lv in levels:
+        n = 2 ** lv
+        h = T / n
+        tspan = np.linspace(0.0, T, n + 1)
+        na = sdb.wiener.series_terms(h, 2, "kpw")
+        terms.append(na)
+        run = lambda nt: sdb.itoSRI2(f, G, y0, tspan, paths=P, seed=303, save_every=n, n_terms=nt,
+                                     commutative=False)[:, -1, :]
+        ylong = run(64 * na)
+        yauto = sdb.itoSRI2(f, G, y0, tspan, paths=P, seed=303, save_every=n, n_terms="auto",
+                            commutative=False)[:, -1, :]
+        assert np.array_equal(yauto, run(na))                                    # "auto" == series_terms
+        e5.append(np.mean(np.linalg.norm(run(5) - ylong, axis=1)))
+        ea.append(np.mean(np.linalg.norm(yauto - ylong, axis=1)))
+    x = np.log2([T / 2 ** lv for lv in levels])
+    s5 = np.polyfit(x, np.log2(e5), 1)[0]
+    sa = np.polyfit(x, np.log2(ea), 1)[0]
+    assert 0.35 <= s5 <= 0.65, (s5, e5)
+    assert 0.85 <= sa <= 1.15, (sa, ea, terms)
+    assert ea[-1] < 0.25 * e5[-1]                 # at h = 2^-8 the fixed series is the larger error by far
+    # and the size of the n = 5 error is the predicted one: per-step area error std
+    # h sqrt(3 a(5) / (2 pi^2)) = 0.166 h, accumulated over T / h independent steps
+    assert 0.2 < e5[-1] / (0.166 * np.sqrt(T / 2 ** levels[-1])) < 5.0
+
+
 def test_strong_orders_kp4446(sdb):
     """E|y_T - y_exact| over h = 2^-5 .. 2^-9 on Brownian paths coarsened from 2^-12
     (I = (dW^2 - h)/2 is exact for m = 1).  The reference delivers slopes 0.53 (itoEuler),

@@ -1170,7 +1170,8 @@ def test_welford_moments_chan_merge(sdb):
     parts = [sdb.ensemble.welford(yd[:, :, a:b].contiguous()) for a, b in ((0, cut), (cut, P))]
     merged = sdb.ensemble.chan_merge(parts)
     assert torch.equal(merged[..., 0], w[..., 0])
-    assert np.max(np.abs((merged[..., 2] / w[..., 2]).cpu().numpy() - 1.0)) <= 1e-12
+    # (a different association of the same merges: the means carry 5e7 x 2^-53 of rounding each)
+    assert np.max(np.abs((merged[..., 2] / w[..., 2]).cpu().numpy() - 1.0)) <= 1e-9
 
 
 def test_second_moments_covariance_quantiles(sdb):
