@@ -33,7 +33,10 @@ extern "C" {
 #define SDB_SCHEME_EULER 0 /* itoEuler    integrate.py:190-240 */
 #define SDB_SCHEME_HEUN 1  /* stratHeun   integrate.py:243-303 */
 #define SDB_SCHEME_SRK2 2  /* itoSRI2 / stratSRS2 = _Roessler2010_SRK2, integrate.py:436-523 */
-#define SDB_SCHEME_KP2IS 3 /* stratKP2iS  integrate.py:526-646 */
+#define SDB_SCHEME_KP2IS 3 /* stratKP2iS  integrate.py:526-646; with Ito integrals I (no SDB_FLAG_STRATONOVICH)
+                            * the Ito version of the same two-step implicit scheme (README.rst:125-128) */
+#define SDB_SCHEME_R2 4    /* Burrage & Burrage (1996) two-stage SRK "R2", Stratonovich, commutative noise
+                            * (README.rst:125-128 to-do); needs only dW, like SDB_SCHEME_HEUN */
 
 /* ---- drift / diffusion operator kinds (sdeint_b200/ops.py) ------------------------- */
 #define SDB_DRIFT_LINEAR 0 /* params A[d][d]               f = A y */

@@ -91,6 +91,32 @@ def heun(f, G, y0, tspan, dW):
     return out
 
 
+def r2(f, G, y0, tspan, dW):
+    """Burrage & Burrage (1996, "High strong order explicit Runge-Kutta methods for stochastic
+    ordinary differential equations", Appl. Numer. Math. 22) two-stage method R2 -- not in the
+    reference, which lists "Burrage and Burrage SRKs" as to-do (README.rst:125-128); restated from the
+    published tableau A = B = [[0, 0], [2/3, 0]], alpha = gamma = (1/4, 3/4) for the Stratonovich
+    equation dy = f dt + G o dW with the increment of every Wiener process in the stochastic part
+    (strong order 1 for one Wiener process or commutative noise):
+        Y2 = y + (2/3) (f(y) h + G(y) dW),   y' = y + (1/4)(f(y) h + G(y) dW) + (3/4)(f(Y2) h + G(Y2) dW),
+    stage 2 evaluated at t + 2h/3; global h like the reference's stratHeun (integrate.py:285)."""
+    y0 = np.asarray(y0, dtype=np.float64)
+    N = len(tspan)
+    h = _global_h(tspan)
+    out = np.empty((N, y0.shape[0]))
+    out[0] = y0
+    for n in range(N - 1):
+        yn = out[n]
+        t0 = tspan[n]
+        w = dW[n]
+        k1 = f(yn, t0) * h + G(yn, t0).dot(w)
+        y2 = yn + (2.0 / 3.0) * k1
+        tm = t0 + (2.0 / 3.0) * h
+        k2 = f(y2, tm) * h + G(y2, tm).dot(w)
+        out[n + 1] = yn + 0.25 * k1 + 0.75 * k2
+    return out
+
+
 def srk2(f, G, y0, tspan, dW, IJ):
     """Roessler (2010) SRI2 / SRS2, sdeint/integrate.py:494-522.
 

@@ -8,7 +8,7 @@ need a GPU, computing does, and there is no CPU fallback."""
 from . import ops  # noqa: F401
 from .wiener import deltaW, Ikpw, Jkpw, Iwik, Jwik, Icomm, Jcomm  # noqa: F401
 from .integrate import (Error, SDEValueError, itoint, stratint, itoEuler, stratHeun,  # noqa: F401
-                        itoSRI2, stratSRS2, stratKP2iS, last_status)
+                        itoSRI2, stratSRS2, stratKP2iS, itoKP2i, stratR2, last_status)
 from ._lib import launch_count, last_kernel  # noqa: F401
 from . import ensemble  # noqa: F401
 

@@ -474,7 +474,7 @@ extern "C" int sdb_integrate_segment(sdb_system* s, const sdb_integrate_args* a,
 static int integrate_impl(sdb_system* s, const sdb_integrate_args* a, const SdbObsArgs* obs, int64_t step0,
                           double h_noise) {
   if (!s || !a) return fail("sdb_integrate: NULL argument");
-  if (a->scheme < SDB_SCHEME_EULER || a->scheme > SDB_SCHEME_KP2IS)
+  if (a->scheme < SDB_SCHEME_EULER || a->scheme > SDB_SCHEME_R2)
     return fail("sdb_integrate: unknown scheme");
   if (a->noise < SDB_NOISE_HOST || a->noise > SDB_NOISE_COMM)
     return fail("sdb_integrate: unknown noise source");

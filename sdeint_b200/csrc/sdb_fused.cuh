@@ -55,6 +55,9 @@
 #ifndef SDB_FUSED_BATCH_ORDER
 #define SDB_FUSED_BATCH_ORDER 0  // 1: angle polynomials before the table-dependent log part
 #endif
+#ifndef SDB_FUSED_SWP
+#define SDB_FUSED_SWP 1  // 1: software pipeline of the series loop -- the random bits (32-bit ALU / IMAD work) of
+#endif                   //    the NEXT batch are produced next to the FP64 transform of the current one
 #ifndef SDB_FUSED_BATCH_XZ
 #define SDB_FUSED_BATCH_XZ 0  // 1: X_k and Y_k pairs of one series term in ONE lock-step batch of M
 #endif
@@ -728,6 +731,13 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
       double At[MM];
 #pragma unroll
       for (int r = 0; r < MM; ++r) At[r] = 0.0;
+#if SDB_FUSED_BATCH && SDB_FUSED_SWP && !SDB_FUSED_BATCH_XZ
+      constexpr bool SWP = M % 2 == 0;
+      uint32_t wA[SWP ? M / 2 : 1][4];   // bits of the next X batch, one batch ahead of their transform
+      if constexpr (SWP) gen.template blocks<M / 2, false>((uint32_t)(M >> 1), wA);
+#else
+      constexpr bool SWP = false;
+#endif
 #pragma unroll(KU)
       for (int k = 1; k <= n_terms; ++k) {
         double X[M], Z[M];
@@ -747,7 +757,15 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
           }
         }
 #else
-        if constexpr (M % 2 == 0) {
+        if constexpr (SWP) {
+#if SDB_FUSED_SWP
+          uint32_t wB[M / 2][4];
+          gen.template blocks<M / 2, false>(sx + M / 2, wB);       // Y_k bits   | integer pipes
+          sdb_normal_batch<M / 2, true, TS>(wA, tab, hk, X);        // X_k        | FP64 pipe
+          if (k < n_terms) gen.template blocks<M / 2, false>(sx + M, wA);   // X_{k+1} bits
+          sdb_normal_batch<M / 2, false, TS>(wB, tab, 1.0, Z);      // Y_k
+#endif
+        } else if constexpr (M % 2 == 0) {
           uint32_t w[M / 2][4];
           gen.template blocks<M / 2, false>(sx, w);
           sdb_normal_batch<M / 2, true, TS>(w, tab, hk, X);

@@ -36,6 +36,7 @@ typedef long long int64_t;
 #define SDB_SCHEME_HEUN 1
 #define SDB_SCHEME_SRK2 2
 #define SDB_SCHEME_KP2IS 3
+#define SDB_SCHEME_R2 4  // Burrage & Burrage (1996) two-stage SRK "R2" (Stratonovich, commutative noise)
 #define SDB_NOISE_HOST 0
 #define SDB_NOISE_KPW 1
 #define SDB_NOISE_WIK 2
@@ -884,6 +885,40 @@ SDB_DEV void sdb_loop_body(const SdbLoopArgs& a, const typename F::Params& fp,
 #pragma unroll
       for (int i = 0; i < D; ++i)
         Y[i] = Y[i] + 0.5 * (f0[i] + f1[i]) * h + 0.5 * (Gw[i] + Gw1[i]);
+    } else if (SCHEME == SDB_SCHEME_R2) {
+      // Burrage & Burrage's R2 (the reference's to-do list, README.rst:125-128): the same tableau for the
+      // deterministic and the stochastic part,  Y2 = y + (2/3) (f h + G dW)(y),
+      // y' = y + (1/4) (f h + G dW)(y) + (3/4) (f h + G dW)(Y2, t + 2h/3); strong order 1 for
+      // Stratonovich equations with commutative noise (restated in oracle/sde_oracle.py: r2).
+      const double h = a.h_global;
+      const double tm = fma(2.0 / 3.0, h, t0);
+      double f0[D], Gw[D], Yb[D];
+      F::eval(fp, Y, t0, f0);
+#pragma unroll
+      for (int i = 0; i < D; ++i) Gw[i] = 0.0;
+#pragma unroll(SMALL ? M : 1)
+      for (int k = 0; k < M; ++k) {
+        double g[D];
+        G::col(gp, k, Y, t0, g);
+#pragma unroll
+        for (int i = 0; i < D; ++i) Gw[i] = fma(g[i], dW[k], Gw[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < D; ++i) Yb[i] = fma(2.0 / 3.0, fma(f0[i], h, Gw[i]), Y[i]);
+      double f1[D], Gw1[D];
+      F::eval(fp, Yb, tm, f1);
+#pragma unroll
+      for (int i = 0; i < D; ++i) Gw1[i] = 0.0;
+#pragma unroll(SMALL ? M : 1)
+      for (int k = 0; k < M; ++k) {
+        double g[D];
+        G::col(gp, k, Yb, tm, g);
+#pragma unroll
+        for (int i = 0; i < D; ++i) Gw1[i] = fma(g[i], dW[k], Gw1[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+        Y[i] = Y[i] + 0.25 * fma(f0[i], h, Gw[i]) + 0.75 * fma(f1[i], h, Gw1[i]);
     } else if (SCHEME == SDB_SCHEME_SRK2) {
       const double h = t1 - t0;  // per-step h: integrate.py:497
       const double rh = sqrt(h);

@@ -53,7 +53,7 @@ from . import _lib, ops
 from . import wiener
 from .wiener import Icomm, Ikpw, Iwik, Jcomm, Jkpw, Jwik, deltaW  # noqa: F401  (re-exported like the reference)
 
-SCHEME_EULER, SCHEME_HEUN, SCHEME_SRK2, SCHEME_KP2IS = 0, 1, 2, 3
+SCHEME_EULER, SCHEME_HEUN, SCHEME_SRK2, SCHEME_KP2IS, SCHEME_R2 = 0, 1, 2, 3, 4
 NOISE_HOST, NOISE_KPW, NOISE_WIK, NOISE_COMM = 0, 1, 2, 3
 FLAG_Y0_BROADCAST, FLAG_STRATONOVICH = 1, 2
 
@@ -204,7 +204,26 @@ def _run(scheme, f, G, y0, tspan, dW, IJ, strat, method, generator, kp2is, paths
     h = (tspan[N - 1] - tspan[0]) / (N - 1)
     if h_noise:
         h = float(h_noise)      # the h of the whole run when this call is one segment of it
-    method_id = _method_id(method, strat) if need_ij else NOISE_KPW
+    if (need_ij and IJ is None and method is not None and callable(method)
+            and method not in (Ikpw, Iwik, Icomm, Jkpw, Jwik, Jcomm)):
+        # Any function (dW, h, generator=...) -> (A, I or J), like the Imethod / Jmethod argument of the
+        # reference (integrate.py:306, :371, called at :487): evaluated on the HOST, one path at a time,
+        # and fed to the kernels as caller-supplied integrals.  Meant for single paths / small ensembles
+        # (the noise of the production path is generated on the device).
+        gen = generator if generator is not None else np.random.default_rng()
+        if dW is None:
+            dW = wiener.deltaW(N - 1, m, h, generator=gen, seed=seed, path_id0=path_id0,
+                               paths=(P if ensemble else None), device=device)
+        dWh = np.asarray(dW, dtype=np.float64)
+        if dWh.ndim == 3:
+            IJ = np.stack([np.asarray(method(dWh[p], h, generator=gen)[1], dtype=np.float64)
+                           for p in range(dWh.shape[0])])
+        else:
+            IJ = np.asarray(method(dWh, h, generator=gen)[1], dtype=np.float64)
+        if tuple(IJ.shape[-3:]) != (N - 1, m, m):
+            raise SDEValueError('the repeated-integral method returned an array of shape %s, expected '
+                                '(len(tspan)-1, m, m) = %s' % (IJ.shape, (N - 1, m, m)))
+    method_id = _method_id(method, strat) if (need_ij and IJ is None) else NOISE_KPW
     if isinstance(n_terms, str):
         if n_terms != "auto":
             raise SDEValueError('n_terms must be an integer or "auto"')
@@ -545,6 +564,41 @@ def stratKP2iS(f, G, y0, tspan, Jmethod=Jkpw, gam=None, al1=None, al2=None, rtol
         pars.append(v)
     return _run(SCHEME_KP2IS, f, G, y0, tspan, dW, J, True, Jmethod, generator,
                 (pars[0], pars[1], pars[2], float(rtol)), **kw)
+
+
+def itoKP2i(f, G, y0, tspan, Imethod=Ikpw, gam=None, al1=None, al2=None, rtol=1e-4, dW=None,
+            I=None, generator=None, **ens):
+    """The Ito version of the Kloeden-Platen two-step implicit order 1.0 strong scheme -- on the
+    reference's to-do list (README.rst:125-128), not in it.  Kloeden & Platen (1992) sec. 12.4: the
+    same recursion as stratKP2iS (integrate.py:603-645) with the Ito drift and the Ito integrals,
+        V_n = G_n dW + (1/sqrt h) sum_{j1} (G(Ybar_j1) - G_n) I[j1, :],  Ybar_j1 = Y_n + f h + G_n[:, j1] sqrt h.
+    Same arguments as stratKP2iS with Imethod / I in place of Jmethod / J."""
+    kw = _ens(ens)
+    if not isinstance(G, ops.DiffusionOp) and isinstance(G, (list, tuple)):
+        raise SDEValueError('G should be a function returning a d x m matrix.')
+    y0a = np.asarray(y0)
+    if np.iscomplexobj(y0a):
+        raise SDEValueError("itoKP2i() can't handle complex variables.")
+    d = 1 if y0a.ndim == 0 else len(y0a)
+    pars = []
+    for v in (gam, al1, al2):
+        v = np.full(d, 0.5) if v is None else np.asarray(v, dtype=np.float64).reshape(-1)
+        if v.shape != (d,):
+            raise SDEValueError('gam, al1, al2 must have shape (d,)')
+        pars.append(v)
+    return _run(SCHEME_KP2IS, f, G, y0, tspan, dW, I, False, Imethod, generator,
+                (pars[0], pars[1], pars[2], float(rtol)), **kw)
+
+
+def stratR2(f, G, y0, tspan, dW=None, generator=None, **ens):
+    """Burrage & Burrage (1996) two-stage Runge-Kutta method R2 for Stratonovich equations -- the
+    reference lists "Burrage and Burrage SRKs" as to-do (README.rst:125-128).  Strong order 1.0 for a
+    single Wiener process or commutative noise with only dW (no repeated integrals): stage 2 at
+    y + (2/3)(f h + G dW), weights (1/4, 3/4) for drift and diffusion alike.  Signature of stratHeun."""
+    kw = _ens(ens)
+    if not isinstance(G, ops.DiffusionOp) and isinstance(G, (list, tuple)):
+        raise TypeError("'tuple' object is not callable")
+    return _run(SCHEME_R2, f, G, y0, tspan, dW, None, True, None, generator, None, **kw)
 
 
 def itoint(f, G, y0, tspan, generator=None, **ens):

@@ -170,7 +170,8 @@ def test_series_length_restores_strong_order_noncommutative(sdb):
     sa = np.polyfit(x, np.log2(ea), 1)[0]
     assert 0.35 <= s5 <= 0.65, (s5, e5)
     assert 0.85 <= sa <= 1.15, (sa, ea, terms)
-    assert ea[-1] < 0.25 * e5[-1]                 # at h = 2^-8 the fixed series is the larger error by far
+    # at h = 2^-8 "auto" sums 39 terms: the truncation error is sqrt(a(39) / a(5)) = 0.37 of the n = 5 one
+    assert ea[-1] < 0.5 * e5[-1]
     # and the size of the n = 5 error is the predicted one: per-step area error std
     # h sqrt(3 a(5) / (2 pi^2)) = 0.166 h, accumulated over T / h independent steps
     assert 0.2 < e5[-1] / (0.166 * np.sqrt(T / 2 ** levels[-1])) < 5.0
@@ -212,6 +213,68 @@ def test_strong_orders_kp4446(sdb):
         assert 0.85 <= slopes[k] <= 1.15, slopes
     # absolute level at h = 2^-9 (6.2e-3, 5.7e-4, 5.8e-4, 5.9e-4)
     assert errs["itoEuler"][-1] < 1.2e-2 and errs["itoSRI2"][-1] < 1.2e-3
+
+
+def test_new_schemes_exact_solutions_and_orders(sdb):
+    """stratR2 and itoKP2i (README.rst:125-128 to-do) on the reference's exactly solvable test
+    equations: pathwise closeness on KP (4.46) and on the commutative two-noise KP (4.59) at the
+    reference's h with its tolerances (1e-2 for the order-1 explicit schemes, 1e-1 for the two-step
+    implicit one, test_integrate.py:117-146), and strong orders from coarsened Brownian paths:
+    R2 order 1.0 on both equations (commutative noise needs no Levy areas); itoKP2i order 1.0 as
+    Kloeden & Platen state for the scheme, while the reference's stratKP2iS recursion delivers only
+    ~0.5 (0.46 through the reference itself; the oracle restatement gives 0.47) -- the
+    behaviour the drop-in reproduces, pinned here as measured, bug or not (README.rst:123)."""
+    a, b, y0s, h, P = 1.0, 0.8, 0.1, 0.0004, 32
+    tspan = np.arange(0.0, 2.0, h)
+    N = len(tspan)
+    f_ito, G, _ = SYSTEMS["kp4446"](False)
+    f_str, _, _ = SYSTEMS["kp4446"](True)
+    dW = sdb.deltaW(N - 1, 1, h, paths=P, seed=21)
+    _, I = sdb.Iwik(dW, h, seed=21, ensemble=True)
+    W = np.concatenate([np.zeros((P, 1)), np.cumsum(dW[:, :, 0], axis=1)], axis=1)
+    exact = _kp4446_exact(y0s, a, b, tspan[None, :], W)
+    _assert_close(sdb.stratR2(f_str, G, y0s, tspan, dW=dW)[:, :, 0], exact, 1e-2, 1e-2)
+    _assert_close(sdb.itoKP2i(f_ito, G, y0s, tspan, dW=dW, I=I)[:, :, 0], exact, 1e-1, 1e-1)
+    # KP (4.59): d = 1, m = 2, commutative
+    a2, b1, b2 = -0.02, 1.0, 2.0
+    tspan2 = np.arange(0.0, 1.0, h)
+    N2 = len(tspan2)
+    f2s, G2, y02 = SYSTEMS["kp4459"](True)
+    dW2 = sdb.deltaW(N2 - 1, 2, h, paths=P, seed=22)
+    W2 = np.concatenate([np.zeros((P, 1, 2)), np.cumsum(dW2, axis=1)], axis=1)
+    exact2 = float(y02[0]) * np.exp((a2 - (b1 ** 2 + b2 ** 2) / 2.0) * tspan2[None, :]
+                                    + b1 * W2[:, :, 0] + b2 * W2[:, :, 1])
+    _assert_close(sdb.stratR2(f2s, G2, y02, tspan2, dW=dW2)[:, :, 0], exact2, 1e-2, 1e-2)
+    # strong orders, E|y_T - exact| over h = 2^-5 .. 2^-9
+    T, Pn, fine = 1.0, 2000, 12
+    hf = 2.0 ** -fine
+    dWf = sdb.deltaW(2 ** fine, 2, hf, paths=Pn, seed=2027)                    # (P, 4096, 2)
+    ex1 = _kp4446_exact(y0s, a, b, T, dWf[:, :, 0].sum(axis=1))
+    ex2 = float(y02[0]) * np.exp((a2 - (b1 ** 2 + b2 ** 2) / 2.0) * T + b1 * dWf[:, :, 0].sum(axis=1)
+                                 + b2 * dWf[:, :, 1].sum(axis=1))
+    levels = [5, 6, 7, 8, 9]
+    errs = {"r2_4446": [], "r2_4459": [], "kp2i_4446": [], "kp2is_4446": []}
+    for lv in levels:
+        n = 2 ** lv
+        hh = T / n
+        ts = np.linspace(0.0, T, n + 1)
+        dWc = dWf.reshape(Pn, n, -1, 2).sum(axis=2)                              # (P, n, 2)
+        d1 = np.ascontiguousarray(dWc[:, :, 0:1])
+        I1 = (0.5 * (d1[:, :, 0] ** 2 - hh))[:, :, None, None]
+        errs["r2_4446"].append(np.mean(np.abs(sdb.stratR2(f_str, G, y0s, ts, dW=d1)[:, -1, 0] - ex1)))
+        errs["r2_4459"].append(np.mean(np.abs(sdb.stratR2(f2s, G2, y02, ts, dW=dWc)[:, -1, 0] - ex2)))
+        errs["kp2i_4446"].append(np.mean(np.abs(
+            sdb.itoKP2i(f_ito, G, y0s, ts, dW=d1, I=I1, rtol=1e-10)[:, -1, 0] - ex1)))
+        errs["kp2is_4446"].append(np.mean(np.abs(
+            sdb.stratKP2iS(f_str, G, y0s, ts, dW=d1, J=I1 + 0.5 * hh, rtol=1e-10)[:, -1, 0] - ex1)))
+    x = np.log2([T / 2 ** lv for lv in levels])
+    slopes = {k: np.polyfit(x, np.log2(v), 1)[0] for k, v in errs.items()}
+    assert 0.85 <= slopes["r2_4446"] <= 1.15 and 0.85 <= slopes["r2_4459"] <= 1.15, slopes
+    assert 0.85 <= slopes["kp2i_4446"] <= 1.15, slopes
+    # the reference's Stratonovich two-step recursion: strong order ~1/2 in practice (README.rst:123
+    # flags it as probably buggy) -- reproduced as it is
+    assert 0.3 <= slopes["kp2is_4446"] <= 0.65, slopes
+    print("strong-order slopes:", {k: round(v, 3) for k, v in slopes.items()})
 
 
 def test_weak_mean_of_headline_system(sdb):

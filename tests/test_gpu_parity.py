@@ -264,6 +264,70 @@ def test_long_run_parity_every_integrator(sdb, d, wik):
                                              ", ".join("%s %.1e" % kv for kv in worst.items())))
 
 
+@pytest.mark.parametrize("name", ["kp4446", "kp4459", "kps445", "r74", "lin2", "lin10"])
+def test_new_schemes_match_oracle(sdb, name):
+    """The two schemes from the reference's to-do list (README.rst:125-128), which it does not have:
+    stratR2 (Burrage & Burrage's two-stage SRK) against the oracle's restatement of the published
+    tableau, and itoKP2i (the Ito version of the two-step implicit scheme) against the oracle's KP2iS
+    recursion fed with the Ito drift and Ito integrals -- on the golden fixtures' noise."""
+    g = load_golden("integrate_%s.npz" % name)
+    f_ito, G, y0 = SYSTEMS[name](False)
+    f_str, _, _ = SYSTEMS[name](True)
+    tspan, dW, I, y0v = g["tspan"], g["dW"], g["I"], g["y0"]
+    y = sdb.stratR2(f_str, G, y0, tspan, dW=dW)
+    for p in range(dW.shape[0]):
+        assert rel_err(y[p], orc.r2(f_str, G, y0v, tspan, dW[p])) <= TOL
+    yk = sdb.itoKP2i(f_ito, G, y0, tspan, dW=dW, I=I, rtol=1e-12)
+    for p in range(dW.shape[0]):
+        ref = orc.kp2is(f_ito, G, y0v, tspan, dW[p], I[p], rtol=1e-13, solver="newton")
+        assert rel_err(yk[p], ref) <= 1e-11
+    # on-device noise: same generator slots as stratHeun / stratKP2iS
+    P, seed = 5, 77
+    N = len(tspan)
+    h = (tspan[-1] - tspan[0]) / (N - 1)
+    yd = sdb.stratR2(f_str, G, y0, tspan, paths=P, seed=seed)
+    dWd = sdb.deltaW(N - 1, G.m, h, paths=P, seed=seed)
+    for p in range(P):
+        assert rel_err(yd[p], orc.r2(f_str, G, y0v, tspan, dWd[p])) <= TOL
+    ykd = sdb.itoKP2i(f_ito, G, y0, tspan, sdb.Iwik, rtol=1e-12, paths=P, seed=seed)
+    _, Id = sdb.Iwik(dWd, h, seed=seed, ensemble=True)
+    for p in range(P):
+        ref = orc.kp2is(f_ito, G, y0v, tspan, dWd[p], Id[p], rtol=1e-13, solver="newton")
+        assert rel_err(ykd[p], ref) <= 1e-11
+
+
+def test_callable_repeated_integral_method(sdb):
+    """Imethod / Jmethod may be ANY function (dW, h, generator=...) -> (A, I) like in the reference
+    (integrate.py:306, :371, :487): it is evaluated on the host and its integrals are handed to the
+    kernels.  Here: the oracle's Ikpw (numpy PCG64 draws) as the method, single path and ensemble."""
+    f, G, y0 = SYSTEMS["r74"](False)
+    tspan = np.linspace(0.0, 0.1, 21)
+    h = 0.005
+    calls = []
+
+    def my_ikpw(dW, h_, generator=None):
+        calls.append(dW.shape)
+        return orc.ikpw(dW, h_, n=7, generator=generator)
+
+    dW = sdb.deltaW(20, 4, h, seed=3)
+    y = sdb.itoSRI2(f, G, y0, tspan, Imethod=my_ikpw, dW=dW, generator=np.random.default_rng(5))
+    _, I = orc.ikpw(dW, h, n=7, generator=np.random.default_rng(5))
+    assert calls == [(20, 4)] and rel_err(y, orc.srk2(f, G, y0, tspan, dW, I)) <= TOL
+    # ensemble: one host call per path, the generator advancing from path to path
+    dWp = sdb.deltaW(20, 4, h, paths=3, seed=4)
+    yp = sdb.itoSRI2(f, G, y0, tspan, Imethod=my_ikpw, dW=dWp, generator=np.random.default_rng(6))
+    gen = np.random.default_rng(6)
+    for p in range(3):
+        _, Ip = orc.ikpw(dWp[p], h, n=7, generator=gen)
+        assert rel_err(yp[p], orc.srk2(f, G, y0, tspan, dWp[p], Ip)) <= TOL
+    # dW drawn on the device when only the method is given; a method with the wrong shape is refused
+    y2 = sdb.stratSRS2(SYSTEMS["r74"](True)[0], G, y0, tspan,
+                       Jmethod=lambda dW, h_, generator=None: (None, np.zeros((20, 4, 4))), seed=9)
+    assert y2.shape == (21, 5)
+    with pytest.raises(sdb.SDEValueError):
+        sdb.itoSRI2(f, G, y0, tspan, Imethod=lambda dW, h_, generator=None: (None, np.zeros((20, 4))), seed=9)
+
+
 def test_mixed_noise_inputs(sdb):
     """Only one of dW / I supplied: the other is drawn on the device (integrate.py:481-489)."""
     f, G, y0 = SYSTEMS["r74"](False)
