@@ -127,10 +127,13 @@ int sdb_integrate(sdb_system* sys, const sdb_integrate_args* args);
 #define SDB_OBS_MAX 2         /* max over the grid of y[comp] */
 #define SDB_OBS_MIN 3         /* min over the grid of y[comp] */
 #define SDB_OBS_INTEGRAL 4    /* trapezoidal integral of y[comp] dt over the grid */
+#define SDB_OBS_LAGPROD 5     /* sum_{n >= L} y[comp](t_n) y[comp](t_{n-L}), L = (int)level in [0, 32] grid steps:
+                               * time-lagged products at full resolution (autocovariance / spectrum of a
+                               * stationary path, the check test_integrate.py:455-456 leaves as a to-do) */
 typedef struct sdb_observer {
   int kind;     /* SDB_OBS_* */
   int comp;     /* state component, 0 <= comp < d */
-  double level; /* threshold of the FIRST_* kinds */
+  double level; /* threshold of the FIRST_* kinds; lag in grid steps of SDB_OBS_LAGPROD */
 } sdb_observer;
 
 /* sdb_integrate plus n_obs observers: d_obs[o * stride_obs + p * stride_path] receives observer o of

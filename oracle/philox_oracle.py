@@ -6,8 +6,8 @@ oracle restates the PUBLISHED algorithm and is pinned by Random123's known-answe
 (`kat_vectors`: three philox4x32 10-round entries, checked in tests/test_philox.py).
 
 Normal transform (sdeint_b200/csrc/sdb_kernels.cuh, sdb_normal_pair): one 128-bit block
-(w0..w3) -> hi = w0:w1, lo = w2:w3;  u1 = ((hi >> 11) | 1) 2^-53 in (0,1);  rad = sqrt(-2 ln u1);
-t = ((lo >> 9) mod 2^52) 2^-52 in [0,1);  (c, s) = (cos, sin)(pi t / 4);  o = lo >> 61;
+(w0..w3) -> a = (w0 >> 12) 2^32 + w1 (52 bits);  u1 = (2 a + 1) 2^-53 in (0,1);  rad = sqrt(-2 ln u1);
+t = (((w2 >> 9) mod 2^20) 2^32 + w3) 2^-52 in [0,1);  (c, s) = (cos, sin)(pi t / 4);  o = w2 >> 29;
 z0 = (o&2 ? -1 : 1) rad (o&1 ? s : c),  z1 = (o&4 ? -1 : 1) rad (o&1 ? c : s)
 (Box-Muller with the angle folded into one octant and unfolded by three random bits).
 Normal number q of (path, step) is element q&1 of random block q>>1 of (seed, path, step).
@@ -16,7 +16,9 @@ Random block `slot` of (seed, path, step) (sdb_random_block in csrc/sdb_kernels.
   slot 0      the Philox4x32-10 block with counter (path_lo, path_hi, step, 0), key (seed_lo, seed_hi);
   slot s >= 1 MX2(K, s), K = the Philox4x32-10 block with counter (path_lo, path_hi, step, 0xFFFFFFFF):
               x_i = K_i + s G_i;  x_i ^= x_i >> 15;  y_i = x_i C_i + x_{i+1};  y_i ^= y_i >> 13;
-              x_i = y_i C_{i+1} + y_{i+1};  out_i = x_i ^ (x_i >> 16)      (indices mod 4, 32-bit wrap)
+              out_i = y_i C_{i+1} + y_{i+1}                                  (indices mod 4, 32-bit wrap)
+              (the last step is a multiply-add: its high bits are the well-mixed ones, and the transform
+              above takes the leading mantissa bits / octant bits from the top of w0, w2)
 (the 64-bit products of Philox share the FP64 pipe's issue resource on sm_100a, so only two Philox
 blocks are computed per (path, step); the other slots are a 32-bit multiply-xorshift expansion of a
 key block that is never output itself).
@@ -60,8 +62,7 @@ def mx2_block(K, s):
     x = [v ^ (v >> np.uint64(15)) for v in x]
     y = [(x[i] * np.uint64(MX_C[i]) + x[(i + 1) & 3]) & MASK for i in range(4)]
     y = [v ^ (v >> np.uint64(13)) for v in y]
-    x = [(y[i] * np.uint64(MX_C[(i + 1) & 3]) + y[(i + 1) & 3]) & MASK for i in range(4)]
-    return tuple(v ^ (v >> np.uint64(16)) for v in x)
+    return tuple((y[i] * np.uint64(MX_C[(i + 1) & 3]) + y[(i + 1) & 3]) & MASK for i in range(4))
 
 
 def random_block(seed, path, step, slot):
@@ -82,14 +83,13 @@ def random_block(seed, path, step, slot):
 def normal_pairs(seed, path, step, slot):
     """(z0, z1) for broadcastable integer arrays path, step, slot (spec in the module doc)."""
     r0, r1, r2, r3 = random_block(seed, path, step, slot)
-    hi = (r0 << np.uint64(32)) | r1
-    lo = (r2 << np.uint64(32)) | r3
-    x = (hi >> np.uint64(11)) | np.uint64(1)                      # 53-bit odd integer
+    a = ((r0 >> np.uint64(12)) << np.uint64(32)) | r1            # 52 bits
+    x = (a << np.uint64(1)) | np.uint64(1)                        # 53-bit odd integer
     u1 = x.astype(np.float64) * 2.0 ** -53                        # exact, in (0, 1)
     rad = np.sqrt(-2.0 * np.log(u1))
-    t = ((lo >> np.uint64(9)) & np.uint64((1 << 52) - 1)).astype(np.float64) * 2.0 ** -52
+    t = ((((r2 >> np.uint64(9)) & np.uint64((1 << 20) - 1)) << np.uint64(32)) | r3).astype(np.float64) * 2.0 ** -52
     c, s = np.cos(np.pi * t / 4), np.sin(np.pi * t / 4)
-    o = (lo >> np.uint64(61)).astype(np.int64)
+    o = (r2 >> np.uint64(29)).astype(np.int64)
     swap, neg0, neg1 = (o & 1) == 1, (o & 2) != 0, (o & 4) != 0
     a0 = np.where(swap, s, c)
     b0 = np.where(swap, c, s)

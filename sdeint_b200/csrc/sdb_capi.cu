@@ -444,8 +444,12 @@ static int make_observers(sdb_system* s, const sdb_observer* h_obs, int n_obs, d
   memset(o, 0, sizeof *o);
   o->n = n_obs;
   for (int i = 0; i < n_obs; ++i) {
-    if (h_obs[i].kind < SDB_OBS_FIRST_ABOVE || h_obs[i].kind > SDB_OBS_INTEGRAL)
+    if (h_obs[i].kind < SDB_OBS_FIRST_ABOVE || h_obs[i].kind > SDB_OBS_LAGPROD)
       return fail("observers: unknown observer kind");
+    if (h_obs[i].kind == SDB_OBS_LAGPROD &&
+        !(h_obs[i].level >= 0.0 && h_obs[i].level <= (double)SDB_OBS_MAXLAG &&
+          h_obs[i].level == (double)(int)h_obs[i].level))
+      return fail("observers: the lag of a lagged-product observer must be an integer in [0, 32]");
     if (h_obs[i].comp < 0 || h_obs[i].comp >= s->d)
       return fail("observers: observer component out of range");
     o->kind[i] = h_obs[i].kind;

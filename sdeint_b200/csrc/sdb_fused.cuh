@@ -56,8 +56,10 @@
 #define SDB_FUSED_BATCH_ORDER 0  // 1: angle polynomials before the table-dependent log part
 #endif
 #ifndef SDB_FUSED_SWP
-#define SDB_FUSED_SWP 1  // 1: software pipeline of the series loop -- the random bits (32-bit ALU / IMAD work) of
-#endif                   //    the NEXT batch are produced next to the FP64 transform of the current one
+#define SDB_FUSED_SWP 0  // 1: software pipeline of the series loop -- the random bits (32-bit ALU / IMAD work) of
+#endif                   //    the NEXT batch are produced next to the FP64 transform of the current one.  Measured
+                         //    4.7 % SLOWER (1.877e9 vs 1.969e9 path-steps/s): ptxas interleaves the two streams
+                         //    instruction by instruction and the lock-step ILP of the batches is lost
 #ifndef SDB_FUSED_BATCH_XZ
 #define SDB_FUSED_BATCH_XZ 0  // 1: X_k and Y_k pairs of one series term in ONE lock-step batch of M
 #endif
@@ -306,16 +308,14 @@ SDB_DEV void sdb_normal_batch(const uint32_t (&w)[NB][4], const double2* __restr
   int kk[NB];
 #pragma unroll
   for (int b = 0; b < NB; ++b) {
-    x[b] = __hiloint2double((int)(0x43400000u | (w[b][0] >> 12)),
-                            (int)__funnelshift_r(w[b][1], w[b][0], 12)) - 9007199254740991.0;
-    t[b] = __hiloint2double((int)(0x3FF00000u | ((w[b][2] >> 9) & 0x000FFFFFu)),
-                            (int)__funnelshift_r(w[b][3], w[b][2], 9)) - 1.0;
+    x[b] = __hiloint2double((int)(0x3FF00000u | (w[b][0] >> 12)), (int)w[b][1]) - SDB_ONE_M53;
+    t[b] = __hiloint2double((int)(0x3FF00000u | ((w[b][2] >> 9) & 0x000FFFFFu)), (int)w[b][3]) - 1.0;
   }
 #pragma unroll
   for (int b = 0; b < NB; ++b) {
     const int xh = __double2hiint(x[b]);
     const int tmp = xh - 0x3FE60000;
-    kk[b] = (tmp >> 20) - 53;
+    kk[b] = tmp >> 20;
     zz[b] = __hiloint2double(xh - (tmp & (int)0xFFF00000), __double2loint(x[b]));
     tc[b] = tab[((tmp >> 13) & 127) * TS];
   }

@@ -69,6 +69,8 @@ typedef long long int64_t;
 #define SDB_OBS_MAX 2
 #define SDB_OBS_MIN 3
 #define SDB_OBS_INTEGRAL 4
+#define SDB_OBS_LAGPROD 5    // sum over grid points n >= L of y[comp](t_n) y[comp](t_{n-L}), L = (int)level
+#define SDB_OBS_MAXLAG 32    // longest lag (grid steps) of a lagged-product observer: ring in local memory
 struct SdbObsArgs {
   int n;
   int kind[SDB_MAX_OBS];
@@ -171,8 +173,11 @@ SDB_HD void sdb_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3
 // (profiles/r01_microbench.md), so only TWO Philox4x32-10 blocks are computed per (path, step):
 //   slot 0                 -> the block itself (counter word 3 = 0), as before;
 //   slot s >= 1            -> MX2(K, s) with K = Philox4x32-10 at counter word 3 = SDB_RNG_KEYSLOT.
-// MX2 is two rounds of 32-bit multiply-xorshift over four coupled words (12 IMAD + 24 ALU
-// instructions, none on the FP64 pipe); K is never output.  Spec restated in oracle/philox_oracle.py;
+// MX2 is two rounds of 32-bit multiply-xorshift over four coupled words (12 IMAD + 16 ALU
+// instructions, none on the FP64 pipe); K is never output.  It ends on a multiply-add, whose HIGH
+// bits are the well-mixed ones: the normal transform below takes the leading mantissa bits and the
+// octant bits from the top of w0 / w2 and uses w1 / w3 whole as the low mantissa words (their weak
+// low bits are the last bits of a 52-bit uniform).  Spec restated in oracle/philox_oracle.py;
 // avalanche / correlation / normal-distribution tests in tests/test_philox.py.
 #define SDB_RNG_KEYSLOT 0xFFFFFFFFu
 #define SDB_MX_G0 0x9E3779B1u
@@ -190,15 +195,14 @@ SDB_HD void sdb_mx2_block(const uint32_t (&K)[4], uint32_t s, uint32_t (&o)[4]) 
   uint32_t y0 = x0 * SDB_MX_C0 + x1, y1 = x1 * SDB_MX_C1 + x2, y2 = x2 * SDB_MX_C2 + x3,
            y3 = x3 * SDB_MX_C3 + x0;
   y0 ^= y0 >> 13; y1 ^= y1 >> 13; y2 ^= y2 >> 13; y3 ^= y3 >> 13;
-  x0 = y0 * SDB_MX_C1 + y1; x1 = y1 * SDB_MX_C2 + y2; x2 = y2 * SDB_MX_C3 + y3; x3 = y3 * SDB_MX_C0 + y0;
-  o[0] = x0 ^ (x0 >> 16); o[1] = x1 ^ (x1 >> 16); o[2] = x2 ^ (x2 >> 16); o[3] = x3 ^ (x3 >> 16);
+  o[0] = y0 * SDB_MX_C1 + y1; o[1] = y1 * SDB_MX_C2 + y2; o[2] = y2 * SDB_MX_C3 + y3; o[3] = y3 * SDB_MX_C0 + y0;
 }
 
 // Counter layout: (path low, path high, step, slot); key = seed.  One 128-bit block yields one
 // Box-Muller pair (spec restated in oracle/philox_oracle.py):
-//   hi = w0:w1, lo = w2:w3;  x = (hi >> 11) | 1 (53-bit odd integer), u1 = x 2^-53 in (0,1)
-//   rad = sqrt(-2 ln u1);  t = ((lo >> 9) & (2^52-1)) 2^-52 in [0,1);  (c, s) = cos, sin(pi t / 4)
-//   octant bits o = lo >> 61: swap = o&1, neg0 = o&2, neg1 = o&4
+//   a = (w0 >> 12) 2^32 + w1 (52 bits: the top 20 of w0, all of w1), u1 = (2 a + 1) 2^-53 in (0,1)
+//   rad = sqrt(-2 ln u1);  t = (((w2 >> 9) & (2^20-1)) 2^32 + w3) 2^-52 in [0,1);  (c, s) = cos, sin(pi t / 4)
+//   octant bits o = w2 >> 29: swap = o&1, neg0 = o&2, neg1 = o&4
 //   z0 = +-rad * (swap ? s : c),  z1 = +-rad * (swap ? c : s)        -- a uniform angle, by symmetry
 // Normal number q of a path-step is element (q & 1) of slot (q >> 1):
 //   dW_j -> q = j;  X_k[j] -> m + 2(k-1)m + j;  Y_k[j] -> m + (2(k-1)+1)m + j;  Gtail_r -> m + 2nm + r.
@@ -207,6 +211,7 @@ SDB_HD void sdb_mx2_block(const uint32_t (&K)[4], uint32_t s, uint32_t (&o)[4]) 
 // rest on the integer / XU pipes): ln u1 by a 128-entry table (1/c, -2 ln c) + degree-6 log1p,
 // sqrt by MUFU.RSQ64H + one Newton step + one residual correction, sin/cos by degree-6
 // polynomials in t^2.  Accuracy ~1e-16 relative (tests compare with numpy's libm).
+#define SDB_ONE_M53 0.99999999999999988898  // 1 - 2^-53 (0x3FEFFFFFFFFFFFFF)
 SDB_DEV double sdb_rsqrt_approx(double x) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
@@ -216,14 +221,13 @@ SDB_DEV double sdb_rsqrt_approx(double x) {
 SDB_DEV void sdb_normal_pair(const uint32_t (&w)[4], const double2* __restrict__ tab, double& z0,
                              double& z1) {
   // ---- radius -----------------------------------------------------------------------------------
-  // x = 2 a + 1, a = (w0:w1) >> 12: 2^53 + 2a is exactly representable, and subtracting 2^53 - 1
-  // is exact, so one DADD converts and normalises; the rest works on the high word only.
-  const double x = __hiloint2double((int)(0x43400000u | (w[0] >> 12)),
-                                    (int)__funnelshift_r(w[1], w[0], 12)) - 9007199254740991.0;
+  // u1 = (2 a + 1) 2^-53 with a = (w0 >> 12):w1: 1 + a 2^-52 is a double with those mantissa words, and
+  // subtracting 1 - 2^-53 is exact, so one DADD converts; the rest works on the high word only.
+  const double x = __hiloint2double((int)(0x3FF00000u | (w[0] >> 12)), (int)w[1]) - SDB_ONE_M53;
   const int xh = __double2hiint(x);
   const int tmp = xh - 0x3FE60000;  // high word of SDB_LOG_OFF
   const int i = (tmp >> 13) & 127;
-  const int k = (tmp >> 20) - 53;   // u1 = x 2^-53 = 2^k z,  z in [0.6875, 1.375)
+  const int k = tmp >> 20;          // u1 = 2^k z,  z in [0.6875, 1.375)
   const double z = __hiloint2double(xh - (tmp & (int)0xFFF00000), __double2loint(x));
   const double2 tc = tab[i];  // {1/c, -2 ln c}
   const double r = fma(z, tc.x, -1.0);
@@ -242,8 +246,7 @@ SDB_DEV void sdb_normal_pair(const uint32_t (&w)[4], const double2* __restrict__
   g = fma(g, e, g);
   const double rad = fma(fma(-g, g, L), hh, g);
   // ---- angle ------------------------------------------------------------------------------------
-  const double t = __hiloint2double((int)(0x3FF00000u | ((w[2] >> 9) & 0x000FFFFFu)),
-                                    (int)__funnelshift_r(w[3], w[2], 9)) - 1.0;
+  const double t = __hiloint2double((int)(0x3FF00000u | ((w[2] >> 9) & 0x000FFFFFu)), (int)w[3]) - 1.0;
   const double t2 = t * t;
   double sn = fma(t2, SDB_SIN6, SDB_SIN5);
   sn = fma(t2, sn, SDB_SIN4);
@@ -706,6 +709,10 @@ SDB_DEV void sdb_finish(const SdbLoopArgs& a, int64_t p, const double (&Y)[D]) {
 template <int D>
 struct SdbObs {
   double v[SDB_MAX_OBS], prev[SDB_MAX_OBS];
+  // lagged products (autocovariance at FULL time resolution, the spectral check the reference leaves
+  // as a to-do, test_integrate.py:455-456): the last L values of the component, written round-robin
+  double ring[SDB_MAX_OBS][SDB_OBS_MAXLAG];
+  int pos[SDB_MAX_OBS], seen[SDB_MAX_OBS];
   static SDB_DEV double pick(const double (&Y)[D], int c) {
     double r = Y[0];
 #pragma unroll
@@ -726,7 +733,13 @@ struct SdbObs {
         if (kind == SDB_OBS_FIRST_ABOVE) v[o] = y >= a.obs.level[o] ? t0 : inf;
         else if (kind == SDB_OBS_FIRST_BELOW) v[o] = y <= a.obs.level[o] ? t0 : inf;
         else if (kind == SDB_OBS_INTEGRAL) v[o] = 0.0;
-        else v[o] = y;
+        else if (kind == SDB_OBS_LAGPROD) {
+          const int L = (int)a.obs.level[o];
+          v[o] = L == 0 ? y * y : 0.0;
+          ring[o][0] = y;
+          pos[o] = L > 1 ? 1 : 0;
+          seen[o] = 1;
+        } else v[o] = y;
       }
     }
   }
@@ -743,6 +756,18 @@ struct SdbObs {
         else if (kind == SDB_OBS_FIRST_BELOW) v[o] = (y <= a.obs.level[o] && t1 < v[o]) ? t1 : v[o];
         else if (kind == SDB_OBS_MAX) v[o] = y > v[o] ? y : v[o];
         else if (kind == SDB_OBS_MIN) v[o] = y < v[o] ? y : v[o];
+        else if (kind == SDB_OBS_LAGPROD) {
+          const int L = (int)a.obs.level[o];
+          if (L == 0) {
+            v[o] = fma(y, y, v[o]);
+          } else {
+            const int i = pos[o];
+            if (seen[o] >= L) v[o] = fma(y, ring[o][i], v[o]);  // ring[i] holds y(t_{n+1-L})
+            ring[o][i] = y;
+            pos[o] = i + 1 == L ? 0 : i + 1;
+            seen[o] += 1;
+          }
+        }
         else v[o] = fma(0.5 * (t1 - t0), prev[o] + y, v[o]);  // trapezoid
         prev[o] = y;
       }

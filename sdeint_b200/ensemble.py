@@ -158,6 +158,27 @@ def first_passage_cdf(times_dev, bins, t0, t1, paths, group=None):
     return edges, np.cumsum(c, axis=1) / float(paths)
 
 
+def stationary_autocovariance(lag_sums, lags, n_points, mean=0.0, group=None):
+    """Autocovariance of a stationary component at FULL time resolution from the in-loop
+    lagged-product observers (`observe=[("lagprod", comp, L), ...]`: per path sum_{n >= L} y_n y_{n-L}
+    over the n_points grid points): C(L) = E[sum] / (n_points - L) - mean^2, the expectation over the
+    paths (and over the ranks of `group`).  lag_sums: (P, n_lags) array or device tensor (n_lags, P)."""
+    torch = dev.torch_mod()
+    if isinstance(lag_sums, torch.Tensor):
+        tot = lag_sums.sum(dim=1).to(torch.float64)
+        cnt = torch.tensor([float(lag_sums.shape[1])], dtype=torch.float64, device=lag_sums.device)
+    else:
+        arr = np.asarray(lag_sums, dtype=np.float64)
+        tot = torch.from_numpy(arr.sum(axis=0))
+        cnt = torch.tensor([float(arr.shape[0])], dtype=torch.float64)
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=group)
+    lags = np.asarray(lags, dtype=np.float64)
+    return tot.cpu().numpy() / float(cnt.item()) / (float(n_points) - lags) - float(mean) ** 2
+
+
 def autocovariance(y_dev, comp, paths=None, group=None):
     """Ensemble autocovariance of one component across the saved times of a device trajectory tensor
     (n_saved, d, P):  C[s, t] = E[(y_s - E y_s)(y_t - E y_t)], the expectation over paths.

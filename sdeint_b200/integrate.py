@@ -487,7 +487,8 @@ def _run_pipelined(lib, system, a, host_out, P, path_id0, n_saved, d, device, ob
 _ENS = dict(paths=None, seed=None, path_id0=0, save_every=1, n_terms=5, device=None, out="numpy",
             y0_paths=None, host_out=None, commutative=None, observe=None, step0=0, h_noise=None)
 
-_OBS_KINDS = {"first_above": 0, "first_below": 1, "max": 2, "min": 3, "integral": 4}
+_OBS_KINDS = {"first_above": 0, "first_below": 1, "max": 2, "min": 3, "integral": 4, "lagprod": 5}
+MAX_LAG = 32
 MAX_OBSERVERS = 4
 
 
@@ -502,13 +503,16 @@ def _observers(observe, d):
         kind = spec[0]
         if kind not in _OBS_KINDS:
             raise SDEValueError('unknown observer %r (one of %s)' % (kind, ", ".join(sorted(_OBS_KINDS))))
-        need_level = kind.startswith("first_")
+        need_level = kind.startswith("first_") or kind == "lagprod"
         if len(spec) != (3 if need_level else 2):
             raise SDEValueError('observer %r takes %s' % (kind, "(kind, comp, level)" if need_level
                                                           else "(kind, comp)"))
         comp = int(spec[1])
         if not 0 <= comp < d:
             raise SDEValueError('observer component %d out of range for d=%d' % (comp, d))
+        if kind == "lagprod" and not (float(spec[2]) == int(spec[2]) and 0 <= int(spec[2]) <= MAX_LAG):
+            raise SDEValueError('the lag of a "lagprod" observer must be an integer number of grid steps '
+                                'in [0, %d]' % MAX_LAG)
         arr[i].kind, arr[i].comp = _OBS_KINDS[kind], comp
         arr[i].level = float(spec[2]) if need_level else 0.0
     return arr

@@ -424,6 +424,41 @@ def test_device_normals_independent_across_slots(sdb):
     assert abs((a * b).mean().item()) < 6.0 / np.sqrt(a.numel())
 
 
+def test_inloop_lagged_products_ou(sdb):
+    """Time-correlation statistics accumulated INSIDE the step loop at full resolution (the
+    to-do of test_integrate.py:455-456): lagged-product observers on a stationary Euler-discretised
+    Ornstein-Uhlenbeck ensemble (= AR(1): variance sigma^2 h / (1 - a^2), autocorrelation a^L,
+    a = 1 - theta h) -- against the exact values, against the same sums formed from the stored
+    trajectory of the same launch, and on the fused headline kernel against its stored trajectory."""
+    theta, sigma, h = 2.0, 0.6, 0.01
+    f, G, _ = sdb.ops.sys_ou(theta, sigma)
+    N, P = 2001, 20000
+    tspan = np.arange(N) * h
+    a = 1.0 - theta * h
+    var = sigma ** 2 * h / (1.0 - a * a)
+    y0p = np.random.default_rng(8).normal(0.0, np.sqrt(var), (P, 1))          # stationary start
+    lags = [0, 1, 5, 32]
+    y, obs = sdb.itoEuler(f, G, 0.0, tspan, paths=P, seed=5, y0_paths=y0p,
+                          observe=[("lagprod", 0, L) for L in lags])            # (P, N, 1), (P, 4)
+    x = y[:, :, 0]
+    for i, L in enumerate(lags):
+        direct = (x[:, L:] * x[:, :N - L]).sum(axis=1)
+        assert np.allclose(obs[:, i], direct, rtol=1e-12, atol=1e-14), L
+    C = sdb.ensemble.stationary_autocovariance(obs, lags, N)
+    want = var * a ** np.array(lags, dtype=float)
+    # sampling error of a time-and-ensemble average of correlated products: generous 6 sigma bound
+    tol = 6.0 * var * np.sqrt(2.0 / (theta * h * N) / P)
+    assert np.all(np.abs(C - want) < tol), (C, want, tol)
+    with pytest.raises(sdb.SDEValueError):
+        sdb.itoEuler(f, G, 0.0, tspan, paths=4, seed=5, observe=[("lagprod", 0, 33)])
+    # the fused SRI2 kernel carries the same observers
+    f10, G10, y10 = SYSTEMS["lin10"](False)
+    ts = np.linspace(0.0, 0.1, 101)
+    y2, o2 = sdb.itoSRI2(f10, G10, y10, ts, paths=300, seed=6, observe=[("lagprod", 3, 7), ("lagprod", 9, 0)])
+    assert np.allclose(o2[:, 0], (y2[:, 7:, 3] * y2[:, :-7, 3]).sum(axis=1), rtol=1e-12)
+    assert np.allclose(o2[:, 1], (y2[:, :, 9] ** 2).sum(axis=1), rtol=1e-12)
+
+
 def test_ou_autocovariance_and_spectrum(sdb):
     """Stationary statistics of an Ornstein-Uhlenbeck ensemble against the exact values of the
     discrete (Euler-Maruyama = AR(1)) process: variance sigma^2 / (2 theta - theta^2 h), autocorrelation
