@@ -669,7 +669,11 @@ static int integrate_impl(sdb_system* s, const sdb_integrate_args* a, const SdbO
   // paths, so computed once here with IEEE sqrt / division) and the KP2iS coefficients go to
   // the device in one stream-ordered copy.
   const size_t nt = (size_t)a->N, ns = nt - 1;
-  const size_t nk = a->scheme == SDB_SCHEME_KP2IS ? 3 * (size_t)s->d : 0;
+  // KP2iS coefficients gam, al1, al2 (3 d); for a linear drift also (1 - diag(al2) h A)^-1 (d x d):
+  // the implicit equation of the two-step scheme is then one fixed linear system (sdb_kernels.cuh)
+  const bool kp_lin = a->scheme == SDB_SCHEME_KP2IS && s->fk == SDB_DRIFT_LINEAR;
+  const size_t nd = (size_t)s->d;
+  const size_t nk = a->scheme == SDB_SCHEME_KP2IS ? 3 * nd + (kp_lin ? nd * nd : 0) : 0;
   std::vector<double> aux(nt + 3 * ns + nk);
   for (size_t i = 0; i < nt; ++i) aux[i] = a->h_tspan[i];
   for (size_t i = 0; i < ns; ++i) {
@@ -679,7 +683,36 @@ static int integrate_impl(sdb_system* s, const sdb_integrate_args* a, const SdbO
     aux[nt + ns + i] = rh;
     aux[nt + 2 * ns + i] = 1.0 / rh;
   }
-  for (size_t i = 0; i < nk; ++i) aux[nt + 3 * ns + i] = a->h_kp2is[i];
+  for (size_t i = 0; i < (nk ? 3 * nd : 0); ++i) aux[nt + 3 * ns + i] = a->h_kp2is[i];
+  if (kp_lin) {
+    const double hg = (a->h_tspan[a->N - 1] - a->h_tspan[0]) / (double)(a->N - 1);
+    const int d = s->d;
+    std::vector<double> Mx((size_t)d * 2 * d);  // [1 - diag(al2) h A | 1] -> [1 | inverse]
+    for (int i = 0; i < d; ++i)
+      for (int j = 0; j < d; ++j) {
+        Mx[(size_t)i * 2 * d + j] = (i == j ? 1.0 : 0.0) - a->h_kp2is[2 * d + i] * hg * s->fp[(size_t)i * d + j];
+        Mx[(size_t)i * 2 * d + d + j] = i == j ? 1.0 : 0.0;
+      }
+    for (int c = 0; c < d; ++c) {
+      int piv = c;
+      for (int r = c + 1; r < d; ++r)
+        if (fabs(Mx[(size_t)r * 2 * d + c]) > fabs(Mx[(size_t)piv * 2 * d + c])) piv = r;
+      if (Mx[(size_t)piv * 2 * d + c] == 0.0)
+        return fail("sdb_integrate: the implicit equation of KP2iS is singular (1 - al2 h A)");
+      if (piv != c)
+        for (int q = 0; q < 2 * d; ++q) std::swap(Mx[(size_t)c * 2 * d + q], Mx[(size_t)piv * 2 * d + q]);
+      const double inv = 1.0 / Mx[(size_t)c * 2 * d + c];
+      for (int q = 0; q < 2 * d; ++q) Mx[(size_t)c * 2 * d + q] *= inv;
+      for (int r = 0; r < d; ++r) {
+        if (r == c) continue;
+        const double fct = Mx[(size_t)r * 2 * d + c];
+        if (fct != 0.0)
+          for (int q = 0; q < 2 * d; ++q) Mx[(size_t)r * 2 * d + q] -= fct * Mx[(size_t)c * 2 * d + q];
+      }
+    }
+    for (int i = 0; i < d; ++i)
+      for (int j = 0; j < d; ++j) aux[nt + 3 * ns + 3 * nd + (size_t)i * d + j] = Mx[(size_t)i * 2 * d + d + j];
+  }
   double* d_aux = nullptr;
   keep_pool_memory();
   SDB_CUDA(cudaMallocAsync(&d_aux, aux.size() * sizeof(double), st));

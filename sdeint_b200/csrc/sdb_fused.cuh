@@ -37,8 +37,13 @@
 #define SDB_CX constexpr
 #endif
 
-#define SDB_FUSED_THREADS 256
+#ifndef SDB_FUSED_THREADS
+#define SDB_FUSED_THREADS 256  // 384: three warps per sub-partition (needs <= 168 registers: RB 2, PARK_Y, DW_REGS)
+#endif
 #define SDB_FUSED_WARPS (SDB_FUSED_THREADS / 32)
+#ifndef SDB_FUSED_DW_REGS
+#define SDB_FUSED_DW_REGS 0  // 1: dW stays in registers through the row blocks (no dW rows in shared memory)
+#endif
 #define SDB_FUSED_MAX_TERMS 256
 #ifndef SDB_FUSED_KUNROLL
 #define SDB_FUSED_KUNROLL 1  // unroll factor of the Levy-series loop over k
@@ -128,7 +133,7 @@ struct SdbFusedShape {
     return o;
   }
   static SDB_CX int n_left() { return left_off(NB); }
-  static SDB_CX int warp_doubles() { return (grows() + M) * 32; }
+  static SDB_CX int warp_doubles() { return (grows() + (SDB_FUSED_DW_REGS ? 0 : M)) * 32; }
   static SDB_CX size_t smem_base() {
     return ((size_t)MM * SDB_FUSED_THREADS + (size_t)warp_doubles() * SDB_FUSED_WARPS) * sizeof(double) +
            (SDB_FUSED_MAX_TERMS + 1 + n_left() + 1) * sizeof(double);
@@ -491,7 +496,7 @@ struct SdbFusedBlock {
                           double* gbuf, SDB_SMEM_CV double* sA, SDB_SMEM_CV double* sW,
                           const double (&Yf)[Sh::LT][4], double h, double dg, int lane,
                           double (&H20)[D], double (&Yacc)[D], double (&w)[4][2],
-                          double (&wv)[Sh::IL > 0 ? Sh::IL : 1]) {
+                          double (&wv)[Sh::IL > 0 ? Sh::IL : 1], const double (&dWr)[M]) {
     constexpr int LT = Sh::LT;
     const int fr = lane >> 2, fc = lane & 3;
     // ---- P1: staging[n][p] = sum_l Bmat[n][l] Y[l][p] -----------------------------------------
@@ -534,7 +539,7 @@ struct SdbFusedBlock {
 #pragma unroll
       for (int j = 0; j < M; ++j) {
         double gj[RN];
-        const double dWj = sW[j * 32];
+        const double dWj = SDB_FUSED_DW_REGS ? dWr[j] : sW[j * 32];
 #pragma unroll
         for (int r = 0; r < RN; ++r) {
           const int n = j * RN + r;
@@ -557,7 +562,7 @@ struct SdbFusedBlock {
       }
 #pragma unroll
       for (int k = 0; k < M; ++k) {
-        const double hd = 0.5 * sW[k * 32];
+        const double hd = 0.5 * (SDB_FUSED_DW_REGS ? dWr[k] : sW[k * 32]);
 #pragma unroll
         for (int r = 0; r < RN; ++r) s[r][k] = fma(hd, GdW[r], s[r][k]);
       }
@@ -641,7 +646,7 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   // shared: Levy areas [MM][NT] | per warp { staging [GR][32], dW [M][32] } | tables
-  double* warp_base = smem + (size_t)MM * NT + (size_t)warp * (GR + M) * 32;
+  double* warp_base = smem + (size_t)MM * NT + (size_t)warp * Sh::warp_doubles();
   double* gbuf = warp_base;
   double2* tab =
       reinterpret_cast<double2*>(smem + (size_t)MM * NT + (size_t)Sh::warp_doubles() * SDB_FUSED_WARPS);
@@ -702,10 +707,10 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
     __syncwarp();
 #endif
     // ---- noise: dW (wiener.py:52), Levy areas (wiener.py:67-74, :102-105), one lane per path ------
+    double dW[M];  // lives through the row blocks only with SDB_FUSED_DW_REGS
     {
       const SdbStream st(pkey, path, SDB_STEP(n), tab);
       const SdbGen gen(pkey, st.p_lo, st.p_hi, SDB_STEP(n));
-      double dW[M];
 #if SDB_FUSED_BATCH
       if constexpr (M % 2 == 0) {
         uint32_t w[M / 2][4];
@@ -861,7 +866,7 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
       }
 #pragma unroll
       for (int r = 0; r < MM; ++r) sA[r * NT] = At[r];
-#if !SDB_FUSED_PARK_DW
+#if !SDB_FUSED_PARK_DW && !SDB_FUSED_DW_REGS
 #pragma unroll
       for (int j = 0; j < M; ++j) sW[j * 32] = dW[j];
 #endif
@@ -904,7 +909,7 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
       SDB_SMEM_CV double* sAv = sA;
       SDB_SMEM_CV double* sWv = sW;
       SdbFusedBlocks<D, M, Sh::NB - 1>::run(frag, s_left_c, gbuf, sAv, sWv, Yf, h, dg, lane, Y,
-                                            Yacc, w, wv);
+                                            Yacc, w, wv, dW);
     }
     // Y now holds H20 = Y + f(Y) h
 

@@ -581,6 +581,11 @@ struct DiffLinearCols {  // g_k = B_k y
   }
 };
 
+// g_k linear in y (no offset): differences g_k(a) - g_k(b) = g_k(a - b) exactly
+template <class G_> struct SdbGLinear { static constexpr bool value = false; };
+template <int D_, int M_, class PS>
+struct SdbGLinear<DiffLinearCols<D_, M_, PS>> { static constexpr bool value = true; };
+
 template <int D_, class PS>
 struct DiffDiagLinear {  // g_k = b_k y_k e_k: diagonal noise (m = d)
   static constexpr int D = D_, M = D_;
@@ -1007,6 +1012,28 @@ SDB_DEV void sdb_loop_body(const SdbLoopArgs& a, const typename F::Params& fp,
           V[i] = fma(g[i], dW[k], V[i]);
         }
       }
+      if constexpr (SdbGLinear<G>::value) {
+        // Linear g_k = B_k y: G(Ybar_j1) - G_n = [B_k (f h + G_n[:, j1] sqrt h)]_k, so the m^2 column
+        // evaluations of integrate.py:626-627 collapse to m:  sum1 = sum_k B_k v_k,
+        // v_k = f h sum_j1 J[j1, k] + sqrt h (G_n J)[:, k]   (same value up to rounding)
+#pragma unroll 1
+        for (int k = 0; k < (NEED_IJ ? M : 0); ++k) {
+          double v[D], g[D];
+          double cs = 0.0;
+#pragma unroll
+          for (int j1 = 0; j1 < M; ++j1) cs += IJ[j1][k];
+#pragma unroll
+          for (int i = 0; i < D; ++i) {
+            double s = Gn[i][0] * IJ[0][k];
+#pragma unroll
+            for (int j1 = 1; j1 < M; ++j1) s = fma(Gn[i][j1], IJ[j1][k], s);
+            v[i] = fma(f0[i] * h, cs, rh * s);
+          }
+          G::col(gp, k, v, t0, g);
+#pragma unroll
+          for (int i = 0; i < D; ++i) acc[i] += g[i];
+        }
+      } else
 #pragma unroll 1
       for (int j1 = 0; j1 < (NEED_IJ ? M : 0); ++j1) {
         double yb[D];
@@ -1041,6 +1068,34 @@ SDB_DEV void sdb_loop_body(const SdbLoopArgs& a, const typename F::Params& fp,
 #pragma unroll
         for (int i = 0; i < D; ++i) Ynew[i] = Y[i];
         bool conv = false;
+        if constexpr (F::LINEAR) {
+          // Linear drift f = A y on a uniform grid: the implicit equation (1 - diag(al2) h A) x = cst
+          // is the SAME linear system for every path and step, so the host inverts it once
+          // (sdb_capi.cu: kp[3 D ..] = (1 - diag(al2) h A)^-1, Gauss-Jordan with partial pivoting) and a
+          // step is one matrix-vector product, followed by one Newton correction with the same
+          // inverse (residual of the first solve: removes the rounding of the inverse).
+          const double* __restrict__ Mi = a.kp + 3 * D;
+          double x0[D], fx[D];
+#pragma unroll
+          for (int i = 0; i < D; ++i) {
+            double acc = Mi[i * D] * cst[0];
+#pragma unroll
+            for (int j = 1; j < D; ++j) acc = fma(Mi[i * D + j], cst[j], acc);
+            x0[i] = acc;
+          }
+          F::eval(fp, x0, t1, fx);
+          double r[D];
+#pragma unroll
+          for (int i = 0; i < D; ++i) r[i] = fma(a.kp[2 * D + i] * h, fx[i], cst[i]) - x0[i];
+#pragma unroll
+          for (int i = 0; i < D; ++i) {
+            double acc = Mi[i * D] * r[0];
+#pragma unroll
+            for (int j = 1; j < D; ++j) acc = fma(Mi[i * D + j], r[j], acc);
+            Ynew[i] = x0[i] + acc;
+          }
+          conv = true;
+        }
 #pragma unroll 1
         for (int it = 0; it < 50 && !conv; ++it) {
           double fx[D], r[D];
