@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import hashlib
 import threading
 import weakref
 
@@ -9,7 +10,8 @@ import numpy as np
 
 from . import _lib, ops
 
-_systems = {}
+_systems = {}            # insertion-ordered: least recently used first
+_SYSTEMS_MAX = 64
 _systems_lock = threading.Lock()
 
 
@@ -66,8 +68,7 @@ class System:
 
     def __init__(self, f, G, device):
         lib = _lib.load()
-        self.f, self.G = f, G
-        self.d, self.m = G.d, G.m
+        self.d, self.m = G.d, G.m      # (f and G themselves are not kept: the cache is keyed by content)
         fp = np.ascontiguousarray(f.params, dtype=np.float64)
         gp = np.ascontiguousarray(G.params, dtype=np.float64)
         handle = C.c_void_p()
@@ -87,16 +88,22 @@ class System:
         self._fin = weakref.finalize(self, lib.sdb_system_destroy, handle)
 
 
+def _op_key(op):
+    p = np.ascontiguousarray(op.params, dtype=np.float64)
+    return (int(op.kind), hashlib.sha256(p.tobytes()).hexdigest(), getattr(op, "source", None))
+
+
 def get_system(f, G, device):
-    """Cache systems per (operator objects, device) so repeated calls reuse compiled kernels."""
-    key = (id(f), id(G), str(device))
+    """Device systems cached by CONTENT -- operator kinds, parameter values, CUDA source, device -- in a
+    small LRU: a parameter sweep that builds a new operator per point reuses the handle when the values
+    repeat and drops the oldest handles (device buffers, fragment tables, NVRTC modules) otherwise, and
+    changing `f.params` / `f.A` between calls is seen (it changes the key)."""
+    key = (_op_key(f), _op_key(G), int(G.d), int(G.m), str(device))
     with _systems_lock:
-        hit = _systems.get(key)
-        if hit is not None and hit[0]() is f and hit[1]() is G:
-            return hit[2]
-        sysobj = System(f, G, device)
-        _systems[key] = (weakref.ref(f), weakref.ref(G), sysobj)
-        if len(_systems) > 256:
-            for k in [k for k, v in _systems.items() if v[0]() is None or v[1]() is None]:
-                _systems.pop(k, None)
-        return sysobj
+        hit = _systems.pop(key, None)
+        if hit is None:
+            hit = System(f, G, device)
+        _systems[key] = hit                      # most recently used last
+        while len(_systems) > _SYSTEMS_MAX:
+            _systems.pop(next(iter(_systems)))
+        return hit

@@ -691,6 +691,22 @@ SDB_DEV void sdb_step_noise(const SdbLoopArgs& a, int64_t p, int n, double (&dW)
   }
 }
 
+// On-device noise for the large-system SRK2 path: dW and the Levy-area vector only -- I / J is never
+// materialised (m^2 doubles of local memory); the step loop applies it to G_n row by row from dW and
+// the areas, which stay in registers.
+template <int M, int NOISE>
+SDB_DEV void sdb_step_noise_areas(const SdbLoopArgs& a, int64_t p, int n, double (&dW)[M],
+                                  double (&At)[M * (M - 1) / 2 + 1]) {
+  const SdbPhiloxKey key(a.seed);
+  const SdbStream st(key, (uint64_t)(a.path_id0 + p), SDB_STEP(n));
+  const double rh = sqrt(a.h_global);
+  SdbNormalSeq s(st, 0u);
+#pragma unroll
+  for (int j = 0; j < M; ++j) dW[j] = rh * s.next();
+  const SdbNormalsPhilox<M> ns{st, a.n_terms};
+  sdb_levy_areas<M>(dW, a.h_global, a.n_terms, NOISE, ns, At);
+}
+
 template <int D>
 SDB_DEV void sdb_store(const SdbLoopArgs& a, int64_t p, int64_t s, const double (&Y)[D]) {
   double* o = a.y + s * a.y_sS + p * a.y_sP;
@@ -869,7 +885,16 @@ SDB_DEV void sdb_loop_body(const SdbLoopArgs& a, const typename F::Params& fp,
     const double t1 = a.tspan[n + 1];
     double dW[M];
     double IJ[M][M];  // dead (and removed by the compiler) for Euler / Heun
-    sdb_step_noise<M, NOISE, NEED_IJ, (G::DIAGONAL && SCHEME == SDB_SCHEME_SRK2)>(a, p, n, dW, IJ);
+    // Large systems (column loops rolled, G_n and I in local memory), SRI2 / SRS2 on device noise: keep
+    // the Levy areas in registers and never build I (see the SRK2 branch)
+    constexpr bool AREAS = !SMALL && NEED_IJ && SCHEME == SDB_SCHEME_SRK2 && !G::DIAGONAL &&
+                           NOISE != SDB_NOISE_HOST && M >= 2 && M <= 12;
+    double At[AREAS ? M * (M - 1) / 2 + 1 : 1];
+    if constexpr (AREAS) {
+      sdb_step_noise_areas<M, NOISE>(a, p, n, dW, At);
+    } else {
+      sdb_step_noise<M, NOISE, NEED_IJ, (G::DIAGONAL && SCHEME == SDB_SCHEME_SRK2)>(a, p, n, dW, IJ);
+    }
 
     if (SCHEME == SDB_SCHEME_EULER) {
       const double h = a.h_global;
@@ -975,15 +1000,52 @@ SDB_DEV void sdb_loop_body(const SdbLoopArgs& a, const typename F::Params& fp,
         }
       }
       const double half_rh = 0.5 * rh;
+      double S[AREAS ? D : 1][AREAS ? M : 1];
+      if constexpr (AREAS) {
+        // S = G_n I / sqrt(h) row by row, I = dW dW^T / 2 + diag + antisymmetric areas (sdb_assemble_IJ)
+        // applied from registers: 2 local-memory accesses per entry of G_n instead of 2 m.
+        const bool strat = (a.flags & SDB_FLAG_STRATONOVICH) != 0;
+        const double dgv = strat ? 0.0 : -0.5 * a.h_global;
+#pragma unroll 1
+        for (int i = 0; i < D; ++i) {
+          double gi[M], si[M];
+          double gdw = 0.0;
+#pragma unroll
+          for (int j = 0; j < M; ++j) {
+            gi[j] = Gn[i][j];
+            gdw = fma(gi[j], dW[j], gdw);
+          }
+#pragma unroll
+          for (int kk = 0; kk < M; ++kk) si[kk] = fma(0.5 * gdw, dW[kk], dgv * gi[kk]);
+          int r = 0;
+#pragma unroll
+          for (int j = 0; j < M; ++j) {
+#pragma unroll
+            for (int kk = j + 1; kk < M; ++kk) {
+              const double av = NOISE == SDB_NOISE_WIK ? -At[r] : At[r];
+              si[kk] = fma(gi[j], av, si[kk]);
+              si[j] = fma(-gi[kk], av, si[j]);
+              ++r;
+            }
+          }
+#pragma unroll
+          for (int kk = 0; kk < M; ++kk) S[i][kk] = si[kk] * inv_rh;
+        }
+      }
 #pragma unroll(SMALL ? M : 1)
       for (int k = 0; k < (NEED_IJ ? M : 0); ++k) {
         double up[D], dn[D], gu[D], gd[D];
 #pragma unroll
         for (int i = 0; i < D; ++i) {
-          double s = Gn[i][0] * IJ[0][k];
+          double s;
+          if constexpr (AREAS) {
+            s = S[i][k];
+          } else {
+            s = Gn[i][0] * IJ[0][k];
 #pragma unroll
-          for (int j = 1; j < M; ++j) s = fma(Gn[i][j], IJ[j][k], s);
-          s *= inv_rh;
+            for (int j = 1; j < M; ++j) s = fma(Gn[i][j], IJ[j][k], s);
+            s *= inv_rh;
+          }
           up[i] = base[i] + s;
           dn[i] = base[i] - s;
         }

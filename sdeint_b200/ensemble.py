@@ -242,12 +242,29 @@ def checkpointed(integrator, f, G, y0, tspan, *, paths, seed, segment, checkpoin
         raise ValueError("checkpointed: segment must be >= 1")
     h = (tspan[-1] - tspan[0]) / n_int
     finger = np.array([tspan[0], tspan[-1], float(n_int)])
+    # what the run IS: integrator, operators (kinds, parameter values, source), y0, grid and the options
+    # that change the numbers -- a checkpoint of anything else must not be resumed
+    import hashlib
+    hh = hashlib.sha256()
+    hh.update(getattr(integrator, "__name__", repr(integrator)).encode())
+    for op in (f, G):
+        hh.update(repr((int(op.kind), getattr(op, "source", None))).encode())
+        hh.update(np.ascontiguousarray(op.params, dtype=np.float64).tobytes())
+    hh.update(np.ascontiguousarray(np.atleast_1d(np.asarray(y0, dtype=np.float64))).tobytes())
+    hh.update(tspan.tobytes())
+    hh.update(repr(sorted((k, getattr(v, "__name__", v)) for k, v in kw.items() if k != "device")).encode())
+    run_id = hh.hexdigest()
     step, states = 0, None
     if os.path.exists(checkpoint):
         with np.load(checkpoint) as ck:
-            if (int(ck["seed"]) == int(seed) and int(ck["paths"]) == int(paths)
-                    and np.array_equal(ck["grid"], finger)):
-                step, states = int(ck["step"]), ck["states"]
+            same = (int(ck["seed"]) == int(seed) and int(ck["paths"]) == int(paths)
+                    and np.array_equal(ck["grid"], finger)
+                    and "run_id" in ck.files and str(ck["run_id"]) == run_id)
+            if not same:
+                raise ValueError("checkpointed: %s is the checkpoint of a different run (system, integrator, "
+                                 "y0, grid, seed, paths or options differ); remove it to start over"
+                                 % checkpoint)
+            step, states = int(ck["step"]), ck["states"]
     managed = {"save_every", "step0", "y0_paths", "out", "h_noise", "host_out", "observe", "dW", "I", "J"}
     if managed & set(kw):
         raise ValueError("checkpointed manages %s itself" % ", ".join(sorted(managed & set(kw))))
@@ -263,8 +280,11 @@ def checkpointed(integrator, f, G, y0, tspan, *, paths, seed, segment, checkpoin
         if on_segment is not None:
             on_segment(step, cur)
         tmp = checkpoint + ".tmp.npz"
-        np.savez(tmp, step=step, states=cur.contiguous().cpu().numpy(), seed=int(seed), paths=int(paths),
-                 grid=finger)
+        with open(tmp, "wb") as fh:
+            np.savez(fh, step=step, states=cur.contiguous().cpu().numpy(), seed=int(seed),
+                     paths=int(paths), grid=finger, run_id=np.array(run_id))
+            fh.flush()
+            os.fsync(fh.fileno())
         os.replace(tmp, checkpoint)
     return cur.contiguous().cpu().numpy() if cur is not None else np.asarray(states)
 

@@ -1061,10 +1061,20 @@ def test_checkpointed_run_resumes_bit_for_bit(sdb, tmp_path):
     final = sdb.ensemble.checkpointed(sdb.itoSRI2, f, G, y0, tspan, paths=P, seed=seed, segment=16,
                                       checkpoint=ck, on_segment=lambda s_, y_: seen.append(s_))
     assert seen == [32, 48, 60] and np.array_equal(final, whole)
-    # a finished run returns its states without integrating again; another seed ignores the file
+    # a finished run returns its states without integrating again
     n0 = sdb.launch_count()
     again = sdb.ensemble.checkpointed(sdb.itoSRI2, f, G, y0, tspan, paths=P, seed=seed, segment=16, checkpoint=ck)
     assert sdb.launch_count() == n0 and np.array_equal(again, whole)
+    # the checkpoint of a DIFFERENT run (seed, integrator, system parameters, y0, options) is refused
+    # instead of being resumed from unrelated states
+    f2 = sdb.ops.LinearDrift(np.array(f.A) * 1.01)
+    for args, kw in (((sdb.itoSRI2, f, G, y0), dict(seed=seed + 1)), ((sdb.stratSRS2, f, G, y0), dict(seed=seed)),
+                     ((sdb.itoSRI2, f2, G, y0), dict(seed=seed)), ((sdb.itoSRI2, f, G, y0 * 2.0), dict(seed=seed)),
+                     ((sdb.itoSRI2, f, G, y0), dict(seed=seed, n_terms=7))):
+        with pytest.raises(ValueError):
+            sdb.ensemble.checkpointed(*args, tspan, paths=P, segment=30, checkpoint=ck, **kw)
+    import os
+    os.remove(ck)
     other = sdb.ensemble.checkpointed(sdb.itoSRI2, f, G, y0, tspan, paths=P, seed=seed + 1, segment=30,
                                       checkpoint=ck)
     assert not np.array_equal(other, whole)
