@@ -130,6 +130,7 @@ int sdb_integrate(sdb_system* sys, const sdb_integrate_args* args);
 #define SDB_OBS_LAGPROD 5     /* sum_{n >= L} y[comp](t_n) y[comp](t_{n-L}), L = (int)level in [0, 32] grid steps:
                                * time-lagged products at full resolution (autocovariance / spectrum of a
                                * stationary path, the check test_integrate.py:455-456 leaves as a to-do) */
+#define SDB_OBS_MAXLAG 32     /* longest lag of SDB_OBS_LAGPROD, in grid steps */
 typedef struct sdb_observer {
   int kind;     /* SDB_OBS_* */
   int comp;     /* state component, 0 <= comp < d */

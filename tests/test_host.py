@@ -308,6 +308,7 @@ def test_python_constants_match_the_header():
     for kind, value in integrate._OBS_KINDS.items():
         assert defs["OBS_" + kind.upper()] == value
     assert defs["MAX_OBSERVERS"] == integrate.MAX_OBSERVERS
+    assert defs["OBS_MAXLAG"] == integrate.MAX_LAG
     # and the kernel-side copies of the same enumerators (sdb_kernels.cuh) agree with the header
     kern = open(os.path.join(ROOT, "sdeint_b200", "csrc", "sdb_kernels.cuh")).read()
     for m in re.finditer(r"#define\s+SDB_((?:SCHEME|NOISE|FLAG|DRIFT|DIFF|OBS)_\w+)\s+(\d+)\b", kern):
