@@ -245,7 +245,7 @@ SDB_DEV void sdb_srk2_fusedx_body(const SdbLoopArgs& a, const PInline<D * D>& fp
     obs.init(a, Y);
 #endif
 #pragma unroll
-    for (int l = 0; l < D; ++l) ybuf[l * 32 + (lane ^ sdb_swz(l))] = Y[l];
+    for (int l = 0; l < D; ++l) ybuf[l * 32 + (lane ^ sdb_swz3(l))] = Y[l];
     __syncwarp();
   }
 
@@ -308,7 +308,7 @@ SDB_DEV void sdb_srk2_fusedx_body(const SdbLoopArgs& a, const PInline<D * D>& fp
           const int lc = ok ? l : 0;
 #pragma unroll
           for (int pt = 0; pt < 4; ++pt) {
-            const double v = ybuf[lc * 32 + ((8 * pt + fr) ^ sdb_swz(lc))];
+            const double v = ybuf[lc * 32 + ((8 * pt + fr) ^ sdb_swz3(lc))];
             Yf[lt][pt] = ok ? v : 0.0;
           }
         }
@@ -418,7 +418,7 @@ SDB_DEV void sdb_srk2_fusedx_body(const SdbLoopArgs& a, const PInline<D * D>& fp
             const int nn = M * RN + r;
             const double f0h = gv[nn * 32 + (lane ^ sdb_swz(nn))] * h;
             const int yr = R0 + r;
-            const double yv = ybuf[yr * 32 + (lane ^ ((yr & 1) | (((yr >> 1) & 1) << 3)))];
+            const double yv = ybuf[yr * 32 + (lane ^ ((yr & 3) << 2))];
             piece[r] = yv + f0h;                      // H20
             piece[RN + r] = fma(-0.5, f0h, GdW[r]);   // Yacc
           }
@@ -443,7 +443,7 @@ SDB_DEV void sdb_srk2_fusedx_body(const SdbLoopArgs& a, const PInline<D * D>& fp
 #pragma unroll
           for (int k = 0; k < M; ++k) {
             const int K = r * M + k;
-            gbuf[K * 32 + (lane ^ sdb_swz(K))] = s[r][k];
+            gbuf[K * 32 + (lane ^ sdb_swz3(K))] = s[r][k];
           }
       }
       __syncwarp();
@@ -454,7 +454,7 @@ SDB_DEV void sdb_srk2_fusedx_body(const SdbLoopArgs& a, const PInline<D * D>& fp
         for (int kt = 0; kt < KT3; ++kt) {
           const int K = 4 * kt + fc;
           const double* row = gbuf + K * 32;
-          const int sw = sdb_swz(K);
+          const int sw = sdb_swz3(K);
           double bf[4];
 #pragma unroll
           for (int pt = 0; pt < 4; ++pt) bf[pt] = row[(8 * pt + fr) ^ sw];
@@ -511,7 +511,7 @@ SDB_DEV void sdb_srk2_fusedx_body(const SdbLoopArgs& a, const PInline<D * D>& fp
       for (int i = 0; i < D; ++i) Y[i] = H20[i] + Yacc[i];
     }
 #pragma unroll
-    for (int l = 0; l < D; ++l) ybuf[l * 32 + (lane ^ sdb_swz(l))] = Y[l];
+    for (int l = 0; l < D; ++l) ybuf[l * 32 + (lane ^ sdb_swz3(l))] = Y[l];
     __syncwarp();
 
 #if SDB_OBSERVE

@@ -177,7 +177,7 @@ SDB_DEV void sdb_srk2_fusedx2_body(const SdbLoopArgs& a, const PInline<D * D>& f
 #endif
     if (lead) {
 #pragma unroll
-      for (int l = 0; l < D; ++l) ybuf[l * 32 + (lane ^ sdb_swz(l))] = Y[l];
+      for (int l = 0; l < D; ++l) ybuf[l * 32 + (lane ^ sdb_swz3(l))] = Y[l];
     }
   }
   sdb_pair_sync(bar_id);
@@ -321,7 +321,7 @@ SDB_DEV void sdb_srk2_fusedx2_body(const SdbLoopArgs& a, const PInline<D * D>& f
           const int lc = ok ? l : 0;
 #pragma unroll
           for (int pt = 0; pt < 4; ++pt) {
-            const double v = ybuf[lc * 32 + ((8 * pt + fr) ^ sdb_swz(lc))];
+            const double v = ybuf[lc * 32 + ((8 * pt + fr) ^ sdb_swz3(lc))];
             Yf[lt][pt] = ok ? v : 0.0;
           }
         }
@@ -428,7 +428,7 @@ SDB_DEV void sdb_srk2_fusedx2_body(const SdbLoopArgs& a, const PInline<D * D>& f
             const int nn = M * RN + r;
             const double f0h = gv[nn * 32 + (lane ^ sdb_swz(nn))] * h;
             const int yr = R0 + r;
-            const double yv = ybuf[yr * 32 + (lane ^ ((yr & 1) | (((yr >> 1) & 1) << 3)))];
+            const double yv = ybuf[yr * 32 + (lane ^ ((yr & 3) << 2))];
             piece[r] = yv + f0h;                      // H20
             piece[RN + r] = fma(-0.5, f0h, GdW[r]);   // Yacc
           }
@@ -452,7 +452,7 @@ SDB_DEV void sdb_srk2_fusedx2_body(const SdbLoopArgs& a, const PInline<D * D>& f
 #pragma unroll
           for (int k = 0; k < M; ++k) {
             const int K = r * M + k;
-            gbuf[K * 32 + (lane ^ sdb_swz(K))] = s[r][k];
+            gbuf[K * 32 + (lane ^ sdb_swz3(K))] = s[r][k];
           }
       }
       __syncwarp();
@@ -463,7 +463,7 @@ SDB_DEV void sdb_srk2_fusedx2_body(const SdbLoopArgs& a, const PInline<D * D>& f
         for (int kt = 0; kt < KT3; ++kt) {
           const int K = 4 * kt + fc;
           const double* row = gbuf + K * 32;
-          const int sw = sdb_swz(K);
+          const int sw = sdb_swz3(K);
           double bf[4];
 #pragma unroll
           for (int pt = 0; pt < 4; ++pt) bf[pt] = row[(8 * pt + fr) ^ sw];
@@ -520,7 +520,7 @@ SDB_DEV void sdb_srk2_fusedx2_body(const SdbLoopArgs& a, const PInline<D * D>& f
         sdb_x2_final_rows<D, 0, DH>(fp, H20, Yacc, h, Yn);
         // (every reader of the old Y -- P1, the drift rows -- finished before the barrier above)
 #pragma unroll
-        for (int i = 0; i < DH; ++i) ybuf[i * 32 + (lane ^ sdb_swz(i))] = Yn[i];
+        for (int i = 0; i < DH; ++i) ybuf[i * 32 + (lane ^ sdb_swz3(i))] = Yn[i];
       } else {
         double Yacc[D - DH], Yn[D - DH];
 #pragma unroll
@@ -528,7 +528,7 @@ SDB_DEV void sdb_srk2_fusedx2_body(const SdbLoopArgs& a, const PInline<D * D>& f
           Yacc[i - DH] = rows[2 * RN * (i / RN) + RN + i % RN] + (wp[i] + gpart[(i - DH) * 32 + lane]);
         sdb_x2_final_rows<D, DH, D>(fp, H20, Yacc, h, Yn);
 #pragma unroll
-        for (int i = DH; i < D; ++i) ybuf[i * 32 + (lane ^ sdb_swz(i))] = Yn[i - DH];
+        for (int i = DH; i < D; ++i) ybuf[i * 32 + (lane ^ sdb_swz3(i))] = Yn[i - DH];
       }
     }
     sdb_pair_sync(bar_id);  // the pair's copy of Y_{n+1} is complete
@@ -541,7 +541,7 @@ SDB_DEV void sdb_srk2_fusedx2_body(const SdbLoopArgs& a, const PInline<D * D>& f
     if (lead && (save || n + 1 == steps || SDB_OBSERVE)) {
       double Y[D];
 #pragma unroll
-      for (int l = 0; l < D; ++l) Y[l] = ybuf[l * 32 + (lane ^ sdb_swz(l))];
+      for (int l = 0; l < D; ++l) Y[l] = ybuf[l * 32 + (lane ^ sdb_swz3(l))];
 #if SDB_OBSERVE
       obs.step(a, n, Y);
 #endif
