@@ -434,17 +434,17 @@ def run_gpu(args):
                            "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}
         roofline["hbm"]["frac"] = roofline["hbm"]["achieved"] / hbm_peak
         # Issue model: per warp-step (32 path-steps) of a sub-partition the SASS
-        # executes 3940 DFMA-class x 2 + 280 DMMA x 16 = 12360 FP64-pipe cycles; the two Philox
+        # executes 3820 DFMA-class x 2 + 280 DMMA x 16 = 12120 FP64-pipe cycles; the two Philox
         # blocks left per path-step (2 x 74 cycles) are the only IMAD.WIDE work on that pipe.
         sm_hz = 1e6 * float((clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0))
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        floor = sms * 4 * 32 * sm_hz / (12360.0 + 148.0)
+        floor = sms * 4 * 32 * sm_hz / (12120.0 + 148.0)
         roofline["issue_model"] = {
-            "fp64_pipe_cycles_per_warp_step": 12360, "philox_cycles_per_warp_step": 148,
+            "fp64_pipe_cycles_per_warp_step": 12120, "philox_cycles_per_warp_step": 148,
             "floor_path_steps_per_s": floor,
             "frac_of_floor": (path_steps / (ms_kernel * 1e-3)) / floor,
             "dmma_note": "the 4480 DMMA cycles do not co-issue with other instructions "
-                         "(tools/micro/dmma_coissue.cu): DESIGN.md 4.2 puts the realistic floor at ~13300 cycles",
+                         "(tools/micro/dmma_coissue.cu): DESIGN.md 4.2 puts the realistic floor at ~12500-13000 cycles",
             "source": "SASS instruction counts (profiles/r02_fused_v0_final_ncu_summary.txt) "
                       "x measured issue costs (tools/micro/rng.cu, dmma_coissue.cu, philox.cu, coissue.cu)"}
         line = {
