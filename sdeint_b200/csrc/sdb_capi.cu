@@ -628,6 +628,7 @@ static int integrate_impl(sdb_system* s, const sdb_integrate_args* a, const SdbO
                                   SdbFusedDims::THREADS, SDB_NOISE_KPW, SDB_SCHEME_SRK2};
       } else {
         jit_rb = 2;
+        jit_xr = SDB_FUSED_A2;
         jit_entry = SdbFusedEntry{s->d, s->m, 0, (const void*)it->second.kern,
                                   use_x2 ? x2dims.smem_bytes() : xdims.smem_bytes(),
                                   xdims.sh.table_doubles(), nullptr,

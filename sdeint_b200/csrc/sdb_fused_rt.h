@@ -98,7 +98,7 @@ struct SdbFusedDims {
 // Run-time mirror of SdbXShape (sdb_fusedx.cuh): the TMEM-resident kernel, 2-row blocks.
 struct SdbFusedXDims {
   SdbFusedDims sh;
-  constexpr SdbFusedXDims(int d, int m) : sh(d, m, 2) {}
+  constexpr SdbFusedXDims(int d, int m) : sh(d, m, 2, 1) {}  // 2-row blocks, rows of A^2 in the P1 product
   constexpr int MM() const { return sh.MM(); }
   constexpr int MMP() const { return (MM() + 15) / 16 * 16; }
   constexpr int C_END() const { return 2 * MMP() + (2 * sh.M + 7) / 8 * 8 + 4 * sh.D; }

@@ -12,8 +12,8 @@
   SDB_FUSEDX_KERNEL(sdbk_fusedx_srk2_d##D##_m##M##_##TAG, D, M, WIK)                           \
   static SdbFusedRegistrar sdbreg_fusedx_d##D##_m##M##_##TAG(                                  \
       SdbFusedEntry{D, M, VARIANT, (const void*)sdbk_fusedx_srk2_d##D##_m##M##_##TAG,          \
-                    SdbXShape<D, M>::smem_bytes(), sdb_fused_table_doubles<D, M>(),            \
-                    &sdb_fused_build_tables<D, M>, SdbXShape<D, M>::THREADS,                   \
+                    SdbXShape<D, M>::smem_bytes(), sdb_fused_table_doubles<D, M, SDB_FUSED_A2>(),            \
+                    &sdb_fused_build_tables<D, M, SDB_FUSED_A2>, SdbXShape<D, M>::THREADS,                   \
                     SdbXShape<D, M>::PATHS,                                                    \
                     WIK ? SDB_NOISE_WIK : SDB_NOISE_KPW, SDB_SCHEME_SRK2});
 
@@ -28,8 +28,8 @@ SDB_FUSEDX_AOT(10, 10, 1, wik, 0)
   static_assert(SdbFusedXDims(D, M).smem_bytes() == SdbXShape<D, M>::smem_bytes() &&            \
                     SdbFusedXDims(D, M).C_END() == SdbXShape<D, M>::C_END &&                    \
                     SdbFusedXDims(D, M).threads() == SdbXShape<D, M>::THREADS &&                \
-                    SdbFusedXDims(D, M).sh.n_frags() == SdbFusedShape<D, M>::n_frags() &&       \
-                    SdbFusedXDims(D, M).sh.n_left() == SdbFusedShape<D, M>::n_left(),           \
+                    SdbFusedXDims(D, M).sh.n_frags() == SdbFusedShape<D, M, SDB_FUSED_A2>::n_frags() &&       \
+                    SdbFusedXDims(D, M).sh.n_left() == SdbFusedShape<D, M, SDB_FUSED_A2>::n_left(),           \
                 "sdb_fused_rt.h disagrees with SdbXShape");
 SDB_CHECK_XDIMS(20, 20) SDB_CHECK_XDIMS(10, 10) SDB_CHECK_XDIMS(16, 12) SDB_CHECK_XDIMS(4, 6)
 SDB_CHECK_XDIMS(12, 14) SDB_CHECK_XDIMS(6, 4)

@@ -35,7 +35,7 @@ namespace SDB_FUSED_NS {
 
 template <int D, int M>
 struct SdbXShape {
-  typedef SdbFusedShape<D, M> Sh;
+  typedef SdbFusedShape<D, M, SDB_FUSED_A2> Sh;  // rows of A^2 ride in the P1 product (sdb_fused.cuh)
   static constexpr int MM = Sh::MM;
   static constexpr int CH = 16;                              // areas per TMEM chunk (32 columns)
   static constexpr int NCH = (MM + CH - 1) / CH;
@@ -201,7 +201,7 @@ SDB_DEV void sdb_x_levy_areas(const SdbGen& gen,
 template <int D, int M, int WIK>
 SDB_DEV void sdb_srk2_fusedx_body(const SdbLoopArgs& a, const PInline<D * D>& fp,
                                   const double* __restrict__ frag, double* smem) {
-  typedef SdbFusedShape<D, M> Sh;
+  typedef SdbFusedShape<D, M, SDB_FUSED_A2> Sh;  // rows of A^2 ride in the P1 product (sdb_fused.cuh)
   typedef SdbXShape<D, M> Xs;
   constexpr int MM = Xs::MM, CH = Xs::CH, NCH = Xs::NCH, RN = Xs::RN, NB = Xs::NB, LT = Xs::LT;
   constexpr int T1 = Xs::T1, KT3 = Xs::KT3, IT = Xs::IT, IL = Xs::IL;
@@ -420,7 +420,12 @@ SDB_DEV void sdb_srk2_fusedx_body(const SdbLoopArgs& a, const PInline<D * D>& fp
             const int yr = R0 + r;
             const double yv = ybuf[yr * 32 + (lane ^ ((yr & 3) << 2))];
             piece[r] = yv + f0h;                      // H20
+#if SDB_FUSED_A2
+            const int n2 = (M + 1) * RN + r;          // f(H20) h = f0 h + h^2 A^2 Y: no second drift loop
+            piece[RN + r] = fma(0.5 * h * h, gv[n2 * 32 + (lane ^ sdb_swz(n2))], GdW[r]);
+#else
             piece[RN + r] = fma(-0.5, f0h, GdW[r]);   // Yacc
+#endif
           }
           sdb_tm_st<2 * RN>(tm + Xs::C_ROW + 4 * R0, piece);
         }
@@ -483,7 +488,8 @@ SDB_DEV void sdb_srk2_fusedx_body(const SdbLoopArgs& a, const PInline<D * D>& fp
           Yacc[i] = rows[2 * RN * (i / RN) + RN + i % RN];
         }
       }
-      // second drift evaluation f(H20, t_{n+1}) h (integrate.py:514)
+      // second drift evaluation f(H20, t_{n+1}) h (integrate.py:514): in Yacc already with SDB_FUSED_A2
+#if !SDB_FUSED_A2
 #pragma unroll
       for (int i = 0; i < D; ++i) {
         double acc = fp.v[i * D] * H20[0];
@@ -491,6 +497,7 @@ SDB_DEV void sdb_srk2_fusedx_body(const SdbLoopArgs& a, const PInline<D * D>& fp
         for (int l = 1; l < D; ++l) acc = fma(fp.v[i * D + l], H20[l], acc);
         Yacc[i] = fma(0.5 * h, acc, Yacc[i]);
       }
+#endif
 #pragma unroll
       for (int it = 0; it < IT; ++it) {  // stage-2 sum back to one lane per path
         double* row = gbuf + fr * 32;

@@ -12,8 +12,8 @@
   SDB_FUSEDX2_KERNEL(sdbk_fusedx2_srk2_d##D##_m##M##_##TAG, D, M, WIK)                         \
   static SdbFusedRegistrar sdbreg_fusedx2_d##D##_m##M##_##TAG(                                 \
       SdbFusedEntry{D, M, VARIANT, (const void*)sdbk_fusedx2_srk2_d##D##_m##M##_##TAG,         \
-                    SdbX2Shape<D, M>::smem_bytes(), sdb_fused_table_doubles<D, M>(),           \
-                    &sdb_fused_build_tables<D, M>, SdbX2Shape<D, M>::THREADS,                  \
+                    SdbX2Shape<D, M>::smem_bytes(), sdb_fused_table_doubles<D, M, SDB_FUSED_A2>(),           \
+                    &sdb_fused_build_tables<D, M, SDB_FUSED_A2>, SdbX2Shape<D, M>::THREADS,                  \
                     SdbX2Shape<D, M>::PATHS,                                                   \
                     WIK ? SDB_NOISE_WIK : SDB_NOISE_KPW, SDB_SCHEME_SRK2});
 

@@ -25,7 +25,7 @@ namespace SDB_FUSED_NS {
 
 template <int D, int M>
 struct SdbX2Shape {
-  typedef SdbFusedShape<D, M> Sh;
+  typedef SdbFusedShape<D, M, SDB_FUSED_A2> Sh;
   typedef SdbXShape<D, M> Xs;
   static constexpr int NB = Xs::NB, NCH = Xs::NCH;
   static constexpr int NBH = NB / 2;     // row blocks of role 0
@@ -112,17 +112,21 @@ SDB_DEV void sdb_x2_final_rows(const PInline<D * D>& fp, const double (&H20)[D],
                                double h, double (&Y)[I1 - I0]) {
 #pragma unroll
   for (int i = I0; i < I1; ++i) {
+#if SDB_FUSED_A2
+    Y[i - I0] = H20[i] + Yacc[i - I0];   // (h/2) f(H20) is in Yacc: the rows of A^2 ride in the P1 product
+#else
     double acc = fp.v[i * D] * H20[0];
 #pragma unroll
     for (int l = 1; l < D; ++l) acc = fma(fp.v[i * D + l], H20[l], acc);
     Y[i - I0] = H20[i] + fma(0.5 * h, acc, Yacc[i - I0]);
+#endif
   }
 }
 
 template <int D, int M, int WIK>
 SDB_DEV void sdb_srk2_fusedx2_body(const SdbLoopArgs& a, const PInline<D * D>& fp,
                                    const double* __restrict__ frag, double* smem) {
-  typedef SdbFusedShape<D, M> Sh;
+  typedef SdbFusedShape<D, M, SDB_FUSED_A2> Sh;
   typedef SdbXShape<D, M> Xs;
   typedef SdbX2Shape<D, M> X2;
   constexpr int MM = Xs::MM, CH = Xs::CH, NCH = Xs::NCH, RN = Xs::RN, NB = Xs::NB, LT = Xs::LT;
@@ -430,7 +434,12 @@ SDB_DEV void sdb_srk2_fusedx2_body(const SdbLoopArgs& a, const PInline<D * D>& f
             const int yr = R0 + r;
             const double yv = ybuf[yr * 32 + (lane ^ ((yr & 3) << 2))];
             piece[r] = yv + f0h;                      // H20
+#if SDB_FUSED_A2
+            const int n2 = (M + 1) * RN + r;
+            piece[RN + r] = fma(0.5 * h * h, gv[n2 * 32 + (lane ^ sdb_swz(n2))], GdW[r]);
+#else
             piece[RN + r] = fma(-0.5, f0h, GdW[r]);   // Yacc
+#endif
           }
           sdb_tm_st<2 * RN>(tm + Xs::C_ROW + 4 * R0, piece);
         }
