@@ -107,19 +107,19 @@ SDB_DEV void sdb_x2_tail2_chunks(const double (&dW)[M], const double (&u)[M], do
 }
 
 // second drift evaluation and new state for the rows [I0, I1):  Y_i = H20_i + Yacc_i + (h/2) (A H20)_i
-template <int D, int I0, int I1>
+template <int D, int I0, int I1, bool A2>
 SDB_DEV void sdb_x2_final_rows(const PInline<D * D>& fp, const double (&H20)[D], const double (&Yacc)[I1 - I0],
                                double h, double (&Y)[I1 - I0]) {
 #pragma unroll
   for (int i = I0; i < I1; ++i) {
-#if SDB_FUSED_A2
-    Y[i - I0] = H20[i] + Yacc[i - I0];   // (h/2) f(H20) is in Yacc: the rows of A^2 ride in the P1 product
-#else
-    double acc = fp.v[i * D] * H20[0];
+    if constexpr (A2) {
+      Y[i - I0] = H20[i] + Yacc[i - I0];   // (h/2) f(H20) is in Yacc: the rows of A^2 ride in the P1 product
+    } else {
+      double acc = fp.v[i * D] * H20[0];
 #pragma unroll
-    for (int l = 1; l < D; ++l) acc = fma(fp.v[i * D + l], H20[l], acc);
-    Y[i - I0] = H20[i] + fma(0.5 * h, acc, Yacc[i - I0]);
-#endif
+      for (int l = 1; l < D; ++l) acc = fma(fp.v[i * D + l], H20[l], acc);
+      Y[i - I0] = H20[i] + fma(0.5 * h, acc, Yacc[i - I0]);
+    }
   }
 }
 
@@ -129,6 +129,9 @@ SDB_DEV void sdb_srk2_fusedx2_body(const SdbLoopArgs& a, const PInline<D * D>& f
   typedef SdbFusedShape<D, M, SDB_FUSED_A2> Sh;
   typedef SdbXShape<D, M> Xs;
   typedef SdbX2Shape<D, M> X2;
+  // the A^2 rows of the P1 table replace the second drift evaluation; with Wiktorsson's tail compiled in
+  // ptxas allocates worse with it (cfg4: 3.10e8 against 3.21e8 path-steps/s), so that build keeps the loop
+  constexpr bool USE_A2 = SDB_FUSED_A2 && WIK == 0;
   constexpr int MM = Xs::MM, CH = Xs::CH, NCH = Xs::NCH, RN = Xs::RN, NB = Xs::NB, LT = Xs::LT;
   constexpr int T1 = Xs::T1, KT3 = Xs::KT3, IT = Xs::IT, IL = Xs::IL;
   constexpr int NBH = X2::NBH, NCHH = X2::NCHH, DH = X2::DH, GR = X2::GR;
@@ -434,12 +437,12 @@ SDB_DEV void sdb_srk2_fusedx2_body(const SdbLoopArgs& a, const PInline<D * D>& f
             const int yr = R0 + r;
             const double yv = ybuf[yr * 32 + (lane ^ ((yr & 3) << 2))];
             piece[r] = yv + f0h;                      // H20
-#if SDB_FUSED_A2
-            const int n2 = (M + 1) * RN + r;
-            piece[RN + r] = fma(0.5 * h * h, gv[n2 * 32 + (lane ^ sdb_swz(n2))], GdW[r]);
-#else
-            piece[RN + r] = fma(-0.5, f0h, GdW[r]);   // Yacc
-#endif
+            if constexpr (USE_A2) {
+              const int n2 = (M + 1) * RN + r;
+              piece[RN + r] = fma(0.5 * h * h, gv[n2 * 32 + (lane ^ sdb_swz(n2))], GdW[r]);
+            } else {
+              piece[RN + r] = fma(-0.5, f0h, GdW[r]);   // Yacc
+            }
           }
           sdb_tm_st<2 * RN>(tm + Xs::C_ROW + 4 * R0, piece);
         }
@@ -526,7 +529,7 @@ SDB_DEV void sdb_srk2_fusedx2_body(const SdbLoopArgs& a, const PInline<D * D>& f
 #pragma unroll
         for (int i = 0; i < DH; ++i)
           Yacc[i] = rows[2 * RN * (i / RN) + RN + i % RN] + (wp[i] + gpart[i * 32 + lane]);
-        sdb_x2_final_rows<D, 0, DH>(fp, H20, Yacc, h, Yn);
+        sdb_x2_final_rows<D, 0, DH, USE_A2>(fp, H20, Yacc, h, Yn);
         // (every reader of the old Y -- P1, the drift rows -- finished before the barrier above)
 #pragma unroll
         for (int i = 0; i < DH; ++i) ybuf[i * 32 + (lane ^ sdb_swz3(i))] = Yn[i];
@@ -535,7 +538,7 @@ SDB_DEV void sdb_srk2_fusedx2_body(const SdbLoopArgs& a, const PInline<D * D>& f
 #pragma unroll
         for (int i = DH; i < D; ++i)
           Yacc[i - DH] = rows[2 * RN * (i / RN) + RN + i % RN] + (wp[i] + gpart[(i - DH) * 32 + lane]);
-        sdb_x2_final_rows<D, DH, D>(fp, H20, Yacc, h, Yn);
+        sdb_x2_final_rows<D, DH, D, USE_A2>(fp, H20, Yacc, h, Yn);
 #pragma unroll
         for (int i = DH; i < D; ++i) ybuf[i * 32 + (lane ^ sdb_swz3(i))] = Yn[i - DH];
       }

@@ -12,6 +12,6 @@
 SDB_FUSEDX_KERNEL(sdbk_fusedx_t3_srk2_d10_m10_kpw, 10, 10, 0)
 static SdbFusedRegistrar sdbreg_fusedx_t3(
     SdbFusedEntry{10, 10, SDB_FUSED_VARIANT, (const void*)sdbk_fusedx_t3_srk2_d10_m10_kpw,
-                  SdbXShape<10, 10>::smem_bytes(), sdb_fused_table_doubles<10, 10>(),
-                  &sdb_fused_build_tables<10, 10>, SdbXShape<10, 10>::THREADS, SdbXShape<10, 10>::PATHS,
+                  SdbXShape<10, 10>::smem_bytes(), sdb_fused_table_doubles<10, 10, SDB_FUSED_A2>(),
+                  &sdb_fused_build_tables<10, 10, SDB_FUSED_A2>, SdbXShape<10, 10>::THREADS, SdbXShape<10, 10>::PATHS,
                   SDB_NOISE_KPW, SDB_SCHEME_SRK2});
