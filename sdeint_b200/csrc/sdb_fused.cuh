@@ -30,6 +30,18 @@
 // Shared memory per warp: staging 48 x 32, Levy areas 45 x 32, dW 10 x 32 doubles (26.4 KB).
 #pragma once
 #include "sdb_kernels.cuh"
+#ifndef SDB_FUSED_AHEAD
+#define SDB_FUSED_AHEAD 0  // 1: the random bits of step n + 1 (32-bit integer work) are produced between the
+#endif                     //    FP64 instructions of the row blocks of step n -- where issue slots are idle --
+                           //    and wait in tensor memory (one 32x32b lane per path, 4 columns per 128-bit
+                           //    block); the noise phase then only loads, converts and transforms them.
+                           //    Needs n_terms <= SDB_FUSED_AHEAD_TERMS and an even number of Wiener processes.
+#ifndef SDB_FUSED_AHEAD_TERMS
+#define SDB_FUSED_AHEAD_TERMS 5
+#endif
+#if SDB_FUSED_AHEAD
+#include "sdb_tmem.cuh"
+#endif
 
 #ifdef __CUDACC__
 #define SDB_CX __host__ __device__ constexpr
@@ -96,13 +108,18 @@ namespace SDB_FUSED_NS {
 #ifndef SDB_FUSED_A2
 #define SDB_FUSED_A2 1  // 1: rows of A^2 ride in the P1 product (its padding rows at d = m = 10): the second
 #endif                  //    drift evaluation f(Y + f h) h = f h + h^2 A^2 Y needs no DFMA loop of its own
+#ifndef SDB_FUSED_KSPLIT
+#define SDB_FUSED_KSPLIT 0  // 1: when d mod 4 is 1 or 2 the last one or two state components do not pad a
+#endif                      //    third DMMA k-tile of the P1 product: their contribution is added to the
+                            //    accumulator fragments with DFMAs (d = 10: 16 DFMA instead of 4 DMMA per row tile)
 // XR: extra row groups of the P1 product after the drift rows (1: the rows of A^2)
 template <int D, int M, int XR = 0>
 struct SdbFusedShape {
   static constexpr int MM = M * (M - 1) / 2;
+  static constexpr int KS = (SDB_FUSED_KSPLIT && D >= 4 && (D % 4 == 1 || D % 4 == 2)) ? D % 4 : 0;
   static constexpr int RB = (SDB_FUSED_RB > 0 && D > SDB_FUSED_RB) ? SDB_FUSED_RB : 4;  // rows per block
   static constexpr int NB = (D + RB - 1) / RB;        // row blocks
-  static constexpr int LT = (D + 3) / 4;              // k-tiles over the state index l
+  static constexpr int LT = KS ? D / 4 : (D + 3) / 4;  // DMMA k-tiles over the state index l
   static constexpr int IT = D / 8;                    // 8-row tiles of the stage-2 sum done by DMMA
   static constexpr int IL = D - 8 * IT;               // leftover rows done by DFMA
   static SDB_CX int rn(int b) { return b < NB - 1 ? RB : D - RB * (NB - 1); }
@@ -133,6 +150,8 @@ struct SdbFusedShape {
     return o;
   }
   static SDB_CX int n_left() { return left_off(NB); }
+  static SDB_CX int p1_tiles(int b) { return p1_off(b) / (LT > 0 ? LT : 1); }  // row tiles before block b
+  static SDB_CX int n_ks() { return p1_tiles(NB) * KS * 8; }  // columns 4 LT.. of the P1 matrix, by tile row
   static SDB_CX int warp_doubles() { return (grows() + (SDB_FUSED_DW_REGS ? 0 : M)) * 32; }
   static SDB_CX size_t smem_base() {
     return ((size_t)MM * SDB_FUSED_THREADS + (size_t)warp_doubles() * SDB_FUSED_WARPS) * sizeof(double) +
@@ -140,7 +159,11 @@ struct SdbFusedShape {
   }
   // copies of the log table: 8 (conflict-free, see sdb_normal_batch) when an SM's shared memory has room
   static SDB_CX int tab_copies() { return smem_base() + 8 * 128 * 16 <= 227u * 1024u ? 8 : 1; }
-  static SDB_CX size_t smem_bytes() { return smem_base() + (size_t)tab_copies() * 128 * 16; }
+  static SDB_CX size_t smem_bytes() {
+    return smem_base() + (size_t)tab_copies() * 128 * 16 + (SDB_FUSED_AHEAD ? 16 : 0);
+  }
+  // SDB_FUSED_AHEAD: 128-bit blocks per step that wait in tensor memory (dW + the Levy series)
+  static constexpr int AHEAD_SLOTS = M / 2 + SDB_FUSED_AHEAD_TERMS * M;
 };
 
 #ifndef __CUDACC_RTC__  // host functions are not allowed in NVRTC; sdb_fused_rt.h serves JIT shapes
@@ -184,11 +207,25 @@ inline void sdb_fused_build_tables(const double* A, const double* B, double* out
       for (int K = 0; K < Sh::rn(b) * M; ++K)
         left[Sh::left_off(b) + q * Sh::rn(b) * M + K] =
             B[((K % M) * D + 8 * Sh::IT + q) * D + Sh::r0(b) + K / M];
+  double* ks = left + Sh::n_left();  // [row tile][q < KS][row in tile]: column 4 LT + q of the P1 matrix
+  for (int b = 0; b < Sh::NB; ++b) {
+    const int rn = Sh::rn(b), r0 = Sh::r0(b);
+    for (int t = 0; t < Sh::t1(b); ++t)
+      for (int q = 0; q < Sh::KS; ++q)
+        for (int fr = 0; fr < 8; ++fr) {
+          const int n = 8 * t + fr, l = 4 * Sh::LT + q;
+          double v = 0.0;
+          if (n < M * rn) v = B[((n / rn) * D + r0 + n % rn) * D + l];
+          else if (n < (M + 1) * rn) v = A[(r0 + n - M * rn) * D + l];
+          else if (n < Sh::nr(b)) v = A2[(r0 + n - (M + 1) * rn) * D + l];
+          ks[((Sh::p1_tiles(b) + t) * Sh::KS + q) * 8 + fr] = v;
+        }
+  }
 }
 template <int D, int M, int XR = 0>
 inline size_t sdb_fused_table_doubles() {
   typedef SdbFusedShape<D, M, XR> Sh;
-  return (size_t)Sh::n_frags() * 32 + Sh::n_left();
+  return (size_t)Sh::n_frags() * 32 + Sh::n_left() + Sh::n_ks();
 }
 #endif  // !__CUDACC_RTC__
 
@@ -308,7 +345,7 @@ struct SdbGen {
 template <int NB, bool SCALED, int TS = 1>
 SDB_DEV void sdb_normal_batch(const uint32_t (&w)[NB][4], const double2* __restrict__ tab,
                               double scale, double (&z)[2 * NB]) {
-  double x[NB], zz[NB], r[NB], r2[NB], q[NB], L[NB], t[NB], t2[NB], sn[NB], cs[NB], rad[NB];
+  double x[NB], zz[NB], r[NB], q[NB], L[NB], t[NB], t2[NB], sn[NB], cs[NB], rad[NB];
   double2 tc[NB];
   int kk[NB];
 #pragma unroll
@@ -329,7 +366,6 @@ SDB_DEV void sdb_normal_batch(const uint32_t (&w)[NB][4], const double2* __restr
   for (int b = 0; b < NB; ++b) { r[b] = fma(zz[b], tc[b].x, -1.0); t2[b] = t[b] * t[b]; }
 #pragma unroll
   for (int b = 0; b < NB; ++b) {
-    r2[b] = r[b] * r[b];
     q[b] = fma(r[b], 1.0 / 3.0, -0.4);
     L[b] = fma((double)kk[b], SDB_M2LN2, tc[b].y);
     sn[b] = fma(t2[b], SDB_SIN6, SDB_SIN5);
@@ -338,7 +374,6 @@ SDB_DEV void sdb_normal_batch(const uint32_t (&w)[NB][4], const double2* __restr
 #pragma unroll
   for (int b = 0; b < NB; ++b) {
     q[b] = fma(r[b], q[b], 0.5);
-    L[b] = fma(r[b], -2.0, L[b]);
     sn[b] = fma(t2[b], sn[b], SDB_SIN4);
     cs[b] = fma(t2[b], cs[b], SDB_COS4);
   }
@@ -356,10 +391,12 @@ SDB_DEV void sdb_normal_batch(const uint32_t (&w)[NB][4], const double2* __restr
   }
 #pragma unroll
   for (int b = 0; b < NB; ++b) {
-    L[b] = fma(r2[b], q[b], L[b]);  // -2 ln u1 > 0
+    q[b] = fma(r[b], q[b], -2.0);
     sn[b] = fma(t2[b], sn[b], SDB_SIN1);
     cs[b] = fma(t2[b], cs[b], SDB_COS1);
   }
+#pragma unroll
+  for (int b = 0; b < NB; ++b) L[b] = fma(r[b], q[b], L[b]);  // -2 ln u1 > 0 (sdb_normal_pair)
 #else
   // the angle polynomials first: they do not need the table entry, so they cover its latency
 #pragma unroll
@@ -395,11 +432,7 @@ SDB_DEV void sdb_normal_batch(const uint32_t (&w)[NB][4], const double2* __restr
     L[b] = fma((double)kk[b], SDB_M2LN2, tc[b].y);
   }
 #pragma unroll
-  for (int b = 0; b < NB; ++b) {
-    r2[b] = r[b] * r[b];
-    q[b] = fma(r[b], 1.0 / 3.0, -0.4);
-    L[b] = fma(r[b], -2.0, L[b]);
-  }
+  for (int b = 0; b < NB; ++b) q[b] = fma(r[b], 1.0 / 3.0, -0.4);
 #pragma unroll
   for (int b = 0; b < NB; ++b) q[b] = fma(r[b], q[b], 0.5);
 #pragma unroll
@@ -407,9 +440,12 @@ SDB_DEV void sdb_normal_batch(const uint32_t (&w)[NB][4], const double2* __restr
 #pragma unroll
   for (int b = 0; b < NB; ++b) q[b] = fma(r[b], q[b], 1.0);
 #pragma unroll
-  for (int b = 0; b < NB; ++b) L[b] = fma(r2[b], q[b], L[b]);  // -2 ln u1 > 0
+  for (int b = 0; b < NB; ++b) q[b] = fma(r[b], q[b], -2.0);
+#pragma unroll
+  for (int b = 0; b < NB; ++b) L[b] = fma(r[b], q[b], L[b]);  // -2 ln u1 > 0
 #endif
-  double y[NB], g[NB], hh[NB], e[NB];
+  // sqrt(L) by three terms of g / sqrt(1 - e) (see sdb_normal_pair)
+  double y[NB], g[NB], ge[NB], e[NB];
 #pragma unroll
   for (int b = 0; b < NB; ++b) {
     y[b] = sdb_rsqrt_approx(L[b]);
@@ -419,15 +455,17 @@ SDB_DEV void sdb_normal_batch(const uint32_t (&w)[NB][4], const double2* __restr
 #pragma unroll
   for (int b = 0; b < NB; ++b) {
     g[b] = L[b] * y[b];
-    hh[b] = 0.5 * y[b];
     sn[b] *= t[b];
   }
 #pragma unroll
-  for (int b = 0; b < NB; ++b) e[b] = fma(-hh[b], g[b], 0.5);
+  for (int b = 0; b < NB; ++b) e[b] = fma(-g[b], y[b], 1.0);
 #pragma unroll
-  for (int b = 0; b < NB; ++b) g[b] = fma(g[b], e[b], g[b]);
+  for (int b = 0; b < NB; ++b) {
+    ge[b] = g[b] * e[b];
+    e[b] = fma(e[b], 0.375, 0.5);
+  }
 #pragma unroll
-  for (int b = 0; b < NB; ++b) rad[b] = fma(fma(-g[b], g[b], L[b]), hh[b], g[b]);
+  for (int b = 0; b < NB; ++b) rad[b] = fma(ge[b], e[b], g[b]);
   if (SCALED) {
 #pragma unroll
     for (int b = 0; b < NB; ++b) rad[b] *= scale;
@@ -486,6 +524,40 @@ SDB_CX int sdb_pair_k(int idx) {
   return idx - (j * M - j * (j + 1) / 2) + j + 1;
 }
 
+#if SDB_FUSED_AHEAD
+// Blocks slot0 .. slot0 + NB - 1 of the current step from tensor memory (written one step earlier).
+template <int NB>
+SDB_DEV void sdb_ahead_load(uint32_t tc, uint32_t slot0, uint32_t (&w)[NB][4]) {
+  uint32_t r[4 * NB];
+  sdb_static_for<0, NB>([&](auto bb) {
+    constexpr int b = decltype(bb)::value;
+    SdbTm<4>::template ld<4 * b, 4 * NB>(tc + 4u * (slot0 + (uint32_t)b), r);
+  });
+  sdb_tm_wait_ld();
+  sdb_static_for<0, NB>([&](auto bb) {
+    constexpr int b = decltype(bb)::value;
+    SdbTm<4>::template touch<4 * b, 4 * NB>(r);
+  });
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    w[b][0] = r[4 * b]; w[b][1] = r[4 * b + 1]; w[b][2] = r[4 * b + 2]; w[b][3] = r[4 * b + 3];
+  }
+}
+// The share of the next step's blocks that is produced at position (row block rows r0.., column j) of the
+// row-block pipeline: proportional to the FP64 work of that position.
+template <int D, int M, int NS>
+SDB_DEV void sdb_ahead_emit(const uint32_t (&K)[4], uint32_t tc, int ns, int r0, int rn, int j) {
+  const int lo = NS * (M * r0 + j * rn) / (M * D), hi = NS * (M * r0 + (j + 1) * rn) / (M * D);
+#pragma unroll
+  for (int sl = lo; sl < hi; ++sl)
+    if (sl >= 1) {  // no test against the run-time count ns: a branch here would fence the blocks off from
+      uint32_t w[4];  // the FP64 instructions they are meant to be scheduled between
+      sdb_mx2_block(K, (uint32_t)sl, w);
+      SdbTm<4>::template st<0, 4>(tc + 4u * (uint32_t)sl, w);
+    }
+}
+#endif
+
 template <int D, int M, int B_>
 struct SdbFusedBlock {
   typedef SdbFusedShape<D, M, SDB_FUSED_A2> Sh;
@@ -494,9 +566,11 @@ struct SdbFusedBlock {
   // P1 + P2 + P3 for row block B_.
   static SDB_DEV void run(const double* __restrict__ frag, const double* __restrict__ s_left,
                           double* gbuf, SDB_SMEM_CV double* sA, SDB_SMEM_CV double* sW,
-                          const double (&Yf)[Sh::LT][4], double h, double dg, int lane,
+                          const double (&Yf)[Sh::LT][4], const double (&Yx)[Sh::KS > 0 ? Sh::KS : 1][4][2],
+                          double h, double dg, int lane,
                           double (&H20)[D], double (&Yacc)[D], double (&w)[4][2],
-                          double (&wv)[Sh::IL > 0 ? Sh::IL : 1], const double (&dWr)[M]) {
+                          double (&wv)[Sh::IL > 0 ? Sh::IL : 1], const double (&dWr)[M],
+                          const uint32_t (&aK)[4], uint32_t tc, int ahead_ns) {
     constexpr int LT = Sh::LT;
     const int fr = lane >> 2, fc = lane & 3;
     // ---- P1: staging[n][p] = sum_l Bmat[n][l] Y[l][p] -----------------------------------------
@@ -507,10 +581,32 @@ struct SdbFusedBlock {
 #pragma unroll
       for (int lt = 0; lt < LT; ++lt) a[lt] = __ldg(f1 + (t * LT + lt) * 32);
       double c[4][2];
+      if constexpr (Sh::KS > 0) {
+        // columns 4 LT.. of the matrix: this lane's row (8 t + fr) times the state components 4 LT + q of
+        // the eight paths its accumulator fragments belong to
+        const double* kst = frag + (size_t)Sh::n_frags() * 32 + Sh::n_left() +
+                            (size_t)(Sh::p1_tiles(B_) + t) * Sh::KS * 8 + fr;
+        const double k0 = __ldg(kst);
 #pragma unroll
-      for (int pt = 0; pt < 4; ++pt) {
-        c[pt][0] = 0.0;
-        c[pt][1] = 0.0;
+        for (int pt = 0; pt < 4; ++pt) {
+          c[pt][0] = k0 * Yx[0][pt][0];
+          c[pt][1] = k0 * Yx[0][pt][1];
+        }
+#pragma unroll
+        for (int q = 1; q < Sh::KS; ++q) {
+          const double kq = __ldg(kst + q * 8);
+#pragma unroll
+          for (int pt = 0; pt < 4; ++pt) {
+            c[pt][0] = fma(kq, Yx[q][pt][0], c[pt][0]);
+            c[pt][1] = fma(kq, Yx[q][pt][1], c[pt][1]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int pt = 0; pt < 4; ++pt) {
+          c[pt][0] = 0.0;
+          c[pt][1] = 0.0;
+        }
       }
 #pragma unroll
       for (int lt = 0; lt < LT; ++lt)  // consecutive DMMAs hit independent accumulators
@@ -559,6 +655,9 @@ struct SdbFusedBlock {
 #pragma unroll
           for (int r = 0; r < RN; ++r) s[r][k] = fma(gj[r], a, s[r][k]);
         }
+#if SDB_FUSED_AHEAD
+        sdb_ahead_emit<D, M, Sh::AHEAD_SLOTS>(aK, tc, ahead_ns, R0, RN, j);
+#endif
       }
 #pragma unroll
       for (int k = 0; k < M; ++k) {
@@ -659,6 +758,19 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
     s_hk[i] = i == 0 ? 0.0 : a.h_global * SDB_INV_2PI / (double)i;
   for (int i = tid; i < Sh::n_left(); i += NT) s_left[i] = frag[(size_t)Sh::n_frags() * 32 + i];
   __syncthreads();
+#if SDB_FUSED_AHEAD
+  static_assert(M % 2 == 0 && WIK == 0 && SDB_FUSED_BATCH && !SDB_FUSED_SWP && !SDB_FUSED_BATCH_XZ,
+                "SDB_FUSED_AHEAD: even m, Ikpw/Jkpw, batched generator");
+  static_assert(4 * Sh::AHEAD_SLOTS <= 256 && NT == 256, "two warps share the 512 columns of a TMEM lane quarter");
+  // warps w and w + 4 run on the same sub-partition and see the same 32 TMEM lanes: 256 columns each
+  uint32_t* tm_slot = reinterpret_cast<uint32_t*>(s_left + Sh::n_left() + 1);
+  const uint32_t tm_base = sdb_tm_alloc512(tm_slot);
+  const uint32_t tc = tm_base + (warp >= 4 ? 256u : 0u);
+  const int ahead_ns = M / 2 + a.n_terms * M;  // blocks per step in use (n_terms <= SDB_FUSED_AHEAD_TERMS)
+#else
+  const uint32_t tc = 0u;
+  const int ahead_ns = 0;
+#endif
 
   const int64_t p = (int64_t)blockIdx.x * NT + tid;
   const bool active = p < a.P;  // idle lanes of the last warp still take part in the DMMAs
@@ -695,6 +807,19 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
   int64_t slot = 1;
   const int fr = lane >> 2, fc = lane & 3;
 
+#if SDB_FUSED_AHEAD
+  {  // the blocks of the first step
+    const SdbGen g0(pkey, (uint32_t)path, (uint32_t)(path >> 32), SDB_STEP(0));
+    SdbTm<4>::template st<0, 4>(tc, g0.B0);
+#pragma unroll 1
+    for (int sl = 1; sl < ahead_ns; ++sl) {
+      uint32_t w4[4];
+      sdb_mx2_block(g0.K, (uint32_t)sl, w4);
+      SdbTm<4>::template st<0, 4>(tc + 4u * (uint32_t)sl, w4);
+    }
+    sdb_tm_wait_st();
+  }
+#endif
 #pragma unroll 1
   for (int n = 0; n < steps; ++n) {
     const double h = hs[n];
@@ -710,8 +835,14 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
     double dW[M];  // lives through the row blocks only with SDB_FUSED_DW_REGS
     {
       const SdbStream st(pkey, path, SDB_STEP(n), tab);
-      const SdbGen gen(pkey, st.p_lo, st.p_hi, SDB_STEP(n));
-#if SDB_FUSED_BATCH
+      const SdbGen gen(pkey, st.p_lo, st.p_hi, SDB_STEP(n));  // (unused, hence removed, with SDB_FUSED_AHEAD)
+#if SDB_FUSED_AHEAD
+      {
+        uint32_t w[M / 2][4];
+        sdb_ahead_load<M / 2>(tc, 0u, w);
+        sdb_normal_batch<M / 2, true, TS>(w, tab, rh_g, dW);
+      }
+#elif SDB_FUSED_BATCH
       if constexpr (M % 2 == 0) {
         uint32_t w[M / 2][4];
         gen.template blocks<M / 2, true>(0u, w);
@@ -772,10 +903,17 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
 #endif
         } else if constexpr (M % 2 == 0) {
           uint32_t w[M / 2][4];
+#if SDB_FUSED_AHEAD
+          sdb_ahead_load<M / 2>(tc, sx, w);
+          sdb_normal_batch<M / 2, true, TS>(w, tab, hk, X);
+          sdb_ahead_load<M / 2>(tc, sx + M / 2, w);
+          sdb_normal_batch<M / 2, false, TS>(w, tab, 1.0, Z);
+#else
           gen.template blocks<M / 2, false>(sx, w);
           sdb_normal_batch<M / 2, true, TS>(w, tab, hk, X);
           gen.template blocks<M / 2, false>(sx + M / 2, w);
           sdb_normal_batch<M / 2, false, TS>(w, tab, 1.0, Z);
+#endif
         } else {  // X_k starts at the odd normal index M (2k - 1), Y_k at the even one 2 k M
           sdb_normals_m<M, 1, true, false, TS>(gen, sx, tab, hk, X);
           sdb_normals_m<M, 0, false, false, TS>(gen, sx + (M + 1) / 2, tab, 1.0, Z);
@@ -872,6 +1010,15 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
 #endif
     }
 
+    uint32_t aK[4] = {0u, 0u, 0u, 0u};
+#if SDB_FUSED_AHEAD
+    {  // the two Philox blocks of the NEXT step: slot 0 goes to tensor memory, the expansion key stays in
+       // registers through the row blocks, which produce the other blocks between their FP64 instructions
+      const SdbGen g1(pkey, (uint32_t)path, (uint32_t)(path >> 32), SDB_STEP(n + 1));
+      SdbTm<4>::template st<0, 4>(tc, g1.B0);
+      aK[0] = g1.K[0]; aK[1] = g1.K[1]; aK[2] = g1.K[2]; aK[3] = g1.K[3];
+    }
+#endif
     // ---- P0: Y -> DMMA B-fragments Yf[lt][pt] = Y[4 lt + fc][path 8 pt + fr] ---------------------
     double Yf[LT][4];
 #if SDB_FUSED_PARK_Y
@@ -893,6 +1040,17 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
         Yf[lt][pt] = ok ? v : 0.0;
       }
     }
+    double Yx[Sh::KS > 0 ? Sh::KS : 1][4][2];  // components 4 LT.. of the paths 8 pt + 2 fc, + 1 (accumulator layout)
+#pragma unroll
+    for (int q = 0; q < Sh::KS; ++q) {
+      const int l = 4 * LT + q;
+#pragma unroll
+      for (int pt = 0; pt < 4; ++pt) {
+        const double2 v = *reinterpret_cast<const double2*>(gbuf + l * 32 + ((8 * pt + 2 * fc) ^ sdb_swz3(l)));
+        Yx[q][pt][0] = v.x;
+        Yx[q][pt][1] = v.y;
+      }
+    }
     __syncwarp();
 
     // ---- row blocks ----------------------------------------------------------------------------
@@ -908,9 +1066,12 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
       const double* s_left_c = s_left;
       SDB_SMEM_CV double* sAv = sA;
       SDB_SMEM_CV double* sWv = sW;
-      SdbFusedBlocks<D, M, Sh::NB - 1>::run(frag, s_left_c, gbuf, sAv, sWv, Yf, h, dg, lane, Y,
-                                            Yacc, w, wv, dW);
+      SdbFusedBlocks<D, M, Sh::NB - 1>::run(frag, s_left_c, gbuf, sAv, sWv, Yf, Yx, h, dg, lane, Y,
+                                            Yacc, w, wv, dW, aK, tc, ahead_ns);
     }
+#if SDB_FUSED_AHEAD
+    sdb_tm_wait_st();
+#endif
     // Y now holds H20 = Y + f(Y) h
 
     // ---- second drift evaluation f(H20, t_{n+1}) h (integrate.py:514) ----------------------------
@@ -954,6 +1115,9 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
   if (active) sdb_finish<D>(a, p, Y);
 #if SDB_OBSERVE
   if (active) obs.finish(a, p);
+#endif
+#if SDB_FUSED_AHEAD
+  sdb_tm_free512(tm_base);
 #endif
 }
 

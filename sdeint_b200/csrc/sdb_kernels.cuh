@@ -231,20 +231,19 @@ SDB_DEV void sdb_normal_pair(const uint32_t (&w)[4], const double2* __restrict__
   const double z = __hiloint2double(xh - (tmp & (int)0xFFF00000), __double2loint(x));
   const double2 tc = tab[i];  // {1/c, -2 ln c}
   const double r = fma(z, tc.x, -1.0);
-  const double r2 = r * r;
   double q = fma(r, 1.0 / 3.0, -0.4);
   q = fma(r, q, 0.5);
   q = fma(r, q, -2.0 / 3.0);
   q = fma(r, q, 1.0);
+  q = fma(r, q, -2.0);
   double L = fma((double)k, SDB_M2LN2, tc.y);
-  L = fma(r, -2.0, L);
-  L = fma(r2, q, L);  // -2 ln u1 > 0
+  L = fma(r, q, L);  // -2 ln u1 = -2 k ln 2 - 2 ln c - 2 r + r^2 - (2/3) r^3 + ... > 0
+  // sqrt(L) = g / sqrt(1 - e), g = L y, e = 1 - L y^2 (|e| < 2^-19 after MUFU.RSQ64H): three terms of
+  // the binomial series leave 5 e^3 / 16 < 2^-58
   const double y = sdb_rsqrt_approx(L);
-  double g = L * y;
-  const double hh = 0.5 * y;
-  const double e = fma(-hh, g, 0.5);
-  g = fma(g, e, g);
-  const double rad = fma(fma(-g, g, L), hh, g);
+  const double g = L * y;
+  const double e = fma(-g, y, 1.0);
+  const double rad = fma(g * e, fma(e, 0.375, 0.5), g);
   // ---- angle ------------------------------------------------------------------------------------
   const double t = __hiloint2double((int)(0x3FF00000u | ((w[2] >> 9) & 0x000FFFFFu)), (int)w[3]) - 1.0;
   const double t2 = t * t;
