@@ -36,6 +36,13 @@
                            //    and wait in tensor memory (one 32x32b lane per path, 4 columns per 128-bit
                            //    block); the noise phase then only loads, converts and transforms them.
                            //    Needs n_terms <= SDB_FUSED_AHEAD_TERMS and an even number of Wiener processes.
+#ifndef SDB_FUSED_ANTIPHASE
+#define SDB_FUSED_ANTIPHASE 0  // 1: the two warps of a sub-partition (w, w + 4) are held half a step apart by a
+#endif                         //    named barrier: one generates noise while the other runs its row blocks
+#ifndef SDB_FUSED_INPHASE
+#define SDB_FUSED_INPHASE 0  // 1: the two warps of a sub-partition enter every phase together (named barrier at the
+#endif                       //    top of the step and before the P1 / P3 tensor phases of every row block)
+#define SDB_PAIR_BAR() asm volatile("bar.sync %0, 64;" ::"r"(1 + (((int)threadIdx.x >> 5) & 3)) : "memory")
 #ifndef SDB_FUSED_AHEAD_TERMS
 #define SDB_FUSED_AHEAD_TERMS 5
 #endif
@@ -574,6 +581,9 @@ struct SdbFusedBlock {
     constexpr int LT = Sh::LT;
     const int fr = lane >> 2, fc = lane & 3;
     // ---- P1: staging[n][p] = sum_l Bmat[n][l] Y[l][p] -----------------------------------------
+#if SDB_FUSED_INPHASE
+    SDB_PAIR_BAR();
+#endif
     const double* f1 = frag + (size_t)Sh::p1_off(B_) * 32 + lane;
 #pragma unroll
     for (int t = 0; t < T1; ++t) {
@@ -703,6 +713,9 @@ struct SdbFusedBlock {
     }
     __syncwarp();
     // ---- P3: w[i][p] += sum_K Bst[i][K] s~[K][p], rows i < 8 IT ------------------------------------
+#if SDB_FUSED_INPHASE
+    SDB_PAIR_BAR();
+#endif
     if (Sh::IT > 0) {
       const double* f3 = frag + (size_t)Sh::p3_off(B_) * 32 + lane;
 #pragma unroll
@@ -823,6 +836,12 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
 #pragma unroll 1
   for (int n = 0; n < steps; ++n) {
     const double h = hs[n];
+#if SDB_FUSED_ANTIPHASE
+    if (warp < 4) asm volatile("bar.sync %0, 64;" ::"r"(1 + (warp & 3)) : "memory");
+#endif
+#if SDB_FUSED_INPHASE
+    SDB_PAIR_BAR();
+#endif
 
 #if SDB_FUSED_PARK_Y
     // The state waits in the staging buffer (where P0 needs it anyway) while the noise is generated:
@@ -1010,6 +1029,9 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
 #endif
     }
 
+#if SDB_FUSED_ANTIPHASE
+    if (warp >= 4) asm volatile("bar.sync %0, 64;" ::"r"(1 + (warp & 3)) : "memory");
+#endif
     uint32_t aK[4] = {0u, 0u, 0u, 0u};
 #if SDB_FUSED_AHEAD
     {  // the two Philox blocks of the NEXT step: slot 0 goes to tensor memory, the expansion key stays in
