@@ -559,6 +559,39 @@ static int integrate_impl(sdb_system* s, const sdb_integrate_args* a, const SdbO
           (e.variant == want || (!fused && e.variant == 0)))
         fused = &e;
   }
+  // ANY drift (built-in or NVRTC source) with linear diffusion g_k = B_k y, SRI2/SRS2 + Ikpw/Jkpw on device
+  // noise: the fused kernel with the drift evaluated per lane (SDB_FUSED_A2 -1 in sdb_fused.cuh) -- the
+  // products with the B_k stay on the tensor instructions, only the two drift evaluations are user code.
+  bool jit_ud = false;
+  if (!fused && a->scheme == SDB_SCHEME_SRK2 && noise == SDB_NOISE_KPW && need_ij &&
+      s->fk != SDB_DRIFT_LINEAR && s->gk == SDB_DIFF_LINEAR_COLS && n_terms <= SDB_FUSED_MAX_TERMS &&
+      !getenv("SDB_DISABLE_FUSED") && !getenv("SDB_DISABLE_FUSED_JIT") && s->d * s->m >= 16 &&
+      SdbFusedDims(s->d, s->m, 4, -1).supported()) {
+    const SdbFusedDims dims(s->d, s->m, 4, -1);
+    const std::string key = std::string("fusedjit|ud") + ext_suffix(ext);
+    std::lock_guard<std::mutex> lk(s->mu);
+    auto it = s->jit.find(key);
+    if (it == s->jit.end()) {
+      std::ostringstream src;
+      src << ext_defines(ext);
+      if (s->fk == SDB_DRIFT_USER) src << "#define SDB_USER_DRIFT 1\n";
+      src << "#include \"sdb_kernels.cuh\"\n";
+      if (s->fk == SDB_DRIFT_USER) src << "#line 1 \"user_source.cu\"\n" << s->src << "\n";
+      src << "typedef " << type_of(s, true) << " F_jit;\n";
+      src << "#define SDB_FUSED_A2 (-1)\n#define SDB_FUSED_DRIFT_T F_jit\n#include \"sdb_fused.cuh\"\n"
+          << "SDB_FUSED_KERNEL_UD(sdb_jit_fused, " << s->d << ", " << s->m << ")\n";
+      JitKernel k;
+      if (jit_compile(src.str(), "sdb_jit_fused", &k)) return 1;
+      it = s->jit.emplace(key, k).first;
+    }
+    jit_xr = -1;
+    jit_ud = true;
+    jit_entry = SdbFusedEntry{s->d, s->m, 0, (const void*)it->second.kern, dims.smem_bytes(),
+                              dims.table_doubles(), nullptr, SdbFusedDims::THREADS,
+                              SdbFusedDims::THREADS, SDB_NOISE_KPW, SDB_SCHEME_SRK2};
+    fused = &jit_entry;
+    label = "jit:" + key;
+  }
   // No ahead-of-time instantiation for this (d, m, method): compile a fused kernel with NVRTC when
   // the shape is one it supports -- sdb_fused.cuh (8 warps per SM; Ikpw/Jkpw, m <= 10, d < 16) or
   // sdb_fusedx.cuh (Levy areas in tensor memory; Iwik/Jwik and larger shapes) -- else the generic loop.
@@ -748,7 +781,7 @@ static int integrate_impl(sdb_system* s, const sdb_integrate_args* a, const SdbO
   args[2] = s->inline_params ? (void*)s->gp.data() : (void*)&gg;
   if (fused) {
     if (fused->scheme == SDB_SCHEME_SRK2 && fused->noise != SDB_NOISE_COMM) {
-      args[1] = (void*)s->fp.data();
+      if (!jit_ud) args[1] = (void*)s->fp.data();  // the matrix A (jit_ud: the drift functor's parameters)
       args[2] = (void*)&d_frag;
     } else {  // fused Euler / Heun and the commutative-noise kernel: (a, frag)
       args[1] = (void*)&d_frag;

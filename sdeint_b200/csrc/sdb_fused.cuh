@@ -115,6 +115,9 @@ namespace SDB_FUSED_NS {
 #ifndef SDB_FUSED_A2
 #define SDB_FUSED_A2 1  // 1: rows of A^2 ride in the P1 product (its padding rows at d = m = 10): the second
 #endif                  //    drift evaluation f(Y + f h) h = f h + h^2 A^2 Y needs no DFMA loop of its own
+                        // -1: ANY drift with linear diffusion g_k = B_k y (NVRTC builds): no drift rows in the
+                        //    tables; the functor SDB_FUSED_DRIFT_T (F::eval(params, y, t, out), sdb_kernels.cuh)
+                        //    is evaluated one lane per path at Y_n and at H20 (integrate.py:509, :514)
 #ifndef SDB_FUSED_KSPLIT
 #define SDB_FUSED_KSPLIT 0  // 1: when d mod 4 is 1 or 2 the last one or two state components do not pad a
 #endif                      //    third DMMA k-tile of the P1 product: their contribution is added to the
@@ -182,7 +185,7 @@ inline void sdb_fused_build_tables(const double* A, const double* B, double* out
   for (int i = 0; i < D; ++i)
     for (int j = 0; j < D; ++j) {
       double acc = 0.0;
-      for (int l = 0; l < D; ++l) acc += A[i * D + l] * A[l * D + j];
+      for (int l = 0; l < D && XR >= 0; ++l) acc += A[i * D + l] * A[l * D + j];
       A2[i * D + j] = acc;
     }
   for (int b = 0; b < Sh::NB; ++b) {
@@ -194,6 +197,7 @@ inline void sdb_fused_build_tables(const double* A, const double* B, double* out
           double v = 0.0;
           if (l < D) {
             if (n < M * rn) v = B[((n / rn) * D + r0 + n % rn) * D + l];       // B_j[r0+r][l]
+            else if (XR < 0) v = 0.0;                                          // no drift rows (SDB_FUSED_A2 -1)
             else if (n < (M + 1) * rn) v = A[(r0 + n - M * rn) * D + l];       // drift rows
             else if (n < Sh::nr(b)) v = A2[(r0 + n - (M + 1) * rn) * D + l];   // rows of A^2 (XR)
           }
@@ -675,6 +679,11 @@ struct SdbFusedBlock {
 #pragma unroll
         for (int r = 0; r < RN; ++r) s[r][k] = fma(hd, GdW[r], s[r][k]);
       }
+#if SDB_FUSED_A2 < 0
+      // the drift was evaluated before the row blocks: H20 = Y + f0 h, Yacc = -f0 h / 2 so far
+#pragma unroll
+      for (int r = 0; r < RN; ++r) Yacc[R0 + r] += GdW[r];
+#else
       // drift rows of this block: H20 = Y + f h (integrate.py:509), update without the f1 term
 #pragma unroll
       for (int r = 0; r < RN; ++r) {
@@ -689,6 +698,7 @@ struct SdbFusedBlock {
 #endif
         H20[R0 + r] += f0h;  // H20 held Y
       }
+#endif
       // rows 8.. of the stage-2 sum on the FMA pipe (uniform operands from shared memory)
       if (Sh::IL > 0) {
 #pragma unroll
@@ -746,8 +756,8 @@ struct SdbFusedBlocks<D, M, -1> {
   static SDB_DEV void run(Args&...) {}
 };
 
-template <int D, int M, int WIK = 0>
-SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * D>& fp,
+template <int D, int M, int WIK = 0, class FP = PInline<D * D>>
+SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const FP& fp,
                                         const double* __restrict__ frag, double* smem) {
   typedef SdbFusedShape<D, M, SDB_FUSED_A2> Sh;
   constexpr int NT = SDB_FUSED_THREADS;
@@ -1084,6 +1094,18 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
     }
 #pragma unroll
     for (int q = 0; q < (Sh::IL > 0 ? Sh::IL : 1); ++q) wv[q] = 0.0;
+#if SDB_FUSED_A2 < 0
+    {  // f(Y_n, t_n) (integrate.py:508): the DMMA fragments of Y_n are already in Yf, so Y may become H20 now
+      double f0[D];
+      SDB_FUSED_DRIFT_T::eval(fp, Y, a.tspan[n], f0);
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        const double f0h = f0[i] * h;
+        Yacc[i] = -0.5 * f0h;
+        Y[i] += f0h;
+      }
+    }
+#endif
     {
       const double* s_left_c = s_left;
       SDB_SMEM_CV double* sAv = sA;
@@ -1097,13 +1119,20 @@ SDB_DEV void sdb_srk2_fused_linear_body(const SdbLoopArgs& a, const PInline<D * 
     // Y now holds H20 = Y + f(Y) h
 
     // ---- second drift evaluation f(H20, t_{n+1}) h (integrate.py:514) ----------------------------
-#if !SDB_FUSED_A2
+#if SDB_FUSED_A2 == 0
 #pragma unroll
     for (int i = 0; i < D; ++i) {
       double acc = fp.v[i * D] * Y[0];
 #pragma unroll
       for (int l = 1; l < D; ++l) acc = fma(fp.v[i * D + l], Y[l], acc);
       Yacc[i] = fma(0.5 * h, acc, Yacc[i]);
+    }
+#elif SDB_FUSED_A2 < 0
+    {
+      double f1[D];
+      SDB_FUSED_DRIFT_T::eval(fp, Y, a.tspan[n + 1], f1);
+#pragma unroll
+      for (int i = 0; i < D; ++i) Yacc[i] = fma(0.5 * h, f1[i], Yacc[i]);
     }
 #endif
     // ---- stage-2 sum back to one lane per path ---------------------------------------------------
@@ -1154,6 +1183,14 @@ using namespace SDB_FUSED_NS;
     sdb_srk2_fused_linear_body<D, M, WIK>(a, fp, frag, sdb_fused_smem);                       \
   }
 #define SDB_FUSED_KERNEL(NAME, D, M) SDB_FUSED_KERNEL_W(NAME, D, M, 0)
+// SDB_FUSED_A2 -1: the drift functor's parameter struct takes the place of the matrix A
+#define SDB_FUSED_KERNEL_UD(NAME, D, M)                                                       \
+  extern "C" __global__ void __launch_bounds__(SDB_FUSED_THREADS, 1)                          \
+      NAME(const __grid_constant__ SdbLoopArgs a,                                             \
+           const __grid_constant__ SDB_FUSED_DRIFT_T::Params fp, const double* __restrict__ frag) { \
+    extern __shared__ __align__(16) double sdb_fused_smem[];                                  \
+    sdb_srk2_fused_linear_body<D, M, 0, SDB_FUSED_DRIFT_T::Params>(a, fp, frag, sdb_fused_smem); \
+  }
 #endif  // __CUDACC__
 #ifndef __CUDACC__
 }  // namespace SDB_FUSED_NS

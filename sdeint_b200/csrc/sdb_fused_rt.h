@@ -7,7 +7,7 @@
 
 struct SdbFusedDims {
   int D, M, RB;  // RB: state rows per block (4: sdb_fused.cuh default; 2: sdb_fusedx.cuh)
-  int XR;        // extra P1 row groups after the drift rows (1: the rows of A^2, sdb_fused.cuh)
+  int XR;        // extra P1 row groups after the drift rows (1: the rows of A^2; -1: no drift rows, sdb_fused.cuh)
   constexpr SdbFusedDims(int d, int m, int rb = 4, int xr = 0) : D(d), M(m), RB(d > rb ? rb : 4), XR(xr) {}
   static constexpr int THREADS = 256, WARPS = 8, MAX_TERMS = 256;
   constexpr int MM() const { return M * (M - 1) / 2; }
@@ -60,7 +60,7 @@ struct SdbFusedDims {
     for (int i = 0; i < D; ++i)
       for (int j = 0; j < D; ++j) {
         double acc = 0.0;
-        for (int l = 0; l < D; ++l) acc += A[i * D + l] * A[l * D + j];
+        for (int l = 0; l < D && XR >= 0; ++l) acc += A[i * D + l] * A[l * D + j];
         A2[i * D + j] = acc;
       }
     for (int b = 0; b < NB(); ++b) {
@@ -72,6 +72,7 @@ struct SdbFusedDims {
             double v = 0.0;
             if (l < D) {
               if (n < M * rnb) v = B[((n / rnb) * D + r0b + n % rnb) * D + l];
+              else if (XR < 0) v = 0.0;  // any drift, evaluated per lane (SDB_FUSED_A2 -1): no drift rows
               else if (n < (M + 1) * rnb) v = A[(r0b + n - M * rnb) * D + l];
               else if (n < nr(b)) v = A2[(r0b + n - (M + 1) * rnb) * D + l];
             }

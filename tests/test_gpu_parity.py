@@ -204,6 +204,44 @@ def test_fused_device_noise_matches_oracle(sdb, name, strat, method):
     assert rel_err(y2, y) <= TOL
 
 
+@pytest.mark.parametrize("d,m,strat", [(10, 10, False), (6, 4, True), (7, 5, False)])
+def test_fused_user_drift_linear_diffusion(sdb, monkeypatch, d, m, strat):
+    """Nonlinear drift given as source + linear diffusion g_k = B_k y: the fused kernel with the drift
+    evaluated per lane (`jit:fusedjit|ud`), against the oracle on the noise the device generated and
+    against the generic loop kernel; time-dependent drift, decimated storage, resumed runs."""
+    _, G, y0 = sdb.ops.sys_lin(d, m)
+    exprs = ["-p[0]*y[%d] + p[1]*y[%d] - p[2]*y[%d]*y[%d]*y[%d] + 0.1*sin(3*t)" % (i, (i + 1) % d, i, i, i)
+             for i in range(d)]
+    f = sdb.ops.ExprDrift(exprs, params=[1.5, 0.3, 0.2])
+    tspan = np.linspace(0.0, 0.25, 51)
+    N = len(tspan)
+    h = (tspan[-1] - tspan[0]) / (N - 1)
+    P, seed = 70, 4242
+    integ = sdb.stratSRS2 if strat else sdb.itoSRI2
+    rep = sdb.Jkpw if strat else sdb.Ikpw
+    y = integ(f, G, y0, tspan, rep, paths=P, seed=seed, path_id0=5, commutative=False)
+    assert sdb.last_kernel() == "jit:fusedjit|ud"
+    dW = sdb.deltaW(N - 1, m, h, paths=P, seed=seed, path_id0=5)
+    _, IJ = rep(dW, h, seed=seed, path_id0=5, ensemble=True)
+    for p in (0, 31, 32, P - 1):
+        ref = orc.srk2(f, G, np.asarray(y0, float), tspan, dW[p], IJ[p])
+        assert rel_err(y[p], ref) <= TOL
+    yd = integ(f, G, y0, tspan, rep, paths=P, seed=seed, path_id0=5, save_every=10, commutative=False)
+    assert np.array_equal(yd, y[:, ::10])
+    # the generic loop kernel on the same noise
+    monkeypatch.setenv("SDB_DISABLE_FUSED", "1")
+    yg = integ(f, G, y0, tspan, rep, paths=P, seed=seed, path_id0=5, commutative=False)
+    assert sdb.last_kernel().startswith("jit:loop")
+    monkeypatch.delenv("SDB_DISABLE_FUSED")
+    assert rel_err(yg, y) <= TOL
+    # in-loop observers ride in the same kernel
+    yo, obs = integ(f, G, y0, tspan, rep, paths=P, seed=seed, path_id0=5, commutative=False,
+                    observe=[("max", 0)])
+    assert sdb.last_kernel() == "jit:fusedjit|ud|obs"
+    assert rel_err(yo, y) <= TOL and obs.shape == (P, 1)
+    assert np.array_equal(obs[:, 0], yo[:, :, 0].max(axis=1))
+
+
 def test_euler_heun_device_noise(sdb):
     f, G, y0 = SYSTEMS["lin2"](False)
     tspan = np.linspace(0.0, 1.0, 101)

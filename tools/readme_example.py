@@ -13,3 +13,6 @@ y = sdb.itoint(f, G, [1.0, 1.0, 20.0], tspan, paths=10**5, seed=2, save_every=10
 y, obs = sdb.itoint(f, G, [1.0, 1.0, 20.0], tspan, paths=10**5, seed=2, save_every=100,
                     observe=[("first_above", 0, 15.0), ("max", 2)])
 print(obs.shape, np.isfinite(obs[:, 0]).mean(), obs[:, 1].mean())
+_, GL, y0L = sdb.ops.sys_lin(10, 10)
+fN = sdb.ops.ExprDrift(["-1.5*y[%d] + 0.3*y[%d] - 0.2*y[%d]*y[%d]*y[%d]" % (i, (i + 1) % 10, i, i, i) for i in range(10)])
+yN = sdb.itoSRI2(fN, GL, y0L, tspan, paths=10**5, seed=3, save_every=100); print(yN.shape, sdb.last_kernel())
