@@ -421,32 +421,38 @@ def run_gpu(args):
             "collapse; normal transforms and random-bit generation not counted")
         roofline["kernel"] = "sdb fused SRI2 step loop (one launch per step)"
         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from one `ncu --set full`
-        # capture of a 10^6-path launch with the bench's tspan / save_every: 875.1 MB against
-        # 880.0 MB of algorithmic stores (profiles/r02_fused_v0_final_ncu_summary.txt; the last
-        # lines written are still in L2 when the kernel ends); the traffic is the decimated store and
-        # nothing else, so it scales with the paths.
-        roofline["traffic"] = 875.14e6 * (P / 1e6)
+        # capture of a 10^6-path launch with the bench's tspan / save_every: 880.4 MB against
+        # 880.0 MB of algorithmic stores (profiles/r02_fused_v0_final_ncu_summary.txt); the traffic is
+        # the decimated store and nothing else, so it scales with the paths.
+        roofline["traffic"] = 880.38e6 * (P / 1e6)
         roofline["traffic_unit"] = "B per launch"
-        roofline["traffic_source"] = ("ncu --set full at 1e6 paths (36.4 MB read + 838.7 MB "
+        roofline["traffic_source"] = ("ncu --set full at 1e6 paths (38.2 MB read + 842.2 MB "
                                       "written), scaled linearly to this launch")
         roofline["hbm"] = {"achieved": BYTES_PER_PATH_STEP * path_steps / (ms_kernel * 1e-3) / 1e9,
                            "peak": hbm_peak, "unit": "GB/s",
                            "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}
         roofline["hbm"]["frac"] = roofline["hbm"]["achieved"] / hbm_peak
         # Issue model: per warp-step (32 path-steps) of a sub-partition the SASS
-        # executes 3820 DFMA-class x 2 + 280 DMMA x 16 = 12120 FP64-pipe cycles; the two Philox
-        # blocks left per path-step (2 x 74 cycles) are the only IMAD.WIDE work on that pipe.
+        # executes 3709 DFMA-class x 2 + 280 DMMA x 16 = 11898 FP64-pipe cycles (ncu:
+        # sm__pipe_shared_cycles_active 65.8 % = fp64 41.0 % + dmma 24.8 %); the two Philox blocks left
+        # per path-step (2 x 74 cycles) are the only IMAD.WIDE work on that pipe.  An outer-product DFMA
+        # (one multiplicand in the reuse cache, two fresh 64-bit operands) measures 2.42 cycles, not 2
+        # (tools/micro/dfma_rf.cu): 3709 x 2.42 + 4480 = 13456 cycles of pipe + operand ports.
         sm_hz = 1e6 * float((clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0))
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        floor = sms * 4 * 32 * sm_hz / (12120.0 + 148.0)
+        floor = sms * 4 * 32 * sm_hz / (11898.0 + 148.0)
+        floor_rf = sms * 4 * 32 * sm_hz / (13456.0 + 148.0)
         roofline["issue_model"] = {
-            "fp64_pipe_cycles_per_warp_step": 12120, "philox_cycles_per_warp_step": 148,
+            "fp64_pipe_cycles_per_warp_step": 11898, "philox_cycles_per_warp_step": 148,
             "floor_path_steps_per_s": floor,
             "frac_of_floor": (path_steps / (ms_kernel * 1e-3)) / floor,
+            "fp64_pipe_and_operand_port_cycles_per_warp_step": 13456,
+            "frac_of_operand_port_floor": (path_steps / (ms_kernel * 1e-3)) / floor_rf,
+            "ncu_pipe_shared_cycles_active_pct": 65.8,
             "dmma_note": "the 4480 DMMA cycles do not co-issue with other instructions "
-                         "(tools/micro/dmma_coissue.cu): DESIGN.md 4.2 puts the realistic floor at ~12500-13000 cycles",
+                         "(tools/micro/dmma_coissue.cu)",
             "source": "SASS instruction counts (profiles/r02_fused_v0_final_ncu_summary.txt) "
-                      "x measured issue costs (tools/micro/rng.cu, dmma_coissue.cu, philox.cu, coissue.cu)"}
+                      "x measured issue costs (tools/micro/rng.cu, dmma_coissue.cu, dfma_rf.cu, philox.cu, coissue.cu)"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
