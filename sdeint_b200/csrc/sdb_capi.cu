@@ -592,6 +592,37 @@ static int integrate_impl(sdb_system* s, const sdb_integrate_args* a, const SdbO
     fused = &jit_entry;
     label = "jit:" + key;
   }
+  // ... and the fused Euler / Heun kernels likewise (SDB_EH_XR -1 in sdb_fusedeh.cuh)
+  if (!fused && explicit_em && noise != SDB_NOISE_HOST && s->fk != SDB_DRIFT_LINEAR &&
+      s->gk == SDB_DIFF_LINEAR_COLS && !getenv("SDB_DISABLE_FUSED") && !getenv("SDB_DISABLE_FUSED_JIT") &&
+      s->d * s->m >= (a->scheme == SDB_SCHEME_HEUN ? 48 : 96) &&
+      SdbFusedEhDims(s->d, s->m, a->scheme == SDB_SCHEME_HEUN, -1).supported()) {
+    const bool heun = a->scheme == SDB_SCHEME_HEUN;
+    const SdbFusedEhDims edims(s->d, s->m, heun, -1);
+    const std::string key = std::string(heun ? "fusedehjit|heun|ud" : "fusedehjit|euler|ud") + ext_suffix(ext);
+    std::lock_guard<std::mutex> lk(s->mu);
+    auto it = s->jit.find(key);
+    if (it == s->jit.end()) {
+      std::ostringstream src;
+      src << ext_defines(ext);
+      if (s->fk == SDB_DRIFT_USER) src << "#define SDB_USER_DRIFT 1\n";
+      src << "#include \"sdb_kernels.cuh\"\n";
+      if (s->fk == SDB_DRIFT_USER) src << "#line 1 \"user_source.cu\"\n" << s->src << "\n";
+      src << "typedef " << type_of(s, true) << " F_jit;\n";
+      src << "#define SDB_EH_XR (-1)\n#define SDB_FUSED_DRIFT_T F_jit\n#include \"sdb_fusedeh.cuh\"\n"
+          << "SDB_FUSEDEH_KERNEL_UD(sdb_jit_fused, " << s->d << ", " << s->m << ", " << (heun ? 1 : 0) << ")\n";
+      JitKernel k;
+      if (jit_compile(src.str(), "sdb_jit_fused", &k)) return 1;
+      it = s->jit.emplace(key, k).first;
+    }
+    jit_xr = -1;
+    jit_ud = true;
+    jit_entry = SdbFusedEntry{s->d, s->m, 0, (const void*)it->second.kern, edims.smem_bytes(),
+                              edims.sh.table_doubles(), nullptr, edims.threads(), edims.threads(),
+                              SDB_NOISE_KPW, a->scheme};
+    fused = &jit_entry;
+    label = "jit:" + key;
+  }
   // No ahead-of-time instantiation for this (d, m, method): compile a fused kernel with NVRTC when
   // the shape is one it supports -- sdb_fused.cuh (8 warps per SM; Ikpw/Jkpw, m <= 10, d < 16) or
   // sdb_fusedx.cuh (Levy areas in tensor memory; Iwik/Jwik and larger shapes) -- else the generic loop.
@@ -780,8 +811,10 @@ static int integrate_impl(sdb_system* s, const sdb_integrate_args* a, const SdbO
   args[1] = s->inline_params ? (void*)s->fp.data() : (void*)&gf;
   args[2] = s->inline_params ? (void*)s->gp.data() : (void*)&gg;
   if (fused) {
-    if (fused->scheme == SDB_SCHEME_SRK2 && fused->noise != SDB_NOISE_COMM) {
-      if (!jit_ud) args[1] = (void*)s->fp.data();  // the matrix A (jit_ud: the drift functor's parameters)
+    if (jit_ud) {  // (a, parameters of the drift functor, frag)
+      args[2] = (void*)&d_frag;
+    } else if (fused->scheme == SDB_SCHEME_SRK2 && fused->noise != SDB_NOISE_COMM) {
+      args[1] = (void*)s->fp.data();  // the matrix A
       args[2] = (void*)&d_frag;
     } else {  // fused Euler / Heun and the commutative-noise kernel: (a, frag)
       args[1] = (void*)&d_frag;

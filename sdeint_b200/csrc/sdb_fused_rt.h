@@ -152,7 +152,7 @@ struct SdbRepintXDims {
 struct SdbFusedEhDims {
   SdbFusedDims sh;
   int heun;
-  constexpr SdbFusedEhDims(int d, int m, int heun_) : sh(d, m, 4), heun(heun_) {}
+  constexpr SdbFusedEhDims(int d, int m, int heun_, int xr = 0) : sh(d, m, 4, xr), heun(heun_) {}
   constexpr int threads() const { return heun ? 256 : 384; }
   constexpr int grows() const {
     int g = SdbFusedDims::max2(8, sh.D);

@@ -12,6 +12,9 @@
 #pragma once
 #include "sdb_fused.cuh"
 
+#ifndef SDB_EH_XR
+#define SDB_EH_XR 0  // -1 (NVRTC builds): ANY drift with linear diffusion g_k = B_k y -- no drift rows in the
+#endif               //    tables, the functor SDB_FUSED_DRIFT_T is evaluated one lane per path (sdb_fused.cuh)
 // Euler: 12 warps per SM at 168 registers; Heun holds two evaluations: 8 warps at 255 registers
 #define SDB_EH_THREADS(HEUN) ((HEUN) ? 256 : 384)
 
@@ -19,7 +22,7 @@ namespace SDB_FUSED_NS {
 
 template <int D, int M>
 struct SdbEhShape {
-  typedef SdbFusedShape<D, M> Sh;
+  typedef SdbFusedShape<D, M, SDB_EH_XR> Sh;
   static SDB_CX int grows() {  // staging rows: the widest P1 block, at least the state
     int g = Sh::max2(8, D);
     for (int b = 0; b < Sh::NB; ++b) g = Sh::max2(g, 8 * Sh::t1(b));
@@ -35,7 +38,7 @@ struct SdbEhShape {
 template <int D, int M>
 SDB_DEV void sdb_eh_eval(const double* __restrict__ frag, double* gbuf, const double (&Yin)[D],
                          const double (&dW)[M], int lane, double (&GdW)[D], double (&f)[D]) {
-  typedef SdbFusedShape<D, M> Sh;
+  typedef SdbFusedShape<D, M, SDB_EH_XR> Sh;
   constexpr int LT = Sh::LT;
   const int fr = lane >> 2, fc = lane & 3;
   double Yf[LT][4];
@@ -92,15 +95,18 @@ SDB_DEV void sdb_eh_eval(const double* __restrict__ frag, double* gbuf, const do
         acc = fma(gv[n * 32 + (lane ^ sdb_swz(n))], dW[j], acc);
       }
       GdW[R0 + r] = acc;
+#if SDB_EH_XR >= 0
       const int n = M * RN + r;
       f[R0 + r] = gv[n * 32 + (lane ^ sdb_swz(n))];
+#endif
     }
     __syncwarp();
   });
 }
 
-template <int D, int M, int HEUN>
-SDB_DEV void sdb_fusedeh_body(const SdbLoopArgs& a, const double* __restrict__ frag, double* smem) {
+template <int D, int M, int HEUN, class FP = int>
+SDB_DEV void sdb_fusedeh_body(const SdbLoopArgs& a, const double* __restrict__ frag, double* smem,
+                              const FP& fp = FP()) {
   typedef SdbEhShape<D, M> Es;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double2* tab = reinterpret_cast<double2*>(smem + (size_t)Es::grows() * 32 * (SDB_EH_THREADS(HEUN) / 32));
@@ -147,6 +153,9 @@ SDB_DEV void sdb_fusedeh_body(const SdbLoopArgs& a, const double* __restrict__ f
     }
     double GdW[D], f0[D];
     sdb_eh_eval<D, M>(frag, gbuf, Y, dW, lane, GdW, f0);
+#if SDB_EH_XR < 0
+    SDB_FUSED_DRIFT_T::eval(fp, Y, a.tspan[n], f0);  // f(Y_n, t_n): integrate.py:236, :295
+#endif
     if (!HEUN) {
 #pragma unroll
       for (int i = 0; i < D; ++i) Y[i] = fma(f0[i], h, Y[i]) + GdW[i];  // integrate.py:239
@@ -155,6 +164,9 @@ SDB_DEV void sdb_fusedeh_body(const SdbLoopArgs& a, const double* __restrict__ f
 #pragma unroll
       for (int i = 0; i < D; ++i) Yb[i] = fma(f0[i], h, Y[i]) + GdW[i];  // integrate.py:299
       sdb_eh_eval<D, M>(frag, gbuf, Yb, dW, lane, GdW1, f1);
+#if SDB_EH_XR < 0
+      SDB_FUSED_DRIFT_T::eval(fp, Yb, a.tspan[n + 1], f1);  // f(Ybar, t_{n+1}): integrate.py:300
+#endif
 #pragma unroll
       for (int i = 0; i < D; ++i)  // integrate.py:300-302
         Y[i] = Y[i] + 0.5 * (f0[i] + f1[i]) * h + 0.5 * (GdW[i] + GdW1[i]);
@@ -178,6 +190,13 @@ SDB_DEV void sdb_fusedeh_body(const SdbLoopArgs& a, const double* __restrict__ f
 }  // namespace SDB_FUSED_NS
 using namespace SDB_FUSED_NS;
 
+#define SDB_FUSEDEH_KERNEL_UD(NAME, D, M, HEUN)                                               \
+  extern "C" __global__ void __launch_bounds__(SDB_EH_THREADS(HEUN), 1)                       \
+      NAME(const __grid_constant__ SdbLoopArgs a,                                             \
+           const __grid_constant__ SDB_FUSED_DRIFT_T::Params fp, const double* __restrict__ frag) { \
+    extern __shared__ __align__(16) double sdb_fused_smem[];                                  \
+    sdb_fusedeh_body<D, M, HEUN, SDB_FUSED_DRIFT_T::Params>(a, frag, sdb_fused_smem, fp);      \
+  }
 #define SDB_FUSEDEH_KERNEL(NAME, D, M, HEUN)                                                  \
   extern "C" __global__ void __launch_bounds__(SDB_EH_THREADS(HEUN), 1)                       \
       NAME(const __grid_constant__ SdbLoopArgs a, const double* __restrict__ frag) {          \
