@@ -242,6 +242,31 @@ def test_fused_user_drift_linear_diffusion(sdb, monkeypatch, d, m, strat):
     assert np.array_equal(obs[:, 0], yo[:, :, 0].max(axis=1))
 
 
+@pytest.mark.parametrize("scheme", ["euler", "heun"])
+def test_fused_euler_heun_user_drift(sdb, monkeypatch, scheme):
+    """itoEuler / stratHeun with a nonlinear, time-dependent drift from source and linear diffusion: the fused
+    kernels with the drift evaluated per lane (`jit:fusedehjit|...|ud`) against the oracle on the device's
+    increments and against the generic loop kernel."""
+    d, m = 10, 10
+    _, G, y0 = sdb.ops.sys_lin(d, m)
+    f = sdb.ops.ExprDrift(["-p[0]*y[%d] + p[1]*y[%d] - p[2]*y[%d]*y[%d]*y[%d] + 0.1*cos(2*t)"
+                           % (i, (i + 3) % d, i, i, i) for i in range(d)], params=[1.2, 0.25, 0.15])
+    tspan = np.linspace(0.0, 0.3, 61)
+    h = 0.3 / 60
+    P, seed = 45, 77
+    integ, ref = (sdb.itoEuler, orc.euler) if scheme == "euler" else (sdb.stratHeun, orc.heun)
+    y = integ(f, G, y0, tspan, paths=P, seed=seed)
+    assert sdb.last_kernel() == "jit:fusedehjit|%s|ud" % scheme
+    dW = sdb.deltaW(60, m, h, paths=P, seed=seed)
+    for p in (0, 31, 32, P - 1):
+        assert rel_err(y[p], ref(f, G, np.asarray(y0, float), tspan, dW[p])) <= TOL
+    monkeypatch.setenv("SDB_DISABLE_FUSED", "1")
+    yg = integ(f, G, y0, tspan, paths=P, seed=seed)
+    assert sdb.last_kernel().startswith("jit:loop")
+    monkeypatch.delenv("SDB_DISABLE_FUSED")
+    assert rel_err(yg, y) <= TOL
+
+
 def test_euler_heun_device_noise(sdb):
     f, G, y0 = SYSTEMS["lin2"](False)
     tspan = np.linspace(0.0, 1.0, 101)
