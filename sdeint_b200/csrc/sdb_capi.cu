@@ -563,10 +563,11 @@ static int integrate_impl(sdb_system* s, const sdb_integrate_args* a, const SdbO
   // noise: the fused kernel with the drift evaluated per lane (SDB_FUSED_A2 -1 in sdb_fused.cuh) -- the
   // products with the B_k stay on the tensor instructions, only the two drift evaluations are user code.
   bool jit_ud = false;
-  if (!fused && a->scheme == SDB_SCHEME_SRK2 && noise == SDB_NOISE_KPW && need_ij &&
-      s->fk != SDB_DRIFT_LINEAR && s->gk == SDB_DIFF_LINEAR_COLS && n_terms <= SDB_FUSED_MAX_TERMS &&
-      !getenv("SDB_DISABLE_FUSED") && !getenv("SDB_DISABLE_FUSED_JIT") && s->d * s->m >= 16 &&
-      SdbFusedDims(s->d, s->m, 4, -1).supported()) {
+  const bool ud_ok = !fused && a->scheme == SDB_SCHEME_SRK2 && noise != SDB_NOISE_HOST && need_ij &&
+                     s->fk != SDB_DRIFT_LINEAR && s->gk == SDB_DIFF_LINEAR_COLS &&
+                     n_terms <= SDB_FUSED_MAX_TERMS && !getenv("SDB_DISABLE_FUSED") &&
+                     !getenv("SDB_DISABLE_FUSED_JIT") && s->d * s->m >= 16;
+  if (ud_ok && noise == SDB_NOISE_KPW && SdbFusedDims(s->d, s->m, 4, -1).supported()) {
     const SdbFusedDims dims(s->d, s->m, 4, -1);
     const std::string key = std::string("fusedjit|ud") + ext_suffix(ext);
     std::lock_guard<std::mutex> lk(s->mu);
@@ -589,6 +590,36 @@ static int integrate_impl(sdb_system* s, const sdb_integrate_args* a, const SdbO
     jit_entry = SdbFusedEntry{s->d, s->m, 0, (const void*)it->second.kern, dims.smem_bytes(),
                               dims.table_doubles(), nullptr, SdbFusedDims::THREADS,
                               SdbFusedDims::THREADS, SDB_NOISE_KPW, SDB_SCHEME_SRK2};
+    fused = &jit_entry;
+    label = "jit:" + key;
+  }
+  // ... Iwik/Jwik and the larger shapes through the TMEM-resident kernel (sdb_fusedx.cuh, one lane per path)
+  if (ud_ok && !fused && SdbFusedXDims(s->d, s->m, -1).supported()) {
+    const SdbFusedXDims xdims(s->d, s->m, -1);
+    const bool wik = noise == SDB_NOISE_WIK;
+    const std::string key = std::string(wik ? "fusedxjit|wik|ud" : "fusedxjit|kpw|ud") + ext_suffix(ext);
+    std::lock_guard<std::mutex> lk(s->mu);
+    auto it = s->jit.find(key);
+    if (it == s->jit.end()) {
+      std::ostringstream src;
+      src << ext_defines(ext);
+      if (s->fk == SDB_DRIFT_USER) src << "#define SDB_USER_DRIFT 1\n";
+      src << "#include \"sdb_kernels.cuh\"\n";
+      if (s->fk == SDB_DRIFT_USER) src << "#line 1 \"user_source.cu\"\n" << s->src << "\n";
+      src << "typedef " << type_of(s, true) << " F_jit;\n";
+      src << "#define SDB_FUSED_RB 2\n#define SDB_FUSED_VOL_MMA 0\n#define SDB_FUSED_A2 (-1)\n"
+          << "#define SDB_FUSED_DRIFT_T F_jit\n#include \"sdb_fusedx.cuh\"\n"
+          << "SDB_FUSEDX_KERNEL_UD(sdb_jit_fused, " << s->d << ", " << s->m << ", " << (wik ? 1 : 0) << ")\n";
+      JitKernel k;
+      if (jit_compile(src.str(), "sdb_jit_fused", &k)) return 1;
+      it = s->jit.emplace(key, k).first;
+    }
+    jit_rb = 2;
+    jit_xr = -1;
+    jit_ud = true;
+    jit_entry = SdbFusedEntry{s->d, s->m, 0, (const void*)it->second.kern, xdims.smem_bytes(),
+                              xdims.sh.table_doubles(), nullptr, xdims.threads(), xdims.threads(), noise,
+                              SDB_SCHEME_SRK2};
     fused = &jit_entry;
     label = "jit:" + key;
   }

@@ -99,14 +99,16 @@ struct SdbFusedDims {
 // Run-time mirror of SdbXShape (sdb_fusedx.cuh): the TMEM-resident kernel, 2-row blocks.
 struct SdbFusedXDims {
   SdbFusedDims sh;
-  constexpr SdbFusedXDims(int d, int m) : sh(d, m, 2, 1) {}  // 2-row blocks, rows of A^2 in the P1 product
+  // 2-row blocks; xr = 1: rows of A^2 in the P1 product, -1: no drift rows (any drift, evaluated per lane:
+  // D more shared-memory rows per warp hold f(Y_n) h)
+  constexpr SdbFusedXDims(int d, int m, int xr = 1) : sh(d, m, 2, xr) {}
   constexpr int MM() const { return sh.MM(); }
   constexpr int MMP() const { return (MM() + 15) / 16 * 16; }
   constexpr int C_END() const { return 2 * MMP() + (2 * sh.M + 7) / 8 * 8 + 4 * sh.D; }
   constexpr int WPQ() const { return 2 * C_END() <= 512 ? 2 : 1; }
   constexpr int threads() const { return 128 * WPQ(); }
   constexpr size_t smem_bytes() const {
-    const size_t b = (size_t)(sh.grows() + sh.D) * 32 * 8 * 4 * WPQ() + 128 * 16 +
+    const size_t b = (size_t)(sh.grows() + sh.D + (sh.XR < 0 ? sh.D : 0)) * 32 * 8 * 4 * WPQ() + 128 * 16 +
                      (SdbFusedDims::MAX_TERMS + 1 + sh.n_left() + 1) * sizeof(double) + 16;
     return b < 120u * 1024u ? 120u * 1024u : b;
   }

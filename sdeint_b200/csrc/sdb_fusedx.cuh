@@ -50,7 +50,8 @@ struct SdbXShape {
   static constexpr int T1 = Sh::t1(0), KT3 = Sh::kt3(0), LT = Sh::LT, IT = Sh::IT, IL = Sh::IL;
   static constexpr int GR = Sh::grows();
   static constexpr int R_Y = GR;                             // shared-memory rows of one warp
-  static constexpr int WROWS = R_Y + D;
+  static constexpr int R_F = R_Y + D;                        // SDB_FUSED_A2 -1: f(Y_n) h of the user's drift
+  static constexpr int WROWS = R_Y + D + (SDB_FUSED_A2 < 0 ? D : 0);
   // warps per SM sub-partition: two when two warps' columns fit the 512 of a TMEM lane (and the
   // register file: 2 x 255 registers per lane slot)
 #ifdef SDB_X_WPQ
@@ -198,8 +199,8 @@ SDB_DEV void sdb_x_levy_areas(const SdbGen& gen,
   }
 }
 
-template <int D, int M, int WIK>
-SDB_DEV void sdb_srk2_fusedx_body(const SdbLoopArgs& a, const PInline<D * D>& fp,
+template <int D, int M, int WIK, class FP = PInline<D * D>>
+SDB_DEV void sdb_srk2_fusedx_body(const SdbLoopArgs& a, const FP& fp,
                                   const double* __restrict__ frag, double* smem) {
   typedef SdbFusedShape<D, M, SDB_FUSED_A2> Sh;  // rows of A^2 ride in the P1 product (sdb_fused.cuh)
   typedef SdbXShape<D, M> Xs;
@@ -283,6 +284,17 @@ SDB_DEV void sdb_srk2_fusedx_body(const SdbLoopArgs& a, const PInline<D * D>& fp
     sdb_x_levy_areas<M, WIK>(gen, tab, s_hk, hg, cz, tail_scale, n_terms,
                              tm + Xs::C_AT, tm + Xs::C_DW);
 
+#if SDB_FUSED_A2 < 0
+    {  // any drift, evaluated one lane per path (sdb_fused.cuh): f(Y_n, t_n) h waits in shared memory
+      double Yv[D], f0[D];
+#pragma unroll
+      for (int l = 0; l < D; ++l) Yv[l] = ybuf[l * 32 + (lane ^ sdb_swz3(l))];
+      SDB_FUSED_DRIFT_T::eval(fp, Yv, a.tspan[n], f0);
+#pragma unroll
+      for (int l = 0; l < D; ++l) gbuf[(Xs::R_F + l) * 32 + lane] = f0[l] * h;
+      __syncwarp();
+    }
+#endif
     // ---- row blocks (runtime loop: every block has RN rows) ------------------------------------------
     double w[IT > 0 ? IT : 1][4][2], wv[IL > 0 ? IL : 1];
 #pragma unroll
@@ -415,12 +427,16 @@ SDB_DEV void sdb_srk2_fusedx_body(const SdbLoopArgs& a, const PInline<D * D>& fp
           double piece[2 * RN];
 #pragma unroll
           for (int r = 0; r < RN; ++r) {
+            const int yr = R0 + r;
+#if SDB_FUSED_A2 < 0
+            const double f0h = gv[(Xs::R_F + yr) * 32 + lane];
+#else
             const int nn = M * RN + r;
             const double f0h = gv[nn * 32 + (lane ^ sdb_swz(nn))] * h;
-            const int yr = R0 + r;
+#endif
             const double yv = ybuf[yr * 32 + (lane ^ ((yr & 3) << 2))];
             piece[r] = yv + f0h;                      // H20
-#if SDB_FUSED_A2
+#if SDB_FUSED_A2 > 0
             const int n2 = (M + 1) * RN + r;          // f(H20) h = f0 h + h^2 A^2 Y: no second drift loop
             piece[RN + r] = fma(0.5 * h * h, gv[n2 * 32 + (lane ^ sdb_swz(n2))], GdW[r]);
 #else
@@ -489,13 +505,20 @@ SDB_DEV void sdb_srk2_fusedx_body(const SdbLoopArgs& a, const PInline<D * D>& fp
         }
       }
       // second drift evaluation f(H20, t_{n+1}) h (integrate.py:514): in Yacc already with SDB_FUSED_A2
-#if !SDB_FUSED_A2
+#if SDB_FUSED_A2 == 0
 #pragma unroll
       for (int i = 0; i < D; ++i) {
         double acc = fp.v[i * D] * H20[0];
 #pragma unroll
         for (int l = 1; l < D; ++l) acc = fma(fp.v[i * D + l], H20[l], acc);
         Yacc[i] = fma(0.5 * h, acc, Yacc[i]);
+      }
+#elif SDB_FUSED_A2 < 0
+      {
+        double f1[D];
+        SDB_FUSED_DRIFT_T::eval(fp, H20, a.tspan[n + 1], f1);
+#pragma unroll
+        for (int i = 0; i < D; ++i) Yacc[i] = fma(0.5 * h, f1[i], Yacc[i]);
       }
 #endif
 #pragma unroll
@@ -541,6 +564,13 @@ SDB_DEV void sdb_srk2_fusedx_body(const SdbLoopArgs& a, const PInline<D * D>& fp
 }  // namespace SDB_FUSED_NS
 using namespace SDB_FUSED_NS;
 
+#define SDB_FUSEDX_KERNEL_UD(NAME, D, M, WIK)                                                 \
+  extern "C" __global__ void __launch_bounds__((SdbXShape<D, M>::THREADS), 1)                 \
+      NAME(const __grid_constant__ SdbLoopArgs a,                                             \
+           const __grid_constant__ SDB_FUSED_DRIFT_T::Params fp, const double* __restrict__ frag) { \
+    extern __shared__ __align__(16) double sdb_fused_smem[];                                  \
+    sdb_srk2_fusedx_body<D, M, WIK, SDB_FUSED_DRIFT_T::Params>(a, fp, frag, sdb_fused_smem);  \
+  }
 #define SDB_FUSEDX_KERNEL(NAME, D, M, WIK)                                                    \
   extern "C" __global__ void __launch_bounds__((SdbXShape<D, M>::THREADS), 1)                 \
       NAME(const __grid_constant__ SdbLoopArgs a, const __grid_constant__ PInline<D * D> fp,  \

@@ -242,6 +242,31 @@ def test_fused_user_drift_linear_diffusion(sdb, monkeypatch, d, m, strat):
     assert np.array_equal(obs[:, 0], yo[:, :, 0].max(axis=1))
 
 
+@pytest.mark.parametrize("d,m,wik", [(10, 10, True), (16, 12, False), (8, 6, True)])
+def test_fusedx_user_drift(sdb, monkeypatch, d, m, wik):
+    """Nonlinear drift + linear diffusion through the TMEM-resident kernel (Iwik/Jwik, or shapes beyond the
+    8-warp kernel): `jit:fusedxjit|...|ud` against the oracle on replayed device noise and the generic kernel."""
+    _, G, y0 = sdb.ops.sys_lin(d, m)
+    f = sdb.ops.ExprDrift(["-p[0]*y[%d] + p[1]*y[%d] - p[2]*y[%d]*y[%d]*y[%d] + 0.05*sin(5*t)"
+                           % (i, (i + 2) % d, i, i, i) for i in range(d)], params=[1.4, 0.2, 0.1])
+    tspan = np.linspace(0.0, 0.1, 21)
+    N = len(tspan)
+    h = (tspan[-1] - tspan[0]) / (N - 1)
+    P, seed = 40, 909
+    rep = sdb.Iwik if wik else sdb.Ikpw
+    y = sdb.itoSRI2(f, G, y0, tspan, rep, paths=P, seed=seed, commutative=False)
+    assert sdb.last_kernel() == "jit:fusedxjit|%s|ud" % ("wik" if wik else "kpw")
+    dW = sdb.deltaW(N - 1, m, h, paths=P, seed=seed)
+    _, I = rep(dW, h, seed=seed, ensemble=True)
+    for p in (0, 33, P - 1):
+        assert rel_err(y[p], orc.srk2(f, G, np.asarray(y0, float), tspan, dW[p], I[p])) <= TOL
+    monkeypatch.setenv("SDB_DISABLE_FUSED", "1")
+    yg = sdb.itoSRI2(f, G, y0, tspan, rep, paths=P, seed=seed, commutative=False)
+    assert sdb.last_kernel().startswith("jit:loop")
+    monkeypatch.delenv("SDB_DISABLE_FUSED")
+    assert rel_err(yg, y) <= TOL
+
+
 @pytest.mark.parametrize("scheme", ["euler", "heun"])
 def test_fused_euler_heun_user_drift(sdb, monkeypatch, scheme):
     """itoEuler / stratHeun with a nonlinear, time-dependent drift from source and linear diffusion: the fused

@@ -34,3 +34,26 @@ for label, env in (("fused, drift per lane", None), ("generic loop kernel", "SDB
           % (d, m, label, P, T, best, P * T / best * 1e3, sdb.last_kernel()), flush=True)
     if env:
         del os.environ[env]
+if d == 10 and m == 10:
+    for label, fn, kw in (("itoSRI2+Iwik", sdb.itoSRI2, {"Imethod": sdb.Iwik}), ("stratHeun", sdb.stratHeun, {}),
+                          ("itoEuler", sdb.itoEuler, {})):
+        for env in (None, "SDB_DISABLE_FUSED"):
+            if env:
+                os.environ[env] = "1"
+            best = None
+            for rep in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                e0.record()
+                if "Imethod" in kw:
+                    fn(f, G, y0, tspan, kw["Imethod"], paths=P, seed=7, save_every=T, out="torch", commutative=False)
+                else:
+                    fn(f, G, y0, tspan, paths=P, seed=7, save_every=T, out="torch")
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1)
+                best = ms if best is None else min(best, ms)
+            print("user drift d=%d m=%d %-14s %.3e path-steps/s  [%s]" % (d, m, label, P * T / best * 1e3, sdb.last_kernel()),
+                  flush=True)
+            if env:
+                del os.environ[env]
