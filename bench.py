@@ -513,6 +513,27 @@ def side_configs(sdb, torch, args, peak, peak_sus, hbm_peak):
         res["kernel_symbol"],
         "executed flop: SURVEY 8d count 76263 minus 2md^2+2dm=16800 for the linear stage-2 collapse")
     out[name] = res
+    # Extension beyond BASELINE.json's configs: a NONLINEAR drift given as source
+    # (NVRTC) with the linear diffusion of cfg3 -- the fused kernel with the drift evaluated per lane.
+    fL, GL, y0L = sdb.ops.sys_lin(D, M)
+    fU = sdb.ops.ExprDrift(["-p[0]*y[%d] + p[1]*y[%d] - p[2]*y[%d]*y[%d]*y[%d]" % (i, (i + 1) % D, i, i, i)
+                            for i in range(D)], params=[1.5, 0.3, 0.2])
+    PU, TU, seU = 10 ** 6, 1000, 100
+    tsU = np.linspace(0.0, 1.0, TU + 1)
+    name, res = run_side_config(
+        sdb, torch, "ext_user_drift_itoSRI2",
+        lambda **kw: sdb.itoSRI2(fU, GL, y0L, tsU, paths=PU, seed=SEED, save_every=seU, commutative=False, **kw),
+        (TU // seU + 1, D, PU), float(PU) * TU, K, W)
+    res["workload"] = ("cubic drift f_i = -1.5 y_i + 0.3 y_(i+1) - 0.2 y_i^3 (ExprDrift -> NVRTC) + g_k = B_k y of "
+                       "SYS_LIN(10,10), itoSRI2 + Ikpw(n=5), %d paths x %d steps, save_every=%d" % (PU, TU, seU))
+    f_user = 7 * D                                      # flop of one evaluation of this drift
+    ref_form = flops_srk2(D, M) + flops_ikpw(M, N_TERMS) - 4 * D * D + 2 * f_user
+    res["roofline"] = fp64_roofline(
+        ref_form - collapse(D, M), ref_form, float(PU) * TU, res["ms_per_step"], peak, peak_sus,
+        res["kernel_symbol"],
+        "executed flop: SURVEY 8d count 10280 with the two dense drift products (4 d^2) replaced by two "
+        "evaluations of the user's drift (7 d flop each), minus 2md^2+2dm for the linear stage-2 collapse")
+    out[name] = res
     return out
 
 
