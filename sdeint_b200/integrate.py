@@ -129,6 +129,12 @@ def _check_args(f, G, y0, tspan, dW=None, IJ=None):
             'a Python callable cannot run inside a CUDA kernel.')
     if Gop.d != d:
         raise SDEValueError(message)
+    # expressions that are exactly linear get the kernels of the linear operators (ops.as_linear); only where
+    # those exist (d m >= 16: below that the unrolled source, whose structural zeros vanish, is the faster one)
+    if d * Gop.m >= 16:
+        Gop = ops.as_linear(Gop)
+        if Gop.kind == ops.DIFF_LINEAR_COLS:
+            f = ops.as_linear(f, dense_only=True)
     m = Gop.m
     N = len(tspan)
     if dW is not None:

@@ -409,6 +409,60 @@ class ExprDiffusion(CudaDiffusion):
                                                       for k in range(m)] for i in range(d)]))
 
 
+def as_linear(op, dense_only=False):
+    """An `ExprDrift` / `ExprDiffusion` whose expressions are exactly linear in y and do not depend on t,
+    as the equivalent `LinearDrift` / `LinearDiffusion` -- those have tensor-instruction kernels (DESIGN.md
+    section 4) -- else the operator itself.  The matrices are read off at the unit vectors; linearity is
+    then checked at random points and two times (a nonlinear or affine expression fails it by many orders
+    of magnitude more than rounding).  `dense_only`: keep a drift with fewer than d^2 / 2 nonzero
+    coefficients as source (evaluated per lane it is cheaper than rows of a dense product).  Diffusions
+    flagged `diagonal=True` keep their own fast path.  Cached on the operator; SDB_NO_PROMOTE=1 disables."""
+    import os
+    if os.environ.get("SDB_NO_PROMOTE") or not isinstance(op, (ExprDrift, ExprDiffusion)):
+        return op
+    key = "_as_linear_dense" if dense_only else "_as_linear"
+    if key in op.__dict__:
+        return op.__dict__[key]
+    d = op.d
+    res = op
+    try:
+        rng = np.random.default_rng(12345)
+        eye = np.eye(d)
+        if isinstance(op, ExprDrift):
+            A = np.stack([np.asarray(op(eye[l], 0.0), dtype=np.float64) for l in range(d)], axis=1)   # (d, d)
+            lin = lambda y: A @ y
+            scale = max(1.0, float(np.abs(A).max()))
+            ok = np.abs(np.asarray(op(np.zeros(d), 0.0), dtype=np.float64)).max() == 0.0
+            cand = None
+            if ok and not (dense_only and np.count_nonzero(A) < 0.5 * d * d):
+                cand = LinearDrift(A)
+            ok = ok and cand is not None
+        else:
+            if op.kind == DIFF_USER_DIAG:
+                op.__dict__[key] = op
+                return op
+            cols = [np.asarray(op(eye[l], 0.0), dtype=np.float64) for l in range(d)]                   # each (d, m)
+            B = np.stack([np.stack([cols[l][:, k] for l in range(d)], axis=1) for k in range(op.m)])  # (m, d, d)
+            lin = lambda y: np.dot(B, y).T
+            scale = max(1.0, float(np.abs(B).max()))
+            ok = np.abs(np.asarray(op(np.zeros(d), 0.0), dtype=np.float64)).max() == 0.0
+            cand = LinearDiffusion(B) if ok else None
+        for trial in range(4):
+            if not ok:
+                break
+            y = rng.standard_normal(d) * (1.0 + trial)
+            t = (0.0, 0.731, 2.9, -1.3)[trial]
+            got = np.asarray(op(y, t), dtype=np.float64)
+            ok = bool(np.all(np.isfinite(got))) and \
+                float(np.abs(got - lin(y)).max()) <= 64 * np.finfo(float).eps * scale * float(np.abs(y).sum() + 1.0)
+        if ok:
+            res = cand
+    except Exception:
+        res = op                                   # anything odd (domain errors at the probes): leave it alone
+    op.__dict__[key] = res
+    return res
+
+
 # ---- named systems of SURVEY.md 8(d) --------------------------------------------------
 
 def sys_lin(d, m):

@@ -242,6 +242,29 @@ def test_fused_user_drift_linear_diffusion(sdb, monkeypatch, d, m, strat):
     assert np.array_equal(obs[:, 0], yo[:, :, 0].max(axis=1))
 
 
+def test_linear_expressions_run_the_linear_kernels(sdb):
+    """An SDE written as expressions that happen to be linear gets the kernels of the linear operators
+    (ops.as_linear): bit-identical to LinearDrift / LinearDiffusion; with a nonlinear drift, the fused kernel
+    that evaluates the drift per lane."""
+    d = m = 10
+    fL, GL, y0 = sdb.ops.sys_lin(d, m)
+    A, B = np.asarray(fL.A), np.asarray(GL.B)
+    GE = sdb.ops.ExprDiffusion([["+".join("p[%d]*y[%d]" % ((k * d + i) * d + l, l) for l in range(d))
+                                 for k in range(m)] for i in range(d)], B.ravel())
+    fE = sdb.ops.ExprDrift(["+".join("p[%d]*y[%d]" % (i * d + l, l) for l in range(d)) for i in range(d)], A.ravel())
+    ts = np.linspace(0.0, 0.05, 26)
+    kw = dict(paths=40, seed=11)
+    y_lin = sdb.itoSRI2(fL, GL, y0, ts, **kw)
+    y_exp = sdb.itoSRI2(fE, GE, y0, ts, **kw)
+    assert sdb.last_kernel() == "sdbk_fused_srk2_d10_m10_v0"
+    assert np.array_equal(y_exp, y_lin)
+    fN = sdb.ops.ExprDrift(["-1.5*y[%d] - 0.2*y[%d]*y[%d]*y[%d]" % (i, i, i, i) for i in range(d)])
+    y_n = sdb.itoSRI2(fN, GE, y0, ts, **kw)
+    assert sdb.last_kernel() == "jit:fusedjit|ud"
+    y_n2 = sdb.itoSRI2(fN, GL, y0, ts, **kw)
+    assert np.array_equal(y_n, y_n2)
+
+
 @pytest.mark.parametrize("d,m,wik", [(10, 10, True), (16, 12, False), (8, 6, True)])
 def test_fusedx_user_drift(sdb, monkeypatch, d, m, wik):
     """Nonlinear drift + linear diffusion through the TMEM-resident kernel (Iwik/Jwik, or shapes beyond the

@@ -359,3 +359,40 @@ def test_integration_md_stub_structure_matches_binding():
     assert C.sizeof(doc) == C.sizeof(_lib.IntegrateArgs)
     for name, _ in doc._fields_:
         assert getattr(doc, name).offset == getattr(_lib.IntegrateArgs, name).offset, name
+
+
+def test_linear_expressions_are_promoted_to_linear_operators():
+    """ops.as_linear: expression operators that are exactly linear in y (and time-independent) become
+    LinearDrift / LinearDiffusion -- the operators with tensor-instruction kernels; anything else stays."""
+    from sdeint_b200 import ops
+    d, m = 4, 4
+    rng = np.random.default_rng(5)
+    B = rng.standard_normal((m, d, d)).round(3)
+    B[1, 2, :] = 0.0
+    G = ops.ExprDiffusion([["+".join("%r*y[%d]" % (float(B[k, i, l]), l) for l in range(d)) for k in range(m)]
+                           for i in range(d)])
+    GL = ops.as_linear(G)
+    assert isinstance(GL, ops.LinearDiffusion) and np.array_equal(GL.B, B)
+    assert ops.as_linear(G) is GL                                             # cached
+    y = rng.standard_normal(d)
+    assert np.allclose(GL(y, 0.3), G(y, 0.3), rtol=0, atol=1e-14)
+    A = rng.standard_normal((d, d)).round(3)
+    fd = ops.ExprDrift(["+".join("p[%d]*y[%d]" % (i * d + l, l) for l in range(d)) for i in range(d)], A.ravel())
+    fL = ops.as_linear(fd, dense_only=True)
+    assert isinstance(fL, ops.LinearDrift) and np.array_equal(fL.A, A)
+    sparse = ops.ExprDrift(["-y[%d]" % i for i in range(d)])
+    assert ops.as_linear(sparse, dense_only=True) is sparse                   # cheap drift: stays source
+    assert isinstance(ops.as_linear(sparse), ops.LinearDrift)
+    for bad in (ops.ExprDiffusion([["y[0]*y[1]", "y[1]"], ["y[0]", "0.5*y[1]"]]),          # nonlinear
+                ops.ExprDiffusion([["y[0] + 0.1", "y[1]"], ["y[0]", "0.5*y[1]"]]),         # affine
+                ops.ExprDiffusion([["y[0]*cos(t)", "y[1]"], ["y[0]", "0.5*y[1]"]]),        # time-dependent
+                ops.ExprDiffusion([["y[0]", "0"], ["0", "y[1]"]], diagonal=True),          # own fast path
+                ops.ExprDrift(["sin(y[0])", "y[1]"])):
+        assert ops.as_linear(bad) is bad
+    # the shim promotes where the linear operators have fused kernels (d m >= 16), and only there
+    ts = np.linspace(0.0, 1.0, 11)
+    _, _, f2, G2, *_ = integrate._check_args(fd, G, np.ones(d), ts, None, None)
+    assert isinstance(G2, ops.LinearDiffusion) and isinstance(f2, ops.LinearDrift)
+    small = ops.ExprDiffusion([["0.3*y[0]", "0.1*y[1]"], ["0.2*y[1]", "0.4*y[0]"]])
+    _, _, _, G3, *_ = integrate._check_args(ops.ExprDrift(["-y[0]", "-y[1]"]), small, np.ones(2), ts, None, None)
+    assert G3 is small
