@@ -74,6 +74,13 @@ int sdb_version(void);
 /* Number of kernels launched by this library in the calling process (bench "gpu_launches"). */
 uint64_t sdb_launch_count(void);
 
+/* NVRTC-built kernels (user drift / diffusion source, shapes without an ahead-of-time kernel) are kept as
+ * cubins under $SDB_CACHE_DIR (default ~/.cache/sdeint_b200; SDB_JIT_CACHE=0 disables), keyed by a hash of
+ * the generated source, the embedded headers, the options and the NVRTC / library versions: how many
+ * kernels of this process came from that cache, and how many were compiled.  (The reference has no
+ * counterpart: its f and G are Python callables, integrate.py:124-146.) */
+void sdb_jit_cache_stats(long* hits, long* misses);
+
 /* A (drift, diffusion) pair of built-in kinds; parameters are copied.
  * Replaces the callables f, G of every integrator (integrate.py:124-146). */
 int sdb_system_builtin(int drift_kind, const double* h_drift_params, int64_t n_drift,

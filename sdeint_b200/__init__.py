@@ -9,7 +9,7 @@ from . import ops  # noqa: F401
 from .wiener import deltaW, Ikpw, Jkpw, Iwik, Jwik, Icomm, Jcomm  # noqa: F401
 from .integrate import (Error, SDEValueError, itoint, stratint, itoEuler, stratHeun,  # noqa: F401
                         itoSRI2, stratSRS2, stratKP2iS, itoKP2i, stratR2, last_status)
-from ._lib import launch_count, last_kernel  # noqa: F401
+from ._lib import jit_cache_stats, launch_count, last_kernel  # noqa: F401
 from . import ensemble  # noqa: F401
 
 __version__ = '0.1.0'

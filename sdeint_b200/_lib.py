@@ -65,6 +65,7 @@ SIGNATURES = {
     "sdb_version": (C.c_int, []),
     "sdb_last_kernel": (C.c_char_p, []),
     "sdb_launch_count": (c_u64, []),
+    "sdb_jit_cache_stats": (None, [C.POINTER(C.c_long), C.POINTER(C.c_long)]),
     "sdb_system_builtin": (C.c_int, [C.c_int, c_dp, c_i64, C.c_int, c_dp, c_i64, C.c_int, C.c_int,
                                      C.POINTER(C.c_void_p)]),
     "sdb_system_nvrtc": (C.c_int, [C.c_char_p, C.c_int, c_dp, c_i64, C.c_int, c_dp, c_i64, C.c_int,
@@ -123,6 +124,13 @@ def check(rc):
 
 def launch_count():
     return int(load().sdb_launch_count())
+
+
+def jit_cache_stats():
+    """(hits, misses): NVRTC-built kernels of this process loaded from the on-disk cache / compiled."""
+    h, m = C.c_long(0), C.c_long(0)
+    load().sdb_jit_cache_stats(C.byref(h), C.byref(m))
+    return int(h.value), int(m.value)
 
 
 def last_kernel():

@@ -5,6 +5,9 @@
 #include <dlfcn.h>
 #include <stdio.h>
 #include <string.h>
+#include <sys/stat.h>
+#include <sys/types.h>
+#include <unistd.h>
 
 #include <atomic>
 #include <map>
@@ -118,6 +121,7 @@ struct Nvrtc {
   int (*GetCUBIN)(nvrtcProgram, char*) = nullptr;
   int (*DestroyProgram)(nvrtcProgram*) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
+  int (*Version)(int*, int*) = nullptr;
 };
 
 static int nvrtc_load(Nvrtc** out) {
@@ -139,7 +143,7 @@ static int nvrtc_load(Nvrtc** out) {
   if (!rt.name) return fail("NVRTC symbol nvrtc" #name " missing");
     SDB_SYM(CreateProgram) SDB_SYM(CompileProgram) SDB_SYM(GetProgramLogSize)
     SDB_SYM(GetProgramLog) SDB_SYM(GetCUBINSize) SDB_SYM(GetCUBIN) SDB_SYM(DestroyProgram)
-    SDB_SYM(GetErrorString)
+    SDB_SYM(GetErrorString) SDB_SYM(Version)
 #undef SDB_SYM
   }
   *out = &rt;
@@ -177,6 +181,35 @@ static size_t cubin_text_bytes(const std::vector<char>& elf) {
   return total;
 }
 
+// ---- on-disk cache of NVRTC results ------------------------------------------------------------
+// A fused kernel takes NVRTC several seconds; a user system is compiled again by every process that
+// integrates it.  The cubin is therefore kept under $SDB_CACHE_DIR (default $XDG_CACHE_HOME/sdeint_b200 or
+// ~/.cache/sdeint_b200), named by a 128-bit hash of everything that determines it: the generated source
+// (which contains the user's code and every #define), the embedded headers, the compile options, the NVRTC
+// version and this library's version.  SDB_JIT_CACHE=0 switches it off; an unwritable directory is ignored.
+static uint64_t fnv1a64(const void* data, size_t n, uint64_t h) {
+  const unsigned char* p = (const unsigned char*)data;
+  for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 0x100000001B3ull; }
+  return h;
+}
+static std::string jit_cache_dir() {
+  const char* off = getenv("SDB_JIT_CACHE");
+  if (off && !strcmp(off, "0")) return "";
+  if (const char* d = getenv("SDB_CACHE_DIR")) return d;
+  if (const char* x = getenv("XDG_CACHE_HOME")) if (*x) return std::string(x) + "/sdeint_b200";
+  if (const char* h = getenv("HOME")) if (*h) return std::string(h) + "/.cache/sdeint_b200";
+  return "";
+}
+static void mkdirs(const std::string& dir) {
+  for (size_t i = 1; i <= dir.size(); ++i)
+    if (i == dir.size() || dir[i] == '/') mkdir(dir.substr(0, i).c_str(), 0755);
+}
+static std::atomic<long> g_jit_hits{0}, g_jit_misses{0};
+extern "C" void sdb_jit_cache_stats(long* hits, long* misses) {
+  if (hits) *hits = g_jit_hits.load();
+  if (misses) *misses = g_jit_misses.load();
+}
+
 static int jit_compile(const std::string& source, const char* kernel_name, JitKernel* out,
                        size_t* text_bytes = nullptr) {
   Nvrtc* rt;
@@ -184,6 +217,44 @@ static int jit_compile(const std::string& source, const char* kernel_name, JitKe
   nvrtcProgram prog;
   const char* hdr_src[] = {kKernelHeader, kTablesHeader, kFusedHeader, kTmemHeader, kFusedWsHeader,
                            kFusedXHeader, kRepintXHeader, kFusedEhHeader, kFusedCHeader, kFusedX2Header};
+  static const char* kOpts = "--gpu-architecture=sm_100a -std=c++17 -lineinfo --fmad=true -default-device";
+  std::string cache_file;
+  const std::string dir = jit_cache_dir();
+  if (!dir.empty()) {
+    static uint64_t hdr_hash[2] = {0, 0};
+    static std::once_flag once;
+    std::call_once(once, [&] {
+      uint64_t a = 0xCBF29CE484222325ull, b = 0x9AE16A3B2F90404Full;
+      for (const char* h : hdr_src) { a = fnv1a64(h, strlen(h), a); b = fnv1a64(h, strlen(h), b); }
+      int major = 0, minor = 0;
+      if (rt->Version) rt->Version(&major, &minor);
+      const int ver[3] = {major, minor, SDB_VERSION};
+      a = fnv1a64(ver, sizeof ver, a); b = fnv1a64(ver, sizeof ver, b);
+      a = fnv1a64(kOpts, strlen(kOpts), a); b = fnv1a64(kOpts, strlen(kOpts), b);
+      hdr_hash[0] = a; hdr_hash[1] = b;
+    });
+    const uint64_t a = fnv1a64(source.data(), source.size(), hdr_hash[0]);
+    const uint64_t b = fnv1a64(source.data(), source.size(), hdr_hash[1]);
+    char name[64];
+    snprintf(name, sizeof name, "/%016llx%016llx.cubin", (unsigned long long)a, (unsigned long long)b);
+    cache_file = dir + name;
+    if (FILE* fh = fopen(cache_file.c_str(), "rb")) {
+      std::vector<char> cubin;
+      char buf[1 << 16];
+      size_t n;
+      while ((n = fread(buf, 1, sizeof buf, fh)) > 0) cubin.insert(cubin.end(), buf, buf + n);
+      fclose(fh);
+      if (cubin.size() > 64 &&
+          cudaLibraryLoadData(&out->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) == cudaSuccess &&
+          cudaLibraryGetKernel(&out->kern, out->lib, kernel_name) == cudaSuccess) {
+        if (text_bytes) *text_bytes = cubin_text_bytes(cubin);
+        g_jit_hits.fetch_add(1);
+        return 0;
+      }
+      cudaGetLastError();  // a truncated or foreign file: compile as if it were not there
+    }
+  }
+  g_jit_misses.fetch_add(1);
   const char* hdr_name[] = {"sdb_kernels.cuh", "sdb_tables.cuh", "sdb_fused.cuh", "sdb_tmem.cuh",
                             "sdb_fusedws.cuh", "sdb_fusedx.cuh", "sdb_repintx.cuh", "sdb_fusedeh.cuh",
                             "sdb_fusedc.cuh", "sdb_fusedx2.cuh"};
@@ -192,7 +263,7 @@ static int jit_compile(const std::string& source, const char* kernel_name, JitKe
   // -default-device: un-annotated functions (the generic lambdas of the compile-time loops) are
   // device functions in JIT mode
   const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo",
-                        "--fmad=true", "-default-device"};
+                        "--fmad=true", "-default-device"};  // (kOpts above is the same list, hashed)
   rc = rt->CompileProgram(prog, 5, opts);
   if (rc) {
     size_t n = 0;
@@ -210,6 +281,15 @@ static int jit_compile(const std::string& source, const char* kernel_name, JitKe
   if (text_bytes) *text_bytes = cubin_text_bytes(cubin);
   SDB_CUDA(cudaLibraryLoadData(&out->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
   SDB_CUDA(cudaLibraryGetKernel(&out->kern, out->lib, kernel_name));
+  if (!cache_file.empty()) {  // publish atomically: write a private file, then rename
+    mkdirs(dir);
+    const std::string tmp = cache_file + "." + std::to_string((long)getpid()) + ".tmp";
+    if (FILE* fh = fopen(tmp.c_str(), "wb")) {
+      const bool ok = fwrite(cubin.data(), 1, cubin.size(), fh) == cubin.size();
+      if (fclose(fh) == 0 && ok) rename(tmp.c_str(), cache_file.c_str());
+      else remove(tmp.c_str());
+    }
+  }
   return 0;
 }
 

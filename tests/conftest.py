@@ -13,6 +13,9 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # NVRTC results of the test run go to a scratch directory, not to the user's ~/.cache
+    import tempfile
+    os.environ.setdefault("SDB_CACHE_DIR", os.path.join(tempfile.gettempdir(), "sdeint_b200_jit_tests"))
 
 
 def load_golden(name):

@@ -5,10 +5,12 @@ oracle on seeded inputs.  Tolerance: 1e-12 relative (fp64), the north-star bound
 KP2iS scheme, whose implicit solve the reference delegates to MINPACK hybrd (fixtures generated at
 the tightest xtol it completes with, 1e-12 / 1e-11; its termination leaves a few 1e-12 relative
 against an exact solve), gets 5e-12 against the reference and 1e-11 against the oracle's Newton solve."""
+import os
+
 import numpy as np
 import pytest
 
-from conftest import SYSTEMS, load_golden, rel_err
+from conftest import ROOT, SYSTEMS, load_golden, rel_err
 from oracle import philox_oracle as po
 from oracle import sde_oracle as orc
 
@@ -240,6 +242,36 @@ def test_fused_user_drift_linear_diffusion(sdb, monkeypatch, d, m, strat):
     assert sdb.last_kernel() == "jit:fusedjit|ud|obs"
     assert rel_err(yo, y) <= TOL and obs.shape == (P, 1)
     assert np.array_equal(obs[:, 0], yo[:, :, 0].max(axis=1))
+
+
+def test_nvrtc_results_are_cached_on_disk(tmp_path):
+    """A second process integrating the same user system loads its kernels from $SDB_CACHE_DIR instead of
+    compiling them again (same results, bit for bit); SDB_JIT_CACHE=0 compiles."""
+    import subprocess, sys, json
+    code = (
+        "import sys, json, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "import sdeint_b200 as sdb\n"
+        "f = sdb.ops.ExprDrift(['-y[0] + 0.2*y[1]*y[1]', '-0.5*y[1] + 0.1*sin(y[0])'])\n"
+        "G = sdb.ops.ExprDiffusion([['0.3*(1.0+0.5*sin(y[1]))', '0.1'], ['0.05', '0.2*cos(y[0])']])\n"
+        "y = sdb.itoSRI2(f, G, np.array([0.5, -0.2]), np.linspace(0, 0.1, 11), paths=8, seed=3)\n"
+        "h, m = sdb.jit_cache_stats()\n"
+        "print(json.dumps({'hits': h, 'misses': m, 'sum': float(y.sum()), 'kernel': sdb.last_kernel()}))\n"
+    ) % ROOT
+    env = dict(os.environ, SDB_CACHE_DIR=str(tmp_path / "jit"))
+    env.pop("SDB_JIT_CACHE", None)
+    runs = []
+    for extra in ({}, {}, {"SDB_JIT_CACHE": "0"}):
+        out = subprocess.run([sys.executable, "-c", code], env=dict(env, **extra), capture_output=True,
+                             text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        runs.append(json.loads(out.stdout.strip().splitlines()[-1]))
+    first, second, off = runs
+    assert first["kernel"].startswith("jit:") and first["misses"] >= 1 and first["hits"] == 0
+    assert second["misses"] == 0 and second["hits"] == first["misses"]
+    assert off["hits"] == 0 and off["misses"] == first["misses"]
+    assert first["sum"] == second["sum"] == off["sum"]
+    assert len(list((tmp_path / "jit").glob("*.cubin"))) == first["misses"]
 
 
 def test_linear_expressions_run_the_linear_kernels(sdb):
