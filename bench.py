@@ -41,6 +41,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# NVRTC results of the benchmark run (the extension config) go to a scratch directory
+import tempfile  # noqa: E402
+os.environ.setdefault("SDB_CACHE_DIR", os.path.join(tempfile.gettempdir(), "sdeint_b200_jit_bench"))
 REF_DIR = os.path.join(ROOT, "baseline", "_ref")
 
 D = M = 10
