@@ -12,7 +12,10 @@ names, running on the GPU.
 
 Differences from the reference, all forced by "the loop runs in a CUDA kernel":
   * `f` and `G` are operator objects from `sdeint_b200.ops` (built-in families or NVRTC
-    source), not arbitrary Python callables; `G` may also be the list `G.columns()`.
+    source), or plain Python callables f(y, t), G(y, t) / [g_1, ..., g_m] made of arithmetic and
+    elementary functions, which are traced into such operators (trace.py); a callable that
+    branches on the value of y cannot be traced and raises SDEValueError; `G` may also be the
+    list `G.columns()`.
   * fp64 only (the north-star scope); other dtypes raise SDEValueError.
   * noise that the reference would draw from numpy's generator is drawn by an on-device
     Philox generator (see sdeint_b200/wiener.py); results on host-supplied `dW`, `I`/`J`
@@ -49,7 +52,7 @@ import numbers
 import numpy as np
 
 from . import _device as dev
-from . import _lib, ops
+from . import _lib, ops, trace
 from . import wiener
 from .wiener import Icomm, Ikpw, Iwik, Jcomm, Jkpw, Jwik, deltaW  # noqa: F401  (re-exported like the reference)
 
@@ -88,6 +91,7 @@ def _check_args(f, G, y0, tspan, dW=None, IJ=None):
     steps = np.diff(tspan)
     if not np.isclose(steps.min(), steps.max()):
         raise SDEValueError('Currently time steps must be equally spaced.')
+    scalar_y0 = isinstance(y0, numbers.Number)
     if isinstance(y0, numbers.Number):
         if isinstance(y0, numbers.Complex) and not isinstance(y0, numbers.Real):
             raise SDEValueError('sdeint_b200 integrates real float64 systems only.')
@@ -104,10 +108,24 @@ def _check_args(f, G, y0, tspan, dW=None, IJ=None):
             raise SDEValueError('y0 must be a scalar or a 1-d array of length d.')
     d = len(y0)
     if not isinstance(f, ops.DriftOp):
-        raise SDEValueError(
-            'f must be a drift operator from sdeint_b200.ops (LinearDrift, KP4446Drift, ..., '
-            'or CudaDrift with NVRTC source): a Python callable cannot run inside a CUDA '
-            'kernel and this package has no CPU fallback.')
+        # a plain Python callable, as the reference takes it (integrate.py:124-146): traced once with
+        # symbolic y, t into an expression operator (trace.py); what cannot be traced is refused
+        if not callable(f):
+            raise SDEValueError(
+                'f must be a callable f(y, t) or a drift operator from sdeint_b200.ops (LinearDrift, '
+                'KP4446Drift, ..., ExprDrift, or CudaDrift with NVRTC source).')
+        try:
+            f = trace.trace_drift(f, d, scalar_y0)
+        except trace.TraceError as exc:
+            raise SDEValueError(
+                'f is a Python callable that could not be turned into a device function: %s.  Give it as '
+                'sdeint_b200.ops.ExprDrift / CudaDrift instead (a Python callable cannot run inside a CUDA '
+                'kernel and this package has no CPU fallback).' % exc)
+        except SDEValueError:
+            raise
+        except Exception as exc:
+            raise SDEValueError('y0 and f have incompatible shapes, or f could not be traced (%s: %s).'
+                                % (type(exc).__name__, exc))
     if f.d != d:
         raise SDEValueError('y0 and f have incompatible shapes.')
     message = ("y0 has length %d. So G must either be a single diffusion operator of shape "
@@ -115,7 +133,7 @@ def _check_args(f, G, y0, tspan, dW=None, IJ=None):
                % (d, d, d))
     if isinstance(G, ops.DiffusionOp):
         Gop = G
-    elif isinstance(G, (list, tuple)) and len(G) > 0:
+    elif isinstance(G, (list, tuple)) and len(G) > 0 and any(isinstance(c, ops.DiffusionColumn) for c in G):
         cols = tuple(G)
         if not all(isinstance(c, ops.DiffusionColumn) for c in cols):
             raise SDEValueError(message)
@@ -123,10 +141,20 @@ def _check_args(f, G, y0, tspan, dW=None, IJ=None):
         if (len(cols) != Gop.m or any(c.parent is not Gop for c in cols)
                 or [c.k for c in cols] != list(range(Gop.m))):
             raise SDEValueError('a list G must be exactly G.columns() of one diffusion operator.')
+    elif callable(G) or (isinstance(G, (list, tuple)) and len(G) > 0 and all(callable(g) for g in G)):
+        try:
+            Gop = trace.trace_diffusion(G, d, scalar_y0)   # G(y, t) -> (d, m), or the list of its columns
+        except trace.TraceError as exc:
+            raise SDEValueError(
+                'G is a Python callable that could not be turned into a device function: %s.  Give it as '
+                'sdeint_b200.ops.ExprDiffusion / CudaDiffusion instead (a Python callable cannot run inside '
+                'a CUDA kernel).' % exc)
+        except Exception as exc:
+            raise SDEValueError('%s (%s: %s)' % (message, type(exc).__name__, exc))
     else:
         raise SDEValueError(
-            'G must be a diffusion operator from sdeint_b200.ops (or its .columns() list): '
-            'a Python callable cannot run inside a CUDA kernel.')
+            'G must be a callable G(y, t), the list of its column callables, or a diffusion operator from '
+            'sdeint_b200.ops (or its .columns() list).')
     if Gop.d != d:
         raise SDEValueError(message)
     # expressions that are exactly linear get the kernels of the linear operators (ops.as_linear); only where

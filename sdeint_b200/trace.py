@@ -1,0 +1,262 @@
+"""Plain Python callables f(y, t), G(y, t) -- what the reference takes (sdeint/integrate.py:124-146) -- turned
+into device operators by TRACING: the function is called once with symbolic stand-ins for y and t that record
+the arithmetic done on them, and the recorded expressions become an `ops.ExprDrift` / `ops.ExprDiffusion`
+(CUDA source for NVRTC + the numpy callable used by tests).  Expressions that turn out to be constant or
+exactly linear are handed on to `ConstDiffusion` / `LinearDrift` / `LinearDiffusion`, i.e. to the additive-noise
+path and the tensor-instruction kernels (ops.as_linear).
+
+What can be traced: + - * / **, unary minus, abs, numpy ufuncs sin cos tan exp log sqrt tanh sinh cosh
+(also on arrays of symbols: `np.sin(y)`, `A.dot(y)`, `y**2`, `np.array([...])`), indexing, closures over
+numbers and arrays.  What cannot: anything that needs the VALUE of y or t while tracing -- comparisons and
+branches on y, float(y), np.where / np.maximum on symbols, calls into compiled code.  Those raise TraceError
+and the caller is pointed to ops.ExprDrift / ops.CudaDrift."""
+from __future__ import annotations
+
+import numbers
+
+import numpy as np
+
+_FUNCS = ("sin", "cos", "tan", "exp", "log", "sqrt", "tanh", "sinh", "cosh")
+
+
+class TraceError(Exception):
+    pass
+
+
+def _lit(v):
+    """A float as a literal that survives the round trip (repr) and needs no sign handling."""
+    v = float(v)
+    if not np.isfinite(v):
+        raise TraceError("non-finite constant %r in the traced function" % v)
+    r = repr(v)
+    if "e" not in r and "." not in r:
+        r += ".0"
+    return "(%s)" % r if v < 0 else r
+
+
+class Sym:
+    """A recorded scalar expression: either a constant (`c` is its value) or a string in y[i], t."""
+    __slots__ = ("e", "c")
+    __array_priority__ = 10000.0
+
+    def __init__(self, e=None, c=None):
+        self.e, self.c = e, c
+
+    # -- helpers ---------------------------------------------------------------------------------------
+    @staticmethod
+    def of(x):
+        if isinstance(x, Sym):
+            return x
+        if isinstance(x, (numbers.Real, np.floating, np.integer)) and not isinstance(x, bool):
+            return Sym(c=float(x))
+        if isinstance(x, np.ndarray) and x.ndim == 0:
+            return Sym.of(x.item())
+        raise TraceError("cannot trace an operation with a %s" % type(x).__name__)
+
+    @property
+    def s(self):
+        return _lit(self.c) if self.c is not None else self.e
+
+    def _bin(self, other, op, swap=False):
+        try:
+            o = Sym.of(other)
+        except TraceError:
+            return NotImplemented
+        a, b = (o, self) if swap else (self, o)
+        if a.c is not None and b.c is not None:
+            with np.errstate(all="ignore"):
+                return Sym(c=float({"+": np.add, "-": np.subtract, "*": np.multiply, "/": np.divide}[op](a.c, b.c)))
+        if op == "+":
+            if a.c == 0.0:
+                return b
+            if b.c == 0.0:
+                return a
+        elif op == "-":
+            if b.c == 0.0:
+                return a
+            if a.c == 0.0:
+                return -b
+        elif op == "*":
+            if a.c == 0.0 or b.c == 0.0:
+                return Sym(c=0.0)
+            if a.c == 1.0:
+                return b
+            if b.c == 1.0:
+                return a
+        elif op == "/":
+            if a.c == 0.0:
+                return Sym(c=0.0)
+            if b.c == 1.0:
+                return a
+        return Sym("(%s%s%s)" % (a.s, op, b.s))
+
+    def __add__(self, o): return self._bin(o, "+")
+    def __radd__(self, o): return self._bin(o, "+", True)
+    def __sub__(self, o): return self._bin(o, "-")
+    def __rsub__(self, o): return self._bin(o, "-", True)
+    def __mul__(self, o): return self._bin(o, "*")
+    def __rmul__(self, o): return self._bin(o, "*", True)
+    def __truediv__(self, o): return self._bin(o, "/")
+    def __rtruediv__(self, o): return self._bin(o, "/", True)
+
+    def __neg__(self):
+        return Sym(c=-self.c) if self.c is not None else Sym("(-%s)" % self.e)
+
+    def __pos__(self):
+        return self
+
+    def __abs__(self):
+        return Sym(c=abs(self.c)) if self.c is not None else Sym("fabs(%s)" % self.e)
+
+    def __pow__(self, o):
+        try:
+            o = Sym.of(o)
+        except TraceError:
+            return NotImplemented
+        if self.c is not None and o.c is not None:
+            return Sym(c=float(self.c ** o.c))
+        if o.c is not None:
+            n = o.c
+            if n == 0.0:
+                return Sym(c=1.0)
+            if n == 0.5:
+                return Sym("sqrt(%s)" % self.s)
+            if n == int(n) and 1 <= abs(int(n)) <= 4:           # small integer powers: multiplications
+                prod = "(" + "*".join([self.s] * abs(int(n))) + ")" if abs(int(n)) > 1 else self.s
+                return Sym(prod) if n > 0 else Sym("(1.0/%s)" % prod)
+        return Sym("pow(%s,%s)" % (self.s, o.s))
+
+    def __rpow__(self, o):
+        return Sym.of(o).__pow__(self)
+
+    # numpy calls these by name for object arrays (np.sin(obj_array) -> element.sin())
+    def _fn(self, name):
+        if self.c is not None:
+            with np.errstate(all="ignore"):
+                return Sym(c=float(getattr(np, name)(self.c)))
+        return Sym("%s(%s)" % (name, self.e))
+
+    def sin(self): return self._fn("sin")
+    def cos(self): return self._fn("cos")
+    def tan(self): return self._fn("tan")
+    def exp(self): return self._fn("exp")
+    def log(self): return self._fn("log")
+    def sqrt(self): return self._fn("sqrt")
+    def tanh(self): return self._fn("tanh")
+    def sinh(self): return self._fn("sinh")
+    def cosh(self): return self._fn("cosh")
+
+    def conjugate(self):
+        return self
+
+    # np.sin(sym), np.float64(2) * sym, np.add(arr, sym), ... arrive here
+    def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
+        if method != "__call__" or kwargs.get("out") is not None:
+            return NotImplemented
+        name = ufunc.__name__
+        if any(isinstance(x, np.ndarray) and x.ndim > 0 for x in inputs):   # array (op) symbol: elementwise
+            arrs = [x if isinstance(x, np.ndarray) and x.ndim > 0 else None for x in inputs]
+            shape = np.broadcast(*[a for a in arrs if a is not None]).shape
+            out = np.empty(shape, dtype=object)
+            its = [np.broadcast_to(np.asarray(a, dtype=object), shape) if a is not None else None for a in arrs]
+            for idx in np.ndindex(*shape):
+                args = [it[idx] if it is not None else x for it, x in zip(its, inputs)]
+                out[idx] = Sym._apply(name, args)
+            return out
+        return Sym._apply(name, list(inputs))
+
+    @staticmethod
+    def _apply(name, args):
+        a = [Sym.of(x) for x in args]
+        two = {"add": "+", "subtract": "-", "multiply": "*", "true_divide": "/", "divide": "/"}
+        if name in two and len(a) == 2:
+            return a[0]._bin(a[1], two[name])
+        if name == "power" and len(a) == 2:
+            return a[0] ** a[1]
+        if name == "negative":
+            return -a[0]
+        if name == "positive":
+            return a[0]
+        if name in ("absolute", "fabs"):
+            return abs(a[0])
+        if name == "square":
+            return a[0] ** 2
+        if name == "reciprocal":
+            return 1.0 / a[0]
+        if name in _FUNCS and len(a) == 1:
+            return a[0]._fn(name)
+        raise TraceError("numpy.%s cannot be traced (supported: arithmetic, abs, %s)" % (name, ", ".join(_FUNCS)))
+
+    # anything that needs the value
+    def _no_value(self, *a, **k):
+        raise TraceError("the function inspects the value of y or t (comparison, branch, float(), int()); "
+                         "only arithmetic on y and t can be traced")
+
+    __lt__ = __le__ = __gt__ = __ge__ = __bool__ = __float__ = __int__ = __index__ = _no_value
+    __eq__ = __ne__ = _no_value
+    __hash__ = None
+
+    def __repr__(self):
+        return "Sym(%s)" % self.s
+
+
+def _strings(res, shape, what):
+    """The traced return value as an object array of expression strings of the given shape."""
+    if isinstance(res, (list, tuple)):
+        res = np.array([np.asarray(r, dtype=object) if isinstance(r, (list, tuple, np.ndarray)) else r
+                        for r in res], dtype=object)
+    arr = np.asarray(res, dtype=object)
+    try:
+        arr = arr.reshape(shape)
+    except ValueError:
+        raise TraceError("%s returned an array of shape %s, expected %s" % (what, arr.shape, shape))
+    out = np.empty(shape, dtype=object)
+    for idx in np.ndindex(*shape):
+        out[idx] = Sym.of(arr[idx]).s
+    return out
+
+
+def _symbols(d, scalar):
+    t = Sym("t")
+    if scalar:
+        return Sym("y[0]"), t
+    y = np.empty(d, dtype=object)
+    for i in range(d):
+        y[i] = Sym("y[%d]" % i)
+    return y, t
+
+
+def trace_drift(f, d, scalar=False):
+    """The drift operator of a Python callable f(y, t) -> (d,) (a scalar for scalar y0)."""
+    from . import ops
+    y, t = _symbols(d, scalar)
+    exprs = _strings(f(y, t), (d,), "f(y, t)")
+    op = ops.ExprDrift(list(exprs))
+    op.traced_from = f
+    return op
+
+
+def trace_diffusion(G, d, scalar=False):
+    """The diffusion operator of a callable G(y, t) -> (d, m) (a scalar for scalar y0), or of the list
+    [g_1, ..., g_m] of column callables g_k(y, t) -> (d,) (the reference's alternative form,
+    sdeint/integrate.py:330-334).  Constant results become ops.ConstDiffusion (additive noise)."""
+    from . import ops
+    y, t = _symbols(d, scalar)
+    if isinstance(G, (list, tuple)):
+        cols = [_strings(g(y, t), (d,), "g_k(y, t)") for g in G]
+        table = np.stack(cols, axis=1)
+    else:
+        res = G(y, t)
+        arr = np.asarray(res, dtype=object)
+        if d == 1 and arr.ndim == 0:                           # scalar equation, scalar G (m = 1)
+            arr = arr.reshape(1, 1)
+        if arr.ndim != 2 or arr.shape[0] != d:
+            raise TraceError("G(y, t) must return an array of shape (%d, m), got %s" % (d, arr.shape))
+        table = _strings(arr, arr.shape, "G(y, t)")
+    try:                                                       # no y, no t anywhere: additive noise
+        B = np.array([[float(eval(e, {"__builtins__": {}}, {})) for e in row] for row in table])
+        op = ops.ConstDiffusion(B)
+    except Exception:
+        op = ops.ExprDiffusion([list(row) for row in table])
+    op.traced_from = G
+    return op

@@ -244,6 +244,64 @@ def test_fused_user_drift_linear_diffusion(sdb, monkeypatch, d, m, strat):
     assert np.array_equal(obs[:, 0], yo[:, :, 0].max(axis=1))
 
 
+def test_reference_style_python_callables(sdb):
+    """The reference's own calling convention: plain Python f(y, t), G(y, t) (README.rst:60-97 and the systems
+    of sdeint/tests/test_integrate.py), traced into device operators; every integrator against the oracle
+    running the ORIGINAL Python functions on the same host-supplied noise."""
+    rng = np.random.default_rng(21)
+    # README scalar equation (KP 4.46) through itoint, exactly as the reference's README writes it
+    a, b = 1.0, 0.8
+    tspan = np.linspace(0.0, 5.0, 501)
+    f = lambda x, t: -(a + x * b ** 2) * (1 - x ** 2)
+    g = lambda x, t: b * (1 - x ** 2)
+    h = 0.01
+    dW = rng.normal(0.0, np.sqrt(h), (500, 1))
+    y = sdb.itoEuler(f, g, 0.1, tspan, dW=dW)
+    assert y.shape == (501,) or y.shape == (501, 1)
+    assert rel_err(np.asarray(y).reshape(501, 1), orc.euler(f, g, np.array([0.1]), tspan, dW).reshape(501, 1)) <= TOL
+    y = sdb.itoint(f, g, 0.1, tspan, generator=np.random.default_rng(1))
+    assert np.all(np.isfinite(y)) and np.asarray(y).reshape(-1).shape == (501,)
+    # README 2-d linear system with constant B (additive: no repeated integrals needed)
+    A = np.array([[-0.5, -2.0], [2.0, -1.0]])
+    B = np.diag([0.5, 0.5])
+    fl = lambda x, t: A.dot(x)
+    Gl = lambda x, t: B
+    ts = np.linspace(0.0, 1.0, 101)
+    dW = rng.normal(0.0, 0.1, (100, 2))
+    x0 = np.array([3.0, 3.0])
+    assert rel_err(sdb.itoEuler(fl, Gl, x0, ts, dW=dW), orc.euler(fl, Gl, x0, ts, dW)) <= TOL
+    assert rel_err(sdb.stratHeun(fl, Gl, x0, ts, dW=dW), orc.heun(fl, Gl, x0, ts, dW)) <= TOL
+    _, I = sdb.Ikpw(dW, 0.01, generator=np.random.default_rng(5))
+    assert rel_err(sdb.itoSRI2(fl, Gl, x0, ts, dW=dW, I=I), orc.srk2(fl, Gl, x0, ts, dW, I)) <= TOL
+    # Roessler (7.4)-type system written with np.dot, G as one function and as a list of column functions
+    d, m = 5, 4
+    A5 = -np.eye(d) + 0.1 * rng.standard_normal((d, d))
+    Bm = 0.2 * rng.standard_normal((m, d, d))
+    f5 = lambda y, t: np.dot(A5, y)
+    G5 = lambda y, t: np.dot(Bm, y).T
+    G5_cols = [(lambda y, t, k=k: np.dot(Bm[k], y)) for k in range(m)]
+    y0 = np.ones(d)
+    dW = rng.normal(0.0, 0.1, (100, m))
+    _, J = sdb.Jkpw(dW, 0.01, generator=np.random.default_rng(6))
+    ref = orc.srk2(f5, G5, y0, ts, dW, J)
+    assert rel_err(sdb.stratSRS2(f5, G5, y0, ts, dW=dW, J=J), ref) <= TOL
+    assert rel_err(sdb.stratSRS2(f5, G5_cols, y0, ts, dW=dW, J=J), ref) <= TOL
+    ye = sdb.stratSRS2(f5, G5, y0, ts, paths=64, seed=9)                   # ensemble on device noise
+    assert ye.shape == (64, 101, d) and sdb.last_kernel().startswith(("sdbk_fused", "jit:fused"))
+    # a nonlinear, time-dependent system: every scheme
+    fn = lambda y, t: np.array([-y[0] / (1.0 + y[1] ** 2) + 0.2 * np.cos(3 * t), -0.5 * y[1] + 0.1 * np.sin(y[0])])
+    Gn = lambda y, t: np.array([[0.3 * (1.0 + 0.5 * np.sin(y[1])), 0.1], [0.05, 0.2 * np.cos(y[0]) * np.exp(-t)]])
+    z0 = np.array([0.5, -0.2])
+    dW = rng.normal(0.0, 0.1, (100, 2))
+    _, I = sdb.Iwik(dW, 0.01, generator=np.random.default_rng(7))
+    assert rel_err(sdb.itoEuler(fn, Gn, z0, ts, dW=dW), orc.euler(fn, Gn, z0, ts, dW)) <= TOL
+    assert rel_err(sdb.stratHeun(fn, Gn, z0, ts, dW=dW), orc.heun(fn, Gn, z0, ts, dW)) <= TOL
+    assert rel_err(sdb.itoSRI2(fn, Gn, z0, ts, dW=dW, I=I), orc.srk2(fn, Gn, z0, ts, dW, I)) <= TOL
+    # what cannot be traced is refused, like any other bad argument
+    with pytest.raises(sdb.SDEValueError, match="could not be turned into a device function"):
+        sdb.itoint(lambda y, t: -y if y[0] > 0 else y, Gn, z0, ts)
+
+
 def test_nvrtc_results_are_cached_on_disk(tmp_path):
     """A second process integrating the same user system loads its kernels from $SDB_CACHE_DIR instead of
     compiling them again (same results, bit for bit); SDB_JIT_CACHE=0 compiles."""
@@ -518,8 +576,8 @@ def test_argument_validation(sdb):
         sdb.itoEuler(f, G, y0, tspan, dW=[[0.0] * 4] * 20)
     with pytest.raises(sdb.SDEValueError):                       # wrong I shape
         sdb.itoSRI2(f, G, y0, tspan, dW=np.zeros((20, 4)), I=np.zeros((20, 4, 3)))
-    with pytest.raises(sdb.SDEValueError):                       # Python callables cannot run
-        sdb.itoint(lambda y, t: -y, lambda y, t: np.eye(5), y0, tspan)
+    with pytest.raises(sdb.SDEValueError):                       # Python callables that cannot be traced
+        sdb.itoint(lambda y, t: -y if y[0] > 0 else y, lambda y, t: np.eye(5), y0, tspan)
     with pytest.raises(TypeError):                               # list-G only for SRI2/SRS2
         sdb.itoEuler(f, G.columns(), y0, tspan)
     with pytest.raises(sdb.SDEValueError):

@@ -396,3 +396,66 @@ def test_linear_expressions_are_promoted_to_linear_operators():
     small = ops.ExprDiffusion([["0.3*y[0]", "0.1*y[1]"], ["0.2*y[1]", "0.4*y[0]"]])
     _, _, _, G3, *_ = integrate._check_args(ops.ExprDrift(["-y[0]", "-y[1]"]), small, np.ones(2), ts, None, None)
     assert G3 is small
+
+
+def test_python_callables_are_traced_into_device_operators():
+    """The reference's calling convention -- plain Python f(y, t), G(y, t) (integrate.py:124-146) -- works by
+    tracing (sdeint_b200/trace.py): the functions of the reference's own tests and README become expression
+    operators that evaluate to the same numbers, constants become additive noise, linear systems the linear
+    operators; what needs the value of y while tracing is refused with SDEValueError."""
+    from sdeint_b200 import ops, trace
+    rng = np.random.default_rng(3)
+    ts = np.linspace(0.0, 1.0, 11)
+
+    def same(op, fn, d, scalar=False, shape=None):
+        for _ in range(3):
+            y = rng.standard_normal() if scalar else rng.standard_normal(d)
+            t = float(rng.uniform(0, 2))
+            want = np.asarray(fn(y, t), dtype=float)
+            got = np.asarray(op(np.atleast_1d(y), t), dtype=float)
+            assert np.allclose(got.reshape(want.shape if shape is None else shape), want, rtol=1e-14, atol=1e-15)
+
+    # README.rst:60-69 / test_integrate.py:93-97 (KP 4.46): scalar equation
+    a, b = 1.0, 0.8
+    f = lambda y, t: -(a + y * b ** 2) * (1 - y ** 2)
+    G = lambda y, t: b * (1 - y ** 2)
+    d_, m_, fo, Go, *_ = integrate._check_args(f, G, 0.1, ts)
+    assert (d_, m_) == (1, 1) and isinstance(fo, ops.ExprDrift) and isinstance(Go, ops.ExprDiffusion)
+    same(fo, f, 1, scalar=True, shape=()); same(Go, G, 1, scalar=True, shape=())
+    # test_integrate.py:263-266 (KPS 4.5): numpy ufuncs on the symbol
+    f = lambda y, t: -np.sin(2 * y) - 0.25 * np.sin(4 * y)
+    G = lambda y, t: np.sqrt(2.0) * np.cos(y) ** 2
+    _, _, fo, Go, *_ = integrate._check_args(f, G, 1.0, ts)
+    same(fo, f, 1, scalar=True, shape=()); same(Go, G, 1, scalar=True, shape=())
+    # README.rst:83-95: 2-d linear drift, constant B -> additive noise (no repeated integrals at all)
+    A = np.array([[-0.5, -2.0], [2.0, -1.0]])
+    B = np.diag([0.5, 0.5])
+    _, m_, fo, Go, *_ = integrate._check_args(lambda x, t: A.dot(x), lambda x, t: B, np.array([3.0, 3.0]), ts)
+    assert m_ == 2 and isinstance(Go, ops.ConstDiffusion) and np.array_equal(Go.B, B)
+    same(fo, lambda x, t: A.dot(x), 2)
+    # test_integrate.py:357-369 (Roessler 7.4): np.dot with matrices, G as (m, d, d) . y, and as a list of columns
+    d, m = 5, 4
+    A5 = rng.standard_normal((d, d)); B0 = rng.standard_normal((d, d)); Bm = np.array([B0] * m)
+    f = lambda y, t: np.dot(A5, y)
+    G = lambda y, t: np.dot(Bm, y).T
+    _, m_, fo, Go, *_ = integrate._check_args(f, G, np.ones(d), ts)
+    assert m_ == m and isinstance(fo, ops.LinearDrift) and isinstance(Go, ops.LinearDiffusion)   # d m >= 16
+    assert np.array_equal(fo.A, A5) and np.array_equal(Go.B, Bm)
+    _, m_, _, Gl, *_ = integrate._check_args(f, [lambda y, t: np.dot(B0, y)] * m, np.ones(d), ts)
+    assert m_ == m and np.array_equal(Gl.B, Bm)
+    # time dependence, division, powers, abs, a nonlinear table
+    f = lambda y, t: np.array([-y[0] / (1.0 + y[1] ** 2) + np.cos(3 * t), abs(y[0]) ** 1.5 - y[1] ** -2])
+    G = lambda y, t: np.array([[0.3 * np.exp(-t) * y[0], 0.1], [0.0, 0.2 * np.tanh(y[1]) / 2]])
+    _, m_, fo, Go, *_ = integrate._check_args(f, G, np.array([0.4, 0.9]), ts)
+    assert m_ == 2 and "0.0" == Go.exprs[1][0]
+    same(fo, f, 2); same(Go, G, 2)
+    # not traceable: a branch on y; wrong shapes
+    with pytest.raises(sdb.SDEValueError, match="could not be turned into a device function"):
+        integrate._check_args(lambda y, t: -y if y[0] > 0 else y, G, np.array([0.4, 0.9]), ts)
+    with pytest.raises(sdb.SDEValueError, match="could not be turned into a device function"):
+        integrate._check_args(f, lambda y, t: np.where(y > 0, 1.0, 2.0) * np.eye(2), np.array([0.4, 0.9]), ts)
+    with pytest.raises(sdb.SDEValueError):
+        integrate._check_args(lambda y, t: np.array([1.0, 2.0, 3.0, 4.0]), lambda y, t: np.ones((3, 3)),
+                              np.zeros(3), ts)                       # test_integrate.py:31-32 (mismatched f)
+    with pytest.raises(sdb.SDEValueError):
+        integrate._check_args(3.0, G, np.array([0.4, 0.9]), ts)

@@ -2,6 +2,12 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, sdeint_b200 as sdb
+a, b = 1.0, 0.8
+tspan = np.linspace(0.0, 5.0, 5001)
+def f(x, t): return -(a + x*b**2)*(1 - x**2)
+def g(x, t): return b*(1 - x**2)
+result = sdb.itoint(f, g, 0.1, tspan); print(np.asarray(result).shape, sdb.last_kernel())
+paths = sdb.itoint(f, g, 0.1, tspan, paths=10**5, seed=0, save_every=100); print(paths.shape)
 f, G, y0 = sdb.ops.sys_lin(10, 10)
 tspan = np.linspace(0.0, 1.0, 1001)
 y = sdb.itoSRI2(f, G, y0, tspan, paths=10**5, seed=1, save_every=100); print(y.shape)
