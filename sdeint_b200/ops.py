@@ -325,7 +325,7 @@ class CudaDiffusion(DiffusionOp):
 # fabs tanh -- and generate both the CUDA source (compiled by NVRTC) and the equivalent numpy
 # callable handed to the oracle in tests, so no CUDA has to be written by hand.
 
-_EXPR_FUNCS = ("sin", "cos", "tan", "exp", "log", "sqrt", "pow", "fabs", "tanh", "sinh", "cosh")
+_EXPR_FUNCS = ("sin", "cos", "tan", "exp", "log", "sqrt", "pow", "fabs", "tanh", "sinh", "cosh", "fmax", "fmin")
 
 
 def _check_expr(expr):

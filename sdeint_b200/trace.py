@@ -5,10 +5,10 @@ the arithmetic done on them, and the recorded expressions become an `ops.ExprDri
 exactly linear are handed on to `ConstDiffusion` / `LinearDrift` / `LinearDiffusion`, i.e. to the additive-noise
 path and the tensor-instruction kernels (ops.as_linear).
 
-What can be traced: + - * / **, unary minus, abs, numpy ufuncs sin cos tan exp log sqrt tanh sinh cosh
-(also on arrays of symbols: `np.sin(y)`, `A.dot(y)`, `y**2`, `np.array([...])`), indexing, closures over
+What can be traced: + - * / **, unary minus, abs, numpy ufuncs sin cos tan exp log sqrt tanh sinh cosh,
+np.maximum / np.minimum (also on arrays of symbols: `np.sin(y)`, `A.dot(y)`, `y**2`, `np.array([...])`), indexing, closures over
 numbers and arrays.  What cannot: anything that needs the VALUE of y or t while tracing -- comparisons and
-branches on y, float(y), np.where / np.maximum on symbols, calls into compiled code.  Those raise TraceError
+branches on y, float(y), np.where on symbols, calls into compiled code.  Those raise TraceError
 and the caller is pointed to ops.ExprDrift / ops.CudaDrift."""
 from __future__ import annotations
 
@@ -183,6 +183,13 @@ class Sym:
             return a[0] ** 2
         if name == "reciprocal":
             return 1.0 / a[0]
+        if name in ("maximum", "fmax", "minimum", "fmin") and len(a) == 2:   # e.g. sqrt(max(v, 0)) of CIR / Heston
+            fn = "fmax" if name in ("maximum", "fmax") else "fmin"
+            if a[0].c is not None and a[1].c is not None:
+                return Sym(c=float(getattr(np, fn)(a[0].c, a[1].c)))
+            return Sym("%s(%s,%s)" % (fn, a[0].s, a[1].s))
+        if name == "clip" and len(a) == 3:
+            return Sym._apply("minimum", [Sym._apply("maximum", [a[0], a[1]]), a[2]])
         if name in _FUNCS and len(a) == 1:
             return a[0]._fn(name)
         raise TraceError("numpy.%s cannot be traced (supported: arithmetic, abs, %s)" % (name, ", ".join(_FUNCS)))

@@ -449,6 +449,15 @@ def test_python_callables_are_traced_into_device_operators():
     _, m_, fo, Go, *_ = integrate._check_args(f, G, np.array([0.4, 0.9]), ts)
     assert m_ == 2 and "0.0" == Go.exprs[1][0]
     same(fo, f, 2); same(Go, G, 2)
+    # np.maximum / np.minimum (full-truncation Heston: sqrt(max(v, 0)))
+    kappa, theta, xi = 2.0, 0.04, 0.3
+    f = lambda y, t: np.array([0.05 * y[0], kappa * (theta - np.maximum(y[1], 0.0))])
+    G = lambda y, t: np.array([[np.sqrt(np.maximum(y[1], 0.0)) * y[0], 0.0],
+                               [0.0, xi * np.sqrt(np.maximum(y[1], 0.0))]])
+    _, _, fo, Go, *_ = integrate._check_args(f, G, np.array([1.0, 0.04]), ts)
+    assert "fmax(y[1],0.0)" in fo.exprs[1] and "fmax" in Go.source
+    for y in (np.array([1.2, 0.05]), np.array([0.9, -0.01])):
+        assert np.allclose(fo(y, 0.0), f(y, 0.0)) and np.allclose(Go(y, 0.0), G(y, 0.0))
     # not traceable: a branch on y; wrong shapes
     with pytest.raises(sdb.SDEValueError, match="could not be turned into a device function"):
         integrate._check_args(lambda y, t: -y if y[0] > 0 else y, G, np.array([0.4, 0.9]), ts)
