@@ -196,8 +196,9 @@ class Sym:
 
     # anything that needs the value
     def _no_value(self, *a, **k):
-        raise TraceError("the function inspects the value of y or t (comparison, branch, float(), int()); "
-                         "only arithmetic on y and t can be traced")
+        raise TraceError("the function needs the value of y or t while it is traced (a comparison or branch, "
+                         "float() / math.* on y, or storing into a preallocated float array: build the result with "
+                         "np.array([...]) instead); only arithmetic and numpy's elementary functions can be traced")
 
     __lt__ = __le__ = __gt__ = __ge__ = __bool__ = __float__ = __int__ = __index__ = _no_value
     __eq__ = __ne__ = _no_value
