@@ -423,6 +423,16 @@ def as_linear(op, dense_only=False):
     key = "_as_linear_dense" if dense_only else "_as_linear"
     if key in op.__dict__:
         return op.__dict__[key]
+    # operators traced from Python callables are new objects on every call: remember the verdict by content
+    if isinstance(op, ExprDrift):
+        ckey = (key, "f", tuple(op.exprs), op.params.tobytes())
+    else:
+        ckey = (key, "G", tuple(tuple(r) for r in op.exprs), op.params.tobytes(), op.kind)
+    hit = _AS_LINEAR_CACHE.get(ckey)
+    if hit is not None:
+        res = op if hit is False else hit
+        op.__dict__[key] = res
+        return res
     d = op.d
     res = op
     try:
@@ -460,7 +470,13 @@ def as_linear(op, dense_only=False):
     except Exception:
         res = op                                   # anything odd (domain errors at the probes): leave it alone
     op.__dict__[key] = res
+    if len(_AS_LINEAR_CACHE) >= 256:
+        _AS_LINEAR_CACHE.clear()
+    _AS_LINEAR_CACHE[ckey] = False if res is op else res
     return res
+
+
+_AS_LINEAR_CACHE = {}
 
 
 # ---- named systems of SURVEY.md 8(d) --------------------------------------------------
