@@ -170,7 +170,12 @@ struct SdbFusedShape {
   // copies of the log table: 8 (conflict-free, see sdb_normal_batch) when an SM's shared memory has room
   static SDB_CX int tab_copies() { return smem_base() + 8 * 128 * 16 <= 227u * 1024u ? 8 : 1; }
   static SDB_CX size_t smem_bytes() {
-    return smem_base() + (size_t)tab_copies() * 128 * 16 + (SDB_FUSED_AHEAD ? 16 : 0);
+    const size_t b = smem_base() + (size_t)tab_copies() * 128 * 16 + (SDB_FUSED_AHEAD ? 16 : 0);
+#ifdef SDB_FUSED_MIN_SMEM  // diagnostic builds with fewer threads: keep one block per SM
+    return b < (size_t)SDB_FUSED_MIN_SMEM ? (size_t)SDB_FUSED_MIN_SMEM : b;
+#else
+    return b;
+#endif
   }
   // SDB_FUSED_AHEAD: 128-bit blocks per step that wait in tensor memory (dW + the Levy series)
   static constexpr int AHEAD_SLOTS = M / 2 + SDB_FUSED_AHEAD_TERMS * M;
