@@ -325,7 +325,26 @@ class CudaDiffusion(DiffusionOp):
 # fabs tanh -- and generate both the CUDA source (compiled by NVRTC) and the equivalent numpy
 # callable handed to the oracle in tests, so no CUDA has to be written by hand.
 
-_EXPR_FUNCS = ("sin", "cos", "tan", "exp", "log", "sqrt", "pow", "fabs", "tanh", "sinh", "cosh", "fmax", "fmin")
+_EXPR_FUNCS = ("sin", "cos", "tan", "exp", "log", "sqrt", "pow", "fabs", "tanh", "sinh", "cosh", "fmax", "fmin",
+               "lt", "le", "gt", "ge")   # comparisons as 0.0 / 1.0 (masks for piecewise formulas)
+# device definitions of the names that are not C math functions (guarded: drift and diffusion sources of one
+# system are compiled as one translation unit)
+_EXPR_PRELUDE = (
+    "#ifndef SDB_EXPR_PRELUDE\n#define SDB_EXPR_PRELUDE\n"
+    "__device__ __forceinline__ double lt(double a, double b) { return a < b ? 1.0 : 0.0; }\n"
+    "__device__ __forceinline__ double le(double a, double b) { return a <= b ? 1.0 : 0.0; }\n"
+    "__device__ __forceinline__ double gt(double a, double b) { return a > b ? 1.0 : 0.0; }\n"
+    "__device__ __forceinline__ double ge(double a, double b) { return a >= b ? 1.0 : 0.0; }\n"
+    "#endif\n")
+_EXPR_PY = {"fabs": np.abs, "pow": np.power,
+            "lt": lambda a, b: float(a < b), "le": lambda a, b: float(a <= b),
+            "gt": lambda a, b: float(a > b), "ge": lambda a, b: float(a >= b)}
+
+
+def _prelude(exprs):
+    import re
+    used = set(re.findall(r"[A-Za-z_]\w*", " ".join(exprs)))
+    return _EXPR_PRELUDE if used & {"lt", "le", "gt", "ge"} else ""
 
 
 def _check_expr(expr):
@@ -367,7 +386,7 @@ def _c_expr(expr):
 
 
 def _expr_eval(expr, y, t, p):
-    env = {k: getattr(np, {"fabs": "abs", "pow": "power"}.get(k, k)) for k in _EXPR_FUNCS}
+    env = {k: _EXPR_PY[k] if k in _EXPR_PY else getattr(np, k) for k in _EXPR_FUNCS}
     env.update(y=y, t=t, p=p)
     return float(eval(expr, {"__builtins__": {}}, env))      # names were whitelisted by _check_expr
 
@@ -379,7 +398,8 @@ class ExprDrift(CudaDrift):
     def __init__(self, exprs, params=()):
         self.exprs = [_check_expr(e) for e in exprs]
         body = "\n".join("  out[%d] = %s;" % (i, _c_expr(e)) for i, e in enumerate(self.exprs))
-        src = ("__device__ void sde_drift(const double* y, double t, const double* p, double* out) {\n"
+        src = (_prelude(self.exprs) +
+               "__device__ void sde_drift(const double* y, double t, const double* p, double* out) {\n"
                "%s\n}\n" % body)
         par = np.asarray(params, dtype=np.float64).reshape(-1)
         super().__init__(src, len(self.exprs), par,
@@ -401,7 +421,8 @@ class ExprDiffusion(CudaDiffusion):
         for k in range(m):
             lines = "\n".join("      out[%d] = %s;" % (i, _c_expr(rows[i][k])) for i in range(d))
             cases.append("    case %d:\n%s\n      break;" % (k, lines))
-        src = ("__device__ void sde_diffusion_col(int k, const double* y, double t, const double* p, "
+        src = (_prelude([e for row in rows for e in row]) +
+               "__device__ void sde_diffusion_col(int k, const double* y, double t, const double* p, "
                "double* out) {\n  switch (k) {\n%s\n  }\n}\n" % "\n".join(cases))
         par = np.asarray(params, dtype=np.float64).reshape(-1)
         super().__init__(src, d, m, par, diagonal=diagonal, commutative=commutative,

@@ -6,7 +6,7 @@ exactly linear are handed on to `ConstDiffusion` / `LinearDrift` / `LinearDiffus
 path and the tensor-instruction kernels (ops.as_linear).
 
 What can be traced: + - * / **, unary minus, abs, numpy ufuncs sin cos tan exp log sqrt tanh sinh cosh,
-np.maximum / np.minimum (also on arrays of symbols: `np.sin(y)`, `A.dot(y)`, `y**2`, `np.array([...])`), indexing, closures over
+np.maximum / np.minimum / np.sign / np.heaviside, comparisons used as 0/1 masks (also on arrays of symbols: `np.sin(y)`, `A.dot(y)`, `y**2`, `np.array([...])`), indexing, closures over
 numbers and arrays.  What cannot: anything that needs the VALUE of y or t while tracing -- comparisons and
 branches on y, float(y), np.where on symbols, calls into compiled code.  Those raise TraceError
 and the caller is pointed to ops.ExprDrift / ops.CudaDrift."""
@@ -188,11 +188,36 @@ class Sym:
             if a[0].c is not None and a[1].c is not None:
                 return Sym(c=float(getattr(np, fn)(a[0].c, a[1].c)))
             return Sym("%s(%s,%s)" % (fn, a[0].s, a[1].s))
+        cmp = {"less": "lt", "less_equal": "le", "greater": "gt", "greater_equal": "ge"}
+        if name in cmp and len(a) == 2:
+            return a[0]._cmp(a[1], cmp[name], False)
+        if name == "sign" and len(a) == 1:
+            return a[0]._cmp(0.0, "gt", False) - a[0]._cmp(0.0, "lt", False)
+        if name == "heaviside" and len(a) == 2:          # 0 for x < 0, h0 at 0, 1 for x > 0
+            x, h0 = a
+            return x._cmp(0.0, "gt", False) + h0 * (x._cmp(0.0, "ge", False) - x._cmp(0.0, "gt", False))
         if name == "clip" and len(a) == 3:
             return Sym._apply("minimum", [Sym._apply("maximum", [a[0], a[1]]), a[2]])
         if name in _FUNCS and len(a) == 1:
             return a[0]._fn(name)
         raise TraceError("numpy.%s cannot be traced (supported: arithmetic, abs, %s)" % (name, ", ".join(_FUNCS)))
+
+    # comparisons are recorded as 0.0 / 1.0 masks ((y > 0) * a + (y <= 0) * b); using one as the condition of a
+    # Python `if` still needs its value and is refused by __bool__
+    def _cmp(self, o, fn, swapped):
+        try:
+            o = Sym.of(o)
+        except TraceError:
+            return NotImplemented
+        a, b = (o, self) if swapped else (self, o)
+        if a.c is not None and b.c is not None:
+            return Sym(c=float({"lt": a.c < b.c, "le": a.c <= b.c, "gt": a.c > b.c, "ge": a.c >= b.c}[fn]))
+        return Sym("%s(%s,%s)" % (fn, a.s, b.s))
+
+    def __lt__(self, o): return self._cmp(o, "lt", False)
+    def __le__(self, o): return self._cmp(o, "le", False)
+    def __gt__(self, o): return self._cmp(o, "gt", False)
+    def __ge__(self, o): return self._cmp(o, "ge", False)
 
     # anything that needs the value
     def _no_value(self, *a, **k):
@@ -200,12 +225,41 @@ class Sym:
                          "float() / math.* on y, or storing into a preallocated float array: build the result with "
                          "np.array([...]) instead); only arithmetic and numpy's elementary functions can be traced")
 
-    __lt__ = __le__ = __gt__ = __ge__ = __bool__ = __float__ = __int__ = __index__ = _no_value
+    __bool__ = __float__ = __int__ = __index__ = _no_value
     __eq__ = __ne__ = _no_value
     __hash__ = None
 
     def __repr__(self):
         return "Sym(%s)" % self.s
+
+
+import operator as _op
+
+_CMP = {name: np.frompyfunc(getattr(_op, name), 2, 1) for name in ("lt", "le", "gt", "ge")}
+
+
+class SymArray(np.ndarray):
+    """The object array of symbols handed to the traced function as y: numpy's own comparison of object arrays
+    converts every result with bool(); here `y > 0` stays an array of recorded 0/1 masks, and np.where on such a
+    mask becomes mask * a + (1 - mask) * b."""
+
+    def __lt__(self, o): return _CMP["lt"](np.asarray(self), np.asarray(o, dtype=object)).view(SymArray)
+    def __le__(self, o): return _CMP["le"](np.asarray(self), np.asarray(o, dtype=object)).view(SymArray)
+    def __gt__(self, o): return _CMP["gt"](np.asarray(self), np.asarray(o, dtype=object)).view(SymArray)
+    def __ge__(self, o): return _CMP["ge"](np.asarray(self), np.asarray(o, dtype=object)).view(SymArray)
+
+    def __array_function__(self, func, types, args, kwargs):
+        def plain(x):
+            if isinstance(x, SymArray):
+                return np.asarray(x)
+            if isinstance(x, (list, tuple)):
+                return type(x)(plain(v) for v in x)
+            return x
+        if func is np.where and len(args) == 3 and not kwargs:
+            c, a, b = (np.asarray(plain(v), dtype=object) for v in args)
+            return (c * a + (1.0 - c) * b).view(SymArray)
+        out = func(*plain(args), **{k: plain(v) for k, v in kwargs.items()})
+        return out.view(SymArray) if isinstance(out, np.ndarray) and out.dtype == object else out
 
 
 def _strings(res, shape, what):
@@ -231,7 +285,7 @@ def _symbols(d, scalar):
     y = np.empty(d, dtype=object)
     for i in range(d):
         y[i] = Sym("y[%d]" % i)
-    return y, t
+    return y.view(SymArray), t
 
 
 def trace_drift(f, d, scalar=False):

@@ -297,6 +297,12 @@ def test_reference_style_python_callables(sdb):
     assert rel_err(sdb.itoEuler(fn, Gn, z0, ts, dW=dW), orc.euler(fn, Gn, z0, ts, dW)) <= TOL
     assert rel_err(sdb.stratHeun(fn, Gn, z0, ts, dW=dW), orc.heun(fn, Gn, z0, ts, dW)) <= TOL
     assert rel_err(sdb.itoSRI2(fn, Gn, z0, ts, dW=dW, I=I), orc.srk2(fn, Gn, z0, ts, dW, I)) <= TOL
+    # piecewise formulas: comparisons as masks, np.where, np.sign, np.maximum (device prelude lt/le/gt/ge)
+    fp = lambda y, t: np.array([np.where(y > 0.3, -2.0 * y, 0.5 - y)[0] + 0.2 * np.heaviside(t - 0.5, 0.5),
+                                -np.sign(y[1]) * np.sqrt(np.maximum(abs(y[1]), 1e-3))])
+    Gp = lambda y, t: np.array([[0.3 * (y[0] > 0) * y[0], 0.1], [0.05 * (y[1] <= 0.1), 0.2]])
+    assert rel_err(sdb.stratHeun(fp, Gp, z0, ts, dW=dW), orc.heun(fp, Gp, z0, ts, dW)) <= TOL
+    assert rel_err(sdb.itoSRI2(fp, Gp, z0, ts, dW=dW, I=I), orc.srk2(fp, Gp, z0, ts, dW, I)) <= TOL
     # what cannot be traced is refused, like any other bad argument
     with pytest.raises(sdb.SDEValueError, match="could not be turned into a device function"):
         sdb.itoint(lambda y, t: -y if y[0] > 0 else y, Gn, z0, ts)

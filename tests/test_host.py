@@ -461,8 +461,21 @@ def test_python_callables_are_traced_into_device_operators():
     # not traceable: a branch on y; wrong shapes
     with pytest.raises(sdb.SDEValueError, match="could not be turned into a device function"):
         integrate._check_args(lambda y, t: -y if y[0] > 0 else y, G, np.array([0.4, 0.9]), ts)
+    import math
     with pytest.raises(sdb.SDEValueError, match="could not be turned into a device function"):
-        integrate._check_args(f, lambda y, t: np.where(y > 0, 1.0, 2.0) * np.eye(2), np.array([0.4, 0.9]), ts)
+        integrate._check_args(lambda y, t: np.array([math.sin(y[0]), y[1]]), G, np.array([0.4, 0.9]), ts)
+    # comparisons as 0/1 masks, np.where, np.sign, np.heaviside: piecewise formulas
+    fp = lambda y, t: np.array([-1.0 * (y[0] > 0.2) * y[0] + (y[0] <= 0.2) * 0.5,
+                                -np.sign(y[1]) * abs(y[1]) ** 0.5 + np.heaviside(t - 0.5, 0.5)])
+    Gp = lambda y, t: np.array([[0.3 * (y > 0)[0], 0.1], [0.0, 0.2 * np.where(y > 0.5, 1.0, y * y)[1]]])
+    _, _, fo, Go, *_ = integrate._check_args(fp, Gp, np.array([1.0, 0.04]), ts)
+    assert "gt(y[0],0.2)" in fo.exprs[0] and "SDB_EXPR_PRELUDE" in fo.source and "SDB_EXPR_PRELUDE" in Go.source
+    for y, t in ((np.array([1.2, 0.05]), 0.1), (np.array([0.1, -0.01]), 0.7), (np.array([0.2, 0.0]), 0.5),
+                 (np.array([0.3, 0.9]), 0.5)):
+        assert np.allclose(fo(y, t), fp(y, t)) and np.allclose(Go(y, t), np.asarray(Gp(y, t), float))
+    fw = lambda x, t: np.where(x > 0, -x, x / 2)
+    _, _, fo, *_ = integrate._check_args(fw, lambda x, t: np.eye(2), np.array([3.0, 3.0]), ts)
+    assert np.allclose(fo(np.array([0.3, -0.7]), 0.0), fw(np.array([0.3, -0.7]), 0.0))
     with pytest.raises(sdb.SDEValueError):
         integrate._check_args(lambda y, t: np.array([1.0, 2.0, 3.0, 4.0]), lambda y, t: np.ones((3, 3)),
                               np.zeros(3), ts)                       # test_integrate.py:31-32 (mismatched f)
