@@ -319,6 +319,14 @@ def trace_diffusion(G, d, scalar=False):
         B = np.array([[float(eval(e, {"__builtins__": {}}, {})) for e in row] for row in table])
         op = ops.ConstDiffusion(B)
     except Exception:
-        op = ops.ExprDiffusion([list(row) for row in table])
+        # diagonal noise -- G_ik = 0 off the diagonal and G_kk a function of y_k and t only, the common case of
+        # one independent noise per component -- needs no Levy areas (SRI2/SRS2 use I_kk alone): read off the
+        # recorded expressions, so it is exact
+        import re
+        diag = table.shape[0] == table.shape[1] and all(
+            (table[i, k] in ("0.0", "(-0.0)") if i != k
+             else set(re.findall(r"y\[(\d+)\]", table[i, k])) <= {str(k)})
+            for i in range(table.shape[0]) for k in range(table.shape[1]))
+        op = ops.ExprDiffusion([list(row) for row in table], diagonal=bool(diag))
     op.traced_from = G
     return op

@@ -303,6 +303,17 @@ def test_reference_style_python_callables(sdb):
     Gp = lambda y, t: np.array([[0.3 * (y[0] > 0) * y[0], 0.1], [0.05 * (y[1] <= 0.1), 0.2]])
     assert rel_err(sdb.stratHeun(fp, Gp, z0, ts, dW=dW), orc.heun(fp, Gp, z0, ts, dW)) <= TOL
     assert rel_err(sdb.itoSRI2(fp, Gp, z0, ts, dW=dW, I=I), orc.srk2(fp, Gp, z0, ts, dW, I)) <= TOL
+    # one independent multiplicative noise per component is recognised as diagonal: no Levy areas are drawn,
+    # and the paths equal those of the full construction on the same seed
+    sig = np.array([0.2, 0.3, 0.1])
+    fd = lambda y, t: -y + 0.1 * np.sin(y)
+    Gd = lambda y, t: np.diag(sig * y * (1 + 0.1 * np.cos(t)))
+    yd = sdb.itoSRI2(fd, Gd, np.ones(3), ts, paths=50, seed=4)
+    from sdeint_b200 import integrate as _integ
+    _, _, fo, Go, *_ = _integ._check_args(fd, Gd, np.ones(3), ts)
+    assert Go.kind == sdb.ops.DIFF_USER_DIAG
+    yfull = sdb.itoSRI2(fo, sdb.ops.ExprDiffusion(Go.exprs, diagonal=False), np.ones(3), ts, paths=50, seed=4)
+    assert rel_err(yd, yfull) <= TOL
     # what cannot be traced is refused, like any other bad argument
     with pytest.raises(sdb.SDEValueError, match="could not be turned into a device function"):
         sdb.itoint(lambda y, t: -y if y[0] > 0 else y, Gn, z0, ts)

@@ -458,6 +458,13 @@ def test_python_callables_are_traced_into_device_operators():
     assert "fmax(y[1],0.0)" in fo.exprs[1] and "fmax" in Go.source
     for y in (np.array([1.2, 0.05]), np.array([0.9, -0.01])):
         assert np.allclose(fo(y, 0.0), f(y, 0.0)) and np.allclose(Go(y, 0.0), G(y, 0.0))
+    # one independent multiplicative noise per component: recognised as diagonal (no Levy areas needed)
+    sig = np.array([0.2, 0.3, 0.1])
+    _, _, _, Gd, *_ = integrate._check_args(lambda y, t: -y, lambda y, t: np.diag(sig * y * (1 + 0.1 * np.cos(t))),
+                                            np.ones(3), ts)
+    assert Gd.kind == ops.DIFF_USER_DIAG
+    _, _, _, Gn, *_ = integrate._check_args(lambda y, t: -y, lambda y, t: np.diag(sig * y[::-1]), np.ones(3), ts)
+    assert Gn.kind == ops.DIFF_USER                                   # G_kk depends on another component
     # not traceable: a branch on y; wrong shapes
     with pytest.raises(sdb.SDEValueError, match="could not be turned into a device function"):
         integrate._check_args(lambda y, t: -y if y[0] > 0 else y, G, np.array([0.4, 0.9]), ts)
