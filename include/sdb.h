@@ -48,6 +48,7 @@ extern "C" {
 #define SDB_DIFF_KP4446 2      /* params b                 G = b (1 - y^2) */
 #define SDB_DIFF_KPS445 3      /* params sqrt2             G = sqrt2 cos^2 y */
 #define SDB_DIFF_DIAG_LINEAR 4 /* params b[d]              g_k = b_k y_k e_k, m = d: DIAGONAL noise */
+#define SDB_DIFF_AFFINE_COLS 5 /* params B[m][d][d], C[d][m]  g_k = B_k y + c_k (multiplicative + additive noise) */
 #define SDB_DIFF_USER 9 /* NVRTC: __device__ void sde_diffusion_col(int k, const double* y, double t, const double* p, double* out) */
 #define SDB_DIFF_USER_DIAG 10 /* as SDB_DIFF_USER, and the caller guarantees diagonal noise (m = d, column k has
                                  only component k and depends only on y_k): SRI2/SRS2 then need only the

@@ -325,6 +325,7 @@ static int expected_params(int kind, bool drift, int d, int m, int64_t* n) {
       case SDB_DIFF_KP4446: *n = 1; return (d == 1 && m == 1) ? 0 : 1;
       case SDB_DIFF_KPS445: *n = 1; return (d == 1 && m == 1) ? 0 : 1;
       case SDB_DIFF_DIAG_LINEAR: *n = d; return d == m ? 0 : 1;
+      case SDB_DIFF_AFFINE_COLS: *n = (int64_t)m * d * d + (int64_t)d * m; return 0;
       case SDB_DIFF_USER: *n = -1; return 0;
       case SDB_DIFF_USER_DIAG: *n = -1; return d == m ? 0 : 1;
     }
@@ -415,6 +416,8 @@ static std::string type_of(const sdb_system* s, bool drift) {
       case SDB_DIFF_KP4446: o << "DiffKP4446<" << ps_g << ">"; break;
       case SDB_DIFF_KPS445: o << "DiffKPS445<" << ps_g << ">"; break;
       case SDB_DIFF_DIAG_LINEAR: o << "DiffDiagLinear<" << s->d << ", " << ps_g << ">"; break;
+      case SDB_DIFF_AFFINE_COLS:
+        o << "DiffAffineCols<" << s->d << ", " << s->m << ", " << ps_g << ">"; break;
       case SDB_DIFF_USER_DIAG:
         o << "DiffUser<" << s->d << ", " << s->m << ", " << ps_g << ", true>"; break;
       default: o << "DiffUser<" << s->d << ", " << s->m << ", " << ps_g << ">";
@@ -642,14 +645,19 @@ static int integrate_impl(sdb_system* s, const sdb_integrate_args* a, const SdbO
   // ANY drift (built-in or NVRTC source) with linear diffusion g_k = B_k y, SRI2/SRS2 + Ikpw/Jkpw on device
   // noise: the fused kernel with the drift evaluated per lane (SDB_FUSED_A2 -1 in sdb_fused.cuh) -- the
   // products with the B_k stay on the tensor instructions, only the two drift evaluations are user code.
-  bool jit_ud = false;
+  bool jit_ud = false, jit_aff = false;
+  // affine diffusion g_k = B_k y + c_k (SDB_FUSED_AFFINE): the 8-warp kernel only, linear or any drift
+  const bool aff_g = s->gk == SDB_DIFF_AFFINE_COLS;
   const bool ud_ok = !fused && a->scheme == SDB_SCHEME_SRK2 && noise != SDB_NOISE_HOST && need_ij &&
-                     s->fk != SDB_DRIFT_LINEAR && s->gk == SDB_DIFF_LINEAR_COLS &&
+                     (s->fk != SDB_DRIFT_LINEAR || aff_g) && (s->gk == SDB_DIFF_LINEAR_COLS || aff_g) &&
                      n_terms <= SDB_FUSED_MAX_TERMS && !getenv("SDB_DISABLE_FUSED") &&
                      !getenv("SDB_DISABLE_FUSED_JIT") && s->d * s->m >= 16;
-  if (ud_ok && noise == SDB_NOISE_KPW && SdbFusedDims(s->d, s->m, 4, -1).supported()) {
-    const SdbFusedDims dims(s->d, s->m, 4, -1);
-    const std::string key = std::string("fusedjit|ud") + ext_suffix(ext);
+  if (ud_ok && noise == SDB_NOISE_KPW &&
+      SdbFusedDims(s->d, s->m, 4, s->fk == SDB_DRIFT_LINEAR ? SDB_FUSED_A2 : -1).supported()) {
+    // (a linear drift with affine diffusion keeps its table rows: A, A^2)
+    const bool lin_f = s->fk == SDB_DRIFT_LINEAR;
+    const SdbFusedDims dims(s->d, s->m, 4, lin_f ? SDB_FUSED_A2 : -1);
+    const std::string key = std::string(lin_f ? "fusedjit" : "fusedjit|ud") + (aff_g ? "|aff" : "") + ext_suffix(ext);
     std::lock_guard<std::mutex> lk(s->mu);
     auto it = s->jit.find(key);
     if (it == s->jit.end()) {
@@ -659,22 +667,27 @@ static int integrate_impl(sdb_system* s, const sdb_integrate_args* a, const SdbO
       src << "#include \"sdb_kernels.cuh\"\n";
       if (s->fk == SDB_DRIFT_USER) src << "#line 1 \"user_source.cu\"\n" << s->src << "\n";
       src << "typedef " << type_of(s, true) << " F_jit;\n";
-      src << "#define SDB_FUSED_A2 (-1)\n#define SDB_FUSED_DRIFT_T F_jit\n#include \"sdb_fused.cuh\"\n"
-          << "SDB_FUSED_KERNEL_UD(sdb_jit_fused, " << s->d << ", " << s->m << ")\n";
+      if (aff_g) src << "#define SDB_FUSED_AFFINE 1\n";
+      if (lin_f)
+        src << "#include \"sdb_fused.cuh\"\nSDB_FUSED_KERNEL(sdb_jit_fused, " << s->d << ", " << s->m << ")\n";
+      else
+        src << "#define SDB_FUSED_A2 (-1)\n#define SDB_FUSED_DRIFT_T F_jit\n#include \"sdb_fused.cuh\"\n"
+            << "SDB_FUSED_KERNEL_UD(sdb_jit_fused, " << s->d << ", " << s->m << ")\n";
       JitKernel k;
       if (jit_compile(src.str(), "sdb_jit_fused", &k)) return 1;
       it = s->jit.emplace(key, k).first;
     }
-    jit_xr = -1;
-    jit_ud = true;
+    jit_xr = lin_f ? SDB_FUSED_A2 : -1;
+    jit_ud = !lin_f;
+    jit_aff = aff_g;
     jit_entry = SdbFusedEntry{s->d, s->m, 0, (const void*)it->second.kern, dims.smem_bytes(),
-                              dims.table_doubles(), nullptr, SdbFusedDims::THREADS,
-                              SdbFusedDims::THREADS, SDB_NOISE_KPW, SDB_SCHEME_SRK2};
+                              dims.table_doubles() + (aff_g ? (size_t)s->d * s->m : 0), nullptr,
+                              SdbFusedDims::THREADS, SdbFusedDims::THREADS, SDB_NOISE_KPW, SDB_SCHEME_SRK2};
     fused = &jit_entry;
     label = "jit:" + key;
   }
   // ... Iwik/Jwik and the larger shapes through the TMEM-resident kernel (sdb_fusedx.cuh, one lane per path)
-  if (ud_ok && !fused && SdbFusedXDims(s->d, s->m, -1).supported()) {
+  if (ud_ok && !fused && !aff_g && SdbFusedXDims(s->d, s->m, -1).supported()) {
     const SdbFusedXDims xdims(s->d, s->m, -1);
     const bool wik = noise == SDB_NOISE_WIK;
     const std::string key = std::string(wik ? "fusedxjit|wik|ud" : "fusedxjit|kpw|ud") + ext_suffix(ext);
@@ -826,6 +839,12 @@ static int integrate_impl(sdb_system* s, const sdb_integrate_args* a, const SdbO
       if (fused->build) fused->build(s->fp.data(), s->gp.data(), tab.data());
       else if (jit_comm) SdbFusedCDims(s->d, s->m).build_tables(s->fp.data(), s->gp.data(), tab.data());
       else SdbFusedDims(s->d, s->m, jit_rb, jit_xr).build_tables(s->fp.data(), s->gp.data(), tab.data());
+      if (jit_aff) {  // the constants c_k after the tables, as [j][row] (sdb_fused.cuh, SDB_FUSED_AFFINE)
+        const size_t nb = (size_t)s->m * s->d * s->d;
+        double* caff = tab.data() + tab.size() - (size_t)s->d * s->m;
+        for (int j = 0; j < s->m; ++j)
+          for (int r = 0; r < s->d; ++r) caff[(size_t)j * s->d + r] = s->gp[nb + (size_t)r * s->m + j];
+      }
       double* d = nullptr;
       SDB_CUDA(cudaMalloc(&d, tab.size() * sizeof(double)));
       SDB_CUDA(cudaMemcpy(d, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));

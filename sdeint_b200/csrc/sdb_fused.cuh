@@ -36,6 +36,9 @@
                            //    and wait in tensor memory (one 32x32b lane per path, 4 columns per 128-bit
                            //    block); the noise phase then only loads, converts and transforms them.
                            //    Needs n_terms <= SDB_FUSED_AHEAD_TERMS and an even number of Wiener processes.
+#ifndef SDB_FUSED_AFFINE
+#define SDB_FUSED_AFFINE 0  // 1 (NVRTC builds): g_k = B_k y + c_k -- the constants (after the tables, [j][row]) are
+#endif                      //    added to the entries of G_n as P2 reads them; the stage-2 differences cancel them
 #ifndef SDB_FUSED_ANTIPHASE
 #define SDB_FUSED_ANTIPHASE 0  // 1: the two warps of a sub-partition (w, w + 4) are held half a step apart by a
 #endif                         //    named barrier: one generates noise while the other runs its row blocks
@@ -659,6 +662,9 @@ struct SdbFusedBlock {
         for (int r = 0; r < RN; ++r) {
           const int n = j * RN + r;
           gj[r] = g[n * 32 + (lane ^ sdb_swz(n))];
+#if SDB_FUSED_AFFINE
+          gj[r] += __ldg(frag + (size_t)Sh::n_frags() * 32 + Sh::n_left() + Sh::n_ks() + j * D + R0 + r);
+#endif
           GdW[r] = fma(gj[r], dWj, GdW[r]);
         }
 #pragma unroll

@@ -580,6 +580,22 @@ struct DiffLinearCols {  // g_k = B_k y
   }
 };
 
+template <int D_, int M_, class PS>
+struct DiffAffineCols {  // g_k = B_k y + c_k: params B[m][d][d] then C[d][m]
+  static constexpr int D = D_, M = M_;
+  static constexpr bool ADDITIVE = false, DIAGONAL = false;
+  typedef PS Params;
+  static SDB_DEV void col(const PS& p, int k, const double (&y)[D], double, double (&out)[D]) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      double acc = p[M * D * D + i * M + k];
+#pragma unroll
+      for (int j = 0; j < D; ++j) acc = fma(p[(k * D + i) * D + j], y[j], acc);
+      out[i] = acc;
+    }
+  }
+};
+
 // g_k linear in y (no offset): differences g_k(a) - g_k(b) = g_k(a - b) exactly
 template <class G_> struct SdbGLinear { static constexpr bool value = false; };
 template <int D_, int M_, class PS>

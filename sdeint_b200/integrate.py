@@ -161,7 +161,7 @@ def _check_args(f, G, y0, tspan, dW=None, IJ=None):
     # those exist (d m >= 16: below that the unrolled source, whose structural zeros vanish, is the faster one)
     if d * Gop.m >= 16:
         Gop = ops.as_linear(Gop)
-        if Gop.kind == ops.DIFF_LINEAR_COLS:
+        if Gop.kind in (ops.DIFF_LINEAR_COLS, ops.DIFF_AFFINE_COLS):
             f = ops.as_linear(f, dense_only=True)
     m = Gop.m
     N = len(tspan)

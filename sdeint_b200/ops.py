@@ -35,6 +35,7 @@ DIFF_LINEAR_COLS = 1  # params: B[m][d][d]                             g_k = B_k
 DIFF_KP4446 = 2       # params: b                                      G = b (1 - y^2)
 DIFF_KPS445 = 3       # params: (none; one dummy)                      G = sqrt2 cos^2 y
 DIFF_DIAG_LINEAR = 4  # params: b[d]                                   g_k = b_k y_k e_k (m = d)
+DIFF_AFFINE_COLS = 5  # params: B[m][d][d], C[d][m]                    g_k = B_k y + c_k
 DIFF_USER = 9
 DIFF_USER_DIAG = 10   # NVRTC source, diagonal noise promised by the caller
 
@@ -181,6 +182,28 @@ class LinearDiffusion(DiffusionOp):
 
     def column(self, k, y, t):
         return self.B[k].dot(y)
+
+
+class AffineDiffusion(DiffusionOp):
+    """g_k(y, t) = B_k y + c_k: multiplicative and additive noise together (B of shape (m, d, d), C of shape
+    (d, m) with columns c_k).  The stage-2 differences of SRI2/SRS2 do not see the constants, so the fused
+    tensor-instruction kernels apply as for LinearDiffusion (sdb_fused.cuh, SDB_FUSED_AFFINE)."""
+    kind = DIFF_AFFINE_COLS
+
+    def __init__(self, B, C):
+        B = np.asarray(B, dtype=np.float64)
+        C = np.asarray(C, dtype=np.float64)
+        if B.ndim != 3 or B.shape[1] != B.shape[2] or C.shape != (B.shape[1], B.shape[0]):
+            raise ValueError("AffineDiffusion needs B of shape (m, d, d) and C of shape (d, m)")
+        self.B, self.C = np.ascontiguousarray(B), np.ascontiguousarray(C)
+        self.m, self.d = B.shape[0], B.shape[1]
+        self.params = np.concatenate([self.B.reshape(-1), self.C.reshape(-1)])
+
+    def __call__(self, y, t):
+        return np.dot(self.B, y).T + self.C
+
+    def column(self, k, y, t):
+        return self.B[k].dot(y) + self.C[:, k]
 
 
 class DiagLinearDiffusion(DiffusionOp):
@@ -350,7 +373,9 @@ def _prelude(exprs):
 def _check_expr(expr):
     import re
     expr = str(expr)
-    for name in re.findall(r"[A-Za-z_]\w*", expr):
+    # (numeric literals first: the e of 1.5e-06 is not a name; an identifier such as y2 keeps its digits)
+    bare = re.sub(r"(?<![\w.])(?:\d+\.?\d*|\.\d+)(?:[eE][+-]?\d+)?", " ", expr)
+    for name in re.findall(r"[A-Za-z_]\w*", bare):
         if name not in _EXPR_FUNCS and name not in ("y", "t", "p"):
             raise ValueError("unknown name %r in expression %r (allowed: y[i], t, p[i], %s)"
                              % (name, expr, ", ".join(_EXPR_FUNCS)))
@@ -476,8 +501,16 @@ def as_linear(op, dense_only=False):
             B = np.stack([np.stack([cols[l][:, k] for l in range(d)], axis=1) for k in range(op.m)])  # (m, d, d)
             lin = lambda y: np.dot(B, y).T
             scale = max(1.0, float(np.abs(B).max()))
-            ok = np.abs(np.asarray(op(np.zeros(d), 0.0), dtype=np.float64)).max() == 0.0
-            cand = LinearDiffusion(B) if ok else None
+            G0 = np.asarray(op(np.zeros(d), 0.0), dtype=np.float64)                                     # (d, m)
+            ok = bool(np.all(np.isfinite(G0)))
+            if ok and np.abs(G0).max() == 0.0:
+                cand = LinearDiffusion(B)
+            elif ok:                                   # B_k y + c_k: read B off G(e_l) - G(0)
+                B = B - G0.T[:, :, None]
+                lin = lambda y: np.dot(B, y).T + G0
+                cand = AffineDiffusion(B, G0)
+            else:
+                cand = None
         for trial in range(4):
             if not ok:
                 break

@@ -319,6 +319,40 @@ def test_reference_style_python_callables(sdb):
         sdb.itoint(lambda y, t: -y if y[0] > 0 else y, Gn, z0, ts)
 
 
+@pytest.mark.parametrize("d,m,linear_drift", [(10, 10, True), (10, 10, False), (6, 4, False)])
+def test_affine_diffusion_fused(sdb, monkeypatch, d, m, linear_drift):
+    """g_k = B_k y + c_k (multiplicative + additive noise): the fused kernel with the constants added to G_n
+    (`jit:fusedjit|aff`, `jit:fusedjit|ud|aff`) against the oracle on replayed device noise and the generic
+    kernel; an affine ExprDiffusion is promoted to it."""
+    fL, GL, y0 = sdb.ops.sys_lin(d, m)
+    rng = np.random.default_rng(8)
+    Cc = 0.05 * rng.standard_normal((d, m))
+    G = sdb.ops.AffineDiffusion(GL.B, Cc)
+    f = fL if linear_drift else sdb.ops.ExprDrift(
+        ["-1.2*y[%d] + 0.3*y[%d] - 0.2*y[%d]*y[%d]*y[%d]" % (i, (i + 1) % d, i, i, i) for i in range(d)])
+    tspan = np.linspace(0.0, 0.2, 41)
+    h = 0.2 / 40
+    P, seed = 50, 321
+    for strat, integ, rep in ((False, sdb.itoSRI2, sdb.Ikpw), (True, sdb.stratSRS2, sdb.Jkpw)):
+        y = integ(f, G, y0, tspan, rep, paths=P, seed=seed)
+        assert sdb.last_kernel() == ("jit:fusedjit|aff" if linear_drift else "jit:fusedjit|ud|aff")
+        dW = sdb.deltaW(40, m, h, paths=P, seed=seed)
+        _, IJ = rep(dW, h, seed=seed, ensemble=True)
+        for p in (0, 31, 32, P - 1):
+            assert rel_err(y[p], orc.srk2(f, G, np.asarray(y0, float), tspan, dW[p], IJ[p])) <= TOL
+    monkeypatch.setenv("SDB_DISABLE_FUSED", "1")
+    yg = sdb.stratSRS2(f, G, y0, tspan, sdb.Jkpw, paths=P, seed=seed)
+    monkeypatch.delenv("SDB_DISABLE_FUSED")
+    assert rel_err(yg, y) <= TOL
+    # host-supplied noise and the other schemes go through the generic kernels with the same operator
+    assert rel_err(sdb.stratHeun(f, G, y0, tspan, dW=dW[3]), orc.heun(f, G, np.asarray(y0, float), tspan, dW[3])) <= TOL
+    if d * m >= 16 and not linear_drift:
+        GE = sdb.ops.ExprDiffusion([["+".join("%r*y[%d]" % (float(GL.B[k, i, l]), l) for l in range(d)) +
+                                     "+%r" % float(Cc[i, k]) for k in range(m)] for i in range(d)])
+        ye = sdb.stratSRS2(f, GE, y0, tspan, sdb.Jkpw, paths=P, seed=seed)
+        assert sdb.last_kernel() == "jit:fusedjit|ud|aff" and rel_err(ye, y) <= 1e-13
+
+
 def test_nvrtc_results_are_cached_on_disk(tmp_path):
     """A second process integrating the same user system loads its kernels from $SDB_CACHE_DIR instead of
     compiling them again (same results, bit for bit); SDB_JIT_CACHE=0 compiles."""

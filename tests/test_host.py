@@ -384,11 +384,19 @@ def test_linear_expressions_are_promoted_to_linear_operators():
     assert ops.as_linear(sparse, dense_only=True) is sparse                   # cheap drift: stays source
     assert isinstance(ops.as_linear(sparse), ops.LinearDrift)
     for bad in (ops.ExprDiffusion([["y[0]*y[1]", "y[1]"], ["y[0]", "0.5*y[1]"]]),          # nonlinear
-                ops.ExprDiffusion([["y[0] + 0.1", "y[1]"], ["y[0]", "0.5*y[1]"]]),         # affine
                 ops.ExprDiffusion([["y[0]*cos(t)", "y[1]"], ["y[0]", "0.5*y[1]"]]),        # time-dependent
                 ops.ExprDiffusion([["y[0]", "0"], ["0", "y[1]"]], diagonal=True),          # own fast path
                 ops.ExprDrift(["sin(y[0])", "y[1]"])):
         assert ops.as_linear(bad) is bad
+    # linear + additive noise: g_k = B_k y + c_k
+    aff = ops.as_linear(ops.ExprDiffusion([["y[0] + 0.1", "y[1]"], ["y[0] - 0.3", "0.5*y[1]"]]))
+    assert isinstance(aff, ops.AffineDiffusion) and aff.kind == ops.DIFF_AFFINE_COLS
+    assert np.array_equal(aff.C, [[0.1, 0.0], [-0.3, 0.0]])
+    assert np.array_equal(aff.B, [[[1.0, 0.0], [1.0, 0.0]], [[0.0, 1.0], [0.0, 0.5]]])
+    yy = rng.standard_normal(2)
+    assert np.allclose(aff(yy, 0.0), [[yy[0] + 0.1, yy[1]], [yy[0] - 0.3, 0.5 * yy[1]]])
+    assert np.allclose(aff.column(1, yy, 0.0), [yy[1], 0.5 * yy[1]])
+    assert aff.params.shape == (2 * 2 * 2 + 2 * 2,)
     # the shim promotes where the linear operators have fused kernels (d m >= 16), and only there
     ts = np.linspace(0.0, 1.0, 11)
     _, _, f2, G2, *_ = integrate._check_args(fd, G, np.ones(d), ts, None, None)
@@ -488,3 +496,20 @@ def test_python_callables_are_traced_into_device_operators():
                               np.zeros(3), ts)                       # test_integrate.py:31-32 (mismatched f)
     with pytest.raises(sdb.SDEValueError):
         integrate._check_args(3.0, G, np.array([0.4, 0.9]), ts)
+
+
+def test_expression_literals_with_exponents():
+    """Scientific notation in formulas (traced constants such as 1e-05 are written that way): the e of a literal
+    is not a name; unknown names are still refused."""
+    from sdeint_b200 import integrate, ops
+    for e, want in (("9.007211014759403e-06*y[0]+1e5", 9.007211014759403e-06 + 1e5), ("2.5E+3*t", 1250.0),
+                    (".5e-3+y[0]", 1.0005)):
+        assert ops._check_expr(e) == e
+        assert ops._expr_eval(e, np.array([1.0, 2.0]), 0.5, np.zeros(1)) == pytest.approx(want, rel=1e-15)
+    assert "1e-05*y[0]" in ops.ExprDrift(["1e-05*y[0]"]).source
+    for bad in ("e*y[0]", "1e-5*q", "y2+1", "exp2(y[0])"):
+        with pytest.raises(ValueError):
+            ops._check_expr(bad)
+    _, _, fo, *_ = integrate._check_args(lambda y, t: 1e-7 * y - 3e-12, lambda y, t: 2.5e-9, 1.0,
+                                         np.linspace(0, 1, 5))
+    assert np.allclose(fo(np.array([2.0]), 0.0), 2e-7 - 3e-12, rtol=1e-15)
