@@ -349,6 +349,7 @@ class CudaDiffusion(DiffusionOp):
 # callable handed to the oracle in tests, so no CUDA has to be written by hand.
 
 _EXPR_FUNCS = ("sin", "cos", "tan", "exp", "log", "sqrt", "pow", "fabs", "tanh", "sinh", "cosh", "fmax", "fmin",
+               "atan", "asin", "acos", "atan2", "hypot", "log1p", "expm1", "log10", "log2", "cbrt",
                "lt", "le", "gt", "ge")   # comparisons as 0.0 / 1.0 (masks for piecewise formulas)
 # device definitions of the names that are not C math functions (guarded: drift and diffusion sources of one
 # system are compiled as one translation unit)
@@ -359,7 +360,8 @@ _EXPR_PRELUDE = (
     "__device__ __forceinline__ double gt(double a, double b) { return a > b ? 1.0 : 0.0; }\n"
     "__device__ __forceinline__ double ge(double a, double b) { return a >= b ? 1.0 : 0.0; }\n"
     "#endif\n")
-_EXPR_PY = {"fabs": np.abs, "pow": np.power,
+_EXPR_PY = {"fabs": np.abs, "pow": np.power, "atan": np.arctan, "asin": np.arcsin, "acos": np.arccos,
+            "atan2": np.arctan2,
             "lt": lambda a, b: float(a < b), "le": lambda a, b: float(a <= b),
             "gt": lambda a, b: float(a > b), "ge": lambda a, b: float(a >= b)}
 

@@ -5,7 +5,8 @@ the arithmetic done on them, and the recorded expressions become an `ops.ExprDri
 exactly linear are handed on to `ConstDiffusion` / `LinearDrift` / `LinearDiffusion`, i.e. to the additive-noise
 path and the tensor-instruction kernels (ops.as_linear).
 
-What can be traced: + - * / **, unary minus, abs, numpy ufuncs sin cos tan exp log sqrt tanh sinh cosh,
+What can be traced: + - * / **, unary minus, abs, numpy ufuncs sin cos tan exp log sqrt tanh sinh cosh log1p
+expm1 log10 log2 cbrt arctan arcsin arccos arctan2 hypot,
 np.maximum / np.minimum / np.sign / np.heaviside, comparisons used as 0/1 masks (also on arrays of symbols: `np.sin(y)`, `A.dot(y)`, `y**2`, `np.array([...])`), indexing, closures over
 numbers and arrays.  What cannot: anything that needs the VALUE of y or t while tracing -- comparisons and
 branches on y, float(y), np.where on symbols, calls into compiled code.  Those raise TraceError
@@ -16,7 +17,10 @@ import numbers
 
 import numpy as np
 
-_FUNCS = ("sin", "cos", "tan", "exp", "log", "sqrt", "tanh", "sinh", "cosh")
+_FUNCS = ("sin", "cos", "tan", "exp", "log", "sqrt", "tanh", "sinh", "cosh", "log1p", "expm1", "log10", "log2",
+          "cbrt")
+_RENAMED = {"arctan": "atan", "arcsin": "asin", "arccos": "acos"}      # numpy name -> C name
+_BINARY = {"arctan2": "atan2", "hypot": "hypot"}
 
 
 class TraceError(Exception):
@@ -134,7 +138,13 @@ class Sym:
         if self.c is not None:
             with np.errstate(all="ignore"):
                 return Sym(c=float(getattr(np, name)(self.c)))
-        return Sym("%s(%s)" % (name, self.e))
+        return Sym("%s(%s)" % (_RENAMED.get(name, name), self.e))
+
+    def _fn2(self, other, name):
+        a, b = self, Sym.of(other)
+        if a.c is not None and b.c is not None:
+            return Sym(c=float(getattr(np, name)(a.c, b.c)))
+        return Sym("%s(%s,%s)" % (_BINARY[name], a.s, b.s))
 
     def sin(self): return self._fn("sin")
     def cos(self): return self._fn("cos")
@@ -145,6 +155,16 @@ class Sym:
     def tanh(self): return self._fn("tanh")
     def sinh(self): return self._fn("sinh")
     def cosh(self): return self._fn("cosh")
+    def log1p(self): return self._fn("log1p")
+    def expm1(self): return self._fn("expm1")
+    def log10(self): return self._fn("log10")
+    def log2(self): return self._fn("log2")
+    def cbrt(self): return self._fn("cbrt")
+    def arctan(self): return self._fn("arctan")
+    def arcsin(self): return self._fn("arcsin")
+    def arccos(self): return self._fn("arccos")
+    def arctan2(self, o): return self._fn2(o, "arctan2")
+    def hypot(self, o): return self._fn2(o, "hypot")
 
     def conjugate(self):
         return self
@@ -198,8 +218,10 @@ class Sym:
             return x._cmp(0.0, "gt", False) + h0 * (x._cmp(0.0, "ge", False) - x._cmp(0.0, "gt", False))
         if name == "clip" and len(a) == 3:
             return Sym._apply("minimum", [Sym._apply("maximum", [a[0], a[1]]), a[2]])
-        if name in _FUNCS and len(a) == 1:
+        if (name in _FUNCS or name in _RENAMED) and len(a) == 1:
             return a[0]._fn(name)
+        if name in _BINARY and len(a) == 2:
+            return a[0]._fn2(a[1], name)
         raise TraceError("numpy.%s cannot be traced (supported: arithmetic, abs, %s)" % (name, ", ".join(_FUNCS)))
 
     # comparisons are recorded as 0.0 / 1.0 masks ((y > 0) * a + (y <= 0) * b); using one as the condition of a

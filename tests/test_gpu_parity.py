@@ -303,6 +303,9 @@ def test_reference_style_python_callables(sdb):
     Gp = lambda y, t: np.array([[0.3 * (y[0] > 0) * y[0], 0.1], [0.05 * (y[1] <= 0.1), 0.2]])
     assert rel_err(sdb.stratHeun(fp, Gp, z0, ts, dW=dW), orc.heun(fp, Gp, z0, ts, dW)) <= TOL
     assert rel_err(sdb.itoSRI2(fp, Gp, z0, ts, dW=dW, I=I), orc.srk2(fp, Gp, z0, ts, dW, I)) <= TOL
+    fe = lambda y, t: np.array([np.arctan(y[1]) - np.log1p(y[0] * y[0]) + np.expm1(-t),
+                                np.arctan2(y[0], 1.0 + y[1] * y[1]) - np.cbrt(y[1]) + np.hypot(y[0], 0.5) - 0.5])
+    assert rel_err(sdb.stratHeun(fe, Gn, z0, ts, dW=dW), orc.heun(fe, Gn, z0, ts, dW)) <= TOL
     # one independent multiplicative noise per component is recognised as diagonal: no Levy areas are drawn,
     # and the paths equal those of the full construction on the same seed
     sig = np.array([0.2, 0.3, 0.1])

@@ -473,6 +473,12 @@ def test_python_callables_are_traced_into_device_operators():
     assert Gd.kind == ops.DIFF_USER_DIAG
     _, _, _, Gn, *_ = integrate._check_args(lambda y, t: -y, lambda y, t: np.diag(sig * y[::-1]), np.ones(3), ts)
     assert Gn.kind == ops.DIFF_USER                                   # G_kk depends on another component
+    # more elementary functions (numpy name -> C name where they differ)
+    fe = lambda y, t: (np.arctan(y) + np.arctan2(y, 1 + y * y) + np.arcsin(np.tanh(y)) + np.log1p(y * y)
+                       + np.expm1(-y * y) + np.log10(1 + y * y) + np.cbrt(y) + np.hypot(y, 1.0))
+    _, _, fo, *_ = integrate._check_args(fe, lambda y, t: 0.1 * np.eye(3), np.ones(3), ts)
+    yy = rng.standard_normal(3)
+    assert "atan2(" in fo.exprs[0] and np.allclose(fo(yy, 0.0), fe(yy, 0.0), rtol=1e-13)
     # not traceable: a branch on y; wrong shapes
     with pytest.raises(sdb.SDEValueError, match="could not be turned into a device function"):
         integrate._check_args(lambda y, t: -y if y[0] > 0 else y, G, np.array([0.4, 0.9]), ts)
