@@ -244,8 +244,8 @@ class Sym:
     # anything that needs the value
     def _no_value(self, *a, **k):
         raise TraceError("the function needs the value of y or t while it is traced (a comparison or branch, "
-                         "float() / math.* on y, or storing into a preallocated float array: build the result with "
-                         "np.array([...]) instead); only arithmetic and numpy's elementary functions can be traced")
+                         "float() / math.* on y, or storing into an array created with an explicit float dtype); only "
+                         "arithmetic and numpy's elementary functions can be traced")
 
     __bool__ = __float__ = __int__ = __index__ = _no_value
     __eq__ = __ne__ = _no_value
@@ -284,6 +284,38 @@ class SymArray(np.ndarray):
         return out.view(SymArray) if isinstance(out, np.ndarray) and out.dtype == object else out
 
 
+import contextlib
+import threading
+
+_PATCH_LOCK = threading.Lock()
+
+
+@contextlib.contextmanager
+def _object_allocators():
+    """While a function is traced, np.zeros / ones / empty / full without an explicit dtype return OBJECT arrays, so
+    the common `out = np.zeros(d); out[0] = ...; return out` can hold symbols (a float array cannot).  The
+    originals are restored on exit; one trace at a time (the patch is process-wide)."""
+    names = ("zeros", "ones", "empty", "full")
+    orig = {n: getattr(np, n) for n in names}
+
+    def wrap(fn):
+        def alloc(*args, **kwargs):
+            npos = 3 if fn is orig["full"] else 2           # position of dtype among the positional arguments
+            if "dtype" not in kwargs and len(args) < npos:
+                kwargs["dtype"] = object
+            return fn(*args, **kwargs)
+        return alloc
+
+    with _PATCH_LOCK:
+        try:
+            for n in names:
+                setattr(np, n, wrap(orig[n]))
+            yield
+        finally:
+            for n in names:
+                setattr(np, n, orig[n])
+
+
 def _strings(res, shape, what):
     """The traced return value as an object array of expression strings of the given shape."""
     if isinstance(res, (list, tuple)):
@@ -314,7 +346,9 @@ def trace_drift(f, d, scalar=False):
     """The drift operator of a Python callable f(y, t) -> (d,) (a scalar for scalar y0)."""
     from . import ops
     y, t = _symbols(d, scalar)
-    exprs = _strings(f(y, t), (d,), "f(y, t)")
+    with _object_allocators():
+        res = f(y, t)
+    exprs = _strings(res, (d,), "f(y, t)")
     op = ops.ExprDrift(list(exprs))
     op.traced_from = f
     return op
@@ -327,10 +361,13 @@ def trace_diffusion(G, d, scalar=False):
     from . import ops
     y, t = _symbols(d, scalar)
     if isinstance(G, (list, tuple)):
-        cols = [_strings(g(y, t), (d,), "g_k(y, t)") for g in G]
+        with _object_allocators():
+            raw = [g(y, t) for g in G]
+        cols = [_strings(r, (d,), "g_k(y, t)") for r in raw]
         table = np.stack(cols, axis=1)
     else:
-        res = G(y, t)
+        with _object_allocators():
+            res = G(y, t)
         arr = np.asarray(res, dtype=object)
         if d == 1 and arr.ndim == 0:                           # scalar equation, scalar G (m = 1)
             arr = arr.reshape(1, 1)

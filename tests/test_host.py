@@ -473,6 +473,24 @@ def test_python_callables_are_traced_into_device_operators():
     assert Gd.kind == ops.DIFF_USER_DIAG
     _, _, _, Gn, *_ = integrate._check_args(lambda y, t: -y, lambda y, t: np.diag(sig * y[::-1]), np.ones(3), ts)
     assert Gn.kind == ops.DIFF_USER                                   # G_kk depends on another component
+    # the preallocated-result idiom: np.zeros without a dtype gives an object array while tracing (and only then)
+    def fz(y, t):
+        dy = np.zeros(3)
+        dy[0] = -y[0] + y[1] * y[2]
+        dy[1] = np.sin(t) - y[1]
+        dy[2] = 1.0
+        return dy
+
+    def Gz(y, t):
+        Bz = np.zeros((3, 2))
+        Bz[0, 0] = 0.3 * y[0]
+        Bz[1, 1] = 0.1
+        Bz[2, :] = 0.05 * np.ones(2)
+        return Bz
+    _, m_, fo, Go, *_ = integrate._check_args(fz, Gz, np.ones(3), ts)
+    yy = rng.standard_normal(3)
+    assert m_ == 2 and np.allclose(fo(yy, 0.4), fz(yy, 0.4)) and np.allclose(Go(yy, 0.4), Gz(yy, 0.4))
+    assert np.zeros(2).dtype == np.float64 and np.full(2, 1.5).dtype == np.float64      # numpy is itself again
     # more elementary functions (numpy name -> C name where they differ)
     fe = lambda y, t: (np.arctan(y) + np.arctan2(y, 1 + y * y) + np.arcsin(np.tanh(y)) + np.log1p(y * y)
                        + np.expm1(-y * y) + np.log10(1 + y * y) + np.cbrt(y) + np.hypot(y, 1.0))
