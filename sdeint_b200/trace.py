@@ -332,6 +332,31 @@ def _strings(res, shape, what):
     return out
 
 
+_KEEP = (0.0, 0.5, 1.0, 2.0, 3.0, 4.0)
+
+
+def _lift(exprs):
+    """Numeric constants of the recorded expressions -> parameters p[k]: a sweep over the numbers a function
+    closes over then produces the SAME source every time (one NVRTC compilation, found again in the on-disk
+    cache by later processes) and only the parameter vector changes.  Structural constants (0, 1/2, 1 ... 4)
+    stay literals.  Returns (expressions, parameter vector)."""
+    import re
+    values, index = [], {}
+
+    def repl(mt):
+        v = float(mt.group(0))
+        if v in _KEEP:
+            return mt.group(0)
+        if v not in index:
+            index[v] = len(values)
+            values.append(v)
+        return "p[%d]" % index[v]
+
+    # every literal written by _lit has a '.' or an exponent; subscripts (y[3]) are bare integers
+    number = re.compile(r"(?<![\w\[.])(?:\d+\.\d*(?:[eE][+-]?\d+)?|\d+[eE][+-]?\d+)")
+    return [number.sub(repl, e) for e in exprs], np.array(values, dtype=np.float64)
+
+
 def _symbols(d, scalar):
     t = Sym("t")
     if scalar:
@@ -348,8 +373,8 @@ def trace_drift(f, d, scalar=False):
     y, t = _symbols(d, scalar)
     with _object_allocators():
         res = f(y, t)
-    exprs = _strings(res, (d,), "f(y, t)")
-    op = ops.ExprDrift(list(exprs))
+    exprs, params = _lift(list(_strings(res, (d,), "f(y, t)")))
+    op = ops.ExprDrift(exprs, params)
     op.traced_from = f
     return op
 
@@ -386,6 +411,9 @@ def trace_diffusion(G, d, scalar=False):
             (table[i, k] in ("0.0", "(-0.0)") if i != k
              else set(re.findall(r"y\[(\d+)\]", table[i, k])) <= {str(k)})
             for i in range(table.shape[0]) for k in range(table.shape[1]))
-        op = ops.ExprDiffusion([list(row) for row in table], diagonal=bool(diag))
+        flat, params = _lift([e for row in table for e in row])
+        mcols = table.shape[1]
+        op = ops.ExprDiffusion([flat[i * mcols:(i + 1) * mcols] for i in range(table.shape[0])], params,
+                               diagonal=bool(diag))
     op.traced_from = G
     return op

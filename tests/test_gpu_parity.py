@@ -315,7 +315,7 @@ def test_reference_style_python_callables(sdb):
     from sdeint_b200 import integrate as _integ
     _, _, fo, Go, *_ = _integ._check_args(fd, Gd, np.ones(3), ts)
     assert Go.kind == sdb.ops.DIFF_USER_DIAG
-    yfull = sdb.itoSRI2(fo, sdb.ops.ExprDiffusion(Go.exprs, diagonal=False), np.ones(3), ts, paths=50, seed=4)
+    yfull = sdb.itoSRI2(fo, sdb.ops.ExprDiffusion(Go.exprs, Go.params, diagonal=False), np.ones(3), ts, paths=50, seed=4)
     assert rel_err(yd, yfull) <= TOL
     # what cannot be traced is refused, like any other bad argument
     with pytest.raises(sdb.SDEValueError, match="could not be turned into a device function"):

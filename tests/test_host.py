@@ -497,6 +497,17 @@ def test_python_callables_are_traced_into_device_operators():
     _, _, fo, *_ = integrate._check_args(fe, lambda y, t: 0.1 * np.eye(3), np.ones(3), ts)
     yy = rng.standard_normal(3)
     assert "atan2(" in fo.exprs[0] and np.allclose(fo(yy, 0.0), fe(yy, 0.0), rtol=1e-13)
+    # numbers a function closes over become PARAMETERS: a sweep re-uses one source (one NVRTC compilation)
+    def make(a_, b_):
+        return (lambda x, t: -(a_ + x * b_ ** 2) * (1 - x ** 2)), (lambda x, t: b_ * (1 - x ** 2))
+    seen = set()
+    for a_, b_ in ((1.3, 0.7), (0.9, 1e-3), (2.7, 0.11)):
+        fa, ga = make(a_, b_)
+        _, _, fo, Go, *_ = integrate._check_args(fa, ga, 0.1, ts)
+        seen.add((fo.source, Go.source))
+        assert list(fo.params) == [a_, b_ ** 2] and list(Go.params) == [b_]
+        assert np.allclose(fo(np.array([0.37]), 0.0), fa(0.37, 0.0), rtol=1e-15)
+    assert len(seen) == 1
     # not traceable: a branch on y; wrong shapes
     with pytest.raises(sdb.SDEValueError, match="could not be turned into a device function"):
         integrate._check_args(lambda y, t: -y if y[0] > 0 else y, G, np.array([0.4, 0.9]), ts)
@@ -508,7 +519,8 @@ def test_python_callables_are_traced_into_device_operators():
                                 -np.sign(y[1]) * abs(y[1]) ** 0.5 + np.heaviside(t - 0.5, 0.5)])
     Gp = lambda y, t: np.array([[0.3 * (y > 0)[0], 0.1], [0.0, 0.2 * np.where(y > 0.5, 1.0, y * y)[1]]])
     _, _, fo, Go, *_ = integrate._check_args(fp, Gp, np.array([1.0, 0.04]), ts)
-    assert "gt(y[0],0.2)" in fo.exprs[0] and "SDB_EXPR_PRELUDE" in fo.source and "SDB_EXPR_PRELUDE" in Go.source
+    assert "gt(y[0],p[" in fo.exprs[0] and 0.2 in fo.params            # constants travel as parameters
+    assert "SDB_EXPR_PRELUDE" in fo.source and "SDB_EXPR_PRELUDE" in Go.source
     for y, t in ((np.array([1.2, 0.05]), 0.1), (np.array([0.1, -0.01]), 0.7), (np.array([0.2, 0.0]), 0.5),
                  (np.array([0.3, 0.9]), 0.5)):
         assert np.allclose(fo(y, t), fp(y, t)) and np.allclose(Go(y, t), np.asarray(Gp(y, t), float))
