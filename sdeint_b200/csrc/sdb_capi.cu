@@ -220,7 +220,12 @@ static int jit_compile(const std::string& source, const char* kernel_name, JitKe
   static const char* kOpts = "--gpu-architecture=sm_100a -std=c++17 -lineinfo --fmad=true -default-device";
   std::string cache_file;
   const std::string dir = jit_cache_dir();
-  if (!dir.empty()) {
+  // cubins of this process by the same key: a sweep that changes only parameter VALUES creates a new system
+  // per point but the same source -- it is compiled (or read from disk) once
+  static std::map<std::pair<uint64_t, uint64_t>, std::vector<char>> mem_cache;
+  static std::mutex mem_mu;
+  std::pair<uint64_t, uint64_t> mem_key(0, 0);
+  {
     static uint64_t hdr_hash[2] = {0, 0};
     static std::once_flag once;
     std::call_once(once, [&] {
@@ -235,10 +240,22 @@ static int jit_compile(const std::string& source, const char* kernel_name, JitKe
     });
     const uint64_t a = fnv1a64(source.data(), source.size(), hdr_hash[0]);
     const uint64_t b = fnv1a64(source.data(), source.size(), hdr_hash[1]);
+    mem_key = std::make_pair(a, b);
+    {
+      std::lock_guard<std::mutex> lk(mem_mu);
+      auto it = mem_cache.find(mem_key);
+      if (it != mem_cache.end() &&
+          cudaLibraryLoadData(&out->lib, it->second.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) == cudaSuccess &&
+          cudaLibraryGetKernel(&out->kern, out->lib, kernel_name) == cudaSuccess) {
+        if (text_bytes) *text_bytes = cubin_text_bytes(it->second);
+        g_jit_hits.fetch_add(1);
+        return 0;
+      }
+    }
     char name[64];
     snprintf(name, sizeof name, "/%016llx%016llx.cubin", (unsigned long long)a, (unsigned long long)b);
-    cache_file = dir + name;
-    if (FILE* fh = fopen(cache_file.c_str(), "rb")) {
+    if (!dir.empty()) cache_file = dir + name;
+    if (FILE* fh = cache_file.empty() ? nullptr : fopen(cache_file.c_str(), "rb")) {
       std::vector<char> cubin;
       char buf[1 << 16];
       size_t n;
@@ -249,6 +266,9 @@ static int jit_compile(const std::string& source, const char* kernel_name, JitKe
           cudaLibraryGetKernel(&out->kern, out->lib, kernel_name) == cudaSuccess) {
         if (text_bytes) *text_bytes = cubin_text_bytes(cubin);
         g_jit_hits.fetch_add(1);
+        std::lock_guard<std::mutex> lk(mem_mu);
+        if (mem_cache.size() >= 64) mem_cache.clear();
+        mem_cache[mem_key] = std::move(cubin);
         return 0;
       }
       cudaGetLastError();  // a truncated or foreign file: compile as if it were not there
@@ -281,6 +301,11 @@ static int jit_compile(const std::string& source, const char* kernel_name, JitKe
   if (text_bytes) *text_bytes = cubin_text_bytes(cubin);
   SDB_CUDA(cudaLibraryLoadData(&out->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
   SDB_CUDA(cudaLibraryGetKernel(&out->kern, out->lib, kernel_name));
+  {
+    std::lock_guard<std::mutex> lk(mem_mu);
+    if (mem_cache.size() >= 64) mem_cache.clear();
+    mem_cache[mem_key] = cubin;
+  }
   if (!cache_file.empty()) {  // publish atomically: write a private file, then rename
     mkdirs(dir);
     const std::string tmp = cache_file + "." + std::to_string((long)getpid()) + ".tmp";
