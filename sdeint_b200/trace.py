@@ -287,7 +287,7 @@ class SymArray(np.ndarray):
 import contextlib
 import threading
 
-_PATCH_LOCK = threading.Lock()
+_PATCH_LOCK = threading.RLock()   # re-entrant: a traced function may itself trace (nested calls)
 
 
 @contextlib.contextmanager
@@ -307,9 +307,14 @@ def _object_allocators():
         return alloc
 
     with _PATCH_LOCK:
+        if getattr(np.zeros, "_sdb_traced", False):            # nested trace: already patched
+            yield
+            return
         try:
             for n in names:
-                setattr(np, n, wrap(orig[n]))
+                w = wrap(orig[n])
+                w._sdb_traced = True
+                setattr(np, n, w)
             yield
         finally:
             for n in names:
