@@ -714,8 +714,11 @@ static int integrate_impl(sdb_system* s, const sdb_integrate_args* a, const SdbO
   // ... Iwik/Jwik and the larger shapes through the TMEM-resident kernel (sdb_fusedx.cuh, one lane per path)
   if (ud_ok && !fused && !aff_g && SdbFusedXDims(s->d, s->m, -1).supported()) {
     const SdbFusedXDims xdims(s->d, s->m, -1);
+    const SdbFusedX2Dims x2dims(s->d, s->m, -1);   // two lanes per path where one warp per sub-partition is left
+    const bool use_x2 = x2dims.supported() && !getenv("SDB_DISABLE_FUSEDX2");
     const bool wik = noise == SDB_NOISE_WIK;
-    const std::string key = std::string(wik ? "fusedxjit|wik|ud" : "fusedxjit|kpw|ud") + ext_suffix(ext);
+    const std::string key = std::string(wik ? "fusedxjit|wik" : "fusedxjit|kpw") + (use_x2 ? "|x2" : "") + "|ud" +
+                            ext_suffix(ext);
     std::lock_guard<std::mutex> lk(s->mu);
     auto it = s->jit.find(key);
     if (it == s->jit.end()) {
@@ -726,8 +729,9 @@ static int integrate_impl(sdb_system* s, const sdb_integrate_args* a, const SdbO
       if (s->fk == SDB_DRIFT_USER) src << "#line 1 \"user_source.cu\"\n" << s->src << "\n";
       src << "typedef " << type_of(s, true) << " F_jit;\n";
       src << "#define SDB_FUSED_RB 2\n#define SDB_FUSED_VOL_MMA 0\n#define SDB_FUSED_A2 (-1)\n"
-          << "#define SDB_FUSED_DRIFT_T F_jit\n#include \"sdb_fusedx.cuh\"\n"
-          << "SDB_FUSEDX_KERNEL_UD(sdb_jit_fused, " << s->d << ", " << s->m << ", " << (wik ? 1 : 0) << ")\n";
+          << "#define SDB_FUSED_DRIFT_T F_jit\n#include \"" << (use_x2 ? "sdb_fusedx2.cuh" : "sdb_fusedx.cuh")
+          << "\"\n" << (use_x2 ? "SDB_FUSEDX2_KERNEL_UD" : "SDB_FUSEDX_KERNEL_UD") << "(sdb_jit_fused, " << s->d
+          << ", " << s->m << ", " << (wik ? 1 : 0) << ")\n";
       JitKernel k;
       if (jit_compile(src.str(), "sdb_jit_fused", &k)) return 1;
       it = s->jit.emplace(key, k).first;
@@ -735,9 +739,10 @@ static int integrate_impl(sdb_system* s, const sdb_integrate_args* a, const SdbO
     jit_rb = 2;
     jit_xr = -1;
     jit_ud = true;
-    jit_entry = SdbFusedEntry{s->d, s->m, 0, (const void*)it->second.kern, xdims.smem_bytes(),
-                              xdims.sh.table_doubles(), nullptr, xdims.threads(), xdims.threads(), noise,
-                              SDB_SCHEME_SRK2};
+    jit_entry = SdbFusedEntry{s->d, s->m, 0, (const void*)it->second.kern,
+                              use_x2 ? x2dims.smem_bytes() : xdims.smem_bytes(), xdims.sh.table_doubles(), nullptr,
+                              use_x2 ? x2dims.threads() : xdims.threads(),
+                              use_x2 ? x2dims.paths_per_block() : xdims.threads(), noise, SDB_SCHEME_SRK2};
     fused = &jit_entry;
     label = "jit:" + key;
   }

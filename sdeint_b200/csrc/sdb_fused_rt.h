@@ -124,12 +124,13 @@ struct SdbFusedXDims {
 // shapes whose areas leave room for only one warp per sub-partition in SdbFusedXDims.
 struct SdbFusedX2Dims {
   SdbFusedXDims x;
-  constexpr SdbFusedX2Dims(int d, int m) : x(d, m) {}
+  constexpr SdbFusedX2Dims(int d, int m, int xr = 1) : x(d, m, xr) {}   // xr -1: any drift (D more rows per warp)
   static constexpr int threads() { return 256; }
   static constexpr int paths_per_block() { return 128; }
   constexpr int GR() const { return x.sh.grows() >= 2 * x.sh.M ? x.sh.grows() : 2 * x.sh.M; }
   constexpr size_t smem_bytes() const {
-    const size_t b = ((size_t)GR() * 32 * 8 + (size_t)x.sh.D * 32 * 4) * 8 + 128 * 16 +
+    const size_t b = ((size_t)GR() * 32 * 8 + (size_t)x.sh.D * 32 * 4 +
+                      (x.sh.XR < 0 ? (size_t)x.sh.D * 32 * 8 : 0)) * 8 + 128 * 16 +
                      (SdbFusedDims::MAX_TERMS + 1 + x.sh.n_left() + 1) * sizeof(double) + 16;
     return b < 120u * 1024u ? 120u * 1024u : b;
   }

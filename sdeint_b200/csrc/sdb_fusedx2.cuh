@@ -35,8 +35,9 @@ struct SdbX2Shape {
   static constexpr int GR = Xs::GR >= 2 * M ? Xs::GR : 2 * M;  // staging rows of one warp (>= the X/Z swap)
   static constexpr int WARPS = 8, THREADS = 256, PATHS = 128;
   static SDB_CX size_t smem_bytes() {
-    size_t b = ((size_t)GR * 32 * WARPS + (size_t)D * 32 * 4) * 8 + 128 * 16 +
-               (SDB_FUSED_MAX_TERMS + 1 + Sh::n_left() + 1) * sizeof(double) + 16;
+    // (SDB_FUSED_A2 -1, any drift evaluated per lane: D more rows per warp for f(Y_n) h)
+    size_t b = ((size_t)GR * 32 * WARPS + (size_t)D * 32 * 4 + (SDB_FUSED_A2 < 0 ? (size_t)D * 32 * WARPS : 0)) * 8 +
+               128 * 16 + (SDB_FUSED_MAX_TERMS + 1 + Sh::n_left() + 1) * sizeof(double) + 16;
     return b < 120 * 1024 ? 120 * 1024 : b;  // > half an SM: one block (one TMEM allocation) per SM
   }
 };
@@ -107,9 +108,18 @@ SDB_DEV void sdb_x2_tail2_chunks(const double (&dW)[M], const double (&u)[M], do
 }
 
 // second drift evaluation and new state for the rows [I0, I1):  Y_i = H20_i + Yacc_i + (h/2) (A H20)_i
-template <int D, int I0, int I1, bool A2>
-SDB_DEV void sdb_x2_final_rows(const PInline<D * D>& fp, const double (&H20)[D], const double (&Yacc)[I1 - I0],
-                               double h, double (&Y)[I1 - I0]) {
+template <int D, int I0, int I1, bool A2, class FP>
+SDB_DEV void sdb_x2_final_rows(const FP& fp, const double (&H20)[D], const double (&Yacc)[I1 - I0],
+                               double h, double t1, double (&Y)[I1 - I0]) {
+#if SDB_FUSED_A2 < 0
+  double f1[D];  // any drift: f(H20, t_{n+1}) in full (each role of the pair evaluates it), this role's rows kept
+  SDB_FUSED_DRIFT_T::eval(fp, H20, t1, f1);
+#pragma unroll
+  for (int i = I0; i < I1; ++i) Y[i - I0] = H20[i] + fma(0.5 * h, f1[i], Yacc[i - I0]);
+  return;
+#else
+  (void)t1;
+#endif
 #pragma unroll
   for (int i = I0; i < I1; ++i) {
     if constexpr (A2) {
@@ -123,15 +133,15 @@ SDB_DEV void sdb_x2_final_rows(const PInline<D * D>& fp, const double (&H20)[D],
   }
 }
 
-template <int D, int M, int WIK>
-SDB_DEV void sdb_srk2_fusedx2_body(const SdbLoopArgs& a, const PInline<D * D>& fp,
+template <int D, int M, int WIK, class FP = PInline<D * D>>
+SDB_DEV void sdb_srk2_fusedx2_body(const SdbLoopArgs& a, const FP& fp,
                                    const double* __restrict__ frag, double* smem) {
   typedef SdbFusedShape<D, M, SDB_FUSED_A2> Sh;
   typedef SdbXShape<D, M> Xs;
   typedef SdbX2Shape<D, M> X2;
   // the A^2 rows of the P1 table replace the second drift evaluation; with Wiktorsson's tail compiled in
   // ptxas allocates worse with it (cfg4: 3.10e8 against 3.21e8 path-steps/s), so that build keeps the loop
-  constexpr bool USE_A2 = SDB_FUSED_A2 && WIK == 0;
+  constexpr bool USE_A2 = SDB_FUSED_A2 > 0 && WIK == 0;
   constexpr int MM = Xs::MM, CH = Xs::CH, NCH = Xs::NCH, RN = Xs::RN, NB = Xs::NB, LT = Xs::LT;
   constexpr int T1 = Xs::T1, KT3 = Xs::KT3, IT = Xs::IT, IL = Xs::IL;
   constexpr int NBH = X2::NBH, NCHH = X2::NCHH, DH = X2::DH, GR = X2::GR;
@@ -143,7 +153,12 @@ SDB_DEV void sdb_srk2_fusedx2_body(const SdbLoopArgs& a, const PInline<D * D>& f
   const int bar_id = 1 + pair;
 
   double* ybase = smem + (size_t)GR * 32 * X2::WARPS;
+#if SDB_FUSED_A2 < 0
+  double* fbuf = ybase + (size_t)D * 32 * 4 + (size_t)warp * D * 32;  // this warp's f(Y_n) h, one column per lane
+  double2* tab = reinterpret_cast<double2*>(ybase + (size_t)D * 32 * 4 + (size_t)D * 32 * X2::WARPS);
+#else
   double2* tab = reinterpret_cast<double2*>(ybase + (size_t)D * 32 * 4);
+#endif
   double* s_hk = reinterpret_cast<double*>(tab + 128);
   double* s_left = s_hk + SDB_FUSED_MAX_TERMS + 1;
   uint32_t* tm_slot = reinterpret_cast<uint32_t*>(s_left + Sh::n_left() + 1);
@@ -303,6 +318,17 @@ SDB_DEV void sdb_srk2_fusedx2_body(const SdbLoopArgs& a, const PInline<D * D>& f
     }
     sdb_pair_sync(bar_id);  // all areas are in tensor memory; the staging rows are free again
 
+#if SDB_FUSED_A2 < 0
+    {  // any drift, evaluated one lane per path by BOTH roles (each needs the rows of its own blocks)
+      double Yv[D], f0[D];
+#pragma unroll
+      for (int l = 0; l < D; ++l) Yv[l] = ybuf[l * 32 + (lane ^ sdb_swz3(l))];
+      SDB_FUSED_DRIFT_T::eval(fp, Yv, a.tspan[n], f0);
+#pragma unroll
+      for (int l = 0; l < D; ++l) fbuf[l * 32 + lane] = f0[l] * h;
+      __syncwarp();
+    }
+#endif
     // ---- this role's row blocks (runtime loop: every block has RN rows) ------------------------------
     double w[IT > 0 ? IT : 1][4][2], wv[IL > 0 ? IL : 1];
 #pragma unroll
@@ -432,9 +458,13 @@ SDB_DEV void sdb_srk2_fusedx2_body(const SdbLoopArgs& a, const PInline<D * D>& f
           double piece[2 * RN];
 #pragma unroll
           for (int r = 0; r < RN; ++r) {
+            const int yr = R0 + r;
+#if SDB_FUSED_A2 < 0
+            const double f0h = ((const volatile double*)fbuf)[yr * 32 + lane];
+#else
             const int nn = M * RN + r;
             const double f0h = gv[nn * 32 + (lane ^ sdb_swz(nn))] * h;
-            const int yr = R0 + r;
+#endif
             const double yv = ybuf[yr * 32 + (lane ^ ((yr & 3) << 2))];
             piece[r] = yv + f0h;                      // H20
             if constexpr (USE_A2) {
@@ -529,7 +559,7 @@ SDB_DEV void sdb_srk2_fusedx2_body(const SdbLoopArgs& a, const PInline<D * D>& f
 #pragma unroll
         for (int i = 0; i < DH; ++i)
           Yacc[i] = rows[2 * RN * (i / RN) + RN + i % RN] + (wp[i] + gpart[i * 32 + lane]);
-        sdb_x2_final_rows<D, 0, DH, USE_A2>(fp, H20, Yacc, h, Yn);
+        sdb_x2_final_rows<D, 0, DH, USE_A2>(fp, H20, Yacc, h, a.tspan[n + 1], Yn);
         // (every reader of the old Y -- P1, the drift rows -- finished before the barrier above)
 #pragma unroll
         for (int i = 0; i < DH; ++i) ybuf[i * 32 + (lane ^ sdb_swz3(i))] = Yn[i];
@@ -538,7 +568,7 @@ SDB_DEV void sdb_srk2_fusedx2_body(const SdbLoopArgs& a, const PInline<D * D>& f
 #pragma unroll
         for (int i = DH; i < D; ++i)
           Yacc[i - DH] = rows[2 * RN * (i / RN) + RN + i % RN] + (wp[i] + gpart[(i - DH) * 32 + lane]);
-        sdb_x2_final_rows<D, DH, D, USE_A2>(fp, H20, Yacc, h, Yn);
+        sdb_x2_final_rows<D, DH, D, USE_A2>(fp, H20, Yacc, h, a.tspan[n + 1], Yn);
 #pragma unroll
         for (int i = DH; i < D; ++i) ybuf[i * 32 + (lane ^ sdb_swz3(i))] = Yn[i - DH];
       }
@@ -572,6 +602,13 @@ SDB_DEV void sdb_srk2_fusedx2_body(const SdbLoopArgs& a, const PInline<D * D>& f
 }  // namespace SDB_FUSED_NS
 using namespace SDB_FUSED_NS;
 
+#define SDB_FUSEDX2_KERNEL_UD(NAME, D, M, WIK)                                                \
+  extern "C" __global__ void __launch_bounds__((SdbX2Shape<D, M>::THREADS), 1)                \
+      NAME(const __grid_constant__ SdbLoopArgs a,                                             \
+           const __grid_constant__ SDB_FUSED_DRIFT_T::Params fp, const double* __restrict__ frag) { \
+    extern __shared__ __align__(16) double sdb_fused_smem[];                                  \
+    sdb_srk2_fusedx2_body<D, M, WIK, SDB_FUSED_DRIFT_T::Params>(a, fp, frag, sdb_fused_smem); \
+  }
 #define SDB_FUSEDX2_KERNEL(NAME, D, M, WIK)                                                   \
   extern "C" __global__ void __launch_bounds__((SdbX2Shape<D, M>::THREADS), 1)                \
       NAME(const __grid_constant__ SdbLoopArgs a, const __grid_constant__ PInline<D * D> fp,  \

@@ -409,7 +409,7 @@ def test_linear_expressions_run_the_linear_kernels(sdb):
     assert np.array_equal(y_n, y_n2)
 
 
-@pytest.mark.parametrize("d,m,wik", [(10, 10, True), (16, 12, False), (8, 6, True)])
+@pytest.mark.parametrize("d,m,wik", [(10, 10, True), (16, 12, False), (8, 6, True), (20, 20, True), (12, 16, False)])
 def test_fusedx_user_drift(sdb, monkeypatch, d, m, wik):
     """Nonlinear drift + linear diffusion through the TMEM-resident kernel (Iwik/Jwik, or shapes beyond the
     8-warp kernel): `jit:fusedxjit|...|ud` against the oracle on replayed device noise and the generic kernel."""
@@ -422,7 +422,8 @@ def test_fusedx_user_drift(sdb, monkeypatch, d, m, wik):
     P, seed = 40, 909
     rep = sdb.Iwik if wik else sdb.Ikpw
     y = sdb.itoSRI2(f, G, y0, tspan, rep, paths=P, seed=seed, commutative=False)
-    assert sdb.last_kernel() == "jit:fusedxjit|%s|ud" % ("wik" if wik else "kpw")
+    x2 = "|x2" if m >= 16 else ""        # two lanes per path where a path's areas fill its TMEM lane
+    assert sdb.last_kernel() == "jit:fusedxjit|%s%s|ud" % ("wik" if wik else "kpw", x2)
     dW = sdb.deltaW(N - 1, m, h, paths=P, seed=seed)
     _, I = rep(dW, h, seed=seed, ensemble=True)
     for p in (0, 33, P - 1):
