@@ -24,7 +24,10 @@ SDB_FUSED_AOT(5, 4)     // Roessler (7.4) dimensions
                     SdbFusedDims(D, M, 4, 1).smem_bytes() == SdbFusedShape<D, M, 1>::smem_bytes() &&  \
                     SdbFusedDims(D, M, 4, 1).n_frags() == SdbFusedShape<D, M, 1>::n_frags() &&  \
                     SdbFusedDims(D, M, 4, 1).tab_copies() == SdbFusedShape<D, M, 1>::tab_copies() && \
-                    SdbFusedDims(D, M, 4, 1).p3_off(1) == SdbFusedShape<D, M, 1>::p3_off(1),   \
+                    SdbFusedDims(D, M, 4, 1).p3_off(1) == SdbFusedShape<D, M, 1>::p3_off(1) &&  \
+                    SdbFusedDims(D, M, 4, -1).smem_bytes() == SdbFusedShape<D, M, -1>::smem_bytes() && \
+                    SdbFusedDims(D, M, 4, -1).n_frags() == SdbFusedShape<D, M, -1>::n_frags() && \
+                    SdbFusedDims(D, M, 4, -1).p3_off(1) == SdbFusedShape<D, M, -1>::p3_off(1), \
                 "sdb_fused_rt.h disagrees with SdbFusedShape");
 SDB_CHECK_DIMS(10, 10) SDB_CHECK_DIMS(4, 4) SDB_CHECK_DIMS(8, 2) SDB_CHECK_DIMS(5, 4)
 SDB_CHECK_DIMS(3, 2) SDB_CHECK_DIMS(12, 6) SDB_CHECK_DIMS(15, 8) SDB_CHECK_DIMS(7, 10)
