@@ -386,6 +386,29 @@ def test_nvrtc_results_are_cached_on_disk(tmp_path):
     assert len(list((tmp_path / "jit").glob("*.cubin"))) == first["misses"]
 
 
+def test_user_drift_long_run_parity(sdb):
+    """SURVEY 8(d)-style long run for the kernels with the drift evaluated per lane: 64 paths x 1000 steps at
+    d = m = 10, SRI2 (Ikpw: 8-warp kernel; Iwik: TMEM kernel) and Heun, device noise replayed through the oracle."""
+    d = m = 10
+    _, G, y0 = sdb.ops.sys_lin(d, m)
+    f = sdb.ops.ExprDrift(["-p[0]*y[%d] + p[1]*y[%d] - p[2]*y[%d]*y[%d]*y[%d] + 0.05*cos(2*t)"
+                           % (i, (i + 1) % d, i, i, i) for i in range(d)], params=[1.5, 0.3, 0.2])
+    tspan = np.linspace(0.0, 1.0, 1001)
+    P, seed, h = 64, 2026, 1e-3
+    dW = sdb.deltaW(1000, m, h, paths=P, seed=seed)
+    for rep, key in ((sdb.Ikpw, "jit:fusedjit|ud"), (sdb.Iwik, "jit:fusedxjit|wik|ud")):
+        y = sdb.itoSRI2(f, G, y0, tspan, rep, paths=P, seed=seed, save_every=100, commutative=False)
+        assert sdb.last_kernel() == key
+        _, I = rep(dW, h, seed=seed, ensemble=True)
+        for p in (0, 63):
+            ref = orc.srk2(f, G, np.asarray(y0, float), tspan, dW[p], I[p])[::100]
+            assert rel_err(y[p], ref) <= TOL
+    yh = sdb.stratHeun(f, G, y0, tspan, paths=P, seed=seed, save_every=100)
+    assert sdb.last_kernel() == "jit:fusedehjit|heun|ud"
+    for p in (0, 63):
+        assert rel_err(yh[p], orc.heun(f, G, np.asarray(y0, float), tspan, dW[p])[::100]) <= TOL
+
+
 def test_linear_expressions_run_the_linear_kernels(sdb):
     """An SDE written as expressions that happen to be linear gets the kernels of the linear operators
     (ops.as_linear): bit-identical to LinearDrift / LinearDiffusion; with a nonlinear drift, the fused kernel
