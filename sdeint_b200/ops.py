@@ -507,6 +507,8 @@ def as_linear(op, dense_only=False):
             ok = bool(np.all(np.isfinite(G0)))
             if ok and np.abs(G0).max() == 0.0:
                 cand = LinearDiffusion(B)
+                if getattr(op, "commutative", False):      # the caller's promise outlives the promotion
+                    cand._commutative = True
             elif ok:                                   # B_k y + c_k: read B off G(e_l) - G(0)
                 B = B - G0.T[:, :, None]
                 lin = lambda y: np.dot(B, y).T + G0
