@@ -122,9 +122,40 @@ def wiener_fixture():
     print("wrote wiener.npz")
 
 
+def callables_fixture():
+    """Plain Python callables (tests/callable_systems.py) through the unmodified reference: what sdeint_b200
+    must reproduce when it TRACES the same objects into device code."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import callable_systems as cs
+    out = {}
+    for ci, (name, make) in enumerate(sorted(cs.SYSTEMS.items())):
+        made = make()
+        f, G, y0 = made[:3]
+        m = np.asarray(G(y0, 0.0)).shape[1]
+        P, N, T = 2, 201, 0.5
+        tspan = np.linspace(0.0, T, N)
+        h = T / (N - 1)
+        dW, I, J = _noise(900 + ci, P, N, m, h, sdeint.Ikpw)
+        pre = name + "_"
+        out.update({pre + "tspan": tspan, pre + "dW": dW, pre + "I": I, pre + "J": J, pre + "y0": y0})
+        out[pre + "y_itoEuler"] = np.stack([sdeint.itoEuler(f, G, y0, tspan, dW=dW[p]) for p in range(P)])
+        out[pre + "y_stratHeun"] = np.stack([sdeint.stratHeun(f, G, y0, tspan, dW=dW[p]) for p in range(P)])
+        out[pre + "y_itoSRI2"] = np.stack([sdeint.itoSRI2(f, G, y0, tspan, dW=dW[p], I=I[p]) for p in range(P)])
+        out[pre + "y_stratSRS2"] = np.stack([sdeint.stratSRS2(f, G, y0, tspan, dW=dW[p], J=J[p]) for p in range(P)])
+        if len(made) > 3:     # the list-of-columns form of G (integrate.py:330-334)
+            out[pre + "y_itoSRI2_listG"] = np.stack([sdeint.itoSRI2(f, made[3], y0, tspan, dW=dW[p], I=I[p])
+                                                     for p in range(P)])
+    np.savez(os.path.join(OUT, "callables.npz"), **out)
+    print("wrote callables.npz  (%s)" % ", ".join(sorted(cs.SYSTEMS)))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--callables-only" in sys.argv:
+        callables_fixture()
+        return
     wiener_fixture()
+    callables_fixture()
     integrator_fixture("kp4446", lambda s: ops.sys_kp4446(s), P=3, N=251, T=1.0, seed=11,
                        method=sdeint.Iwik, list_g=False)
     integrator_fixture("kp4459", lambda s: ops.sys_kp4459(s), P=3, N=251, T=0.5, seed=12,

@@ -142,3 +142,21 @@ def test_oracle_against_live_reference(reference):
     dW = orc.delta_w(50, 10, hh, g)
     _, I = orc.ikpw(dW, hh, generator=g)
     assert rel_err(orc.srk2(f, G.columns(), y0, tspan, dW, I), y_ref) <= TOL
+
+
+def test_oracle_matches_reference_on_python_callables():
+    """tests/golden/callables.npz: the unmodified reference run on plain Python f, G (tests/callable_systems.py:
+    np.maximum, np.where, masks, preallocated results, np.dot, list-of-columns G); the oracle must reproduce it."""
+    import callable_systems as cs
+    g = load_golden("callables.npz")
+    for name, make in cs.SYSTEMS.items():
+        made = make()
+        f, G, y0 = made[:3]
+        ts, dW, I, J = (g["%s_%s" % (name, k)] for k in ("tspan", "dW", "I", "J"))
+        for p in range(dW.shape[0]):
+            assert rel_err(orc.euler(f, G, y0, ts, dW[p]), g[name + "_y_itoEuler"][p]) <= 1e-13
+            assert rel_err(orc.heun(f, G, y0, ts, dW[p]), g[name + "_y_stratHeun"][p]) <= 1e-13
+            assert rel_err(orc.srk2(f, G, y0, ts, dW[p], I[p]), g[name + "_y_itoSRI2"][p]) <= 1e-13
+            assert rel_err(orc.srk2(f, G, y0, ts, dW[p], J[p]), g[name + "_y_stratSRS2"][p]) <= 1e-13
+            if len(made) > 3:
+                assert rel_err(orc.srk2(f, made[3], y0, ts, dW[p], I[p]), g[name + "_y_itoSRI2_listG"][p]) <= 1e-13
