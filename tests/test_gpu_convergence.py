@@ -532,3 +532,17 @@ def test_levy_area_variances(sdb):
             a2 = ((I - sym)[..., 0, 1].ravel()) ** 2
             slope, icpt = np.polyfit(s2, a2, 1)
             assert abs(slope / c1 - 1.0) < 0.05 and abs(icpt / c0 - 1.0) < 0.08, (n, slope, c1, icpt, c0)
+
+
+def test_reference_1d_additive_statistics(sdb):
+    """sdeint/tests/test_integrate.py:36-54 (test_ito_1D_additive, test_strat_1D_additive), as written there: plain
+    Python f and G, scalar y0, the generator passed positionally, ONE path of 10^6 points; the stationary mean and
+    variance of the Ornstein-Uhlenbeck process within the reference's own tolerances."""
+    tspan = np.arange(0.0, 2000.0, 0.002)
+    f = lambda y, t: -1.0 * y
+    G = lambda y, t: 0.2
+    for integ, seed in ((sdb.itoint, 1), (sdb.stratint, 2)):
+        y = np.asarray(integ(f, G, 0.0, tspan, np.random.default_rng(seed)))
+        assert y.shape[0] == len(tspan)
+        assert np.isclose(np.mean(y), 0.0, rtol=0, atol=1e-02)
+        assert np.isclose(np.var(y), 0.2 * 0.2 / 2, rtol=1e-01, atol=0)
